@@ -1,0 +1,22 @@
+"""CPU oracle for the SCP / fast-SLS robust-MPC hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the product: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it,
+and there only as the checker / the timed CPU baseline.  The product path (``robust-nonlinear-mpc_b200``)
+never imports this package and fails loudly when its CUDA library is missing.
+
+The oracle is a plain NumPy restatement of the reference algorithm
+(``/root/reference/solver/{SCP_SLS_jit,fast_SLS_jit,qp_jit,ocp}.py`` and ``dyn/*.py``); every function cites the
+reference file:line it follows.
+
+Parity pinning:
+  * Riccati backward sweep, Phi propagation and tube back-offs are pinned against the reference's OWN Numba
+    kernels (``solver/fast_SLS_jit.py:43-188``), imported in the build container under import stubs by
+    ``oracle/gen_golden.py``; their outputs are committed as ``tests/golden/sls_*.npz``.
+  * Dynamics/Jacobians are pinned against closed-form SymPy differentiation of the same ODE and against
+    finite differences (the reference evaluates them through CasADi 3.7.1, absent here).
+  * The nominal QP is solved in the reference by OSQP 1.0.4 (absent here, un-vendored) with default
+    tolerances plus polish: PARITY UNPINNED at that boundary.  The QP is strictly convex, so its primal
+    solution is unique; the oracle solves it to KKT residual <= 1e-9 with an independent dense primal-dual
+    interior-point method plus exact active-set refinement.
+"""
