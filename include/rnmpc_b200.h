@@ -1,0 +1,151 @@
+/* rnmpc_b200 -- C ABI of the B200-native robust-nonlinear-MPC inner solve (SCP / fast-SLS / nominal QP).
+ *
+ * The reference (antoineleeman/robust-nonlinear-mpc) has no FFI: its boundary for this path is the Python object
+ * API of solver/SCP_SLS_jit.py, solver/fast_SLS_jit.py and solver/qp_jit.py.  Each entry point below names the
+ * reference interface it replaces (file:line).  The library is batch-first: every call processes `B` independent
+ * MPC instances (Monte-Carlo scenarios); the Python mirror of the reference classes
+ * (robust-nonlinear-mpc_b200/solver/*.py) binds these symbols through ctypes with B = 1 or B = batch.
+ *
+ * Conventions
+ *   - all numeric buffers are float64, C-order, batch-major; `d_` = device pointer (cudaMalloc / torch CUDA tensor
+ *     data_ptr), `h_` = host pointer.  The caller owns every buffer it passes.  A handle is bound to one CUDA device
+ *     and is NOT thread-safe (the reference solver objects are not either).
+ *   - return value: 0 = OK, < 0 = argument / CUDA error (rnmpc_last_error() gives the text).  Solver failure of an
+ *     instance is NOT an error: it is reported per instance in `status` (0 ok, 1 QP not converged, 2 QP infeasible /
+ *     numerical failure), mirroring the reference's {'success': False} (qp_jit.py:397-400, fast_SLS_jit.py:334-341).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous unless stated.
+ *   - sizes: nx, nu from the model; nz = nx+nu; ni = 2*nz; ni_f = 2*nx; nw = nx.
+ *   - box constraints only: G = [I; -I], Gf = [I; -I] (all reference models, dyn/rocket.py:129-139).
+ */
+#ifndef RNMPC_B200_H
+#define RNMPC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rnmpc_handle rnmpc_handle;
+
+enum { RNMPC_PENDULUM = 0, RNMPC_QUADROTOR = 1, RNMPC_ROCKET = 2 };
+
+/* Host-side problem description (all pointers are host pointers, copied at create time).
+ * Replaces the constructor arguments SCP_SLS(N, Q, R, m, Qf, Q_reg, R_reg, Q_reg_f, rti, fast_sls_rti_steps)
+ * (solver/SCP_SLS_jit.py:24-44) and the model attributes m.E, m.g, m.gf (dyn/model.py:4-13, dyn/rocket.py:129-163). */
+typedef struct rnmpc_config {
+    int model_id;            /* RNMPC_PENDULUM / RNMPC_QUADROTOR / RNMPC_ROCKET */
+    int N;                   /* horizon */
+    int rti;                 /* SCP iterations per solve (>0); reference kwarg `rti` */
+    int sls_steps;           /* fast-SLS iterations per SCP iteration (>0); reference kwarg `fast_sls_rti_steps` */
+    const double* Q;         /* [nx*nx] */
+    const double* R;         /* [nu*nu] */
+    const double* Qf;        /* [nx*nx] */
+    const double* Q_reg;     /* [nx*nx] */
+    const double* R_reg;     /* [nu*nu] */
+    const double* Q_reg_f;   /* [nx*nx] */
+    const double* E;         /* [nx*nx] disturbance map (nw == nx) */
+    const double* x_ub;      /* [nx]  g = [x_ub, u_ub, -x_lb, -u_lb] */
+    const double* x_lb;      /* [nx] */
+    const double* u_ub;      /* [nu] */
+    const double* u_lb;      /* [nu] */
+    const double* xf_ub;     /* [nx]  gf = [xf_ub, -xf_lb] */
+    const double* xf_lb;     /* [nx] */
+    double h;                /* RK4 step of ddyn (0.05 on the SCP path, dyn/model.py:15) */
+    int qp_max_iter;         /* interior-point iteration cap (default 60 if <= 0) */
+    double qp_tol_mu;        /* complementarity tolerance (default 1e-14 if <= 0) */
+    double qp_tol_res;       /* dynamics-residual tolerance (default 1e-9 if <= 0) */
+} rnmpc_config;
+
+const char* rnmpc_last_error(void);
+int rnmpc_model_dims(int model_id, int* nx, int* nu);
+
+/* Lifetime.  `capacity` = largest batch the handle's internal workspace serves; `device` = CUDA ordinal. */
+int rnmpc_create(rnmpc_handle** out, const rnmpc_config* cfg, int capacity, int device);
+int rnmpc_destroy(rnmpc_handle* h);
+
+/* ---- stateless kernels on caller-owned device buffers ------------------------------------------------------ */
+
+/* x+ = ddyn(x, u) [+ E w]   (dyn/model.py:15-34; plant step expe/main_rocket_compare_closed_loop.py:159).
+ * d_x [B][nx], d_u [B][nu], d_w [B][nx] or NULL, d_xp [B][nx]. */
+int rnmpc_ddyn(rnmpc_handle* h, int B, const double* d_x, const double* d_u, const double* d_w, double* d_xp, void* stream);
+
+/* A_k, B_k, c_k along a trajectory (SCP_SLS.update_jacobian, solver/SCP_SLS_jit.py:251-277).
+ * d_X [B][N+1][nx], d_U [B][N][nu] -> d_A [B][N][nx][nx], d_B [B][N][nx][nu], d_c [B][N][nx]. */
+int rnmpc_linearize(rnmpc_handle* h, int B, const double* d_X, const double* d_U, double* d_A, double* d_B, double* d_c,
+                    void* stream);
+
+/* fast-SLS backward Riccati sweep + Phi propagation + back-offs with explicit weights
+ * (_backward_solve_numba, _propagate, _backoff_from_phi: solver/fast_SLS_jit.py:65-188).
+ * d_eta [B][N][N][ni], d_eta_f [B][N+1][ni_f] -> d_K [B][N][N+1][nu][nx], d_beta [B][N][N][ni], d_beta_f [B][N+1][ni_f],
+ * d_backoff [B][N][ni], d_backoff_f [B][ni_f]; optional (NULL to skip) d_S [B][N+1][N+1][nx][nx],
+ * d_Phi_x [B][N+1][N+1][nx][nx], d_Phi_u [B][N][N+1][nu][nx].  Entries with j > k are not written (zero them once). */
+int rnmpc_sls(rnmpc_handle* h, int B, const double* d_A, const double* d_B, const double* d_eta, const double* d_eta_f,
+              double* d_K, double* d_S, double* d_Phi_x, double* d_Phi_u, double* d_beta, double* d_beta_f,
+              double* d_backoff, double* d_backoff_f, void* stream);
+
+/* Nominal QP (QP.solve, solver/qp_jit.py:343-402 + _pack_solution :487-513).
+ * tightened = 0: bounds g_k - G z_k + 1e-10, terminal gf - Gf x_N + 1e-10 (after update_dynamics/offset_constraints);
+ * tightened = 1: g_k - G z_k - backoff_k, terminal gf - backoff_f (after fast_SLS.update_tightening, quirk Q4).
+ * Inputs d_A, d_B, d_c, nominal d_X [B][N+1][nx], d_U [B][N][nu], measured state d_x0 [B][nx], d_backoff/d_backoff_f
+ * (tightened only).  Outputs d_dX [B][N+1][nx], d_dU [B][N][nu], d_mu [B][N][ni] (= dual_mu^T), d_mu_f [B][ni_f],
+ * d_cost [B], d_iters [B], d_status [B]. */
+int rnmpc_qp(rnmpc_handle* h, int B, int tightened, const double* d_A, const double* d_B, const double* d_c,
+             const double* d_X, const double* d_U, const double* d_x0, const double* d_backoff, const double* d_backoff_f,
+             double* d_dX, double* d_dU, double* d_mu, double* d_mu_f, double* d_cost, int* d_iters, int* d_status,
+             void* stream);
+
+/* ---- stateful solver on the handle's resident trajectories ----------------------------------------------- */
+
+/* Load the nominal trajectories of B instances (replaces the IPOPT initial guess, SCP_SLS_jit.py:161-188, and is what
+ * reset()/a fresh solver start from).  Clears the warm-start state incl. the Q3 history. */
+int rnmpc_set_nominal(rnmpc_handle* h, int B, const double* d_X, const double* d_U, void* stream);
+
+/* Tube-free SQP initialiser for the first MPC step (replaces NLP.solve / IPOPT, solver/nlp.py:158-217): states
+ * interpolated from x0 to the origin, zero inputs, `iters` full-step nominal-QP iterations. */
+int rnmpc_init_nominal(rnmpc_handle* h, int B, const double* d_x0, int iters, void* stream);
+
+/* One SCP_SLS.solve(x0) (solver/SCP_SLS_jit.py:65-152, RTI policy): rti x [linearise, fast_SLS.solve = sls_steps x
+ * (QP, eta, Q3 test, Riccati, Phi, back-offs, tightening) + final QP, nominal update].  d_x0 [B][nx]. */
+int rnmpc_solve(rnmpc_handle* h, int B, const double* d_x0, void* stream);
+
+/* SCP_SLS.reset_warm_start() (solver/SCP_SLS_jit.py:500-551): shift X, U, roll the terminal state. */
+int rnmpc_reset_warm_start(rnmpc_handle* h, int B, void* stream);
+
+/* Closed-loop plant step with the first nominal input: x <- ddyn(x, U[:,0]) + E w  (d_w may be NULL).
+ * d_x [B][nx] in/out; d_u0 [B][nu] optional output. */
+int rnmpc_plant_step(rnmpc_handle* h, int B, double* d_x, const double* d_w, double* d_u0, void* stream);
+
+/* Device pointers of the resident results of the last solve (valid until the handle is destroyed).
+ * name in: "X" [cap][N+1][nx], "U" [cap][N][nu], "dX", "dU", "mu" [cap][N][ni], "mu_f" [cap][ni_f], "K"
+ * [cap][N][N+1][nu][nx], "beta" [cap][N][N][ni], "beta_f" [cap][N+1][ni_f], "backoff" [cap][N][ni], "backoff_f"
+ * [cap][ni_f], "A", "B", "c", "cost" [cap], "Phi_x", "Phi_u" (only after rnmpc_enable_phi), "flags" (int32 [cap]:
+ * bit0 failed, bit1 Q3 early return in the last fast-SLS step, bit2 tube back-offs valid), "status" (int32 [cap]),
+ * "qp_iters" (int32 [cap], interior-point iterations summed over the QPs of the last solve). */
+int rnmpc_get_buffer(rnmpc_handle* h, const char* name, void** d_ptr, long long* n_bytes);
+int rnmpc_enable_phi(rnmpc_handle* h, int enable);
+/* Synchronous device->host copy of the first n_bytes of a named resident buffer. */
+int rnmpc_copy_buffer(rnmpc_handle* h, const char* name, void* h_dst, long long n_bytes);
+
+/* ---- host-buffer entry points (what a NumPy caller such as expe/main_*_closed_loop.py uses) ------------------ */
+
+/* solve from host x0 [B][nx]; copies back X [B][N+1][nx], U [B][N][nu], backoff [B][N][ni], backoff_f [B][ni_f],
+ * flags [B], status [B] (any output pointer may be NULL).  Synchronous. */
+int rnmpc_solve_host(rnmpc_handle* h, int B, const double* h_x0, double* h_X, double* h_U, double* h_backoff,
+                     double* h_backoff_f, int* h_flags, int* h_status);
+
+/* Whole closed loops (expe/main_rocket_compare_closed_loop.py:104-173 `_run_robust`) for B scenarios:
+ * h_x0 [B][nx], h_W [B][steps][nx] (NULL = noise free), initial nominal h_X0/h_U0 ([B][N+1][nx], [B][N][nu]; NULL ->
+ * rnmpc_init_nominal with init_iters).  Outputs (NULL to skip): h_states [B][steps+1][nx], h_inputs [B][steps][nu],
+ * h_backoff_x0 [B][steps][nx] (first-stage... see INTEGRATION.md), h_nfail [1] number of failed solves.  Synchronous. */
+int rnmpc_closed_loop_host(rnmpc_handle* h, int B, int steps, const double* h_x0, const double* h_W, const double* h_X0,
+                           const double* h_U0, int init_iters, double* h_states, double* h_inputs, long long* h_nfail);
+
+/* Measured FP64 FMA peak of the device (TFLOP/s), for the roofline denominator. */
+int rnmpc_fp64_peak(int device, double* tflops);
+
+/* Number of kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
+long long rnmpc_launch_count(rnmpc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNMPC_B200_H */

@@ -1,0 +1,6 @@
+"""Importable alias of the hyphenated package directory ``robust-nonlinear-mpc_b200/``."""
+import os as _os
+
+__path__ = [_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "robust-nonlinear-mpc_b200")]
+with open(_os.path.join(__path__[0], "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(__path__[0], "__init__.py"), "exec"))

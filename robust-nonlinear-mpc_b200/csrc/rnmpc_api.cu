@@ -1,0 +1,284 @@
+// C ABI of librnmpc_b200.so (declared in include/rnmpc_b200.h).
+#include <chrono>
+#include <mutex>
+#include <vector>
+
+#include "rnmpc_engine.cuh"
+
+namespace rnmpc {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+// DFMA peak probe: 16 independent accumulators per thread
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace rnmpc
+
+using namespace rnmpc;
+
+struct rnmpc_handle {
+    IEngine* e;
+    int nx, nu, N, cap;
+};
+
+#define RN_API_CUDA(call)                                                                      \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                     \
+            return -2;                                                                         \
+        }                                                                                      \
+    } while (0)
+
+extern "C" {
+
+const char* rnmpc_last_error(void) { return g_err.c_str(); }
+
+int rnmpc_model_dims(int model_id, int* nx, int* nu) {
+    switch (model_id) {
+        case RNMPC_PENDULUM: *nx = PendulumModel::NX; *nu = PendulumModel::NU; return 0;
+        case RNMPC_QUADROTOR: *nx = QuadrotorModel::NX; *nu = QuadrotorModel::NU; return 0;
+        case RNMPC_ROCKET: *nx = RocketModel::NX; *nu = RocketModel::NU; return 0;
+    }
+    set_error("unknown model id");
+    return -1;
+}
+
+int rnmpc_create(rnmpc_handle** out, const rnmpc_config* cfg, int capacity, int device) {
+    if (!out || !cfg) { set_error("null argument"); return -1; }
+    if (cfg->N < 1 || cfg->rti < 1 || cfg->sls_steps < 1 || capacity < 1) {
+        set_error("N, rti, sls_steps and capacity must be >= 1");
+        return -1;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: rnmpc_b200 has no CPU fallback");
+        return -3;
+    }
+    if (device < 0 || device >= ndev) { set_error("bad device ordinal"); return -1; }
+    IEngine* e = nullptr;
+    switch (cfg->model_id) {
+        case RNMPC_PENDULUM: e = make_pendulum(cfg, capacity, device); break;
+        case RNMPC_QUADROTOR: e = make_quadrotor(cfg, capacity, device); break;
+        case RNMPC_ROCKET: e = make_rocket(cfg, capacity, device); break;
+        default: set_error("unknown model id"); return -1;
+    }
+    if (!e) return -2;
+    auto* h = new rnmpc_handle();
+    h->e = e;
+    e->dims(&h->nx, &h->nu, &h->N, &h->cap);
+    *out = h;
+    return 0;
+}
+
+int rnmpc_destroy(rnmpc_handle* h) {
+    if (!h) return -1;
+    delete h->e;
+    delete h;
+    return 0;
+}
+
+#define RN_ENTER(h)                                  \
+    if (!(h)) { set_error("null handle"); return -1; } \
+    RN_API_CUDA(cudaSetDevice((h)->e->device));
+
+int rnmpc_ddyn(rnmpc_handle* h, int B, const double* x, const double* u, const double* w, double* xp, void* stream) {
+    RN_ENTER(h);
+    return h->e->ddyn(B, x, u, w, xp, (cudaStream_t)stream);
+}
+int rnmpc_linearize(rnmpc_handle* h, int B, const double* X, const double* U, double* A, double* Bm, double* c, void* stream) {
+    RN_ENTER(h);
+    return h->e->linearize(B, X, U, A, Bm, c, (cudaStream_t)stream);
+}
+int rnmpc_sls(rnmpc_handle* h, int B, const double* A, const double* Bm, const double* eta, const double* eta_f, double* K, double* S,
+              double* Phi_x, double* Phi_u, double* beta, double* beta_f, double* backoff, double* backoff_f, void* stream) {
+    RN_ENTER(h);
+    if (!A || !Bm || !eta || !eta_f || !K || !beta || !beta_f || !backoff || !backoff_f) { set_error("null buffer"); return -1; }
+    return h->e->sls(B, A, Bm, eta, eta_f, K, S, Phi_x, Phi_u, beta, beta_f, backoff, backoff_f, (cudaStream_t)stream);
+}
+int rnmpc_qp(rnmpc_handle* h, int B, int tightened, const double* A, const double* Bm, const double* c, const double* X, const double* U,
+             const double* x0, const double* backoff, const double* backoff_f, double* dX, double* dU, double* mu, double* mu_f,
+             double* cost, int* iters, int* status, void* stream) {
+    RN_ENTER(h);
+    if (tightened && (!backoff || !backoff_f)) { set_error("tightened QP needs back-offs"); return -1; }
+    return h->e->qp(B, tightened, A, Bm, c, X, U, x0, backoff, backoff_f, dX, dU, mu, mu_f, cost, iters, status, (cudaStream_t)stream);
+}
+int rnmpc_set_nominal(rnmpc_handle* h, int B, const double* X, const double* U, void* stream) {
+    RN_ENTER(h);
+    return h->e->set_nominal(B, X, U, (cudaStream_t)stream);
+}
+int rnmpc_init_nominal(rnmpc_handle* h, int B, const double* x0, int iters, void* stream) {
+    RN_ENTER(h);
+    return h->e->init_nominal(B, x0, iters, (cudaStream_t)stream);
+}
+int rnmpc_solve(rnmpc_handle* h, int B, const double* x0, void* stream) {
+    RN_ENTER(h);
+    return h->e->solve(B, x0, (cudaStream_t)stream);
+}
+int rnmpc_reset_warm_start(rnmpc_handle* h, int B, void* stream) {
+    RN_ENTER(h);
+    return h->e->reset_warm_start(B, (cudaStream_t)stream);
+}
+int rnmpc_plant_step(rnmpc_handle* h, int B, double* x, const double* w, double* u0, void* stream) {
+    RN_ENTER(h);
+    return h->e->plant_step(B, x, w, u0, (cudaStream_t)stream);
+}
+int rnmpc_get_buffer(rnmpc_handle* h, const char* name, void** ptr, long long* bytes) {
+    if (!h || !name || !ptr) { set_error("null argument"); return -1; }
+    return h->e->get_buffer(name, ptr, bytes);
+}
+int rnmpc_enable_phi(rnmpc_handle* h, int enable) {
+    RN_ENTER(h);
+    return h->e->enable_phi(enable);
+}
+int rnmpc_copy_buffer(rnmpc_handle* h, const char* name, void* dst, long long n_bytes) {
+    RN_ENTER(h);
+    void* p; long long n;
+    if (!dst || h->e->get_buffer(name, &p, &n)) return -1;
+    if (n_bytes > n) { set_error("copy larger than buffer"); return -1; }
+    RN_API_CUDA(cudaDeviceSynchronize());
+    RN_API_CUDA(cudaMemcpy(dst, p, (size_t)n_bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+long long rnmpc_launch_count(rnmpc_handle* h) { return h ? h->e->launches : -1; }
+
+static int copy_out(rnmpc_handle* h, const char* name, void* dst, size_t bytes, cudaStream_t st) {
+    if (!dst) return 0;
+    void* p; long long n;
+    if (h->e->get_buffer(name, &p, &n)) return -1;
+    RN_API_CUDA(cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+int rnmpc_solve_host(rnmpc_handle* h, int B, const double* h_x0, double* h_X, double* h_U, double* h_backoff, double* h_backoff_f,
+                     int* h_flags, int* h_status) {
+    RN_ENTER(h);
+    if (!h_x0 || B <= 0 || B > h->cap) { set_error("bad arguments"); return -1; }
+    const int nx = h->nx, nu = h->nu, N = h->N, ni = 2 * (nx + nu);
+    double* d_x0;
+    RN_API_CUDA(cudaMalloc((void**)&d_x0, (size_t)B * nx * sizeof(double)));
+    RN_API_CUDA(cudaMemcpy(d_x0, h_x0, (size_t)B * nx * sizeof(double), cudaMemcpyHostToDevice));
+    int rc = h->e->solve(B, d_x0, 0);
+    if (!rc) rc = copy_out(h, "X", h_X, (size_t)B * (N + 1) * nx * sizeof(double), 0);
+    if (!rc) rc = copy_out(h, "U", h_U, (size_t)B * N * nu * sizeof(double), 0);
+    if (!rc) rc = copy_out(h, "backoff", h_backoff, (size_t)B * N * ni * sizeof(double), 0);
+    if (!rc) rc = copy_out(h, "backoff_f", h_backoff_f, (size_t)B * 2 * nx * sizeof(double), 0);
+    if (!rc) rc = copy_out(h, "flags", h_flags, (size_t)B * sizeof(int), 0);
+    if (!rc) rc = copy_out(h, "status", h_status, (size_t)B * sizeof(int), 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(d_x0);
+    if (e != cudaSuccess) { set_error(std::string("solve: ") + cudaGetErrorString(e)); return -2; }
+    return rc;
+}
+
+int rnmpc_closed_loop_host(rnmpc_handle* h, int B, int steps, const double* h_x0, const double* h_W, const double* h_X0,
+                           const double* h_U0, int init_iters, double* h_states, double* h_inputs, long long* h_nfail) {
+    RN_ENTER(h);
+    if (!h_x0 || B <= 0 || B > h->cap || steps < 1) { set_error("bad arguments"); return -1; }
+    const int nx = h->nx, nu = h->nu, N = h->N;
+    double *d_x = nullptr, *d_W = nullptr, *d_states = nullptr, *d_inputs = nullptr, *d_tmp = nullptr;
+    int rc = 0;
+    cudaStream_t st = 0;
+    RN_API_CUDA(cudaMalloc((void**)&d_x, (size_t)B * nx * sizeof(double)));
+    RN_API_CUDA(cudaMalloc((void**)&d_states, (size_t)B * (steps + 1) * nx * sizeof(double)));
+    RN_API_CUDA(cudaMalloc((void**)&d_inputs, (size_t)B * steps * nu * sizeof(double)));
+    RN_API_CUDA(cudaMemcpyAsync(d_x, h_x0, (size_t)B * nx * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (h_W) {
+        // [B][steps][nx] on the host -> step-major [steps][B][nx] slices are gathered with a strided 2-D copy per step
+        RN_API_CUDA(cudaMalloc((void**)&d_W, (size_t)B * steps * nx * sizeof(double)));
+        RN_API_CUDA(cudaMemcpyAsync(d_W, h_W, (size_t)B * steps * nx * sizeof(double), cudaMemcpyHostToDevice, st));
+        RN_API_CUDA(cudaMalloc((void**)&d_tmp, (size_t)B * nx * sizeof(double)));
+    }
+    if (h_X0 && h_U0) {
+        double *dX0, *dU0;
+        RN_API_CUDA(cudaMalloc((void**)&dX0, (size_t)B * (N + 1) * nx * sizeof(double)));
+        RN_API_CUDA(cudaMalloc((void**)&dU0, (size_t)B * N * nu * sizeof(double)));
+        RN_API_CUDA(cudaMemcpyAsync(dX0, h_X0, (size_t)B * (N + 1) * nx * sizeof(double), cudaMemcpyHostToDevice, st));
+        RN_API_CUDA(cudaMemcpyAsync(dU0, h_U0, (size_t)B * N * nu * sizeof(double), cudaMemcpyHostToDevice, st));
+        rc = h->e->set_nominal(B, dX0, dU0, st);
+        cudaStreamSynchronize(st);
+        cudaFree(dX0); cudaFree(dU0);
+    } else {
+        rc = h->e->init_nominal(B, d_x, init_iters > 0 ? init_iters : 10, st);
+    }
+    long long nfail = 0;
+    std::vector<int> fl(B);
+    void* d_flags; long long nb;
+    h->e->get_buffer("flags", &d_flags, &nb);
+    const size_t srow = (size_t)(steps + 1) * nx * sizeof(double);
+    for (int i = 0; i < steps && !rc; ++i) {
+        RN_API_CUDA(cudaMemcpy2DAsync(d_states + (size_t)i * nx, srow, d_x, nx * sizeof(double), nx * sizeof(double), B,
+                                      cudaMemcpyDeviceToDevice, st));
+        if (i > 0) rc = h->e->reset_warm_start(B, st);
+        if (!rc) rc = h->e->solve(B, d_x, st);
+        const double* w = nullptr;
+        if (h_W && !rc) {
+            RN_API_CUDA(cudaMemcpy2DAsync(d_tmp, nx * sizeof(double), d_W + (size_t)i * nx, (size_t)steps * nx * sizeof(double),
+                                          nx * sizeof(double), B, cudaMemcpyDeviceToDevice, st));
+            w = d_tmp;
+        }
+        if (!rc) rc = h->e->plant_step(B, d_x, w, nullptr, st);
+        if (!rc) {
+            void* dU; h->e->get_buffer("U", &dU, &nb);
+            RN_API_CUDA(cudaMemcpy2DAsync(d_inputs + (size_t)i * nu, (size_t)steps * nu * sizeof(double), dU,
+                                          (size_t)N * nu * sizeof(double), nu * sizeof(double), B, cudaMemcpyDeviceToDevice, st));
+        }
+        if (h_nfail && !rc) {
+            RN_API_CUDA(cudaMemcpyAsync(fl.data(), d_flags, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+            RN_API_CUDA(cudaStreamSynchronize(st));
+            for (int b = 0; b < B; ++b) nfail += (fl[b] & 1);
+        }
+    }
+    if (!rc) {
+        RN_API_CUDA(cudaMemcpy2DAsync(d_states + (size_t)steps * nx, srow, d_x, nx * sizeof(double), nx * sizeof(double), B,
+                                      cudaMemcpyDeviceToDevice, st));
+        if (h_states) RN_API_CUDA(cudaMemcpyAsync(h_states, d_states, (size_t)B * srow, cudaMemcpyDeviceToHost, st));
+        if (h_inputs) RN_API_CUDA(cudaMemcpyAsync(h_inputs, d_inputs, (size_t)B * steps * nu * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d_x); cudaFree(d_states); cudaFree(d_inputs);
+    if (d_W) cudaFree(d_W);
+    if (d_tmp) cudaFree(d_tmp);
+    if (h_nfail) *h_nfail = nfail;
+    if (e != cudaSuccess) { set_error(std::string("closed_loop: ") + cudaGetErrorString(e)); return -2; }
+    return rc;
+}
+
+int rnmpc_fp64_peak(int device, double* tflops) {
+    if (!tflops) return -1;
+    RN_API_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    RN_API_CUDA(cudaGetDeviceProperties(&p, device));
+    const int blocks = p.multiProcessorCount * 8, thr = 256, iters = 4096;
+    double* out;
+    RN_API_CUDA(cudaMalloc((void**)&out, sizeof(double) * blocks * thr));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 6; ++r) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, thr>>>(out, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    RN_API_CUDA(cudaGetLastError());
+    *tflops = 2.0 * 16 * iters * (double)blocks * thr / (best * 1e-3) * 1e-12;
+    return 0;
+}
+
+}  // extern "C"

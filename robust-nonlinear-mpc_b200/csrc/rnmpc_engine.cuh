@@ -1,0 +1,412 @@
+// Host-side engine: owns the device workspace of one handle and sequences the kernels of one SCP-SLS solve.
+// One instantiation per model (explicitly instantiated in inst_*.cu so the three models compile in parallel).
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rnmpc_b200.h"
+#include "rnmpc_common.cuh"
+#include "rnmpc_lin.cuh"
+#include "rnmpc_qp.cuh"
+#include "rnmpc_sls.cuh"
+
+namespace rnmpc {
+
+void set_error(const std::string& msg);
+
+#define RN_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" +      \
+                      std::to_string(__LINE__) + ")");                                                  \
+            return -2;                                                                                  \
+        }                                                                                               \
+    } while (0)
+
+struct IEngine {
+    virtual ~IEngine() {}
+    virtual int ddyn(int B, const double* x, const double* u, const double* w, double* xp, cudaStream_t st) = 0;
+    virtual int linearize(int B, const double* X, const double* U, double* A, double* Bm, double* c, cudaStream_t st) = 0;
+    virtual int sls(int B, const double* A, const double* Bm, const double* eta, const double* eta_f, double* K, double* S,
+                    double* Phi_x, double* Phi_u, double* beta, double* beta_f, double* backoff, double* backoff_f,
+                    cudaStream_t st) = 0;
+    virtual int qp(int B, int tightened, const double* A, const double* Bm, const double* c, const double* X, const double* U,
+                   const double* x0, const double* backoff, const double* backoff_f, double* dX, double* dU, double* mu,
+                   double* mu_f, double* cost, int* iters, int* status, cudaStream_t st) = 0;
+    virtual int set_nominal(int B, const double* X, const double* U, cudaStream_t st) = 0;
+    virtual int init_nominal(int B, const double* x0, int iters, cudaStream_t st) = 0;
+    virtual int solve(int B, const double* x0, cudaStream_t st) = 0;
+    virtual int reset_warm_start(int B, cudaStream_t st) = 0;
+    virtual int plant_step(int B, double* x, const double* w, double* u0, cudaStream_t st) = 0;
+    virtual int get_buffer(const char* name, void** ptr, long long* bytes) = 0;
+    virtual int enable_phi(int enable) = 0;
+    virtual int dims(int* nx, int* nu, int* N, int* cap) = 0;
+    long long launches = 0;
+    int device = 0;
+};
+
+IEngine* make_pendulum(const rnmpc_config* cfg, int cap, int device);
+IEngine* make_quadrotor(const rnmpc_config* cfg, int cap, int device);
+IEngine* make_rocket(const rnmpc_config* cfg, int cap, int device);
+
+// ---- small glue kernels ------------------------------------------------------------------------------------------
+// check_convergence_socp (solver/fast_SLS_jit.py:581-600, quirk Q3): per instance max |delta - prev_delta| <= 1e-3 against
+// the previous *first-in-step* QP solution, kept across MPC steps; only the primal test is used.
+static __global__ void q3_check_kernel(int B, int nxs, int nus, const double* __restrict__ dX, const double* __restrict__ dU,
+                                       double* __restrict__ prevX, double* __restrict__ prevU, int* __restrict__ flags) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int f = flags[b];
+    if (f & FLAG_FAIL) return;
+    const double* x = dX + (size_t)b * nxs;
+    const double* u = dU + (size_t)b * nus;
+    double* px = prevX + (size_t)b * nxs;
+    double* pu = prevU + (size_t)b * nus;
+    double m = 0.0;
+    for (int i = 0; i < nxs; ++i) { m = fmax(m, fabs(x[i] - px[i])); px[i] = x[i]; }
+    for (int i = 0; i < nus; ++i) { m = fmax(m, fabs(u[i] - pu[i])); pu[i] = u[i]; }
+    f &= ~FLAG_Q3;
+    if ((f & FLAG_PREV) && m <= 1e-3) f |= FLAG_Q3;
+    f |= FLAG_PREV;
+    flags[b] = f;
+}
+static __global__ void clear_flag_kernel(int B, int* flags, int bits) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) flags[b] &= ~bits;
+}
+static __global__ void set_tight_kernel(int B, int* flags) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B && (flags[b] & (FLAG_FAIL | FLAG_Q3)) == 0) flags[b] |= FLAG_TIGHT;
+}
+// socp_step (solver/SCP_SLS_jit.py:426-430): X += dX, U += dU for instances whose fast-SLS solve succeeded
+static __global__ void apply_step_kernel(int B, int nxs, int nus, const double* __restrict__ dX, const double* __restrict__ dU,
+                                         double* __restrict__ X, double* __restrict__ U, const int* __restrict__ flags) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = nxs + nus;
+    if (gid >= (long long)B * per) return;
+    const int b = (int)(gid / per), e = (int)(gid - (long long)b * per);
+    if (flags[b] & FLAG_FAIL) return;
+    if (e < nxs) X[(size_t)b * nxs + e] += dX[(size_t)b * nxs + e];
+    else U[(size_t)b * nus + (e - nxs)] += dU[(size_t)b * nus + (e - nxs)];
+}
+static __global__ void fail_from_status_kernel(int B, const int* __restrict__ st_tmp, int* __restrict__ flags, int* __restrict__ iters_acc,
+                                               const int* __restrict__ iters, int* __restrict__ st_acc) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (flags[b] & FLAG_FAIL) return;
+    iters_acc[b] += iters[b];
+    if (st_tmp[b] != 0) { flags[b] |= FLAG_FAIL; st_acc[b] = st_tmp[b]; }
+}
+static __global__ void interp_nominal_kernel(int B, int N, int nx, int nu, const double* __restrict__ x0, double* __restrict__ X,
+                                             double* __restrict__ U) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    for (int k = 0; k <= N; ++k)
+        for (int i = 0; i < nx; ++i) X[((size_t)b * (N + 1) + k) * nx + i] = x0[(size_t)b * nx + i] * (1.0 - (double)k / (double)N);
+    for (int k = 0; k < N; ++k)
+        for (int p = 0; p < nu; ++p) U[((size_t)b * N + k) * nu + p] = 0.0;
+}
+
+template <class M>
+__global__ void shift_kernel(int B, int N, double h, double* __restrict__ X, double* __restrict__ U) {
+    // SCP_SLS.reset_warm_start (solver/SCP_SLS_jit.py:505-518): x_k <- x_{k+1}, u_k <- u_{k+1}, u_{N-1} kept,
+    // x_N <- ddyn(x_N, u_{N-1}) evaluated on the un-shifted trajectory.
+    constexpr int NX = M::NX, NU = M::NU;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double* Xb = X + (size_t)b * (N + 1) * NX;
+    double* Ub = U + (size_t)b * N * NU;
+    double xN[NX], uN[NU], xo[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xN[i] = Xb[N * NX + i];
+#pragma unroll
+    for (int p = 0; p < NU; ++p) uN[p] = Ub[(N - 1) * NU + p];
+    rk4_step<M, double>(xN, uN, h, xo);
+    for (int k = 0; k < N; ++k)
+        for (int i = 0; i < NX; ++i) Xb[k * NX + i] = Xb[(k + 1) * NX + i];
+    for (int k = 0; k + 1 < N; ++k)
+        for (int p = 0; p < NU; ++p) Ub[k * NU + p] = Ub[(k + 1) * NU + p];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) Xb[N * NX + i] = xo[i];
+}
+
+template <class M>
+struct Engine : IEngine {
+    static constexpr int NX = M::NX, NU = M::NU, NZ = NX + NU, NI = 2 * NZ, NIF = 2 * NX;
+    using P = Params<NX, NU>;
+    int N, cap, rti, sls_steps, qp_max_iter;
+    double qp_tol_mu, qp_tol_res, h;
+    P* d_prm = nullptr;
+    std::map<std::string, std::pair<void*, size_t>> bufs;
+    bool phi_enabled = false;
+
+    double *X, *U, *A, *Bm, *c, *dX, *dU, *mu, *mu_f, *beta, *beta_f, *backoff, *backoff_f, *K, *cost, *prevX, *prevU;
+    double *Phi_x = nullptr, *Phi_u = nullptr;
+    double *hi, *lo, *gx, *gu, *dXa, *dUa, *dXc, *dUc, *rp, *Sc, *dff, *Kq, *Lq;
+    int *flags, *status, *qp_iters, *iters_tmp, *status_tmp;
+
+    template <class T>
+    int alloc(const char* name, T*& ptr, size_t count) {
+        RN_CUDA(cudaMalloc((void**)&ptr, count * sizeof(T)));
+        RN_CUDA(cudaMemset(ptr, 0, count * sizeof(T)));
+        bufs[name] = {(void*)ptr, count * sizeof(T)};
+        return 0;
+    }
+
+    int init(const rnmpc_config* cfg, int cap_, int device_) {
+        device = device_;
+        RN_CUDA(cudaSetDevice(device));
+        N = cfg->N; cap = cap_; rti = cfg->rti; sls_steps = cfg->sls_steps; h = cfg->h;
+        qp_max_iter = cfg->qp_max_iter > 0 ? cfg->qp_max_iter : 60;
+        qp_tol_mu = cfg->qp_tol_mu > 0 ? cfg->qp_tol_mu : 1e-14;
+        qp_tol_res = cfg->qp_tol_res > 0 ? cfg->qp_tol_res : 1e-9;
+        P hp;
+        memcpy(hp.Q, cfg->Q, sizeof(hp.Q)); memcpy(hp.R, cfg->R, sizeof(hp.R)); memcpy(hp.Qf, cfg->Qf, sizeof(hp.Qf));
+        for (int i = 0; i < NX * NX; ++i) hp.Q2[i] = 2.0 * hp.Q[i];
+        for (int i = 0; i < NU * NU; ++i) hp.R2[i] = 2.0 * hp.R[i];
+        memcpy(hp.Qreg, cfg->Q_reg, sizeof(hp.Qreg)); memcpy(hp.Rreg, cfg->R_reg, sizeof(hp.Rreg));
+        memcpy(hp.Qregf, cfg->Q_reg_f, sizeof(hp.Qregf)); memcpy(hp.E, cfg->E, sizeof(hp.E));
+        memcpy(hp.xub, cfg->x_ub, sizeof(hp.xub)); memcpy(hp.xlb, cfg->x_lb, sizeof(hp.xlb));
+        memcpy(hp.uub, cfg->u_ub, sizeof(hp.uub)); memcpy(hp.ulb, cfg->u_lb, sizeof(hp.ulb));
+        memcpy(hp.xubf, cfg->xf_ub, sizeof(hp.xubf)); memcpy(hp.xlbf, cfg->xf_lb, sizeof(hp.xlbf));
+        hp.h = h;
+        RN_CUDA(cudaMalloc((void**)&d_prm, sizeof(P)));
+        RN_CUDA(cudaMemcpy(d_prm, &hp, sizeof(P), cudaMemcpyHostToDevice));
+        const size_t B = cap, n1 = N + 1;
+        int rc = 0;
+        rc |= alloc("X", X, B * n1 * NX); rc |= alloc("U", U, B * N * NU);
+        rc |= alloc("A", A, B * N * NX * NX); rc |= alloc("B", Bm, B * N * NX * NU); rc |= alloc("c", c, B * N * NX);
+        rc |= alloc("dX", dX, B * n1 * NX); rc |= alloc("dU", dU, B * N * NU);
+        rc |= alloc("mu", mu, B * N * NI); rc |= alloc("mu_f", mu_f, B * NIF);
+        rc |= alloc("beta", beta, B * N * N * NI); rc |= alloc("beta_f", beta_f, B * n1 * NIF);
+        rc |= alloc("backoff", backoff, B * N * NI); rc |= alloc("backoff_f", backoff_f, B * NIF);
+        rc |= alloc("K", K, B * N * n1 * NU * NX); rc |= alloc("cost", cost, B);
+        rc |= alloc("prevX", prevX, B * n1 * NX); rc |= alloc("prevU", prevU, B * N * NU);
+        rc |= alloc("hi", hi, B * n1 * NZ); rc |= alloc("lo", lo, B * n1 * NZ);
+        rc |= alloc("gx", gx, B * n1 * NX); rc |= alloc("gu", gu, B * N * NU);
+        rc |= alloc("dXa", dXa, B * n1 * NX); rc |= alloc("dUa", dUa, B * N * NU);
+        rc |= alloc("dXc", dXc, B * n1 * NX); rc |= alloc("dUc", dUc, B * N * NU);
+        rc |= alloc("rp", rp, B * N * NX); rc |= alloc("Sc", Sc, B * N * NX); rc |= alloc("dff", dff, B * N * NU);
+        rc |= alloc("Kq", Kq, B * N * NU * NX); rc |= alloc("Lq", Lq, B * N * NU * NU);
+        rc |= alloc("flags", flags, B); rc |= alloc("status", status, B); rc |= alloc("qp_iters", qp_iters, B);
+        rc |= alloc("iters_tmp", iters_tmp, B); rc |= alloc("status_tmp", status_tmp, B);
+        if (rc) return -2;
+        const int smem_sls = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * kWarps;
+        RN_CUDA(cudaFuncSetAttribute(sls_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
+        RN_CUDA(cudaFuncSetAttribute(qp_ipm_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
+        return 0;
+    }
+    ~Engine() override {
+        cudaSetDevice(device);
+        for (auto& kv : bufs) cudaFree(kv.second.first);
+        if (d_prm) cudaFree(d_prm);
+    }
+
+    static constexpr int kWarps = 4;   // warps per CTA of the slot kernels (128 threads)
+
+    int dims(int* nx, int* nu, int* N_, int* cap_) override {
+        if (nx) *nx = NX; if (nu) *nu = NU; if (N_) *N_ = N; if (cap_) *cap_ = cap;
+        return 0;
+    }
+    int check_B(int B) {
+        if (B <= 0 || B > cap) { set_error("batch " + std::to_string(B) + " outside (0, capacity=" + std::to_string(cap) + "]"); return -1; }
+        return 0;
+    }
+
+    int ddyn(int B, const double* x, const double* u, const double* w, double* xp, cudaStream_t st) override {
+        if (B <= 0) return -1;
+        ddyn_kernel<M><<<(B + 127) / 128, 128, 0, st>>>(B, x, NX, u, NU, w, d_prm->E, h, xp);
+        ++launches;
+        RN_CUDA(cudaGetLastError());
+        return 0;
+    }
+    int linearize(int B, const double* X_, const double* U_, double* A_, double* B_, double* c_, cudaStream_t st) override {
+        if (B <= 0) return -1;
+        const long long n = (long long)B * N * NZ;
+        linearize_kernel<M><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(B, N, X_, U_, h, A_, B_, c_);
+        ++launches;
+        RN_CUDA(cudaGetLastError());
+        return 0;
+    }
+    int launch_sls(int B, const SlsArgs& a, cudaStream_t st) {
+        const long long items = (long long)B * (N / 2 + 1);
+        const long long warps = (items + Slot<NX>::SPW - 1) / Slot<NX>::SPW;
+        const unsigned grid = (unsigned)((warps + kWarps - 1) / kWarps);
+        const int smem = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * kWarps;
+        sls_kernel<NX, NU><<<grid, kWarps * 32, smem, st>>>(a, d_prm);
+        ++launches;
+        RN_CUDA(cudaGetLastError());
+        const long long n = (long long)B * ((long long)N * NI + NIF);
+        return 0 * n;
+    }
+    int launch_backoff(int B, const double* beta_, const double* beta_f_, const int* fl, int skip_mask, double* bo, double* bof,
+                       cudaStream_t st) {
+        const long long n = (long long)B * ((long long)N * NI + NIF);
+        backoff_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(B, N, NI, NIF, beta_, beta_f_, fl, skip_mask, bo, bof);
+        ++launches;
+        RN_CUDA(cudaGetLastError());
+        return 0;
+    }
+    int sls(int B, const double* A_, const double* B_, const double* eta, const double* eta_f, double* K_, double* S_, double* Phi_x_,
+            double* Phi_u_, double* beta_, double* beta_f_, double* backoff_, double* backoff_f_, cudaStream_t st) override {
+        if (B <= 0) return -1;
+        SlsArgs a{};
+        a.B = B; a.N = N; a.A = A_; a.Bm = B_; a.eta = eta; a.eta_f = eta_f;
+        a.K = K_; a.S = S_; a.Phi_x = Phi_x_; a.Phi_u = Phi_u_; a.beta = beta_; a.beta_f = beta_f_;
+        int rc = launch_sls(B, a, st);
+        if (rc) return rc;
+        return launch_backoff(B, beta_, beta_f_, nullptr, 0, backoff_, backoff_f_, st);
+    }
+    int launch_qp(int B, int tightened, const double* A_, const double* B_, const double* c_, const double* X_, const double* U_,
+                  const double* x0, const double* bo, const double* bof, const int* fl, int skip_mask, double* dX_, double* dU_,
+                  double* mu_, double* mu_f_, double* cost_, int* iters_, int* status_, cudaStream_t st) {
+        QpArgs a{};
+        a.B = B; a.N = N; a.tightened = tightened; a.max_iter = qp_max_iter; a.tol_mu = qp_tol_mu; a.tol_res = qp_tol_res;
+        a.A = A_; a.Bm = B_; a.c = c_; a.Xnom = X_; a.Unom = U_; a.x0 = x0; a.backoff = bo; a.backoff_f = bof;
+        a.flags = fl; a.skip_mask = skip_mask;
+        a.dX = dX_; a.dU = dU_; a.mu = mu_; a.mu_f = mu_f_; a.cost = cost_; a.iters = iters_; a.status = status_;
+        a.hi = hi; a.lo = lo; a.gx = gx; a.gu = gu; a.dXa = dXa; a.dUa = dUa; a.dXc = dXc; a.dUc = dUc; a.rp = rp; a.Sc = Sc;
+        a.dff = dff; a.Kq = Kq; a.Lq = Lq;
+        const long long warps = ((long long)B + Slot<NX>::SPW - 1) / Slot<NX>::SPW;
+        const unsigned grid = (unsigned)((warps + kWarps - 1) / kWarps);
+        const int smem = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * kWarps;
+        qp_ipm_kernel<NX, NU><<<grid, kWarps * 32, smem, st>>>(a, d_prm);
+        ++launches;
+        RN_CUDA(cudaGetLastError());
+        return 0;
+    }
+    int qp(int B, int tightened, const double* A_, const double* B_, const double* c_, const double* X_, const double* U_,
+           const double* x0, const double* bo, const double* bof, double* dX_, double* dU_, double* mu_, double* mu_f_, double* cost_,
+           int* iters_, int* status_, cudaStream_t st) override {
+        if (check_B(B)) return -1;
+        return launch_qp(B, tightened ? 1 : 0, A_, B_, c_, X_, U_, x0, bo, bof, nullptr, 0, dX_, dU_, mu_, mu_f_, cost_, iters_, status_, st);
+    }
+
+    int set_nominal(int B, const double* X_, const double* U_, cudaStream_t st) override {
+        if (check_B(B)) return -1;
+        RN_CUDA(cudaMemcpyAsync(X, X_, (size_t)B * (N + 1) * NX * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        RN_CUDA(cudaMemcpyAsync(U, U_, (size_t)B * N * NU * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        RN_CUDA(cudaMemsetAsync(flags, 0, (size_t)B * sizeof(int), st));
+        return 0;
+    }
+
+    // one QP on the resident trajectories + failure bookkeeping
+    int resident_qp(int B, int tightened, const double* x0, cudaStream_t st) {
+        int rc = launch_qp(B, tightened, A, Bm, c, X, U, x0, backoff, backoff_f, flags, FLAG_FAIL, dX, dU, mu, mu_f, cost, iters_tmp,
+                           status_tmp, st);
+        if (rc) return rc;
+        fail_from_status_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, status_tmp, flags, qp_iters, iters_tmp, status);
+        ++launches;
+        RN_CUDA(cudaGetLastError());
+        return 0;
+    }
+
+    int init_nominal(int B, const double* x0, int iters, cudaStream_t st) override {
+        if (check_B(B)) return -1;
+        interp_nominal_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, N, NX, NU, x0, X, U);
+        ++launches;
+        RN_CUDA(cudaMemsetAsync(flags, 0, (size_t)B * sizeof(int), st));
+        RN_CUDA(cudaMemsetAsync(status, 0, (size_t)B * sizeof(int), st));
+        RN_CUDA(cudaMemsetAsync(qp_iters, 0, (size_t)B * sizeof(int), st));
+        for (int it = 0; it < iters; ++it) {
+            int rc = linearize(B, X, U, A, Bm, c, st);
+            if (rc) return rc;
+            rc = resident_qp(B, 0, x0, st);
+            if (rc) return rc;
+            apply_step_kernel<<<(unsigned)(((long long)B * ((N + 1) * NX + N * NU) + 255) / 256), 256, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, X, U, flags);
+            ++launches;
+        }
+        RN_CUDA(cudaGetLastError());
+        return 0;
+    }
+
+    int solve(int B, const double* x0, cudaStream_t st) override {
+        if (check_B(B)) return -1;
+        // a new solve: failure flags of the previous solve are cleared, the Q3 history (FLAG_PREV) is kept
+        clear_flag_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags, FLAG_FAIL | FLAG_Q3 | FLAG_TIGHT);
+        ++launches;
+        RN_CUDA(cudaMemsetAsync(status, 0, (size_t)B * sizeof(int), st));
+        RN_CUDA(cudaMemsetAsync(qp_iters, 0, (size_t)B * sizeof(int), st));
+        int rc = linearize(B, X, U, A, Bm, c, st);                      // update_jacobian (SCP_SLS_jit.py:80)
+        if (rc) return rc;
+        for (int ii = 0; ii < rti; ++ii) {
+            // fast_SLS.solve (fast_SLS_jit.py:280-296): initialize_backoff, sls_steps x _step, final forward_solve
+            clear_flag_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags, FLAG_Q3 | FLAG_TIGHT);
+            ++launches;
+            for (int i = 0; i < sls_steps; ++i) {
+                rc = resident_qp(B, -1, x0, st);                        // forward_solve
+                if (rc) return rc;
+                q3_check_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, prevX, prevU, flags);
+                ++launches;
+                SlsArgs a{};                                            // evaluate_dual_eta + backward_solve + update_tightening
+                a.B = B; a.N = N; a.A = A; a.Bm = Bm; a.mu = mu; a.mu_f = mu_f; a.beta_in = beta; a.beta_f_in = beta_f;
+                a.flags = flags; a.skip_mask = FLAG_FAIL | FLAG_Q3; a.beta_from_flags = 1;
+                a.K = K; a.Phi_x = phi_enabled ? Phi_x : nullptr; a.Phi_u = phi_enabled ? Phi_u : nullptr;
+                a.beta = beta; a.beta_f = beta_f;
+                rc = launch_sls(B, a, st);
+                if (rc) return rc;
+                rc = launch_backoff(B, beta, beta_f, flags, FLAG_FAIL | FLAG_Q3, backoff, backoff_f, st);
+                if (rc) return rc;
+                set_tight_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags);
+                ++launches;
+            }
+            rc = resident_qp(B, -1, x0, st);                            // final forward_solve
+            if (rc) return rc;
+            apply_step_kernel<<<(unsigned)(((long long)B * ((N + 1) * NX + N * NU) + 255) / 256), 256, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, X, U, flags);   // socp_step
+            ++launches;
+            if (ii + 1 < rti) {
+                rc = linearize(B, X, U, A, Bm, c, st);                  // update_jacobian (SCP_SLS_jit.py:139); the one after
+                if (rc) return rc;                                      // the last iteration is dead work and is not run
+            }
+        }
+        RN_CUDA(cudaGetLastError());
+        return 0;
+    }
+
+    int reset_warm_start(int B, cudaStream_t st) override {
+        if (check_B(B)) return -1;
+        shift_kernel<M><<<(B + 63) / 64, 64, 0, st>>>(B, N, h, X, U);
+        ++launches;
+        RN_CUDA(cudaGetLastError());
+        return 0;
+    }
+    int plant_step(int B, double* x, const double* w, double* u0, cudaStream_t st) override {
+        if (check_B(B)) return -1;
+        ddyn_kernel<M><<<(B + 127) / 128, 128, 0, st>>>(B, x, NX, U, N * NU, w, d_prm->E, h, x);
+        ++launches;
+        if (u0 != nullptr)
+            RN_CUDA(cudaMemcpy2DAsync(u0, NU * sizeof(double), U, (size_t)N * NU * sizeof(double), NU * sizeof(double), B,
+                                      cudaMemcpyDeviceToDevice, st));
+        RN_CUDA(cudaGetLastError());
+        return 0;
+    }
+    int get_buffer(const char* name, void** ptr, long long* bytes) override {
+        auto it = bufs.find(name);
+        if (it == bufs.end()) { set_error(std::string("unknown buffer ") + name); return -1; }
+        *ptr = it->second.first;
+        if (bytes) *bytes = (long long)it->second.second;
+        return 0;
+    }
+    int enable_phi(int enable) override {
+        if (enable && Phi_x == nullptr) {
+            RN_CUDA(cudaSetDevice(device));
+            if (alloc("Phi_x", Phi_x, (size_t)cap * (N + 1) * (N + 1) * NX * NX)) return -2;
+            if (alloc("Phi_u", Phi_u, (size_t)cap * N * (N + 1) * NU * NX)) return -2;
+        }
+        phi_enabled = enable != 0;
+        return 0;
+    }
+};
+
+template <class M>
+IEngine* make_engine(const rnmpc_config* cfg, int cap, int device) {
+    auto* e = new Engine<M>();
+    if (e->init(cfg, cap, device) != 0) { delete e; return nullptr; }
+    return e;
+}
+
+}  // namespace rnmpc
