@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the SCP / fast-SLS robust-MPC hot path (BASELINE.json metric: rocket SCP-SLS solves/s, fp64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+A "step" is one closed-loop MPC step of every scenario of the batch: warm-start shift, one SCP_SLS.solve (linearise,
+nominal QP, eta, Riccati sweep, Phi propagation, back-offs, tightened QP, nominal update) and the disturbed plant
+step -- i.e. `batch` solves.  Workload at N = 1: BASELINE.json configs[3] "rocket compare closed loop batched over 4,096
+disturbance draws" (N = 15 horizon, rti = 1, fast_sls_rti_steps = 1, 29 MPC steps = default warmup 3 + steps 26).  With N > 1
+(torchrun, one rank per GPU) every rank owns its own `batch` scenarios (weak scaling, no collective on the solve path,
+one statistics all_gather at the end): 8 x 8,192 = configs[4]'s 65,536 scenarios when --batch 8192.
+
+`value` times the device-resident loop; `e2e` times the same steps through the host-buffer entry point (pinned host
+x0 / disturbance in, next state + first input + flags out, copies inside the timed region).  `--impl reference` times
+the CPU oracle port of the same path (the reference itself needs CasADi + OSQP, absent from the image) on the box's
+host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rocket SCP-SLS solves/sec (fp64)"
+UNIT = "solves/s"
+
+
+# ------------------------------------------------------------------------------------------------ flop accounting
+def flops_model(nx=17, nu=4, N=15):
+    """Algorithmic flops (canonical box-constraint structure)."""
+    nz, P = nx + nu, N * (N + 1) // 2
+    ni, ni_f = 2 * nz, 2 * nx
+    f_ric = 6 * nu * nx**2 + 4 * nx**3 + 4 * nu**2 * nx + (2 / 3) * nu**3 + 2 * nx**2
+    sls = P * (f_ric + nz) + (N + 1) * nx + P * (2 * nu * nx * nx + 2 * nx**2 * nu + nx**2 + 2 * nx**2 * nx) \
+        + P * 2 * nz * nx + (N + 1) * 2 * nx * nx
+    lin = N * 3 * 2 * nx**2 * nz
+    qp_fact = N * f_ric                                                        # per factorisation
+    qp_solve = N * (4 * nx**2 + 8 * nx * nu + 2 * nu**2) + 10 * (N * ni + ni_f)   # per KKT solve
+    return dict(f_ric=f_ric, sls=sls, lin=lin, qp_fact=qp_fact, qp_solve=qp_solve)
+
+
+# ------------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU baseline
+def _cpu_worker(args):
+    seed, steps = args
+    from oracle import models as om, scp as oscp
+    from tests.helpers import rocket_scenarios
+    m, cfg = om.rocket_config()
+    x0, W = rocket_scenarios(1, seed=seed, steps=steps)
+    X0, U0, ok = oscp.nominal_sqp(m, cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], x0[0], iters=10)
+    t0 = time.perf_counter()
+    out = oscp.closed_loop(m, cfg, x0[0], W[0], steps, X0=X0, U0=U0)
+    return time.perf_counter() - t0, len(out["U"])
+
+
+def cpu_baseline(n_scen, steps, procs):
+    """Oracle port of the whole solve (NumPy restatement of linearisation + QP + fast-SLS + tightened QP), one scenario per
+    process, `procs` processes."""
+    import multiprocessing as mp
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):   # one BLAS thread per worker process
+        os.environ[k] = "1"
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_worker, [(1000 + i, steps) for i in range(n_scen)])
+    wall = time.perf_counter() - t0
+    solves = sum(r[1] for r in res)
+    busy = sum(r[0] for r in res)
+    # throughput with all `procs` cores busy: solves / (sum of per-process busy time / procs)
+    return solves / (busy / procs), dict(solves=solves, wall_s=wall, busy_s=busy)
+
+
+# ------------------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=26)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4096, help="scenarios per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-scenarios", type=int, default=0, help="CPU baseline sample: scenarios (default = host cores)")
+    ap.add_argument("--cpu-steps", type=int, default=2, help="CPU baseline sample: MPC steps per scenario")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    workload = f"rocket robust closed loop (SCP-SLS, N=15, rti=1, fast_sls_rti_steps=1), {a.batch} disturbance-draw scenarios per GPU"
+
+    if a.impl == "reference":
+        # the reference's CPU path; only rank 0 works
+        if rank != 0:
+            return
+        n_scen = a.cpu_scenarios or cores
+        t_steps = []
+        for _ in range(max(1, min(a.steps, 2))):          # bounded: each "step" = cpu_steps MPC steps of n_scen scenarios
+            v, info = cpu_baseline(n_scen, a.cpu_steps, cores)
+            t_steps.append((v, info))
+        v = float(np.mean([t[0] for t in t_steps]))
+        sample = f"{n_scen} rocket scenarios x {a.cpu_steps} MPC steps per timed step, {cores} processes (oracle port, NumPy)"
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * float(np.mean([t[1]["wall_s"] for t in t_steps])), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload, "note": "reference needs CasADi+OSQP (absent); timed: oracle port on host cores"},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from oracle import models as om            # model constants only (no oracle compute on this path)
+    from rnmpc_b200.engine import BatchSolver, fp64_peak_tflops
+    from rnmpc_b200.sharding import gather_statistics
+    from tests.helpers import rocket_scenarios
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, Wm = a.batch, a.steps, a.warmup
+    total_steps = K + Wm
+    m, cfg = om.rocket_config()
+    x0, W = rocket_scenarios(B, seed=2025 + rank, steps=2 * total_steps + 2)
+    s = BatchSolver("rocket", cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], m.E, m.x_ub, m.x_lb,
+                    m.u_ub, m.u_lb, rti=cfg["rti"], sls_steps=cfg["fast_sls_rti_steps"], capacity=B, device=local_rank)
+    s.enable_timing(True)
+    peak = fp64_peak_tflops(local_rank)
+    Wd = s.dev(np.ascontiguousarray(np.swapaxes(W, 0, 1)))     # [steps][B][nx], resident
+    x = s.dev(x0).clone()
+    s.init_nominal(x, 10)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    step_idx = [0]
+    t_qp, t_sls, t_jac, qp_iters = [], [], [], []
+
+    def device_step(record):
+        i = step_idx[0]
+        if i > 0:
+            s.reset_warm_start(B)
+        s.solve(x)
+        s.plant_step(x, Wd[i])
+        step_idx[0] += 1
+        if record:
+            tm = s.timings()
+            t_qp.append(tm["t_qp_ms"]); t_sls.append(tm["t_backward_ms"]); t_jac.append(tm["t_jac_ms"])
+
+    for _ in range(Wm):
+        device_step(False)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    launches0 = s.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        device_step(False)
+    e1.record()
+    barrier()
+    launches = s.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    flags = s.buffer("flags")
+    n_fail_last = int((flags & 1).sum())
+    # per-kernel times + iteration counters on a few extra (untimed) steps so that get_timings' sync stays outside the timed region
+    for _ in range(2):
+        device_step(True)
+        qp_iters.append(s.buffer("qp_iters").astype(np.float64))
+
+    # ---- e2e: same steps through host buffers (pinned host memory in, results out, copies inside the timed region)
+    xh = torch.empty((B, m.nx), dtype=torch.float64, pin_memory=True)
+    wh = torch.empty((B, m.nx), dtype=torch.float64, pin_memory=True)
+    oh = torch.empty((B, m.nx + m.nu), dtype=torch.float64, pin_memory=True)
+    fh = torch.empty((B,), dtype=torch.int32, pin_memory=True)
+    xh.copy_(x)
+    Wpin = torch.as_tensor(np.ascontiguousarray(np.swapaxes(W, 0, 1))).pin_memory()
+    xd, wd = torch.empty_like(x), torch.empty_like(x)
+    n_e2e = max(3, min(K, 10))
+
+    def e2e_step():
+        i = step_idx[0]
+        wh.copy_(Wpin[i])
+        xd.copy_(xh, non_blocking=True)
+        wd.copy_(wh, non_blocking=True)
+        s.reset_warm_start(B)
+        s.solve(xd)
+        s.plant_step(xd, wd)
+        Uv = torch.as_tensor(s.buffer_view("U", B))
+        oh[:, :m.nx].copy_(xd, non_blocking=True)
+        oh[:, m.nx:].copy_(Uv[:, 0], non_blocking=True)
+        fh.copy_(torch.as_tensor(s.buffer_view("flags", B)), non_blocking=True)
+        torch.cuda.synchronize(dev)
+        xh.copy_(oh[:, :m.nx])
+        step_idx[0] += 1
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / n_e2e
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- reduce over ranks: max time, summed solves
+    tvec = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
+    ms_all, e2e_ms_all = float(tvec[0]), float(tvec[1])
+    bo = s.buffer("backoff")
+    stats, per_rank = gather_statistics(dict(solves=B * K, failed_solves=n_fail_last, violations=0, cost_sum=float(s.buffer("cost").sum()),
+                                             max_backoff=float(bo.max()), qp_iters=float(np.mean(qp_iters)) * B, elapsed_ms=ms), device=dev)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = stats["solves"] / (ms_all * 1e-3)
+    e2e_value = (B * world) / (e2e_ms_all * 1e-3)
+    fm = flops_model()
+    iters_per_solve = float(np.mean(qp_iters))                 # interior-point iterations over the 2 QPs of a solve
+    qp_flops_launch = B * (iters_per_solve / 2.0) * (fm["qp_fact"] + 2 * fm["qp_solve"])       # one QP kernel launch
+    t_qp_ms = float(np.mean(t_qp))
+    flops_per_solve = fm["lin"] + fm["sls"] + iters_per_solve * (fm["qp_fact"] + 2 * fm["qp_solve"])
+    achieved = qp_flops_launch / (t_qp_ms * 1e-3) * 1e-12
+    h2d = 2 * B * m.nx * 8
+    d2h = B * (m.nx + m.nu) * 8 + B * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_all / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "global_batch": B * world, "horizon": cfg["N"], "parallelism": f"scenario-sharded x{world}",
+                   "l2": "per-step working set ~%.0f MB per GPU > 126 MB L2 (no flush needed)" % (B * 0.2),
+                   "flops_per_solve": flops_per_solve, "qp_ipm_iters_per_solve": iters_per_solve,
+                   "whole_solve_fp64_frac": value / world * flops_per_solve / (peak * 1e12),
+                   "kernel_ms": {"linearize": float(np.mean(t_jac)), "qp_last": t_qp_ms, "fast_sls": float(np.mean(t_sls))}},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_all},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "fp64", "kernel": "qp_ipm_kernel<17,4>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak, "traffic": None,
+                     "note": "FP64 DFMA pipe binds (SURVEY 8d); peak = DFMA probe measured live on this GPU (MEASURED_PEAKS.json has no "
+                             "fp64 entry); achieved = algorithmic flops of one QP launch / its CUDA-event duration"},
+        "failed_solves_last_step": int(stats["failed_solves"]),
+    }
+    if not a.no_cpu_baseline:
+        n_scen = a.cpu_scenarios or cores
+        v, info = cpu_baseline(n_scen, a.cpu_steps, cores)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{n_scen} rocket scenarios x {a.cpu_steps} MPC steps, {cores} processes, oracle port (NumPy; "
+                                          f"the reference's CasADi+OSQP path is not installable here), {info['wall_s']:.1f} s wall"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

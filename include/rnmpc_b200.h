@@ -65,8 +65,9 @@ int rnmpc_destroy(rnmpc_handle* h);
 /* ---- stateless kernels on caller-owned device buffers ------------------------------------------------------ */
 
 /* x+ = ddyn(x, u) [+ E w]   (dyn/model.py:15-34; plant step expe/main_rocket_compare_closed_loop.py:159).
- * d_x [B][nx], d_u [B][nu], d_w [B][nx] or NULL, d_xp [B][nx]. */
-int rnmpc_ddyn(rnmpc_handle* h, int B, const double* d_x, const double* d_u, const double* d_w, double* d_xp, void* stream);
+ * d_x [B][nx], d_u [B][nu], d_w [B][nx] or NULL, d_xp [B][nx]; step <= 0 selects the handle's h. */
+int rnmpc_ddyn(rnmpc_handle* h, int B, const double* d_x, const double* d_u, const double* d_w, double step, double* d_xp,
+               void* stream);
 
 /* A_k, B_k, c_k along a trajectory (SCP_SLS.update_jacobian, solver/SCP_SLS_jit.py:251-277).
  * d_X [B][N+1][nx], d_U [B][N][nu] -> d_A [B][N][nx][nx], d_B [B][N][nx][nu], d_c [B][N][nx]. */
@@ -118,7 +119,8 @@ int rnmpc_plant_step(rnmpc_handle* h, int B, double* d_x, const double* d_w, dou
  * name in: "X" [cap][N+1][nx], "U" [cap][N][nu], "dX", "dU", "mu" [cap][N][ni], "mu_f" [cap][ni_f], "K"
  * [cap][N][N+1][nu][nx], "beta" [cap][N][N][ni], "beta_f" [cap][N+1][ni_f], "backoff" [cap][N][ni], "backoff_f"
  * [cap][ni_f], "A", "B", "c", "cost" [cap], "Phi_x", "Phi_u" (only after rnmpc_enable_phi), "flags" (int32 [cap]:
- * bit0 failed, bit1 Q3 early return in the last fast-SLS step, bit2 tube back-offs valid), "status" (int32 [cap]),
+ * bit0 failed, bit1 Q3 early return in the last fast-SLS step, bit2 tube back-offs valid, bit3 Q3 history present,
+ * bit4 K/Phi computed since the last warm-start reset), "status" (int32 [cap]),
  * "qp_iters" (int32 [cap], interior-point iterations summed over the QPs of the last solve). */
 int rnmpc_get_buffer(rnmpc_handle* h, const char* name, void** d_ptr, long long* n_bytes);
 int rnmpc_enable_phi(rnmpc_handle* h, int enable);
@@ -141,6 +143,12 @@ int rnmpc_closed_loop_host(rnmpc_handle* h, int B, int steps, const double* h_x0
 
 /* Measured FP64 FMA peak of the device (TFLOP/s), for the roofline denominator. */
 int rnmpc_fp64_peak(int device, double* tflops);
+
+/* Device times (ms) of the last rnmpc_solve when timing is enabled: out[0] linearisation (t_jac_ms), out[1] last QP
+ * (t_qp_ms), out[2] last fast-SLS kernel (t_backward_ms); mirrors SCP_SLS_jit.py:339-341, qp_jit.py:392-395,
+ * fast_SLS_jit.py:504-507.  Synchronises. */
+int rnmpc_enable_timing(rnmpc_handle* h, int enable);
+int rnmpc_get_timings(rnmpc_handle* h, double* out3);
 
 /* Number of kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
 long long rnmpc_launch_count(rnmpc_handle* h);

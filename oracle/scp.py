@@ -346,7 +346,7 @@ def closed_loop(m, cfg, x0, W, steps, X0=None, U0=None, kernels=None, collect=No
         out["Un"].append(sol["primal_u"].copy())
         out["backoff_x"].append(sol["backoff_x"].copy())
         out["backoff_u"].append(sol["backoff_u"].copy())
-        out["skipped"].append(sol.get("K") is None)
+        out["skipped"].append(not np.any(sol["backoff_x"]))   # last fast-SLS solve took the Q3 early return
         out["K"].append(None if sol.get("K") is None else sol["K"].copy())
         if collect is not None:
             collect(i, solver, sol)

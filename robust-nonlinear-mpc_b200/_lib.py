@@ -38,7 +38,7 @@ SYMBOLS = {
     "rnmpc_model_dims": (_I, [_I, C.POINTER(_I), C.POINTER(_I)]),
     "rnmpc_create": (_I, [C.POINTER(_VP), C.POINTER(Config), _I, _I]),
     "rnmpc_destroy": (_I, [_VP]),
-    "rnmpc_ddyn": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP]),
+    "rnmpc_ddyn": (_I, [_VP, _I, _VP, _VP, _VP, _D, _VP, _VP]),
     "rnmpc_linearize": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "rnmpc_sls": (_I, [_VP, _I] + [_VP] * 13),
     "rnmpc_qp": (_I, [_VP, _I, _I] + [_VP] * 16),
@@ -53,6 +53,8 @@ SYMBOLS = {
     "rnmpc_solve_host": (_I, [_VP, _I] + [_VP] * 7),
     "rnmpc_closed_loop_host": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "rnmpc_fp64_peak": (_I, [_I, C.POINTER(_D)]),
+    "rnmpc_enable_timing": (_I, [_VP, _I]),
+    "rnmpc_get_timings": (_I, [_VP, C.POINTER(_D)]),
     "rnmpc_launch_count": (_LL, [_VP]),
 }
 

@@ -93,9 +93,9 @@ int rnmpc_destroy(rnmpc_handle* h) {
     if (!(h)) { set_error("null handle"); return -1; } \
     RN_API_CUDA(cudaSetDevice((h)->e->device));
 
-int rnmpc_ddyn(rnmpc_handle* h, int B, const double* x, const double* u, const double* w, double* xp, void* stream) {
+int rnmpc_ddyn(rnmpc_handle* h, int B, const double* x, const double* u, const double* w, double step, double* xp, void* stream) {
     RN_ENTER(h);
-    return h->e->ddyn(B, x, u, w, xp, (cudaStream_t)stream);
+    return h->e->ddyn(B, x, u, w, step, xp, (cudaStream_t)stream);
 }
 int rnmpc_linearize(rnmpc_handle* h, int B, const double* X, const double* U, double* A, double* Bm, double* c, void* stream) {
     RN_ENTER(h);
@@ -150,6 +150,15 @@ int rnmpc_copy_buffer(rnmpc_handle* h, const char* name, void* dst, long long n_
     RN_API_CUDA(cudaDeviceSynchronize());
     RN_API_CUDA(cudaMemcpy(dst, p, (size_t)n_bytes, cudaMemcpyDeviceToHost));
     return 0;
+}
+int rnmpc_enable_timing(rnmpc_handle* h, int enable) {
+    RN_ENTER(h);
+    return h->e->enable_timing(enable);
+}
+int rnmpc_get_timings(rnmpc_handle* h, double* out3) {
+    RN_ENTER(h);
+    if (!out3) return -1;
+    return h->e->get_timings(out3);
 }
 long long rnmpc_launch_count(rnmpc_handle* h) { return h ? h->e->launches : -1; }
 

@@ -21,6 +21,7 @@ constexpr int FLAG_FAIL = 1;    // a QP of this solve failed: the instance is fr
 constexpr int FLAG_Q3 = 2;      // check_convergence_socp returned True: skip backward solve + tightening (Q3)
 constexpr int FLAG_TIGHT = 4;   // tube back-offs were computed in this fast-SLS solve and are in the QP bounds
 constexpr int FLAG_PREV = 8;    // _prev_primal_vec exists (Q3 state)
+constexpr int FLAG_KVALID = 16; // K / Phi were computed since the last reset_solver_to_zeros (else the reference returns None)
 
 constexpr double kBig = 1e19;           // bounds >= kBig are treated as infinite (qp_jit.py:382 uses 1e20)
 

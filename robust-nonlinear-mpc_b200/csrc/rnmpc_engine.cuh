@@ -29,7 +29,9 @@ void set_error(const std::string& msg);
 
 struct IEngine {
     virtual ~IEngine() {}
-    virtual int ddyn(int B, const double* x, const double* u, const double* w, double* xp, cudaStream_t st) = 0;
+    virtual int ddyn(int B, const double* x, const double* u, const double* w, double step, double* xp, cudaStream_t st) = 0;
+    virtual int enable_timing(int enable) = 0;
+    virtual int get_timings(double* out3) = 0;
     virtual int linearize(int B, const double* X, const double* U, double* A, double* Bm, double* c, cudaStream_t st) = 0;
     virtual int sls(int B, const double* A, const double* Bm, const double* eta, const double* eta_f, double* K, double* S,
                     double* Phi_x, double* Phi_u, double* beta, double* beta_f, double* backoff, double* backoff_f,
@@ -80,7 +82,7 @@ static __global__ void clear_flag_kernel(int B, int* flags, int bits) {
 }
 static __global__ void set_tight_kernel(int B, int* flags) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < B && (flags[b] & (FLAG_FAIL | FLAG_Q3)) == 0) flags[b] |= FLAG_TIGHT;
+    if (b < B && (flags[b] & (FLAG_FAIL | FLAG_Q3)) == 0) flags[b] |= FLAG_TIGHT | FLAG_KVALID;
 }
 // socp_step (solver/SCP_SLS_jit.py:426-430): X += dX, U += dU for instances whose fast-SLS solve succeeded
 static __global__ void apply_step_kernel(int B, int nxs, int nus, const double* __restrict__ dX, const double* __restrict__ dU,
@@ -143,6 +145,8 @@ struct Engine : IEngine {
     P* d_prm = nullptr;
     std::map<std::string, std::pair<void*, size_t>> bufs;
     bool phi_enabled = false;
+    bool timing = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     double *X, *U, *A, *Bm, *c, *dX, *dU, *mu, *mu_f, *beta, *beta_f, *backoff, *backoff_f, *K, *cost, *prevX, *prevU;
     double *Phi_x = nullptr, *Phi_u = nullptr;
@@ -217,9 +221,9 @@ struct Engine : IEngine {
         return 0;
     }
 
-    int ddyn(int B, const double* x, const double* u, const double* w, double* xp, cudaStream_t st) override {
+    int ddyn(int B, const double* x, const double* u, const double* w, double step, double* xp, cudaStream_t st) override {
         if (B <= 0) return -1;
-        ddyn_kernel<M><<<(B + 127) / 128, 128, 0, st>>>(B, x, NX, u, NU, w, d_prm->E, h, xp);
+        ddyn_kernel<M><<<(B + 127) / 128, 128, 0, st>>>(B, x, NX, u, NU, w, d_prm->E, step > 0 ? step : h, xp);
         ++launches;
         RN_CUDA(cudaGetLastError());
         return 0;
@@ -331,7 +335,9 @@ struct Engine : IEngine {
         ++launches;
         RN_CUDA(cudaMemsetAsync(status, 0, (size_t)B * sizeof(int), st));
         RN_CUDA(cudaMemsetAsync(qp_iters, 0, (size_t)B * sizeof(int), st));
+        if (timing) cudaEventRecord(ev[0], st);
         int rc = linearize(B, X, U, A, Bm, c, st);                      // update_jacobian (SCP_SLS_jit.py:80)
+        if (timing) cudaEventRecord(ev[1], st);
         if (rc) return rc;
         for (int ii = 0; ii < rti; ++ii) {
             // fast_SLS.solve (fast_SLS_jit.py:280-296): initialize_backoff, sls_steps x _step, final forward_solve
@@ -347,14 +353,18 @@ struct Engine : IEngine {
                 a.flags = flags; a.skip_mask = FLAG_FAIL | FLAG_Q3; a.beta_from_flags = 1;
                 a.K = K; a.Phi_x = phi_enabled ? Phi_x : nullptr; a.Phi_u = phi_enabled ? Phi_u : nullptr;
                 a.beta = beta; a.beta_f = beta_f;
+                if (timing) cudaEventRecord(ev[4], st);
                 rc = launch_sls(B, a, st);
+                if (timing) cudaEventRecord(ev[5], st);
                 if (rc) return rc;
                 rc = launch_backoff(B, beta, beta_f, flags, FLAG_FAIL | FLAG_Q3, backoff, backoff_f, st);
                 if (rc) return rc;
                 set_tight_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags);
                 ++launches;
             }
+            if (timing) cudaEventRecord(ev[2], st);
             rc = resident_qp(B, -1, x0, st);                            // final forward_solve
+            if (timing) cudaEventRecord(ev[3], st);
             if (rc) return rc;
             apply_step_kernel<<<(unsigned)(((long long)B * ((N + 1) * NX + N * NU) + 255) / 256), 256, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, X, U, flags);   // socp_step
             ++launches;
@@ -371,6 +381,8 @@ struct Engine : IEngine {
         if (check_B(B)) return -1;
         shift_kernel<M><<<(B + 63) / 64, 64, 0, st>>>(B, N, h, X, U);
         ++launches;
+        clear_flag_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags, FLAG_KVALID);   // fast_SLS.reset_solver_to_zeros drops K / Phi
+        ++launches;
         RN_CUDA(cudaGetLastError());
         return 0;
     }
@@ -382,6 +394,24 @@ struct Engine : IEngine {
             RN_CUDA(cudaMemcpy2DAsync(u0, NU * sizeof(double), U, (size_t)N * NU * sizeof(double), NU * sizeof(double), B,
                                       cudaMemcpyDeviceToDevice, st));
         RN_CUDA(cudaGetLastError());
+        return 0;
+    }
+    int enable_timing(int enable) override {
+        if (enable && ev[0] == nullptr)
+            for (auto& e : ev) RN_CUDA(cudaEventCreate(&e));
+        timing = enable != 0;
+        return 0;
+    }
+    int get_timings(double* out3) override {
+        out3[0] = out3[1] = out3[2] = -1.0;
+        if (!timing) return 0;
+        for (int i = 0; i < 3; ++i) {
+            if (cudaEventQuery(ev[2 * i + 1]) == cudaErrorInvalidResourceHandle) continue;
+            cudaEventSynchronize(ev[2 * i + 1]);
+            float ms = -1.f;
+            if (cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]) == cudaSuccess) out3[i] = ms;
+        }
+        cudaGetLastError();
         return 0;
     }
     int get_buffer(const char* name, void** ptr, long long* bytes) override {

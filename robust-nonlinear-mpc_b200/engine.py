@@ -112,12 +112,25 @@ class BatchSolver:
         _lib.check(self.lib.rnmpc_copy_buffer(self._h, name.encode(), C.c_void_p(out.ctypes.data), out.nbytes))
         return out
 
+    def buffer_view(self, name, B=None):
+        """Zero-copy view of a resident device buffer (object exposing __cuda_array_interface__; wrap with torch.as_tensor)."""
+        B = self.capacity if B is None else B
+        ptr, nbytes = C.c_void_p(), C.c_longlong()
+        _lib.check(self.lib.rnmpc_get_buffer(self._h, name.encode(), C.byref(ptr), C.byref(nbytes)))
+        shape = (B,) + tuple(self._SHAPES[name](self))
+        typestr = "<i4" if name in self._INT else "<f8"
+
+        class _View:
+            __cuda_array_interface__ = dict(shape=shape, typestr=typestr, data=(ptr.value, False), version=3, strides=None)
+            _owner = self
+        return _View()
+
     # -- stateless kernels -------------------------------------------------------------------------------------------
-    def ddyn(self, x, u, w=None):
+    def ddyn(self, x, u, w=None, h=0.0):
         x, u = self.dev(x).reshape(-1, self.nx), self.dev(u).reshape(-1, self.nu)
         w = None if w is None else self.dev(w).reshape(-1, self.nx)
         xp = torch.empty_like(x)
-        _lib.check(self.lib.rnmpc_ddyn(self._h, x.shape[0], _ptr(x), _ptr(u), _ptr(w), _ptr(xp), self._stream()))
+        _lib.check(self.lib.rnmpc_ddyn(self._h, x.shape[0], _ptr(x), _ptr(u), _ptr(w), float(h), _ptr(xp), self._stream()))
         return xp
 
     def linearize(self, X, U):
@@ -179,6 +192,14 @@ class BatchSolver:
 
     def enable_phi(self, enable=True):
         _lib.check(self.lib.rnmpc_enable_phi(self._h, int(bool(enable))))
+
+    def enable_timing(self, enable=True):
+        _lib.check(self.lib.rnmpc_enable_timing(self._h, int(bool(enable))))
+
+    def timings(self):
+        out = (C.c_double * 3)()
+        _lib.check(self.lib.rnmpc_get_timings(self._h, out))
+        return dict(t_jac_ms=out[0], t_qp_ms=out[1], t_backward_ms=out[2])
 
     def launch_count(self):
         return int(self.lib.rnmpc_launch_count(self._h))

@@ -1,0 +1,329 @@
+"""GPU parity tests (run with -m gpu on a B200): every CUDA kernel, called through the C ABI, against
+  * the committed golden fixtures (reference Numba kernels, SymPy Jacobians, oracle QPs and closed loops), and
+  * the CPU oracle on seeded inputs,
+plus size-independent properties at the benchmark batch sizes.  Tolerances: linearisation / fast-SLS are pure
+floating-point restatements (<= 1e-9 relative); QP-dependent quantities follow BASELINE.json's north star
+(nominal trajectory, feedback gains, back-offs <= 1e-6 relative; closed-loop states <= 1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as om
+from oracle import scp as oscp
+from oracle import sls as osls
+from oracle.gen_golden import jac_points, sls_inputs
+from tests.helpers import load, make_solver, rel, rocket_scenarios
+
+pytestmark = pytest.mark.gpu
+
+MODELS = ["pendulum", "quadrotor", "rocket"]
+TOL_FP = 1e-9        # kernels that restate floating-point formulas
+TOL_TRAJ = 1e-6      # north star: nominal trajectory, gains, back-offs
+TOL_STATE = 1e-5     # north star: closed-loop states
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_linearize_and_ddyn_vs_sympy_golden(name):
+    g = load(f"jac_{name}.npz")
+    m, cfg, s = make_solver(name, 8)
+    N, nx, nu = cfg["N"], m.nx, m.nu
+    xs, us = g["x"], g["u"]
+    n = len(xs)
+    X = np.zeros((n, N + 1, nx)); U = np.zeros((n, N, nu))
+    X[:, 0], U[:, 0] = xs, us
+    X[:, 1] = g["xp"] + 0.25            # c_0 = f(x0,u0) - x_1 = -0.25
+    A, B, c = (np_(t) for t in s.linearize(X, U))
+    assert np.abs(A[:, 0] - g["A"]).max() < 1e-11
+    assert np.abs(B[:, 0] - g["B"]).max() < 1e-11
+    assert np.abs(c[:, 0] + 0.25).max() < 1e-12
+    xp = np_(s.ddyn(xs, us))
+    assert np.abs(xp - g["xp"]).max() < 1e-12
+    w = np.random.default_rng(0).uniform(-1, 1, size=xs.shape)
+    xpw = np_(s.ddyn(xs, us, w))
+    assert np.abs(xpw - (g["xp"] + w @ m.E.T)).max() < 1e-12
+    # explicit step size (dyn/model.py:15 h argument)
+    assert np.abs(np_(s.ddyn(xs[:1], us[:1], h=0.02))[0] - m.ddyn(xs[0], us[0], 0.02)).max() < 1e-12
+    s.close()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_sls_vs_reference_numba_golden(name):
+    """CUDA fast-SLS kernel vs the outputs of the reference's own Numba kernels."""
+    g = load(f"sls_{name}.npz")
+    m, cfg, A, B, eta, eta_f = sls_inputs(name)
+    _, _, s = make_solver(name, 4)
+    N = cfg["N"]
+    out = {k: (None if v is None else np_(v)[0]) for k, v in s.sls(A[None], B[None], eta[None], eta_f[None], want_S=True, want_phi=True).items()}
+    assert rel(out["K"], g["K"]) < TOL_FP
+    assert rel(np.einsum("kjii->kji", out["S"]), g["S_diag"]) < TOL_FP
+    assert rel(out["S"].sum(axis=(2, 3)), g["S_sum"]) < TOL_FP
+    assert rel(out["Phi_x"][N], g["Phi_x_last"]) < TOL_FP
+    assert rel(out["Phi_x"].sum(axis=(2, 3)), g["Phi_x_sum"]) < TOL_FP
+    assert rel(out["Phi_u"].sum(axis=(2, 3)), g["Phi_u_sum"]) < TOL_FP
+    assert abs(np.abs(out["Phi_x"]).sum() / g["Phi_x_abs"] - 1) < TOL_FP
+    for key in ("beta", "beta_f", "backoff", "backoff_f"):
+        assert rel(out[key], g[key]) < TOL_FP, key
+    for k in range(N):      # strictly causal structure
+        assert not out["K"][k, k + 1:].any() and not out["beta"][k, k + 1:].any()
+    assert np.array_equal(out["S"], np.swapaxes(out["S"], 2, 3))    # symmetrised exactly
+    s.close()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_sls_ragged_batch_and_zero_duals(name):
+    """Batch sizes that do not fill a warp's slots, and all-zero weights (no active constraint: pure LQR tube)."""
+    m, cfg, A, B, eta, eta_f = sls_inputs(name, seed=3)
+    _, _, s = make_solver(name, 16)
+    N, nx, nu = cfg["N"], m.nx, m.nu
+    rng = np.random.default_rng(1)
+    for Bn in (1, 2, 5, 7):
+        As = np.stack([A * (1 + 0.01 * rng.standard_normal()) for _ in range(Bn)])
+        Bs = np.stack([B] * Bn)
+        et = np.stack([eta if b % 2 == 0 else np.zeros_like(eta) for b in range(Bn)])
+        etf = np.stack([eta_f if b % 2 == 0 else np.zeros_like(eta_f) for b in range(Bn)])
+        out = {k: np_(v) for k, v in s.sls(As, Bs, et, etf).items() if v is not None}
+        for b in range(Bn):
+            S, K = osls.backward_solve(N, nx, nu, As[b], Bs[b], m.G, m.Gf, et[b], etf[b], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"])
+            Px, Pu = osls.propagate(As[b], Bs[b], np.stack([m.E] * (N + 1)), K)
+            be, bef, bo, bof = osls.backoff_from_phi(Px, Pu, m.G[:, :nx], m.G[:, nx:], m.Gf, 1e-10)
+            assert rel(out["K"][b], K) < TOL_FP and rel(out["beta"][b], be) < TOL_FP
+            assert rel(out["backoff"][b], bo) < TOL_FP and rel(out["backoff_f"][b], bof) < TOL_FP
+    s.close()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_qp_vs_oracle_golden(name):
+    """CUDA interior-point QP vs the oracle's exact solutions (un-tightened and tightened bounds, quirk Q4)."""
+    g = load(f"qp_{name}.npz")
+    m, cfg, s = make_solver(name, 8)
+    n = len(g["X"])
+    A, B, c = s.linearize(g["X"], g["U"])
+    for tight in (False, True):
+        idx = np.where(g["tight"] == tight)[0]
+        if len(idx) == 0:
+            continue
+        ti = torch.as_tensor(idx, device=A.device)
+        out = s.qp(A[ti], B[ti], c[ti], g["X"][idx], g["U"][idx], g["x0"][idx],
+                   g["backoff"][idx] if tight else None, g["backoff_f"][idx] if tight else None)
+        out = {k: np_(v) for k, v in out.items()}
+        assert not out["status"].any(), out["status"]
+        assert out["iters"].max() <= 30
+        for j, i in enumerate(idx):
+            assert rel(out["dX"][j], g["dX"][i]) < TOL_TRAJ and rel(out["dU"][j], g["dU"][i]) < TOL_TRAJ
+            scale = max(np.abs(g["mu"][i]).max(), 1.0)
+            assert np.abs(out["mu"][j] - g["mu"][i]).max() < TOL_TRAJ * scale
+            assert np.abs(out["mu_f"][j] - g["mu_f"][i]).max() < TOL_TRAJ * scale
+            assert abs(out["cost"][j] - g["cost"][i]) < 1e-7 * max(1.0, abs(g["cost"][i]))
+            assert out["mu"][j].min() > -1e-12          # dual feasibility
+            assert np.abs(out["dX"][j][0] - g["x0"][i] + g["X"][i][0]).max() < 1e-14     # x(0) pinned to the measurement
+    s.close()
+
+
+def test_qp_infeasible_instance_does_not_poison_batch():
+    """A measured state outside the state box makes that instance's QP infeasible (status != 0); its neighbours in the
+    same warp still solve (reference: {'success': False} for that solve only, qp_jit.py:397-400)."""
+    g = load("qp_rocket.npz")
+    m, cfg, s = make_solver("rocket", 8)
+    idx = [0, 0, 0, 0, 0]
+    X, U, x0 = g["X"][idx].copy(), g["U"][idx].copy(), g["x0"][idx].copy()
+    x0[2, 3] = 5.0           # v_x = 5 >> bound 1
+    A, B, c = s.linearize(X, U)
+    out = {k: np_(v) for k, v in s.qp(A, B, c, X, U, x0).items()}
+    assert out["status"][2] != 0
+    good = [0, 1, 3, 4]
+    assert not out["status"][good].any()
+    for j in good:
+        assert rel(out["dX"][j], g["dX"][0]) < TOL_TRAJ
+    s.close()
+
+
+def _run_loop_gpu(name, g, steps):
+    m, cfg, s = make_solver(name, 1)
+    s.set_nominal(g["X0"][None], g["U0"][None])
+    x = s.dev(g["x0"][None]).clone()
+    W = g["W"] if g["W"].size else None
+    out = dict(states=[np_(x)[0].copy()], Xn=[], Un=[], bo=[], flags=[], K=[], inputs=[])
+    for i in range(steps):
+        if i > 0:
+            s.reset_warm_start(1)
+        s.solve(x)
+        out["Xn"].append(s.buffer("X", 1)[0]); out["Un"].append(s.buffer("U", 1)[0])
+        out["bo"].append((s.buffer("backoff", 1)[0], s.buffer("backoff_f", 1)[0]))
+        out["flags"].append(int(s.buffer("flags", 1)[0])); out["K"].append(s.buffer("K", 1)[0])
+        out["inputs"].append(out["Un"][-1][0].copy())
+        s.plant_step(x, None if W is None else W[i][None])
+        out["states"].append(np_(x)[0].copy())
+    s.close()
+    return m, cfg, out
+
+
+@pytest.mark.parametrize("tag,name,steps", [("rocket_w08", "rocket", 29), ("rocket_rng123", "rocket", 29),
+                                            ("pendulum", "pendulum", 60), ("quadrotor", "quadrotor", 30)])
+def test_closed_loop_vs_oracle_golden(tag, name, steps):
+    """Whole closed loops of the reference drivers (configs 1-4 of BASELINE.json) against the oracle's trajectories."""
+    g = load(f"loop_{tag}.npz")
+    assert g["success"].all() and len(g["inputs"]) == steps
+    m, cfg, out = _run_loop_gpu(name, g, steps)
+    nx, nu, N = m.nx, m.nu, cfg["N"]
+    for i in range(steps):
+        skipped = (out["flags"][i] & 4) == 0
+        assert out["flags"][i] & 1 == 0
+        assert skipped == bool(g["skipped"][i]), f"step {i}: Q3 early return differs"
+        assert rel(out["Xn"][i], g["Xn"][i]) < TOL_TRAJ, i
+        assert np.abs(out["Un"][i] - g["Un"][i]).max() < TOL_TRAJ * max(1.0, np.abs(g["Un"][i]).max()), i
+        if not skipped:
+            bo, bof = out["bo"][i]
+            bx = np.vstack([bo[:, :nx], bof[:nx]])
+            assert rel(bx, g["backoff_x"][i]) < TOL_TRAJ and rel(bo[:, nx:nx + nu], g["backoff_u"][i]) < TOL_TRAJ, i
+            assert rel(out["K"][i][:3, 0], g["K_first"][i]) < TOL_TRAJ, i
+            assert abs(np.abs(out["K"][i]).sum() / g["K_abs"][i] - 1) < TOL_TRAJ, i
+    assert rel(np.array(out["states"]), g["states"]) < TOL_STATE
+    assert rel(np.array(out["inputs"]), g["inputs"]) < TOL_STATE
+
+
+def test_solve_vs_oracle_seeded_scenarios():
+    """Fresh seeded rocket scenarios (not in the fixtures): SQP initialiser + two MPC steps, GPU vs oracle."""
+    x0s, W = rocket_scenarios(3, seed=11, steps=2)
+    m, cfg, s = make_solver("rocket", 3)
+    N, nx, nu = cfg["N"], m.nx, m.nu
+    s.init_nominal(x0s, 10)
+    Xg, Ug = s.buffer("X", 3), s.buffer("U", 3)
+    x = s.dev(x0s).clone()
+    res = []
+    for i in range(2):
+        if i > 0:
+            s.reset_warm_start(3)
+        s.solve(x)
+        res.append((s.buffer("X", 3), s.buffer("U", 3), s.buffer("K", 3), s.buffer("backoff", 3), s.buffer("flags", 3)))
+        s.plant_step(x, W[:, i])
+    for b in range(3):
+        X0, U0, ok = oscp.nominal_sqp(m, N, cfg["Q"], cfg["R"], cfg["Qf"], x0s[b], iters=10)
+        assert ok and rel(Xg[b], X0.T) < TOL_TRAJ and rel(Ug[b], U0.T) < TOL_TRAJ
+        ref = oscp.closed_loop(m, cfg, x0s[b], W[b], 2, X0=X0, U0=U0)
+        for i in range(2):
+            Xn, Un, K, bo, fl = (r[b] for r in res[i])
+            assert fl & 1 == 0
+            assert rel(Xn, ref["Xn"][i].T) < TOL_TRAJ and rel(Un, ref["Un"][i].T) < TOL_TRAJ
+            assert rel(K, ref["K"][i]) < TOL_TRAJ
+            assert rel(bo[:, :nx], ref["backoff_x"][i][:N]) < TOL_TRAJ
+    s.close()
+
+
+def test_batch_properties_at_bench_size():
+    """B = 4096 rocket scenarios, one MPC step: properties that hold at any size."""
+    B = 4096
+    x0s, W = rocket_scenarios(B, steps=1)
+    m, cfg, s = make_solver("rocket", B)
+    N, nx, nu, nz = cfg["N"], m.nx, m.nu, m.nx + m.nu
+    s.init_nominal(x0s, 10)
+    s.solve(x0s)
+    flags, X, U = s.buffer("flags"), s.buffer("X"), s.buffer("U")
+    ok = (flags & 1) == 0
+    assert ok.mean() > 0.99
+    K, bo, bof, beta = s.buffer("K"), s.buffer("backoff"), s.buffer("backoff_f"), s.buffer("beta")
+    X, U, K, bo, bof, beta = X[ok], U[ok], K[ok], bo[ok], bof[ok], beta[ok]
+    assert np.abs(X[:, 0] - x0s[ok]).max() < 1e-12                       # nominal starts at the measured state
+    assert np.isfinite(K).all() and np.isfinite(bo).all()
+    for k in range(N):
+        assert not K[:, k, k + 1:].any()                                 # causal gains
+    assert (bo >= N * 0 + 1e-5 - 1e-18).all()                            # every back-off >= sqrt(eps)
+    assert np.array_equal(bo[:, :, :nz], bo[:, :, nz:])                  # symmetric box rows share their back-off
+    assert np.array_equal(beta[:, :, :, :nz], beta[:, :, :, nz:])
+    # back-off at stage 0 is the row norm of E (Phi_x[0,0] = E, no feedback yet)
+    assert np.abs(bo[:, 0, :nx] - np.linalg.norm(m.E, axis=1)[None]).max() < 1e-12
+    # robust feasibility of the tightened nominal QP: nominal +- back-off inside the box (1e-7 slack)
+    Z = np.concatenate([X[:, :N], U], axis=2)
+    ub, lb = np.concatenate([m.x_ub, m.u_ub]), np.concatenate([m.x_lb, m.u_lb])
+    assert (Z[:, 1:] + bo[:, 1:, :nz] <= ub + 1e-7).all() and (Z[:, 1:] - bo[:, 1:, nz:] >= lb - 1e-7).all()
+    # identical scenarios give identical results wherever they sit in the batch (slot / warp independence)
+    xs = np.stack([x0s[0]] * 7)
+    _, _, s2 = make_solver("rocket", 7)
+    s2.init_nominal(xs, 10)
+    s2.solve(xs)
+    X7, K7 = s2.buffer("X"), s2.buffer("K")
+    assert all(np.array_equal(X7[0], X7[i]) and np.array_equal(K7[0], K7[i]) for i in range(1, 7))
+    assert np.array_equal(X7[0], s.buffer("X", 1)[0])
+    s.close(); s2.close()
+
+
+def test_host_entry_points_match_device_path():
+    """rnmpc_solve_host / rnmpc_closed_loop_host (host buffers, copies inside) vs the device-tensor path."""
+    B, steps = 6, 3
+    x0s, W = rocket_scenarios(B, seed=5, steps=steps)
+    m, cfg, s = make_solver("rocket", B)
+    s.init_nominal(x0s, 10)
+    X0, U0 = s.buffer("X"), s.buffer("U")
+    x = s.dev(x0s).clone()
+    states, inputs = [x0s.copy()], []
+    for i in range(steps):
+        if i > 0:
+            s.reset_warm_start(B)
+        s.solve(x)
+        inputs.append(s.buffer("U")[:, 0].copy())
+        s.plant_step(x, W[:, i])
+        states.append(np_(x).copy())
+    _, _, s2 = make_solver("rocket", B)
+    out = s2.closed_loop_host(x0s, W, steps, X0=X0, U0=U0)
+    assert out["n_failed_solves"] == 0
+    assert np.array_equal(out["states"], np.swapaxes(np.array(states), 0, 1))
+    assert np.array_equal(out["inputs"], np.swapaxes(np.array(inputs), 0, 1))
+    out3 = s2.closed_loop_host(x0s, W, steps)            # built-in SQP initialiser
+    assert np.array_equal(out3["states"], out["states"])
+    s2.set_nominal(X0, U0)
+    h = s2.solve_host(x0s)
+    s.set_nominal(X0, U0)
+    s.solve(x0s)
+    assert np.array_equal(h["X"], s.buffer("X")) and np.array_equal(h["backoff"], s.buffer("backoff"))
+    with pytest.raises(Exception):
+        s2.solve(np.zeros((B + 1, m.nx)))               # larger than the handle's capacity
+    s.close(); s2.close()
+
+
+def test_reference_api_drop_in():
+    """The reference's driver loop (expe/main_rocket_compare_closed_loop.py:104-173) against this package's
+    ``solver.SCP_SLS_jit.SCP_SLS`` / ``dyn.rocket.Rocket`` with unchanged call syntax."""
+    from rnmpc_b200.dyn.rocket import Rocket
+    from rnmpc_b200.solver.SCP_SLS_jit import SCP_SLS
+    g = load("loop_rocket_w08.npz")
+    mo, cfg = om.rocket_config()
+    m = Rocket()
+    m.dt = 0.05
+    m.E = mo.E
+    N = 15
+    solver = SCP_SLS(N, cfg["Q"], cfg["R"], m, cfg["Qf"], Q_reg=1e4 * np.eye(m.nx), R_reg=1e4 * np.eye(m.nu),
+                     Q_reg_f=1e4 * np.eye(m.nx), rti=1, fast_sls_rti_steps=1)
+    solver.fast_SLS_solver.solver_forward.export_standard_qp = False
+    solver.fast_SLS_solver.verbose = False
+    solver.fast_SLS_solver.CONV_EPS = 1e-4
+    solver.verbose = False
+    solver.epsilon_convergence = 1e-3
+    solver.set_nominal_trajectory(g["X0"].T, g["U0"].T)
+    x = g["x0"].copy()
+    W = g["W"]
+    for i in range(3):
+        if i > 0 and hasattr(solver, 'reset_warm_start'):
+            solver.reset_warm_start()
+        sol = solver.solve(x)
+        assert sol['success']
+        assert sol['primal_x'].shape == (17, 16) and sol['primal_u'].shape == (4, 15)
+        assert sol['backoff_x'].shape == (16, 17) and sol['backoff_u'].shape == (15, 4)
+        assert sol['K'].shape == (15, 16, 4, 17) and sol['dual_mu'].shape == (42, 15) and sol['dual_eta'].shape == (15, 15, 42)
+        assert sol['t_jac_ms'] > 0 and sol['t_qp_ms'] > 0 and sol['t_backward_ms'] > 0
+        assert rel(sol['primal_x'], g["Xn"][i].T) < TOL_TRAJ and rel(sol['backoff_x'], g["backoff_x"][i]) < TOL_TRAJ
+        assert rel(sol['backoff_u'], g["backoff_u"][i]) < TOL_TRAJ
+        u0 = sol['primal_u'][:, 0]
+        x = np.array(m.ddyn(x, u0) + m.E @ W[i]).reshape(-1)
+        assert np.abs(x - g["states"][i + 1]).max() < TOL_STATE
+    lin = solver.linearization()
+    assert len(lin['A_list']) == 15 and lin['A_list'][0].shape == (17, 17) and len(lin['g_list']) == 16
+    # batch mode of the same class
+    sb = SCP_SLS(N, cfg["Q"], cfg["R"], m, cfg["Qf"], Q_reg=1e4 * np.eye(m.nx), R_reg=1e4 * np.eye(m.nu),
+                 Q_reg_f=1e4 * np.eye(m.nx), rti=1, fast_sls_rti_steps=1, batch=3, verbose=False)
+    sb.set_nominal_trajectory(np.stack([g["X0"].T] * 3), np.stack([g["U0"].T] * 3))
+    solb = sb.solve(np.stack([g["x0"]] * 3))
+    assert solb['success'].all() and solb['primal_x'].shape == (3, 17, 16)
+    assert rel(solb['primal_x'][2], g["Xn"][0].T) < TOL_TRAJ

@@ -1,0 +1,187 @@
+"""CPU tests: the oracle against the golden fixtures (reference Numba kernels, SymPy Jacobians), KKT checks of the
+oracle QP, the host-side layout logic, and the exported C ABI.  No GPU compute."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import models as om
+from oracle import qp as oqp
+from oracle import scp as oscp
+from oracle import sls as osls
+from oracle.gen_golden import jac_points, sls_inputs
+from tests.helpers import load, rel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", ["pendulum", "quadrotor", "rocket"])
+def test_sls_restatement_matches_reference_kernels(name):
+    """oracle/sls.py vs outputs of the reference's own Numba kernels (tests/golden/sls_*.npz)."""
+    g = load(f"sls_{name}.npz")
+    m, cfg, A, B, eta, eta_f = sls_inputs(name)
+    N, nx, nu = cfg["N"], m.nx, m.nu
+    S, K = osls.backward_solve(N, nx, nu, A, B, m.G, m.Gf, eta, eta_f, cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"])
+    Px, Pu = osls.propagate(A, B, np.stack([m.E] * (N + 1)), K)
+    beta, beta_f, bo, bof = osls.backoff_from_phi(Px, Pu, m.G[:, :nx], m.G[:, nx:], m.Gf, 1e-10)
+    assert rel(K, g["K"]) < 1e-13
+    assert rel(np.einsum("kjii->kji", S), g["S_diag"]) < 1e-13
+    assert rel(S.sum(axis=(2, 3)), g["S_sum"]) < 1e-12
+    assert rel(Px[N], g["Phi_x_last"]) < 1e-13
+    assert rel(Pu.sum(axis=(2, 3)), g["Phi_u_sum"]) < 1e-12
+    for a, key in ((beta, "beta"), (beta_f, "beta_f"), (bo, "backoff"), (bof, "backoff_f")):
+        assert rel(a, g[key]) < 1e-13
+    # structure the reference guarantees: K[k, j] = 0 for j > k, beta zero above the diagonal
+    for k in range(N):
+        assert not K[k, k + 1:].any() and not beta[k, k + 1:].any()
+
+
+@pytest.mark.parametrize("name", ["pendulum", "quadrotor", "rocket"])
+def test_jacobians_match_sympy(name):
+    """oracle/models.py complex-step A, B and RK4 step vs SymPy differentiation (tests/golden/jac_*.npz)."""
+    g = load(f"jac_{name}.npz")
+    m = om.MODELS[name]()
+    xs, us = jac_points(name)
+    assert np.array_equal(xs, g["x"]) and np.array_equal(us, g["u"])
+    for x, u, A, B, xp in zip(xs, us, g["A"], g["B"], g["xp"]):
+        a, b = m.jacobians(x, u)
+        assert np.abs(a - A).max() < 1e-12 and np.abs(b - B).max() < 1e-12
+        assert np.abs(m.ddyn(x, u) - xp).max() < 1e-13
+
+
+def test_model_constants_follow_reference():
+    """Sizes and constraint layout of SURVEY.md section 8: g = [x_ub, u_ub, -x_lb, -u_lb], G = [I; -I]."""
+    for name, (nx, nu, ni, nif) in dict(pendulum=(4, 1, 10, 8), quadrotor=(13, 4, 34, 26), rocket=(17, 4, 42, 34)).items():
+        m = om.MODELS[name]()
+        assert (m.nx, m.nu, m.nw, m.ni, m.ni_f) == (nx, nu, nx, ni, nif)
+        nz = nx + nu
+        assert np.array_equal(m.G, np.vstack([np.eye(nz), -np.eye(nz)]))
+        assert np.array_equal(m.g[:nx], m.x_ub) and np.array_equal(m.g[nz:nz + nx], -m.x_lb)
+    r = om.Rocket()
+    assert r.x_ub[3] == 1.0 and r.x_ub[13] == 50.0 and r.u_ub[0] == 50.0
+    assert abs(r.ddyn(om.ROCKET_X0, np.zeros(4))[10] - (-4.92936284)) < 1e-7   # strong roll torque at the fixed x0
+
+
+@pytest.mark.parametrize("name", ["pendulum", "quadrotor", "rocket"])
+def test_oracle_qp_kkt(name):
+    """Every QP fixture: the stored solution satisfies the KKT conditions of the reference's QP to <= 1e-9 and the
+    oracle solver reproduces it."""
+    g = load(f"qp_{name}.npz")
+    m, cfg = om.CONFIGS[name]()
+    N, nx = cfg["N"], m.nx
+    solver = oscp.SCPSLS(N, cfg["Q"], cfg["R"], m, cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], rti=1, fast_sls_rti_steps=1)
+    n_check = 0
+    for i in range(len(g["X"])):
+        X, U = g["X"][i].T, g["U"][i].T
+        solver.set_nominal(X, U)
+        solver.update_jacobian()
+        f = solver.fast
+        if g["tight"][i]:
+            # rebuild the tightened bounds exactly like update_tightening (fast_SLS_jit.py:560-569)
+            tight = np.stack(f.g_list[:-1]) - g["backoff"][i]
+            cmat = np.stack(f.c_list, axis=1)
+            stage = np.vstack([-cmat, tight.T]).reshape(-1, order="F")
+            f.ubg = np.concatenate([stage, f.gf_model - g["backoff_f"][i]])
+        l, u = f.qp.bounds(f.lbg, f.ubg, X[:, 0] - g["x0"][i])
+        y = f.qp.pack(g["dX"][i].T, g["dU"][i].T)
+        lam = np.zeros(f.qp.m)
+        stage_dual = np.full((N, nx + m.ni), np.nan)
+        stage_dual[:, nx:] = g["mu"][i]
+        # dynamics multipliers are not part of the fixture: recover them from stationarity by least squares
+        ineq = np.concatenate([stage_dual.reshape(-1), g["mu_f"][i], np.full(nx, np.nan)])
+        known = ~np.isnan(ineq)
+        lam[known] = ineq[known]
+        rhs = -(2 * f.qp.H @ y + f.q + f.qp.Acon[known].T @ lam[known])
+        sol, *_ = np.linalg.lstsq(f.qp.Acon[~known].T, rhs, rcond=None)
+        lam[~known] = sol
+        res = oqp.kkt_residuals(f.qp.H, f.q, f.qp.Acon, l, u, y, lam)
+        assert res["stat"] < 1e-8 and res["prim"] < 1e-9 and res["comp"] < 1e-8, res
+        if i < 2:
+            x2, y2, info = oqp.solve_qp(f.qp.H, f.q, f.qp.Acon, l, u)
+            assert np.abs(x2 - y).max() < 1e-8 * max(1.0, np.abs(y).max())
+            n_check += 1
+    assert n_check >= 1
+
+
+def test_q3_and_q4_quirks():
+    """Q3: the convergence test uses the previous first-in-step QP across calls and skips the tube update;
+    Q4: the tightened terminal bound is gf - backoff_f (not shifted by x_N)."""
+    m, cfg = om.pendulum_config()
+    N = cfg["N"]
+    s = oscp.SCPSLS(N, cfg["Q"], cfg["R"], m, cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], rti=1, fast_sls_rti_steps=1)
+    X = np.zeros((m.nx, N + 1)); U = np.zeros((m.nu, N))
+    X[0, :] = 0.3                                               # x_N != 0 so that Q4 is visible
+    s.set_nominal(X, U)
+    s.update_jacobian()
+    inner = s.fast.solve(X[:, 0] - np.zeros(m.nx))
+    assert np.allclose(s.fast.ubg[-m.ni_f:], m.gf - inner["backoff_f"])            # Q4: no "- Gf x_N"
+    assert not np.allclose(s.fast.ubg[-m.ni_f:], m.gf - m.Gf @ X[:, N] - inner["backoff_f"])
+    s.fast._prev_primal_vec = None
+    X[0, :] = 0.0
+    s.set_nominal(X, U)
+    sol1 = s.solve(np.zeros(m.nx))
+    assert sol1["success"] and sol1["K"] is not None            # first call: prev is None -> not converged
+    s.reset_warm_start()
+    sol2 = s.solve(np.zeros(m.nx))                               # identical QP -> |delta - prev| = 0 <= 1e-3 -> early return
+    assert sol2["success"] and sol2["K"] is None
+    assert not sol2["backoff_x"].any() and np.allclose(sol2["backoff"], N * 1e-5)
+
+
+def test_pack_unpack_layout():
+    """Stage-wise layout [x0; u0; ...; xN] of solver/ocp.py:43-74 in the oracle and in the product's host mirror."""
+    import rnmpc_b200  # noqa: F401
+    from rnmpc_b200.dyn.rocket import Rocket
+    from rnmpc_b200.solver.ocp import OCP
+    m = Rocket()
+    o = OCP(15, np.eye(17), np.eye(4), m, np.eye(17))
+    rng = np.random.default_rng(0)
+    X, U = rng.random((17, 16)), rng.random((4, 15))
+    y = o.pack_primal_nominal(X, U)
+    q = oqp.QPData(15, 17, 4, np.eye(17), np.eye(4), np.eye(17), m.G, m.Gf)
+    assert np.array_equal(y, q.pack(X, U))
+    assert np.array_equal(y[:17], X[:, 0]) and np.array_equal(y[17:21], U[:, 0]) and np.array_equal(y[-17:], X[:, 15])
+    X2, U2 = o.unpack_primal_nominal(y)
+    assert np.array_equal(X, X2) and np.array_equal(U, U2)
+    assert np.array_equal(o.Q_reg, np.eye(17)) and np.array_equal(o.R_reg, np.eye(4))    # ocp.py:15-26 defaults
+    # product models expose the reference attribute set
+    om_r = om.Rocket()
+    assert np.array_equal(m.g, om_r.g) and np.array_equal(m.gf, om_r.gf) and np.array_equal(m.E, om_r.E)
+    assert np.array_equal(np.concatenate(m.box()[:2]), np.concatenate([om_r.x_ub, om_r.x_lb]))
+    m.G = np.ones_like(m.G)
+    with pytest.raises(NotImplementedError):
+        m.box()
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads and exports every function include/rnmpc_b200.h declares (no compute calls)."""
+    from rnmpc_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "rnmpc_b200.h")).read()
+    declared = set(re.findall(r"\b(rnmpc_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"rnmpc_handle", "rnmpc_config"}
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    nx, nu = ctypes.c_int(), ctypes.c_int()
+    assert lib.rnmpc_model_dims(2, ctypes.byref(nx), ctypes.byref(nu)) == 0 and (nx.value, nu.value) == (17, 4)
+    assert lib.rnmpc_model_dims(9, ctypes.byref(nx), ctypes.byref(nu)) != 0
+    assert b"unknown model" in lib.rnmpc_last_error()
+
+
+def test_product_has_no_cpu_fallback():
+    """Without a CUDA device the product must refuse to run instead of falling back to the oracle / NumPy."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from tests.helpers import make_solver
+    with pytest.raises(RuntimeError):
+        make_solver("pendulum", 1)
+    # and nothing under the product imports the oracle
+    pkg = os.path.join(ROOT, "robust-nonlinear-mpc_b200")
+    for dp, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(dp, fn)).read()
+                assert "import oracle" not in src and "from oracle" not in src, fn
