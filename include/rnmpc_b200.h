@@ -11,8 +11,8 @@
  *     data_ptr), `h_` = host pointer.  The caller owns every buffer it passes.  A handle is bound to one CUDA device
  *     and is NOT thread-safe (the reference solver objects are not either).
  *   - return value: 0 = OK, < 0 = argument / CUDA error (rnmpc_last_error() gives the text).  Solver failure of an
- *     instance is NOT an error: it is reported per instance in `status` (0 ok, 1 QP not converged, 2 QP infeasible /
- *     numerical failure), mirroring the reference's {'success': False} (qp_jit.py:397-400, fast_SLS_jit.py:334-341).
+ *     instance is NOT an error: it is reported per instance in `status` (0 ok, 1 QP not converged, 2 QP infeasible,
+ *     3 numerical failure), mirroring the reference's {'success': False} (qp_jit.py:397-400, fast_SLS_jit.py:334-341).
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous unless stated.
  *   - sizes: nx, nu from the model; nz = nx+nu; ni = 2*nz; ni_f = 2*nx; nw = nx.
  *   - box constraints only: G = [I; -I], Gf = [I; -I] (all reference models, dyn/rocket.py:129-139).

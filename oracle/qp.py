@@ -66,10 +66,22 @@ class QPData:
         Ac[r:r + nx, :nx] = np.eye(nx)
         self.Acon = Ac
 
+    X0_TOL = 1e-3
+
     def bounds(self, lbg, ubg, x0):
-        """solver/qp_jit.py:370-386: append the x0 box and sanitise infinities."""
+        """solver/qp_jit.py:370-386: append the x0 box and sanitise infinities.
+
+        Stage-0 state rows of G only restate the pinned x(0) = -x0: they are either redundant or make the QP
+        infeasible.  OSQP with its default eps_abs = 1e-3 (quirk Q1) accepts violations of that size, an exact solver
+        does not; both the oracle and the CUDA path therefore drop these rows when the violation is <= X0_TOL and keep
+        them (infeasible QP -> success False) beyond."""
         l = np.concatenate([np.asarray(lbg, float).ravel(), -np.asarray(x0, float).ravel() - EPSILON])
         u = np.concatenate([np.asarray(ubg, float).ravel(), -np.asarray(x0, float).ravel() + EPSILON])
+        nx, nz = self.nx, self.nx + self.nu
+        d0 = -np.asarray(x0, float).ravel()
+        up, lo = np.arange(nx, 2 * nx), np.arange(nx + nz, nx + nz + nx)     # rows of stage 0: [dyn nx | G upper nz | G lower nz]
+        if np.all(d0 <= u[up] + self.X0_TOL) and np.all(-d0 <= u[lo] + self.X0_TOL):
+            u[up], u[lo] = np.inf, np.inf
         l = np.where(np.isneginf(l), -BIG, np.where(np.isposinf(l), BIG, l))
         u = np.where(np.isposinf(u), BIG, np.where(np.isneginf(u), -BIG, u))
         return l, u

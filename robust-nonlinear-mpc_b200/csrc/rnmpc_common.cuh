@@ -23,6 +23,7 @@ constexpr int FLAG_TIGHT = 4;   // tube back-offs were computed in this fast-SLS
 constexpr int FLAG_PREV = 8;    // _prev_primal_vec exists (Q3 state)
 constexpr int FLAG_KVALID = 16; // K / Phi were computed since the last reset_solver_to_zeros (else the reference returns None)
 
+constexpr double kX0Tol = 1e-3;         // tolerated violation of the (redundant) stage-0 state box by the measured state
 constexpr double kBig = 1e19;           // bounds >= kBig are treated as infinite (qp_jit.py:382 uses 1e20)
 
 template <int NX, int NU>

@@ -150,7 +150,7 @@ struct Engine : IEngine {
 
     double *X, *U, *A, *Bm, *c, *dX, *dU, *mu, *mu_f, *beta, *beta_f, *backoff, *backoff_f, *K, *cost, *prevX, *prevU;
     double *Phi_x = nullptr, *Phi_u = nullptr;
-    double *hi, *lo, *gx, *gu, *dXa, *dUa, *dXc, *dUc, *rp, *Sc, *dff, *Kq, *Lq;
+    double *wZ, *wSU, *wSL, *wLU, *wLL, *wDZA, *wDZC, *wG, *wSIG, *rp, *Sc, *dff, *Kq, *Lq;
     int *flags, *status, *qp_iters, *iters_tmp, *status_tmp;
 
     template <class T>
@@ -190,10 +190,9 @@ struct Engine : IEngine {
         rc |= alloc("backoff", backoff, B * N * NI); rc |= alloc("backoff_f", backoff_f, B * NIF);
         rc |= alloc("K", K, B * N * n1 * NU * NX); rc |= alloc("cost", cost, B);
         rc |= alloc("prevX", prevX, B * n1 * NX); rc |= alloc("prevU", prevU, B * N * NU);
-        rc |= alloc("hi", hi, B * n1 * NZ); rc |= alloc("lo", lo, B * n1 * NZ);
-        rc |= alloc("gx", gx, B * n1 * NX); rc |= alloc("gu", gu, B * N * NU);
-        rc |= alloc("dXa", dXa, B * n1 * NX); rc |= alloc("dUa", dUa, B * N * NU);
-        rc |= alloc("dXc", dXc, B * n1 * NX); rc |= alloc("dUc", dUc, B * N * NU);
+        rc |= alloc("wZ", wZ, B * n1 * NZ); rc |= alloc("wSU", wSU, B * n1 * NZ); rc |= alloc("wSL", wSL, B * n1 * NZ);
+        rc |= alloc("wLU", wLU, B * n1 * NZ); rc |= alloc("wLL", wLL, B * n1 * NZ); rc |= alloc("wDZA", wDZA, B * n1 * NZ);
+        rc |= alloc("wDZC", wDZC, B * n1 * NZ); rc |= alloc("wG", wG, B * n1 * NZ); rc |= alloc("wSIG", wSIG, B * n1 * NZ);
         rc |= alloc("rp", rp, B * N * NX); rc |= alloc("Sc", Sc, B * N * NX); rc |= alloc("dff", dff, B * N * NU);
         rc |= alloc("Kq", Kq, B * N * NU * NX); rc |= alloc("Lq", Lq, B * N * NU * NU);
         rc |= alloc("flags", flags, B); rc |= alloc("status", status, B); rc |= alloc("qp_iters", qp_iters, B);
@@ -273,7 +272,7 @@ struct Engine : IEngine {
         a.A = A_; a.Bm = B_; a.c = c_; a.Xnom = X_; a.Unom = U_; a.x0 = x0; a.backoff = bo; a.backoff_f = bof;
         a.flags = fl; a.skip_mask = skip_mask;
         a.dX = dX_; a.dU = dU_; a.mu = mu_; a.mu_f = mu_f_; a.cost = cost_; a.iters = iters_; a.status = status_;
-        a.hi = hi; a.lo = lo; a.gx = gx; a.gu = gu; a.dXa = dXa; a.dUa = dUa; a.dXc = dXc; a.dUc = dUc; a.rp = rp; a.Sc = Sc;
+        a.Z = wZ; a.SU = wSU; a.SL = wSL; a.LU = wLU; a.LL = wLL; a.DZA = wDZA; a.DZC = wDZC; a.G = wG; a.SIG = wSIG; a.rp = rp; a.Sc = Sc;
         a.dff = dff; a.Kq = Kq; a.Lq = Lq;
         const long long warps = ((long long)B + Slot<NX>::SPW - 1) / Slot<NX>::SPW;
         const unsigned grid = (unsigned)((warps + kWarps - 1) / kWarps);

@@ -6,7 +6,8 @@
 // Solved per instance by a Mehrotra predictor-corrector primal-dual interior-point method whose every KKT solve is
 // a Riccati factorisation / sweep over the block-tridiagonal structure (riccati_step of rnmpc_common.cuh: the same
 // device function the fast-SLS kernel runs).  One instance per slot (LPS lanes), SPW instances per warp in
-// lock-step; dual variables are written straight into the reference's dual_mu / dual_mu_f layout.
+// lock-step.  Per-instance vectors live in global (L2-resident) workspace in one [N+1][nz] "entry" layout; the
+// element-wise phases load groups of KU stages ahead of the arithmetic so that their latency overlaps.
 #pragma once
 #include "rnmpc_common.cuh"
 
@@ -35,16 +36,18 @@ struct QpArgs {
     double* mu_f;           // [B][ni_f]
     double* cost;           // [B]
     int* iters;             // [B]
-    int* status;            // [B] 0 ok, 1 not converged, 2 infeasible / numerical failure
-    // workspace
-    double* hi;             // [B][N+1][nz]
-    double* lo;             // [B][N+1][nz]
-    double* gx;             // [B][N+1][nx]   2Q(x+xnom)
-    double* gu;             // [B][N][nu]
-    double* dXa;            // [B][N+1][nx]   affine (predictor) step
-    double* dUa;            // [B][N][nu]
-    double* dXc;            // [B][N+1][nx]   combined step
-    double* dUc;            // [B][N][nu]
+    int* status;            // [B] 0 ok, 1 not converged, 2 infeasible (measured state outside the stage-0 box by more than
+                            //     kX0Tol, or crossed bounds), 3 numerical failure (non-positive pivot / NaN)
+    // workspace, entry layout [B][N+1][nz] unless noted
+    double* Z;              // primal iterate (x_k, u_k)
+    double* SU;             // slack of the upper bound  (>= kBig: no bound)
+    double* SL;             // slack of the lower bound
+    double* LU;             // multiplier of the upper bound
+    double* LL;             // multiplier of the lower bound
+    double* DZA;            // affine (predictor) step
+    double* DZC;            // combined step
+    double* G;              // right-hand side of the current KKT solve
+    double* SIG;            // barrier Hessian diagonal  LU/SU + LL/SL
     double* rp;             // [B][N][nx]     dynamics residual at the initial point
     double* Sc;             // [B][N][nx]     S_{k+1} rp_k
     double* dff;            // [B][N][nu]     feed-forward
@@ -52,11 +55,16 @@ struct QpArgs {
     double* Lq;             // [B][N][nu*nu]
 };
 
+template <int V>
+struct IntTag { static constexpr int value = V; };
+
 template <int NX, int NU>
 __global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Params<NX, NU>* __restrict__ prm) {
-    using SL = Slot<NX>;
-    constexpr int LD = SL::LD, LPS = SL::LPS, SPW = SL::SPW;
+    using SL_ = Slot<NX>;
+    constexpr int LD = SL_::LD, LPS = SL_::LPS, SPW = SL_::SPW;
     constexpr int NZ = NX + NU, NI = 2 * NZ, NIF = 2 * NX;
+    constexpr int KU = 4;                        // stages loaded ahead in the element-wise passes
+    static_assert(LPS >= NU, "one lane per input entry");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SlotSmem<NX, NU>* smem = reinterpret_cast<SlotSmem<NX, NU>*>(smem_raw);
 
@@ -77,36 +85,32 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Param
     const int r0 = 2 * sl, r1 = 2 * sl + 1;
     const bool v1 = r1 < NX;
     const int r1c = v1 ? r1 : NX - 1;
+    const bool vu = sl < NU;
+    // the (up to) three entries of every stage this lane owns: x[r0], x[r1], u[sl]
+    const int ei[3] = {r0, r1c, NX + (vu ? sl : 0)};
+    const bool ev[3] = {true, v1, vu};
+
     const double* Ab = a.A + (size_t)b * N * NX * NX;
     const double* Bb = a.Bm + (size_t)b * N * NX * NU;
     const double* cb = a.c + (size_t)b * N * NX;
     const double* Xn = a.Xnom + (size_t)b * (N + 1) * NX;
     const double* Un = a.Unom + (size_t)b * N * NU;
-    double* X = a.dX + (size_t)b * (N + 1) * NX;
-    double* U = a.dU + (size_t)b * N * NU;
-    double* mu = a.mu + (size_t)b * N * NI;
-    double* muf = a.mu_f + (size_t)b * NIF;
-    double* hi = a.hi + (size_t)b * (N + 1) * NZ;
-    double* lo = a.lo + (size_t)b * (N + 1) * NZ;
-    double* gx = a.gx + (size_t)b * (N + 1) * NX;
-    double* gu = a.gu + (size_t)b * N * NU;
-    double* dXa = a.dXa + (size_t)b * (N + 1) * NX;
-    double* dUa = a.dUa + (size_t)b * N * NU;
-    double* dXc = a.dXc + (size_t)b * (N + 1) * NX;
-    double* dUc = a.dUc + (size_t)b * N * NU;
+    const size_t eoff = (size_t)b * (N + 1) * NZ;
+    double* __restrict__ Z = a.Z + eoff;
+    double* __restrict__ SU = a.SU + eoff;
+    double* __restrict__ SLk = a.SL + eoff;
+    double* __restrict__ LU = a.LU + eoff;
+    double* __restrict__ LL = a.LL + eoff;
+    double* __restrict__ DZA = a.DZA + eoff;
+    double* __restrict__ DZC = a.DZC + eoff;
+    double* __restrict__ G = a.G + eoff;
+    double* __restrict__ SIG = a.SIG + eoff;
     double* rp = a.rp + (size_t)b * N * NX;
     double* Sc = a.Sc + (size_t)b * N * NX;
     double* dff = a.dff + (size_t)b * N * NU;
     double* Kq = a.Kq + (size_t)b * N * NU * NX;
     double* Lq = a.Lq + (size_t)b * N * NU * NU;
 
-    // dual variable accessors in the reference layout: stage k<N: mu[k][i]; terminal: mu_f
-    auto lamU_x = [&](int k, int r) -> double& { return (k < N) ? mu[k * NI + r] : muf[r]; };
-    auto lamL_x = [&](int k, int r) -> double& { return (k < N) ? mu[k * NI + NZ + r] : muf[NX + r]; };
-    auto lamU_u = [&](int k, int p) -> double& { return mu[k * NI + NX + p]; };
-    auto lamL_u = [&](int k, int p) -> double& { return mu[k * NI + NZ + NX + p]; };
-
-    // slot-wide reductions through shared memory
     auto slot_sum2 = [&](double& x, double& y) {
         __syncwarp(mask);
         sm.red[2 * sl] = x; sm.red[2 * sl + 1] = y;
@@ -125,107 +129,113 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Param
         for (int i = 1; i < LPS; ++i) { sx = fmin(sx, sm.red[2 * i]); sy = fmin(sy, sm.red[2 * i + 1]); }
         x = sx; y = sy;
     };
-    // visit every box-constrained entry this lane owns: f(value index info)
-    // x entries: stages 1..N rows r0,(r1); u entries: stages 0..N-1, p = sl, sl+LPS, ...
-    int status = 0;
-    const bool tight = a.tightened < 0 ? ((a.flags[b] & FLAG_TIGHT) != 0) : (a.tightened != 0);
-
-    // ------------------------------------------------------------------ bounds + initial point
-    {
-        const double e = tight ? 0.0 : kEpsQP;
-        for (int k = 0; k <= N; ++k) {
+    // element-wise pass over the entries of this lane: NA arrays are loaded for KU stages at a time, then
+    // body(k, idx, vals) runs for every owned entry (idx = k*NZ + i)
+    auto entry_pass = [&](auto na_tag, const double* const* arr, auto&& body) {
+        constexpr int NA = decltype(na_tag)::value;
+        for (int k0 = 0; k0 <= N; k0 += KU) {
+            double v[KU][3][NA];
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int r = rr ? r1 : r0;
-                if (rr && !v1) continue;
-                double h_, l_;
-                const double xn = Xn[k * NX + r];
-                if (k < N) {
-                    const double bu = tight ? a.backoff[((size_t)b * N + k) * NI + r] : 0.0;
-                    const double bl = tight ? a.backoff[((size_t)b * N + k) * NI + NZ + r] : 0.0;
-                    h_ = (prm->xub[r] - xn) - bu + e;
-                    l_ = -((xn - prm->xlb[r]) - bl + e);
-                } else if (tight) {
-                    h_ = prm->xubf[r] - a.backoff_f[(size_t)b * NIF + r];          // Q4: terminal bound not shifted by x_N
-                    l_ = -(-prm->xlbf[r] - a.backoff_f[(size_t)b * NIF + NX + r]);
-                } else {
-                    h_ = (prm->xubf[r] - xn) + e;
-                    l_ = -((xn - prm->xlbf[r]) + e);
-                }
-                hi[k * NZ + r] = h_;
-                lo[k * NZ + r] = l_;
+            for (int j = 0; j < KU; ++j) {
+                const int k = (k0 + j <= N) ? (k0 + j) : N;
+#pragma unroll
+                for (int e = 0; e < 3; ++e)
+#pragma unroll
+                    for (int q = 0; q < NA; ++q) v[j][e][q] = arr[q][k * NZ + ei[e]];
             }
-            if (k < N) {
-                for (int p = sl; p < NU; p += LPS) {
-                    const double un = Un[k * NU + p];
-                    const double bu = tight ? a.backoff[((size_t)b * N + k) * NI + NX + p] : 0.0;
-                    const double bl = tight ? a.backoff[((size_t)b * N + k) * NI + NZ + NX + p] : 0.0;
-                    hi[k * NZ + NX + p] = (prm->uub[p] - un) - bu + e;
-                    lo[k * NZ + NX + p] = -((un - prm->ulb[p]) - bl + e);
+#pragma unroll
+            for (int j = 0; j < KU; ++j) {
+                const int k = k0 + j;
+                if (k <= N) {
+#pragma unroll
+                    for (int e = 0; e < 3; ++e)
+                        if (ev[e]) body(k, k * NZ + ei[e], v[j][e]);
                 }
             }
         }
-        // initial point: x_0 = x0 - xnom_0 (pinned), others = 0 clipped 1 % inside the box, duals = 1
-        double bad = 0.0, dummy = 0.0;
+    };
+    using I4 = IntTag<4>;
+    using I5 = IntTag<5>;
+    using I6 = IntTag<6>;
+
+    int status = 0;
+    const bool tight = a.tightened < 0 ? ((a.flags[b] & FLAG_TIGHT) != 0) : (a.tightened != 0);
+    double n_box = 0.0;
+
+    // ------------------------------------------------------------------ bounds, initial point, slacks, duals
+    {
+        const double e = tight ? 0.0 : kEpsQP;
+        double bad = 0.0;
         for (int k = 0; k <= N; ++k) {
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int r = rr ? r1 : r0;
-                if (rr && !v1) continue;
-                if (k == 0) {
-                    const double d0 = a.x0[(size_t)b * NX + r] - Xn[r];
-                    X[r] = d0;
-                    mu[r] = 0.0; mu[NZ + r] = 0.0;
-                    // the stage-0 state rows are implied by the pinned x_0; violated rows mean an infeasible QP
-                    if (d0 > hi[r] + 1e-9 || d0 < lo[r] - 1e-9) bad = 1.0;
-                    continue;
+            for (int en = 0; en < 3; ++en) {
+                if (!ev[en]) continue;
+                const int i = ei[en];
+                const int idx = k * NZ + i;
+                double h_ = 1e300, l_ = -1e300, z = 0.0;
+                bool box = false;
+                if (en < 2) {                       // state entry
+                    const double xn = Xn[k * NX + i];
+                    if (k < N) {
+                        const double bu = tight ? a.backoff[((size_t)b * N + k) * NI + i] : 0.0;
+                        const double bl = tight ? a.backoff[((size_t)b * N + k) * NI + NZ + i] : 0.0;
+                        h_ = (prm->xub[i] - xn) - bu + e;
+                        l_ = -((xn - prm->xlb[i]) - bl + e);
+                    } else if (tight) {
+                        h_ = prm->xubf[i] - a.backoff_f[(size_t)b * NIF + i];          // Q4: terminal bound not shifted by x_N
+                        l_ = -(-prm->xlbf[i] - a.backoff_f[(size_t)b * NIF + NX + i]);
+                    } else {
+                        h_ = (prm->xubf[i] - xn) + e;
+                        l_ = -((xn - prm->xlbf[i]) + e);
+                    }
+                    if (k == 0) {
+                        // x(0) is pinned to the measurement: its box rows are dropped; a violation beyond kX0Tol (OSQP's
+                        // default eps_abs, which the reference's solver would tolerate) makes the instance infeasible
+                        z = a.x0[(size_t)b * NX + i] - xn;
+                        if (z > h_ + kX0Tol || z < l_ - kX0Tol) bad = 1.0;
+                    } else box = true;
+                } else if (k < N) {                 // input entry
+                    const int p = i - NX;
+                    const double un = Un[k * NU + p];
+                    const double bu = tight ? a.backoff[((size_t)b * N + k) * NI + i] : 0.0;
+                    const double bl = tight ? a.backoff[((size_t)b * N + k) * NI + NZ + i] : 0.0;
+                    h_ = (prm->uub[p] - un) - bu + e;
+                    l_ = -((un - prm->ulb[p]) - bl + e);
+                    box = true;
                 }
-                const double h_ = hi[k * NZ + r], l_ = lo[k * NZ + r];
-                const bool hu = h_ < kBig, hl = l_ > -kBig;
-                double z = 0.0;
-                if (hu && hl) {
-                    const double m = 0.01 * (h_ - l_);
-                    if (!(h_ - l_ > 1e-12)) bad = 1.0;
-                    z = fmin(fmax(0.0, l_ + m), h_ - m);
-                } else if (hu) z = fmin(0.0, h_ - 1.0);
-                else if (hl) z = fmax(0.0, l_ + 1.0);
-                X[k * NX + r] = z;
-                lamU_x(k, r) = hu ? 1.0 : 0.0;
-                lamL_x(k, r) = hl ? 1.0 : 0.0;
-            }
-            if (k < N) {
-                for (int p = sl; p < NU; p += LPS) {
-                    const double h_ = hi[k * NZ + NX + p], l_ = lo[k * NZ + NX + p];
+                double su = 1e300, sl_ = 1e300, lu = 0.0, ll = 0.0;
+                if (box) {
                     const bool hu = h_ < kBig, hl = l_ > -kBig;
-                    double z = 0.0;
                     if (hu && hl) {
                         const double m = 0.01 * (h_ - l_);
                         if (!(h_ - l_ > 1e-12)) bad = 1.0;
                         z = fmin(fmax(0.0, l_ + m), h_ - m);
                     } else if (hu) z = fmin(0.0, h_ - 1.0);
                     else if (hl) z = fmax(0.0, l_ + 1.0);
-                    U[k * NU + p] = z;
-                    lamU_u(k, p) = hu ? 1.0 : 0.0;
-                    lamL_u(k, p) = hl ? 1.0 : 0.0;
+                    if (hu) { su = h_ - z; lu = 1.0; n_box += 1.0; }
+                    if (hl) { sl_ = z - l_; ll = 1.0; n_box += 1.0; }
                 }
+                Z[idx] = z; SU[idx] = su; SLk[idx] = sl_; LU[idx] = lu; LL[idx] = ll;
             }
         }
-        slot_sum2(bad, dummy);
+        slot_sum2(bad, n_box);
         if (bad > 0.0) status = 2;
         __syncwarp(mask);
         // dynamics residual at the initial point: rp_k = A x_k + B u_k + c_k - x_{k+1}
         for (int k = 0; k < N; ++k) {
             const double* Ak = Ab + (size_t)k * NX * NX;
             const double* Bk = Bb + (size_t)k * NX * NU;
-            double acc0 = cb[k * NX + r0] - X[(k + 1) * NX + r0];
-            double acc1 = cb[k * NX + r1c] - X[(k + 1) * NX + r1c];
+            double acc0 = cb[k * NX + r0] - Z[(k + 1) * NZ + r0];
+            double acc1 = cb[k * NX + r1c] - Z[(k + 1) * NZ + r1c];
+#pragma unroll
             for (int m = 0; m < NX; ++m) {
-                const double xm = X[k * NX + m];
+                const double xm = Z[k * NZ + m];
                 acc0 = fma(__ldg(Ak + r0 * NX + m), xm, acc0);
                 acc1 = fma(__ldg(Ak + r1c * NX + m), xm, acc1);
             }
+#pragma unroll
             for (int p = 0; p < NU; ++p) {
-                const double up = U[k * NU + p];
+                const double up = Z[k * NZ + NX + p];
                 acc0 = fma(__ldg(Bk + r0 * NU + p), up, acc0);
                 acc1 = fma(__ldg(Bk + r1c * NU + p), up, acc1);
             }
@@ -235,8 +245,7 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Param
         __syncwarp(mask);
     }
 
-    double rp_scale = 1.0;
-    double rp_inf = 0.0;
+    double rp_scale = 1.0, rp_inf = 0.0;
     {
         double m0 = 0.0, dmy = 0.0;
         for (int k = 0; k < N; ++k) {
@@ -247,110 +256,65 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Param
         slot_min2(m0, dmy);
         rp_inf = -m0;
     }
+    double mu_c = 1.0;     // all complementarity products start at su*1 ... computed below
+    {
+        double acc = 0.0, dmy = 0.0;
+        const double* arr[4] = {SU, SLk, LU, LL};
+        entry_pass(I4{}, arr, [&](int, int, const double (&v)[4]) {
+            if (v[0] < kBig) acc = fma(v[0], v[2], acc);
+            if (v[1] < kBig) acc = fma(v[1], v[3], acc);
+        });
+        slot_sum2(acc, dmy);
+        mu_c = n_box > 0.0 ? acc / n_box : 0.0;
+    }
 
-    // complementarity measure
-    auto compl_mu = [&]() -> double {
-        double acc = 0.0, cnt = 0.0;
-        for (int k = 1; k <= N; ++k) {
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int r = rr ? r1 : r0;
-                if (rr && !v1) continue;
-                const double z = X[k * NX + r], h_ = hi[k * NZ + r], l_ = lo[k * NZ + r];
-                if (h_ < kBig) { acc = fma(h_ - z, lamU_x(k, r), acc); cnt += 1.0; }
-                if (l_ > -kBig) { acc = fma(z - l_, lamL_x(k, r), acc); cnt += 1.0; }
-            }
-        }
-        for (int k = 0; k < N; ++k)
-            for (int p = sl; p < NU; p += LPS) {
-                const double z = U[k * NU + p], h_ = hi[k * NZ + NX + p], l_ = lo[k * NZ + NX + p];
-                if (h_ < kBig) { acc = fma(h_ - z, lamU_u(k, p), acc); cnt += 1.0; }
-                if (l_ > -kBig) { acc = fma(z - l_, lamL_u(k, p), acc); cnt += 1.0; }
-            }
-        slot_sum2(acc, cnt);
-        return cnt > 0.0 ? acc / cnt : 0.0;
-    };
-
-    // Newton direction pieces for one box entry; given step dz returns (ds_u, ds_l, dlu, dll)
-    // target = sigma*mu - corr ;  dlu = (tu)/su - lu + (lu/su) dz ; dll = (tl)/sl - ll - (ll/sl) dz
     int it = 0;
     bool done = (status != 0);
-    double mu_c = compl_mu();
     for (; it < a.max_iter; ++it) {
         if (__all_sync(mask, done)) break;
-        // ---- gradient of the quadratic: gx_k = 2 Q_k (x_k + xnom_k), gu_k = 2 R (u_k + unom_k)
         __syncwarp(mask);
-        for (int k = 1; k <= N; ++k) {
-            const double* Qm = (k < N) ? prm->Q : prm->Qf;
-            double acc0 = 0.0, acc1 = 0.0;
-            for (int m = 0; m < NX; ++m) {
-                const double y = X[k * NX + m] + Xn[k * NX + m];
-                acc0 = fma(Qm[r0 * NX + m], y, acc0);
-                acc1 = fma(Qm[r1c * NX + m], y, acc1);
+        // ---- P1: barrier diagonal SIG and gradient G = 2 H (z + z_nom)
+        {
+            const double* arr[4] = {SU, SLk, LU, LL};
+            entry_pass(I4{}, arr, [&](int, int idx, const double (&v)[4]) {
+                double sg = 0.0;
+                if (v[0] < kBig) sg += v[2] / v[0];
+                if (v[1] < kBig) sg += v[3] / v[1];
+                SIG[idx] = sg;
+            });
+            for (int k = 0; k <= N; ++k) {
+                const double* Qm = (k < N) ? prm->Q : prm->Qf;
+                double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+                for (int m = 0; m < NX; ++m) {
+                    const double y = Z[k * NZ + m] + Xn[k * NX + m];
+                    acc0 = fma(Qm[r0 * NX + m], y, acc0);
+                    acc1 = fma(Qm[r1c * NX + m], y, acc1);
+                }
+                G[k * NZ + r0] = 2.0 * acc0;
+                if (v1) G[k * NZ + r1] = 2.0 * acc1;
+                if (vu && k < N) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int m = 0; m < NU; ++m) acc = fma(prm->R[sl * NU + m], Z[k * NZ + NX + m] + Un[k * NU + m], acc);
+                    G[k * NZ + NX + sl] = 2.0 * acc;
+                }
             }
-            gx[k * NX + r0] = 2.0 * acc0;
-            if (v1) gx[k * NX + r1] = 2.0 * acc1;
         }
-        for (int k = 0; k < N; ++k)
-            for (int p = sl; p < NU; p += LPS) {
-                double acc = 0.0;
-                for (int m = 0; m < NU; ++m) acc = fma(prm->R[p * NU + m], U[k * NU + m] + Un[k * NU + m], acc);
-                gu[k * NU + p] = 2.0 * acc;
-            }
         __syncwarp(mask);
 
-        // two Riccati solves per iteration: pass 0 = factorisation + predictor, pass 1 = corrector
-        double sigma_mu = 0.0;
-        double ap = 1.0, ad = 1.0;
+        double sigma_mu = 0.0, ap = 1.0, ad = 1.0;
+        bool chol_ok = true;
         for (int pass = 0; pass < 2; ++pass) {
-            // right-hand side of one box entry
-            auto rhs_x = [&](int k, int r) -> double {
-                double g = gx[k * NX + r];
-                if (pass == 1) {
-                    const double z = X[k * NX + r], h_ = hi[k * NZ + r], l_ = lo[k * NZ + r], dz = dXa[k * NX + r];
-                    if (h_ < kBig) {
-                        const double s = h_ - z, l = lamU_x(k, r);
-                        const double dl = -l + (l / s) * dz;      // affine dual step
-                        g += (sigma_mu - (-dz) * dl) / s;
-                    }
-                    if (l_ > -kBig) {
-                        const double s = z - l_, l = lamL_x(k, r);
-                        const double dl = -l - (l / s) * dz;
-                        g -= (sigma_mu - dz * dl) / s;
-                    }
-                }
-                return g;
-            };
-            auto rhs_u = [&](int k, int p) -> double {
-                double g = gu[k * NU + p];
-                if (pass == 1) {
-                    const double z = U[k * NU + p], h_ = hi[k * NZ + NX + p], l_ = lo[k * NZ + NX + p], dz = dUa[k * NU + p];
-                    if (h_ < kBig) {
-                        const double s = h_ - z, l = lamU_u(k, p);
-                        const double dl = -l + (l / s) * dz;
-                        g += (sigma_mu - (-dz) * dl) / s;
-                    }
-                    if (l_ > -kBig) {
-                        const double s = z - l_, l = lamL_u(k, p);
-                        const double dl = -l - (l / s) * dz;
-                        g -= (sigma_mu - dz * dl) / s;
-                    }
-                }
-                return g;
-            };
-            // ---- backward: p_N = rx_N
-            sm.vec[r0] = rhs_x(N, r0);
-            if (v1) sm.vec[r1] = rhs_x(N, r1);
+            // ---- backward: p_N = G_N ; pass 0 also builds S_N = 2 Qf + SIG_N
+            sm.vec[r0] = G[N * NZ + r0];
+            if (v1) sm.vec[r1] = G[N * NZ + r1];
             if (pass == 0) {
-                // S_N = 2 Qf + Sigma_N
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
                     const int r = rr ? r1 : r0;
                     if (rr && !v1) continue;
-                    const double z = X[N * NX + r], h_ = hi[N * NZ + r], l_ = lo[N * NZ + r];
-                    double sg = 0.0;
-                    if (h_ < kBig) sg += lamU_x(N, r) / (h_ - z);
-                    if (l_ > -kBig) sg += lamL_x(N, r) / (z - l_);
+                    const double sg = SIG[N * NZ + r];
                     for (int c = 0; c < LD; ++c) sm.S[r * LD + c] = (c < NX) ? (2.0 * prm->Qf[r * NX + c] + (c == r ? sg : 0.0)) : 0.0;
                 }
             }
@@ -358,14 +322,17 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Param
             for (int k = N - 1; k >= 0; --k) {
                 const double* Ak = Ab + (size_t)k * NX * NX;
                 const double* Bk = Bb + (size_t)k * NX * NU;
-                // vector recursion shared by both passes; A columns / K columns / factor in registers
+                // prefetch this stage's scalars before the (long) matrix work
+                const double gx0 = G[k * NZ + r0], gx1 = G[k * NZ + r1c];
+                const double gu_ = vu ? G[k * NZ + NX + sl] : 0.0;
+                const double rp0 = rp[k * NX + r0], rp1 = rp[k * NX + r1c];
                 auto vec_step = [&](const double (&a0)[NX], const double (&a1)[NX], const double (&k0)[NU], const double (&k1)[NU],
                                     const double (&L)[NU][NU]) {
-                    // Sc_k = S_{k+1} rp_k (pass 0) ; g = p + Sc
                     double sc0, sc1;
                     if (pass == 0) {
-                        sm.vec[LD + r0] = rp[k * NX + r0];
-                        if (v1) sm.vec[LD + r1] = rp[k * NX + r1];
+                        // Sc_k = S_{k+1} rp_k
+                        sm.vec[LD + r0] = rp0;
+                        if (v1) sm.vec[LD + r1] = rp1;
                         __syncwarp(mask);
                         sc0 = 0.0; sc1 = 0.0;
 #pragma unroll
@@ -381,33 +348,33 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Param
                         sc0 = Sc[k * NX + r0];
                         sc1 = Sc[k * NX + r1c];
                     }
+                    // g = p_{k+1} + Sc
                     const double g0 = sm.vec[r0] + rp_scale * sc0;
                     const double g1 = v1 ? (sm.vec[r1] + rp_scale * sc1) : 0.0;
                     sm.vec[LD + r0] = g0;
                     if (v1) sm.vec[LD + r1] = g1;
                     __syncwarp(mask);
                     // t = ru + B' g
-                    for (int p = sl; p < NU; p += LPS) {
-                        double t = rhs_u(k, p);
+                    if (vu) {
+                        double t = gu_;
 #pragma unroll
-                        for (int i = 0; i < NX; ++i) t = fma(sm.Bm[i * NU + p], sm.vec[LD + i], t);
-                        sm.vec[2 * LD + p] = t;
+                        for (int i = 0; i < NX; ++i) t = fma(sm.Bm[i * NU + sl], sm.vec[LD + i], t);
+                        sm.vec[2 * LD + sl] = t;
                     }
                     __syncwarp(mask);
                     double tt[NU], dd[NU];
 #pragma unroll
                     for (int p = 0; p < NU; ++p) { tt[p] = sm.vec[2 * LD + p]; dd[p] = tt[p]; }
                     chol_solve<NU>(L, dd);
-                    for (int p = sl; p < NU; p += LPS) {
-                        // static-index select of dd[p]
+                    if (vu) {
                         double v = 0.0;
 #pragma unroll
-                        for (int q = 0; q < NU; ++q) if (q == p) v = dd[q];
-                        dff[k * NU + p] = -v;
+                        for (int q = 0; q < NU; ++q) if (q == sl) v = dd[q];
+                        dff[k * NU + sl] = -v;
                     }
                     if (k > 0) {
                         // p_k = rx_k + A' g + K' t
-                        double p0 = rhs_x(k, r0), p1 = v1 ? rhs_x(k, r1) : 0.0;
+                        double p0 = gx0, p1 = v1 ? gx1 : 0.0;
 #pragma unroll
                         for (int i = 0; i < NX; ++i) {
                             const double gi = sm.vec[LD + i];
@@ -423,27 +390,9 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Param
                     __syncwarp(mask);
                 };
                 if (pass == 0) {
-                    // Sigma_k (k >= 1) and Sigma_u
-                    double cx0 = 0.0, cx1 = 0.0;
-                    if (k > 0) {
-#pragma unroll
-                        for (int rr = 0; rr < 2; ++rr) {
-                            const int r = rr ? r1 : r0;
-                            if (rr && !v1) continue;
-                            const double z = X[k * NX + r], h_ = hi[k * NZ + r], l_ = lo[k * NZ + r];
-                            double sg = 0.0;
-                            if (h_ < kBig) sg += lamU_x(k, r) / (h_ - z);
-                            if (l_ > -kBig) sg += lamL_x(k, r) / (z - l_);
-                            if (rr) cx1 = sg; else cx0 = sg;
-                        }
-                    }
-                    for (int p = sl; p < NU; p += LPS) {
-                        const double z = U[k * NU + p], h_ = hi[k * NZ + NX + p], l_ = lo[k * NZ + NX + p];
-                        double sg = 0.0;
-                        if (h_ < kBig) sg += lamU_u(k, p) / (h_ - z);
-                        if (l_ > -kBig) sg += lamL_u(k, p) / (z - l_);
-                        sm.cu[p] = sg;
-                    }
+                    const double cx0 = (k > 0) ? SIG[k * NZ + r0] : 0.0;
+                    const double cx1 = (k > 0 && v1) ? SIG[k * NZ + r1] : 0.0;
+                    if (vu) sm.cu[sl] = SIG[k * NZ + NX + sl];
                     const bool ok = riccati_step<NX, NU>(
                         sm, sl, mask, Ak, Bk, prm->Q2, prm->R2, cx0, cx1, Kq + (size_t)k * NU * NX,
                         [&](const double (&a0)[NX], const double (&a1)[NX], const double (&k0)[NU], const double (&k1)[NU],
@@ -457,9 +406,8 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Param
                             vec_step(a0, a1, k0, k1, L);
                         },
                         k > 0);
-                    if (!ok) status = 2;
+                    chol_ok = chol_ok && ok;
                 } else {
-                    // corrector: reload A columns, K columns, B and the factor
                     double a0[NX], a1[NX], k0[NU], k1[NU], L[NU][NU];
 #pragma unroll
                     for (int i = 0; i < NX; ++i) {
@@ -478,184 +426,195 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Param
                     vec_step(a0, a1, k0, k1, L);
                 }
             }
-            // ---- forward: dx_0 = 0 ; du_k = K dx_k + d_k ; dx_{k+1} = A dx_k + B du_k + rp_k
-            double* dXo = pass == 0 ? dXa : dXc;
-            double* dUo = pass == 0 ? dUa : dUc;
+            // ---- forward: dx_0 = 0 ; du_k = K dx_k + d_k ; dx_{k+1} = A dx_k + B du_k + rp_k ; fused ratio test
+            double* __restrict__ DZ = pass == 0 ? DZA : DZC;
+            const double tau = pass == 0 ? 1.0 : (mu_c > 1e-8 ? 0.995 : 0.9999);
+            double apl = 1.0, adl = 1.0;
+            // ratio test + dual step of one entry: given dz (and the affine step for the corrector)
+            auto ratio_entry = [&](double su, double sl_, double lu, double ll, double dz, double dza) {
+                if (su < kBig) {
+                    double tgt = 0.0;
+                    if (pass == 1) { const double dla = -lu + (lu / su) * dza; tgt = sigma_mu + dza * dla; }
+                    const double dlu = tgt / su - lu + (lu / su) * dz;
+                    if (dz > 0.0) apl = fmin(apl, tau * su / dz);
+                    if (dlu < 0.0) adl = fmin(adl, -tau * lu / dlu);
+                }
+                if (sl_ < kBig) {
+                    double tgt = 0.0;
+                    if (pass == 1) { const double dla = -ll - (ll / sl_) * dza; tgt = sigma_mu - dza * dla; }
+                    const double dll = tgt / sl_ - ll - (ll / sl_) * dz;
+                    if (dz < 0.0) apl = fmin(apl, -tau * sl_ / dz);
+                    if (dll < 0.0) adl = fmin(adl, -tau * ll / dll);
+                }
+            };
             __syncwarp(mask);
             sm.vec[r0] = 0.0;
             if (v1) sm.vec[r1] = 0.0;
-            dXo[r0] = 0.0;
-            if (v1) dXo[r1] = 0.0;
+            DZ[r0] = 0.0;
+            if (v1) DZ[r1] = 0.0;
             __syncwarp(mask);
             for (int k = 0; k < N; ++k) {
                 const double* Ak = Ab + (size_t)k * NX * NX;
                 const double* Bk = Bb + (size_t)k * NX * NU;
                 const double* Kk = Kq + (size_t)k * NU * NX;
-                for (int p = sl; p < NU; p += LPS) {
-                    double u = dff[k * NU + p];
+                // loads that do not depend on the sweep: rows of A, B, K, and the entry data of the ratio test
+                double ar0[NX], ar1[NX], br0[NU], br1[NU], kr[NX];
 #pragma unroll
-                    for (int m = 0; m < NX; ++m) u = fma(Kk[p * NX + m], sm.vec[m], u);
-                    sm.vec[LD + p] = u;
-                    dUo[k * NU + p] = u;
+                for (int m = 0; m < NX; ++m) { ar0[m] = __ldg(Ak + r0 * NX + m); ar1[m] = __ldg(Ak + r1c * NX + m); }
+#pragma unroll
+                for (int p = 0; p < NU; ++p) { br0[p] = __ldg(Bk + r0 * NU + p); br1[p] = __ldg(Bk + r1c * NU + p); }
+                if (vu) {
+#pragma unroll
+                    for (int m = 0; m < NX; ++m) kr[m] = Kk[sl * NX + m];
+                }
+                const int iu = k * NZ + NX + (vu ? sl : 0), ix0 = (k + 1) * NZ + r0, ix1 = (k + 1) * NZ + r1c;
+                const double e_su[3] = {SU[ix0], SU[ix1], SU[iu]}, e_sl[3] = {SLk[ix0], SLk[ix1], SLk[iu]};
+                const double e_lu[3] = {LU[ix0], LU[ix1], LU[iu]}, e_ll[3] = {LL[ix0], LL[ix1], LL[iu]};
+                double e_da[3] = {0.0, 0.0, 0.0};
+                if (pass == 1) { e_da[0] = DZA[ix0]; e_da[1] = DZA[ix1]; e_da[2] = DZA[iu]; }
+                double n0 = rp_scale * rp[k * NX + r0], n1 = rp_scale * rp[k * NX + r1c];
+                if (vu) {
+                    double u = dff[k * NU + sl];
+#pragma unroll
+                    for (int m = 0; m < NX; ++m) u = fma(kr[m], sm.vec[m], u);
+                    sm.vec[LD + sl] = u;
+                    DZ[iu] = u;
+                    ratio_entry(e_su[2], e_sl[2], e_lu[2], e_ll[2], u, e_da[2]);
                 }
                 __syncwarp(mask);
-                double n0 = rp_scale * rp[k * NX + r0], n1 = rp_scale * rp[k * NX + r1c];
 #pragma unroll
                 for (int m = 0; m < NX; ++m) {
                     const double xm = sm.vec[m];
-                    n0 = fma(__ldg(Ak + r0 * NX + m), xm, n0);
-                    n1 = fma(__ldg(Ak + r1c * NX + m), xm, n1);
+                    n0 = fma(ar0[m], xm, n0);
+                    n1 = fma(ar1[m], xm, n1);
                 }
 #pragma unroll
                 for (int p = 0; p < NU; ++p) {
                     const double up = sm.vec[LD + p];
-                    n0 = fma(__ldg(Bk + r0 * NU + p), up, n0);
-                    n1 = fma(__ldg(Bk + r1c * NU + p), up, n1);
+                    n0 = fma(br0[p], up, n0);
+                    n1 = fma(br1[p], up, n1);
                 }
                 __syncwarp(mask);
                 sm.vec[r0] = n0;
                 if (v1) sm.vec[r1] = n1;
-                dXo[(k + 1) * NX + r0] = n0;
-                if (v1) dXo[(k + 1) * NX + r1] = n1;
+                DZ[ix0] = n0;
+                ratio_entry(e_su[0], e_sl[0], e_lu[0], e_ll[0], n0, e_da[0]);
+                if (v1) {
+                    DZ[ix1] = n1;
+                    ratio_entry(e_su[1], e_sl[1], e_lu[1], e_ll[1], n1, e_da[1]);
+                }
                 __syncwarp(mask);
             }
-            // ---- step lengths (and mu_aff after the predictor)
-            const double tau = pass == 0 ? 1.0 : (mu_c > 1e-8 ? 0.995 : 0.9999);
-            double apl = 1.0, adl = 1.0;
-            auto ratio = [&](double v, double dv, double& amin) {
-                if (dv < 0.0) amin = fmin(amin, -tau * v / dv);
-            };
-            auto entry_step = [&](double z, double h_, double l_, double lu, double ll, double dz, double dza, double& dlu, double& dll) {
-                dlu = 0.0; dll = 0.0;
-                if (h_ < kBig) {
-                    const double s = h_ - z;
-                    double tgt = 0.0;
-                    if (pass == 1) { const double dla = -lu + (lu / s) * dza; tgt = sigma_mu - (-dza) * dla; }
-                    dlu = tgt / s - lu + (lu / s) * dz;
-                    ratio(s, -dz, apl);
-                    ratio(lu, dlu, adl);
-                }
-                if (l_ > -kBig) {
-                    const double s = z - l_;
-                    double tgt = 0.0;
-                    if (pass == 1) { const double dla = -ll - (ll / s) * dza; tgt = sigma_mu - dza * dla; }
-                    dll = tgt / s - ll - (ll / s) * dz;
-                    ratio(s, dz, apl);
-                    ratio(ll, dll, adl);
-                }
-            };
-            for (int k = 1; k <= N; ++k) {
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int r = rr ? r1 : r0;
-                    if (rr && !v1) continue;
-                    double dlu, dll;
-                    entry_step(X[k * NX + r], hi[k * NZ + r], lo[k * NZ + r], lamU_x(k, r), lamL_x(k, r), dXo[k * NX + r],
-                               dXa[k * NX + r], dlu, dll);
-                }
-            }
-            for (int k = 0; k < N; ++k)
-                for (int p = sl; p < NU; p += LPS) {
-                    double dlu, dll;
-                    entry_step(U[k * NU + p], hi[k * NZ + NX + p], lo[k * NZ + NX + p], lamU_u(k, p), lamL_u(k, p), dUo[k * NU + p],
-                               dUa[k * NU + p], dlu, dll);
-                }
             slot_min2(apl, adl);
             ap = apl; ad = adl;
             if (pass == 0) {
-                // mu_aff
-                double acc = 0.0, cnt = 0.0;
-                auto entry_mu = [&](double z, double h_, double l_, double lu, double ll, double dz) {
-                    if (h_ < kBig) {
-                        const double s = h_ - z;
-                        const double dl = -lu + (lu / s) * dz;
-                        acc = fma(s - ap * dz, lu + ad * dl, acc); cnt += 1.0;
-                    }
-                    if (l_ > -kBig) {
-                        const double s = z - l_;
-                        const double dl = -ll - (ll / s) * dz;
-                        acc = fma(s + ap * dz, ll + ad * dl, acc); cnt += 1.0;
-                    }
-                };
-                for (int k = 1; k <= N; ++k) {
-#pragma unroll
-                    for (int rr = 0; rr < 2; ++rr) {
-                        const int r = rr ? r1 : r0;
-                        if (rr && !v1) continue;
-                        entry_mu(X[k * NX + r], hi[k * NZ + r], lo[k * NZ + r], lamU_x(k, r), lamL_x(k, r), dXa[k * NX + r]);
-                    }
-                }
-                for (int k = 0; k < N; ++k)
-                    for (int p = sl; p < NU; p += LPS)
-                        entry_mu(U[k * NU + p], hi[k * NZ + NX + p], lo[k * NZ + NX + p], lamU_u(k, p), lamL_u(k, p), dUa[k * NU + p]);
-                slot_sum2(acc, cnt);
-                const double mu_aff = cnt > 0.0 ? acc / cnt : 0.0;
+                // ---- P2: mu_aff and sigma ; P3: corrector right-hand side G += (sigma mu - corr_u)/su - (sigma mu - corr_l)/sl
+                double acc = 0.0, dmy = 0.0;
+                const double* arr[5] = {SU, SLk, LU, LL, DZA};
+                entry_pass(I5{}, arr, [&](int, int, const double (&v)[5]) {
+                    const double dz = v[4];
+                    if (v[0] < kBig) { const double dl = -v[2] + (v[2] / v[0]) * dz; acc = fma(v[0] - ap * dz, v[2] + ad * dl, acc); }
+                    if (v[1] < kBig) { const double dl = -v[3] - (v[3] / v[1]) * dz; acc = fma(v[1] + ap * dz, v[3] + ad * dl, acc); }
+                });
+                slot_sum2(acc, dmy);
+                const double mu_aff = n_box > 0.0 ? acc / n_box : 0.0;
                 const double ratio_mu = mu_c > 0.0 ? mu_aff / mu_c : 0.0;
                 sigma_mu = ratio_mu * ratio_mu * ratio_mu * mu_c;
+                const double* arr6[6] = {SU, SLk, LU, LL, DZA, G};
+                entry_pass(I6{}, arr6, [&](int, int idx, const double (&v)[6]) {
+                    const double dz = v[4];
+                    double g = v[5];
+                    if (v[0] < kBig) { const double dl = -v[2] + (v[2] / v[0]) * dz; g += (sigma_mu + dz * dl) / v[0]; }
+                    if (v[1] < kBig) { const double dl = -v[3] - (v[3] / v[1]) * dz; g -= (sigma_mu - dz * dl) / v[1]; }
+                    G[idx] = g;
+                });
+                __syncwarp(mask);
             }
         }
-        // ---- update (only slots that are still iterating)
-        if (!done) {
-            auto entry_upd = [&](double& z, double h_, double l_, double& lu, double& ll, double dz, double dza) {
-                double dlu = 0.0, dll = 0.0;
-                if (h_ < kBig) {
-                    const double s = h_ - z;
-                    const double dla = -lu + (lu / s) * dza;
-                    dlu = (sigma_mu - (-dza) * dla) / s - lu + (lu / s) * dz;
+        // ---- P4: update (slots still iterating) and new complementarity
+        double acc = 0.0, dmy = 0.0;
+        {
+            const double* arr6[6] = {SU, SLk, LU, LL, DZA, DZC};
+            const bool upd = !done && chol_ok;
+            entry_pass(I6{}, arr6, [&](int, int idx, const double (&v)[6]) {
+                double su = v[0], sl_ = v[1], lu = v[2], ll = v[3];
+                if (upd) {
+                    const double dza = v[4], dz = v[5];
+                    if (su < kBig) {
+                        const double dla = -lu + (lu / su) * dza;
+                        const double dlu = (sigma_mu + dza * dla) / su - lu + (lu / su) * dz;
+                        su -= ap * dz; lu += ad * dlu;
+                        SU[idx] = su; LU[idx] = lu;
+                    }
+                    if (sl_ < kBig) {
+                        const double dla = -ll - (ll / sl_) * dza;
+                        const double dll = (sigma_mu - dza * dla) / sl_ - ll - (ll / sl_) * dz;
+                        sl_ += ap * dz; ll += ad * dll;
+                        SLk[idx] = sl_; LL[idx] = ll;
+                    }
+                    Z[idx] += ap * dz;
                 }
-                if (l_ > -kBig) {
-                    const double s = z - l_;
-                    const double dla = -ll - (ll / s) * dza;
-                    dll = (sigma_mu - dza * dla) / s - ll - (ll / s) * dz;
-                }
-                z += ap * dz;
-                lu += ad * dlu;
-                ll += ad * dll;
-            };
-            for (int k = 1; k <= N; ++k) {
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int r = rr ? r1 : r0;
-                    if (rr && !v1) continue;
-                    entry_upd(X[k * NX + r], hi[k * NZ + r], lo[k * NZ + r], lamU_x(k, r), lamL_x(k, r), dXc[k * NX + r], dXa[k * NX + r]);
-                }
-            }
-            for (int k = 0; k < N; ++k)
-                for (int p = sl; p < NU; p += LPS)
-                    entry_upd(U[k * NU + p], hi[k * NZ + NX + p], lo[k * NZ + NX + p], lamU_u(k, p), lamL_u(k, p), dUc[k * NU + p],
-                              dUa[k * NU + p]);
-            rp_scale *= (1.0 - ap);
+                if (su < kBig) acc = fma(su, lu, acc);
+                if (sl_ < kBig) acc = fma(sl_, ll, acc);
+            });
+            if (upd) rp_scale *= (1.0 - ap);
         }
-        __syncwarp(mask);
-        const double mu_new = compl_mu();
+        slot_sum2(acc, dmy);
         if (!done) {
-            mu_c = mu_new;
-            if (!(mu_c == mu_c) || status == 2) { status = 2; done = true; }
-            else if (mu_c < a.tol_mu && rp_inf * rp_scale < a.tol_res && it >= 2) done = true;
+            const double mu_new = n_box > 0.0 ? acc / n_box : 0.0;
+            if (!chol_ok) {
+                // a non-positive pivot late in the iteration (barrier weights ~ 1/mu) means the iterate is converged
+                // to working precision: keep it; early on it is a genuine failure
+                if (mu_c > 1e-9) status = 3;
+                done = true;
+            } else if (!(mu_new == mu_new)) { status = 3; done = true; }
+            else {
+                mu_c = mu_new;
+                if (mu_c < a.tol_mu && rp_inf * rp_scale < a.tol_res && it >= 2) done = true;
+            }
         }
     }
-    if (!done && status == 0) status = 1;
+    if (!done && status == 0) status = (mu_c < 1e-9 && rp_inf * rp_scale < 1e-7) ? 0 : 1;
 
-    // ---- objective value  x'Hx + q'x  (qp_jit.py:401 obj_val with P = 2H, q = 2 H y_nom)
+    // ---- outputs in the reference layouts + objective  x'Hx + q'x  (qp_jit.py:401, P = 2H, q = 2 H y_nom)
     {
+        __syncwarp(mask);
+        double* Xo = a.dX + (size_t)b * (N + 1) * NX;
+        double* Uo = a.dU + (size_t)b * N * NU;
+        double* mu = a.mu + (size_t)b * N * NI;
+        double* muf = a.mu_f + (size_t)b * NIF;
         double acc = 0.0, dmy = 0.0;
         for (int k = 0; k <= N; ++k) {
             const double* Qm = (k < N) ? prm->Q : prm->Qf;
             double q0 = 0.0, q1 = 0.0;
+#pragma unroll
             for (int m = 0; m < NX; ++m) {
-                const double y = X[k * NX + m] + 2.0 * Xn[k * NX + m];
+                const double y = Z[k * NZ + m] + 2.0 * Xn[k * NX + m];
                 q0 = fma(Qm[r0 * NX + m], y, q0);
                 q1 = fma(Qm[r1c * NX + m], y, q1);
             }
-            acc = fma(X[k * NX + r0], q0, acc);
-            if (v1) acc = fma(X[k * NX + r1], q1, acc);
-        }
-        for (int k = 0; k < N; ++k)
-            for (int p = sl; p < NU; p += LPS) {
-                double q = 0.0;
-                for (int m = 0; m < NU; ++m) q = fma(prm->R[p * NU + m], U[k * NU + m] + 2.0 * Un[k * NU + m], q);
-                acc = fma(U[k * NU + p], q, acc);
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                if (rr && !v1) continue;
+                const int r = rr ? r1 : r0;
+                const double z = Z[k * NZ + r];
+                acc = fma(z, rr ? q1 : q0, acc);
+                Xo[k * NX + r] = z;
+                const double lu = LU[k * NZ + r], ll = LL[k * NZ + r];
+                if (k < N) { mu[k * NI + r] = lu; mu[k * NI + NZ + r] = ll; }
+                else { muf[r] = lu; muf[NX + r] = ll; }
             }
+            if (vu && k < N) {
+                double q = 0.0;
+#pragma unroll
+                for (int m = 0; m < NU; ++m) q = fma(prm->R[sl * NU + m], Z[k * NZ + NX + m] + 2.0 * Un[k * NU + m], q);
+                const double z = Z[k * NZ + NX + sl];
+                acc = fma(z, q, acc);
+                Uo[k * NU + sl] = z;
+                mu[k * NI + NX + sl] = LU[k * NZ + NX + sl];
+                mu[k * NI + NZ + NX + sl] = LL[k * NZ + NX + sl];
+            }
+        }
         slot_sum2(acc, dmy);
         if (sl == 0) {
             a.cost[b] = acc;

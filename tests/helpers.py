@@ -14,6 +14,12 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
+def relf(a, b, floor=1.0):
+    """max |a-b| / max(floor, max |b|): relative error with an absolute floor (quantities that converge to zero)."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), floor))
+
+
 def load(name):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 
@@ -29,11 +35,13 @@ def make_solver(name, capacity, **kw):
     return m, cfg, s
 
 
-def rocket_scenarios(B, seed=2025, steps=29):
-    """Monte-Carlo scenarios of SURVEY.md 8(d) config 5: perturbed initial states + uniform disturbance draws."""
+def rocket_scenarios(B, seed=2025, steps=29, x0_scale=0.0):
+    """Rocket Monte-Carlo scenarios.  x0_scale = 0: BASELINE.json configs[3] (the fixed x0 of
+    expe/main_rocket_compare_closed_loop.py:75-91 for every scenario, disturbance draws U[-1,1]^nx per step);
+    x0_scale > 0: configs[4] (SURVEY.md 8d #5): x0 perturbed by x0_scale * half-range * U[-1,1], quaternion renormalised."""
     m, _ = om.rocket_config()
     rng = np.random.default_rng(seed)
-    x0 = om.ROCKET_X0[None, :] + 0.05 * (m.x_ub - m.x_lb)[None, :] / 2 * rng.uniform(-1, 1, size=(B, m.nx))
+    x0 = om.ROCKET_X0[None, :] + x0_scale * (m.x_ub - m.x_lb)[None, :] / 2 * rng.uniform(-1, 1, size=(B, m.nx))
     qn = np.linalg.norm(om.ROCKET_X0[6:10])
     x0[:, 6:10] *= (qn / np.linalg.norm(x0[:, 6:10], axis=1))[:, None]
     W = rng.uniform(-1, 1, size=(B, steps, m.nx))
