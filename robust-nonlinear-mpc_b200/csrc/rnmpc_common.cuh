@@ -47,19 +47,23 @@ struct Slot {
 
 __host__ __device__ constexpr int even_up(int n) { return (n + 1) & ~1; }
 
-// acc{0,1}[c] += sum_m in{0,1}[m] * Mat[m*LD + c]   for c in [0, LD)   (Mat in shared memory, 16-byte aligned)
-template <int M, int LD>
-__device__ __forceinline__ void rowmm2(const double (&in0)[M], const double (&in1)[M], const double* __restrict__ Mat,
-                                       double (&acc0)[LD], double (&acc1)[LD]) {
-#pragma unroll
+// acc{0,1}[c] += sum_m in(m).{x,y} * Mat[m*LD + c]   for c in [0, LD)   (Mat in shared memory, 16-byte aligned).
+// The m-loop is deliberately NOT unrolled: one iteration is LD/2 LDS.128 + 2*LD DFMA (~50 instructions), so the hot loops
+// of a Riccati step stay resident in the instruction cache (the fully unrolled version was 136 KB of SASS per kernel and
+// ncu attributed 27 % of the stall samples to instruction fetch).
+template <int M, int LD, class InFn>
+__device__ __forceinline__ void rowmm2(InFn&& in, const double* __restrict__ Mat, double (&acc0)[LD], double (&acc1)[LD]) {
+#pragma unroll 1
     for (int m = 0; m < M; ++m) {
+        const double2 iv = in(m);
+        const double* row = Mat + m * LD;
 #pragma unroll
         for (int c = 0; c < LD; c += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(Mat + m * LD + c);
-            acc0[c] = fma(in0[m], v.x, acc0[c]);
-            acc0[c + 1] = fma(in0[m], v.y, acc0[c + 1]);
-            acc1[c] = fma(in1[m], v.x, acc1[c]);
-            acc1[c + 1] = fma(in1[m], v.y, acc1[c + 1]);
+            const double2 v = *reinterpret_cast<const double2*>(row + c);
+            acc0[c] = fma(iv.x, v.x, acc0[c]);
+            acc0[c + 1] = fma(iv.x, v.y, acc0[c + 1]);
+            acc1[c] = fma(iv.y, v.x, acc1[c]);
+            acc1[c + 1] = fma(iv.y, v.y, acc1[c + 1]);
         }
     }
 }
@@ -117,61 +121,89 @@ struct SlotSmem {
     double Bm[even_up(NX * NU)];    // B_k
     double SB[even_up(NX * NU)];    // S B
     double H[even_up(NU * NU)];     // Cu + B'SB
-    double K[NU * LD];              // K_k (forward) / Phi_u
-    double PU[NU * LD];
     double cu[even_up(NU)];         // diagonal additions of the input cost
-    double vec[4 * LD];             // vector scratch (QP sweeps)
-    double red[even_up(4 * Slot<NX>::LPS)];   // reduction scratch
+    union {                         // the fast-SLS forward pass and the QP sweeps never coexist in one kernel
+        struct { double K[NU * LD]; double PU[NU * LD]; };                               // K_k^T / Phi_u (fast-SLS)
+        struct { double vec[4 * LD]; double red[even_up(2 * Slot<NX>::LPS)]; };          // vector / reduction scratch (QP)
+    };
 };
+
+// Software prefetch of a global range into L2 (no registers held): issued one stage ahead of use, it turns the DRAM round
+// trip at the head of every Riccati / sweep stage into an L2 hit.
+template <int LPS>
+__device__ __forceinline__ void prefetch_l2(const void* p, const int bytes, const int sl) {
+    const char* c = reinterpret_cast<const char*>(p);
+    for (int off = sl * 128; off < bytes; off += LPS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+}
+
+// Cooperative load of an [R][C] global matrix into a shared LDS-strided matrix (zero pad columns).  All loads of a
+// lane are issued before the first store so that their latencies overlap (one L2 round trip per matrix).
+template <int R, int C, int LDS_, int LPS>
+__device__ __forceinline__ void load_matrix_smem(double* __restrict__ dst, const double* __restrict__ src, const int sl) {
+    constexpr int TOT = R * LDS_;
+    constexpr int IT = (TOT + LPS - 1) / LPS;
+    double v[IT];
+#pragma unroll
+    for (int j = 0; j < IT; ++j) {
+        const int e = sl + j * LPS;
+        const int i = e / LDS_, c = e - i * LDS_;
+        v[j] = (e < TOT && c < C) ? __ldg(src + i * C + c) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < IT; ++j) {
+        const int e = sl + j * LPS;
+        if (e < TOT) dst[e] = v[j];
+    }
+}
 
 // One backward Riccati step of a chain (solver/fast_SLS_jit.py:43-62):
 //   x = B'S, y = A'S, H = Cu + xB, F = xA, K = -H^{-1}F, S' = Cx + y(A + BK), S' <- (S'+S'^T)/2
-// On entry sm.S holds S_{k+1}; on exit it holds S_k.  `acol` (columns r0,r1 of A_k), `kcol` (columns of K_k) and the
-// Cholesky factor stay in registers for the caller (the QP fuses its vector recursion here through `Hook`).
-template <int NX, int NU, class Hook>
+// On entry sm.S holds S_{k+1}; on exit it holds S_k.  sm.T is used for A_k and then, in place, for A_k + B_k K_k.
+// `pre()` runs while S_{k+1} is intact; `post(kcol0, kcol1, L)` runs once K_k and the Cholesky factor exist, with A_k
+// still in sm.T (the QP fuses its vector recursion there).
+template <int NX, int NU, class Pre, class Post>
 __device__ __forceinline__ bool riccati_step(SlotSmem<NX, NU>& sm, const int sl, const unsigned mask,
                                              const double* __restrict__ Ag, const double* __restrict__ Bg,
                                              const double* __restrict__ Cx0, const double* __restrict__ Cu0,
-                                             const double cxd0, const double cxd1, double* __restrict__ Kout, Hook&& hook,
-                                             const bool need_S = true) {
+                                             const double cxd0, const double cxd1, double* __restrict__ Kout, Pre&& pre,
+                                             Post&& post, const bool need_S = true, const double* __restrict__ Ag_next = nullptr,
+                                             const double* __restrict__ Bg_next = nullptr) {
     constexpr int LD = Slot<NX>::LD;
     constexpr int LPS = Slot<NX>::LPS;
     const int r0 = 2 * sl, r1 = 2 * sl + 1;
     const bool v1 = r1 < NX;
     const int r1c = v1 ? r1 : NX - 1;
 
-    // (0) columns r0,r1 of A_k into registers, B_k into shared memory
-    double a0[NX], a1[NX];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-        a0[i] = __ldg(Ag + i * NX + r0);
-        a1[i] = v1 ? __ldg(Ag + i * NX + r1c) : 0.0;
+    // (0) A_k -> sm.T, B_k -> sm.Bm
+    load_matrix_smem<NX, NX, LD, LPS>(sm.T, Ag, sl);
+    load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bg, sl);
+    if (Ag_next != nullptr) {
+        prefetch_l2<LPS>(Ag_next, NX * NX * 8, sl);
+        prefetch_l2<LPS>(Bg_next, NX * NU * 8, sl);
     }
-    for (int e = sl; e < NX * NU; e += LPS) sm.Bm[e] = __ldg(Bg + e);
     __syncwarp(mask);
+    pre();
 
-    // (1) Y = A'S  (my rows)
+    // (1) Y = A'S  (my rows r0, r1: columns r0, r1 of A)
     double y0[LD], y1[LD];
 #pragma unroll
     for (int c = 0; c < LD; ++c) { y0[c] = 0.0; y1[c] = 0.0; }
-    rowmm2<NX, LD>(a0, a1, sm.S, y0, y1);
+    rowmm2<NX, LD>([&](int m) { return *reinterpret_cast<const double2*>(sm.T + m * LD + r0); }, sm.S, y0, y1);
 
-    // (2) F[:, r] = (Y B)[r, :]      (3) SB rows
+    // (3) SB rows:  (S B)[r, :]
     double f0[NU], f1[NU];
     {
         double sb0[NU], sb1[NU];
 #pragma unroll
-        for (int p = 0; p < NU; ++p) { f0[p] = 0.0; f1[p] = 0.0; sb0[p] = 0.0; sb1[p] = 0.0; }
-#pragma unroll
+        for (int p = 0; p < NU; ++p) { sb0[p] = 0.0; sb1[p] = 0.0; }
+#pragma unroll 1
         for (int c = 0; c < NX; ++c) {
             const double s0 = sm.S[r0 * LD + c], s1 = sm.S[r1c * LD + c];
 #pragma unroll
             for (int p = 0; p < NU; ++p) {
-                const double b = sm.Bm[c * NU + p];
-                f0[p] = fma(y0[c], b, f0[p]);
-                f1[p] = fma(y1[c], b, f1[p]);
-                sb0[p] = fma(s0, b, sb0[p]);
-                sb1[p] = fma(s1, b, sb1[p]);
+                const double bb = sm.Bm[c * NU + p];
+                sb0[p] = fma(s0, bb, sb0[p]);
+                sb1[p] = fma(s1, bb, sb1[p]);
             }
         }
 #pragma unroll
@@ -180,13 +212,33 @@ __device__ __forceinline__ bool riccati_step(SlotSmem<NX, NU>& sm, const int sl,
             if (v1) sm.SB[r1 * NU + p] = sb1[p];
         }
     }
-    __syncwarp(mask);
+    __syncwarp(mask);          // every lane is done reading S_{k+1}; SB is complete
+    // spill Y (my rows) over the S buffer: the remaining products read it back row-wise
+#pragma unroll
+    for (int c = 0; c < LD; c += 2) {
+        *reinterpret_cast<double2*>(sm.S + r0 * LD + c) = make_double2(y0[c], y0[c + 1]);
+        if (v1) *reinterpret_cast<double2*>(sm.S + r1 * LD + c) = make_double2(y1[c], y1[c + 1]);
+    }
+    // H = Cu + B'(SB)
+#pragma unroll 1
     for (int e = sl; e < NU * NU; e += LPS) {
-        const int p = e / NU, q = e % NU;
+        const int p = e / NU, q = e - p * NU;
         double hsum = 0.0;
 #pragma unroll
         for (int r = 0; r < NX; ++r) hsum = fma(sm.Bm[r * NU + p], sm.SB[r * NU + q], hsum);
         sm.H[e] = __ldg(Cu0 + e) + (p == q ? sm.cu[p] : 0.0) + hsum;
+    }
+    // (2) F[:, r] = (Y B)[r, :]
+#pragma unroll
+    for (int p = 0; p < NU; ++p) { f0[p] = 0.0; f1[p] = 0.0; }
+#pragma unroll
+    for (int c = 0; c < NX; ++c) {
+#pragma unroll
+        for (int p = 0; p < NU; ++p) {
+            const double bb = sm.Bm[c * NU + p];
+            f0[p] = fma(y0[c], bb, f0[p]);
+            f1[p] = fma(y1[c], bb, f1[p]);
+        }
     }
     __syncwarp(mask);
 
@@ -209,47 +261,38 @@ __device__ __forceinline__ bool riccati_step(SlotSmem<NX, NU>& sm, const int sl,
         }
     }
 
-    // caller hook: vector recursion that needs A columns, K columns, the factor and S_{k+1}
-    hook(a0, a1, f0, f1, L);
+    post(f0, f1, L);
     if (!need_S) return ok;
 
-    // (5) closed-loop columns  Acl[:, r] = A[:, r] + B K[:, r]  -> sm.T
-#pragma unroll
+    // (5) closed loop in place:  T[:, r] = A[:, r] + B K[:, r]
+#pragma unroll 1
     for (int i = 0; i < NX; ++i) {
-        double c0 = a0[i], c1 = a1[i];
+        double2 t = *reinterpret_cast<const double2*>(sm.T + i * LD + r0);
 #pragma unroll
         for (int p = 0; p < NU; ++p) {
-            const double b = sm.Bm[i * NU + p];
-            c0 = fma(b, f0[p], c0);
-            c1 = fma(b, f1[p], c1);
+            const double bb = sm.Bm[i * NU + p];
+            t.x = fma(bb, f0[p], t.x);
+            t.y = fma(bb, f1[p], t.y);
         }
-        *reinterpret_cast<double2*>(sm.T + i * LD + r0) = make_double2(c0, v1 ? c1 : 0.0);
+        if (!v1) t.y = 0.0;
+        *reinterpret_cast<double2*>(sm.T + i * LD + r0) = t;
     }
     __syncwarp(mask);
 
-    // (6) S' = Cx + Y Acl   (my rows)
+    // (6) S' = Cx + Y Acl   (my rows; Y read back from the S buffer)
     double s0[LD], s1[LD];
 #pragma unroll
     for (int c = 0; c < LD; ++c) { s0[c] = 0.0; s1[c] = 0.0; }
-    {
-        double yy0[NX], yy1[NX];
-#pragma unroll
-        for (int m = 0; m < NX; ++m) { yy0[m] = y0[m]; yy1[m] = y1[m]; }
-        rowmm2<NX, LD>(yy0, yy1, sm.T, s0, s1);
-    }
+    rowmm2<NX, LD>([&](int m) { return make_double2(sm.S[r0 * LD + m], sm.S[r1c * LD + m]); }, sm.T, s0, s1);
 #pragma unroll
     for (int c = 0; c < NX; ++c) {
         s0[c] = __ldg(Cx0 + r0 * NX + c) + s0[c];
         s1[c] = __ldg(Cx0 + r1c * NX + c) + s1[c];
-    }
-#pragma unroll
-    for (int c = 0; c < NX; ++c) {
         if (c == r0) s0[c] += cxd0;
         if (c == r1) s1[c] += cxd1;
     }
-    __syncwarp(mask);
 
-    // (7) symmetrise through shared memory
+    // (7) symmetrise through shared memory (each lane only overwrites its own rows of the Y spill)
 #pragma unroll
     for (int c = 0; c < LD; c += 2) {
         *reinterpret_cast<double2*>(sm.S + r0 * LD + c) = make_double2(s0[c], (c + 1 < NX) ? s0[c + 1] : 0.0);
@@ -272,9 +315,12 @@ __device__ __forceinline__ bool riccati_step(SlotSmem<NX, NU>& sm, const int sl,
     return ok;
 }
 
-struct NoHook {
-    template <class A, class K, class L>
-    __device__ __forceinline__ void operator()(const A&, const A&, const K&, const K&, const L&) const {}
+struct NoPre {
+    __device__ __forceinline__ void operator()() const {}
+};
+struct NoPost {
+    template <class K, class L>
+    __device__ __forceinline__ void operator()(const K&, const K&, const L&) const {}
 };
 
 }  // namespace rnmpc

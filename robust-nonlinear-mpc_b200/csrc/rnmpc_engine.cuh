@@ -209,7 +209,7 @@ struct Engine : IEngine {
         if (d_prm) cudaFree(d_prm);
     }
 
-    static constexpr int kWarps = 4;   // warps per CTA of the slot kernels (128 threads)
+    static constexpr int kWarps = 5;   // warps per CTA of the slot kernels (160 threads; 2 CTAs = 10 warps per SM by shared memory)
 
     int dims(int* nx, int* nu, int* N_, int* cap_) override {
         if (nx) *nx = NX; if (nu) *nu = NU; if (N_) *N_ = N; if (cap_) *cap_ = cap;

@@ -59,7 +59,7 @@ template <int V>
 struct IntTag { static constexpr int value = V; };
 
 template <int NX, int NU>
-__global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Params<NX, NU>* __restrict__ prm) {
+__global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Params<NX, NU>* __restrict__ prm) {
     using SL_ = Slot<NX>;
     constexpr int LD = SL_::LD, LPS = SL_::LPS, SPW = SL_::SPW;
     constexpr int NZ = NX + NU, NI = 2 * NZ, NIF = 2 * NX;
@@ -326,28 +326,24 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Param
                 const double gx0 = G[k * NZ + r0], gx1 = G[k * NZ + r1c];
                 const double gu_ = vu ? G[k * NZ + NX + sl] : 0.0;
                 const double rp0 = rp[k * NX + r0], rp1 = rp[k * NX + r1c];
-                auto vec_step = [&](const double (&a0)[NX], const double (&a1)[NX], const double (&k0)[NU], const double (&k1)[NU],
-                                    const double (&L)[NU][NU]) {
-                    double sc0, sc1;
-                    if (pass == 0) {
-                        // Sc_k = S_{k+1} rp_k
-                        sm.vec[LD + r0] = rp0;
-                        if (v1) sm.vec[LD + r1] = rp1;
-                        __syncwarp(mask);
-                        sc0 = 0.0; sc1 = 0.0;
-#pragma unroll
-                        for (int c = 0; c < NX; ++c) {
-                            const double cv = sm.vec[LD + c];
-                            sc0 = fma(sm.S[r0 * LD + c], cv, sc0);
-                            sc1 = fma(sm.S[r1c * LD + c], cv, sc1);
-                        }
-                        Sc[k * NX + r0] = sc0;
-                        if (v1) Sc[k * NX + r1] = sc1;
-                        __syncwarp(mask);
-                    } else {
-                        sc0 = Sc[k * NX + r0];
-                        sc1 = Sc[k * NX + r1c];
+                double sc0 = 0.0, sc1 = 0.0;
+                // Sc_k = S_{k+1} rp_k while S_{k+1} is still in shared memory (pass 0); the corrector re-reads it
+                auto pre_step = [&]() {
+                    sm.vec[LD + r0] = rp0;
+                    if (v1) sm.vec[LD + r1] = rp1;
+                    __syncwarp(mask);
+#pragma unroll 1
+                    for (int c = 0; c < NX; ++c) {
+                        const double cv = sm.vec[LD + c];
+                        sc0 = fma(sm.S[r0 * LD + c], cv, sc0);
+                        sc1 = fma(sm.S[r1c * LD + c], cv, sc1);
                     }
+                    Sc[k * NX + r0] = sc0;
+                    if (v1) Sc[k * NX + r1] = sc1;
+                    __syncwarp(mask);
+                };
+                // vector recursion of the KKT solve; A_k is in sm.T, B_k in sm.Bm, K columns / factor in registers
+                auto vec_step = [&](const double (&k0)[NU], const double (&k1)[NU], const double (&L)[NU][NU]) {
                     // g = p_{k+1} + Sc
                     const double g0 = sm.vec[r0] + rp_scale * sc0;
                     const double g1 = v1 ? (sm.vec[r1] + rp_scale * sc1) : 0.0;
@@ -375,11 +371,12 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Param
                     if (k > 0) {
                         // p_k = rx_k + A' g + K' t
                         double p0 = gx0, p1 = v1 ? gx1 : 0.0;
-#pragma unroll
+#pragma unroll 1
                         for (int i = 0; i < NX; ++i) {
                             const double gi = sm.vec[LD + i];
-                            p0 = fma(a0[i], gi, p0);
-                            p1 = fma(a1[i], gi, p1);
+                            const double2 av = *reinterpret_cast<const double2*>(sm.T + i * LD + r0);
+                            p0 = fma(av.x, gi, p0);
+                            p1 = fma(av.y, gi, p1);
                         }
 #pragma unroll
                         for (int p = 0; p < NU; ++p) { p0 = fma(k0[p], tt[p], p0); p1 = fma(k1[p], tt[p], p1); }
@@ -394,27 +391,27 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Param
                     const double cx1 = (k > 0 && v1) ? SIG[k * NZ + r1] : 0.0;
                     if (vu) sm.cu[sl] = SIG[k * NZ + NX + sl];
                     const bool ok = riccati_step<NX, NU>(
-                        sm, sl, mask, Ak, Bk, prm->Q2, prm->R2, cx0, cx1, Kq + (size_t)k * NU * NX,
-                        [&](const double (&a0)[NX], const double (&a1)[NX], const double (&k0)[NU], const double (&k1)[NU],
-                            const double (&L)[NU][NU]) {
+                        sm, sl, mask, Ak, Bk, prm->Q2, prm->R2, cx0, cx1, Kq + (size_t)k * NU * NX, pre_step,
+                        [&](const double (&k0)[NU], const double (&k1)[NU], const double (&L)[NU][NU]) {
                             if (sl == 0) {
 #pragma unroll
                                 for (int p = 0; p < NU; ++p)
 #pragma unroll
                                     for (int q = 0; q < NU; ++q) Lq[k * NU * NU + p * NU + q] = L[p][q];
                             }
-                            vec_step(a0, a1, k0, k1, L);
+                            vec_step(k0, k1, L);
                         },
-                        k > 0);
+                        k > 0, k > 0 ? Ak - NX * NX : nullptr, k > 0 ? Bk - NX * NU : nullptr);
                     chol_ok = chol_ok && ok;
                 } else {
-                    double a0[NX], a1[NX], k0[NU], k1[NU], L[NU][NU];
-#pragma unroll
-                    for (int i = 0; i < NX; ++i) {
-                        a0[i] = __ldg(Ak + i * NX + r0);
-                        a1[i] = v1 ? __ldg(Ak + i * NX + r1c) : 0.0;
+                    double k0[NU], k1[NU], L[NU][NU];
+                    load_matrix_smem<NX, NX, LD, LPS>(sm.T, Ak, sl);
+                    load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bk, sl);
+                    if (k > 0) {
+                        prefetch_l2<LPS>(Ak - NX * NX, NX * NX * 8, sl);
+                        prefetch_l2<LPS>(Bk - NX * NU, NX * NU * 8, sl);
+                        prefetch_l2<LPS>(Kq + (size_t)(k - 1) * NU * NX, NU * NX * 8, sl);
                     }
-                    for (int e = sl; e < NX * NU; e += LPS) sm.Bm[e] = __ldg(Bk + e);
 #pragma unroll
                     for (int p = 0; p < NU; ++p) {
                         k0[p] = Kq[(size_t)k * NU * NX + p * NX + r0];
@@ -422,8 +419,10 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Param
 #pragma unroll
                         for (int q = 0; q < NU; ++q) L[p][q] = Lq[k * NU * NU + p * NU + q];
                     }
+                    sc0 = Sc[k * NX + r0];
+                    sc1 = Sc[k * NX + r1c];
                     __syncwarp(mask);
-                    vec_step(a0, a1, k0, k1, L);
+                    vec_step(k0, k1, L);
                 }
             }
             // ---- forward: dx_0 = 0 ; du_k = K dx_k + d_k ; dx_{k+1} = A dx_k + B du_k + rp_k ; fused ratio test
@@ -457,6 +456,11 @@ __global__ void __launch_bounds__(128) qp_ipm_kernel(const QpArgs a, const Param
                 const double* Ak = Ab + (size_t)k * NX * NX;
                 const double* Bk = Bb + (size_t)k * NX * NU;
                 const double* Kk = Kq + (size_t)k * NU * NX;
+                if (k + 1 < N) {
+                    prefetch_l2<LPS>(Ak + NX * NX, NX * NX * 8, sl);
+                    prefetch_l2<LPS>(Bk + NX * NU, NX * NU * 8, sl);
+                    prefetch_l2<LPS>(Kk + NU * NX, NU * NX * 8, sl);
+                }
                 // loads that do not depend on the sweep: rows of A, B, K, and the entry data of the ratio test
                 double ar0[NX], ar1[NX], br0[NU], br1[NU], kr[NX];
 #pragma unroll

@@ -30,7 +30,7 @@ struct SlsArgs {
 // Chain s of an instance covers column s (N-s steps) followed by column N-s (s steps): N Riccati steps and N
 // propagation steps for every chain, so all slots of a warp run the same trip counts.
 template <int NX, int NU>
-__global__ void __launch_bounds__(128) sls_kernel(const SlsArgs a, const Params<NX, NU>* __restrict__ prm) {
+__global__ void __launch_bounds__(160, 2) sls_kernel(const SlsArgs a, const Params<NX, NU>* __restrict__ prm) {
     using SL = Slot<NX>;
     constexpr int LD = SL::LD, LPS = SL::LPS, SPW = SL::SPW;
     constexpr int NZ = NX + NU, NI = 2 * NZ, NIF = 2 * NX;
@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(128) sls_kernel(const SlsArgs a, const Params<
                     if (v1) So[r1 * NX + c] = sm.S[r1 * LD + c];
                 }
             }
-            __syncwarp(mask);
         }
+        __syncwarp(mask);      // outside the branch: slots of one warp start their second column at different t
         // C_kj = G' diag(eta[k, col]) G : diagonal additions to Q_reg / R_reg
         const double cx0 = weight(k, col, r0) + weight(k, col, r0 + NZ);
         const double cx1 = v1 ? (weight(k, col, r1) + weight(k, col, r1 + NZ)) : 0.0;
@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(128) sls_kernel(const SlsArgs a, const Params<
         if (LPS < NU) { for (int p = LPS + sl; p < NU; p += LPS) sm.cu[p] = weight(k, col, NX + p) + weight(k, col, NX + p + NZ); }
         double* Kout = a.K + (((size_t)b * N + k) * (N + 1) + col) * kstride;
         riccati_step<NX, NU>(sm, sl, mask, Ab + (size_t)k * NX * NX, Bb + (size_t)k * NX * NU, prm->Qreg, prm->Rreg, cx0, cx1,
-                             Kout, NoHook());
+                             Kout, NoPre(), NoPost(), true, k > 0 ? Ab + (size_t)(k - 1) * NX * NX : nullptr,
+                             k > 0 ? Bb + (size_t)(k - 1) * NX * NU : nullptr);
         if (a.S != nullptr) {
             double* So = a.S + ((((size_t)b * (N + 1) + k) * (N + 1)) + col) * NX * NX;
             for (int c = 0; c < NX; ++c) {
@@ -150,11 +151,19 @@ __global__ void __launch_bounds__(128) sls_kernel(const SlsArgs a, const Params<
                 }
             }
         }
-        // K[k, col] -> shared
+        // K[k, col] -> shared, transposed (Kt[m][p]); A_k -> sm.T; loads batched so their latencies overlap
         const double* Kin = a.K + (((size_t)b * N + k) * (N + 1) + col) * kstride;
-        for (int e = sl; e < NU * NX; e += LPS) {
-            const int p = e / NX, m = e - p * NX;
-            sm.K[p * LD + m] = Kin[e];
+        {
+            constexpr int ITK = (NU * NX + LPS - 1) / LPS;
+            double kv[ITK];
+#pragma unroll
+            for (int j = 0; j < ITK; ++j) { const int e = sl + j * LPS; kv[j] = (e < NU * NX) ? Kin[e] : 0.0; }
+            load_matrix_smem<NX, NX, LD, LPS>(sm.T, Ab + (size_t)k * NX * NX, sl);
+#pragma unroll
+            for (int j = 0; j < ITK; ++j) {
+                const int e = sl + j * LPS;
+                if (e < NU * NX) { const int p = e / NX, m = e - p * NX; sm.K[m * NU + p] = kv[j]; }
+            }
         }
         __syncwarp(mask);
         // Phi_u[k, col] = K Phi_x : my two columns
@@ -162,12 +171,12 @@ __global__ void __launch_bounds__(128) sls_kernel(const SlsArgs a, const Params<
             double pu0[NU], pu1[NU];
 #pragma unroll
             for (int p = 0; p < NU; ++p) { pu0[p] = 0.0; pu1[p] = 0.0; }
-#pragma unroll
+#pragma unroll 1
             for (int m = 0; m < NX; ++m) {
                 const double2 ph = *reinterpret_cast<const double2*>(sm.S + m * LD + r0);
 #pragma unroll
                 for (int p = 0; p < NU; ++p) {
-                    const double kk = sm.K[p * LD + m];
+                    const double kk = sm.K[m * NU + p];
                     pu0[p] = fma(kk, ph.x, pu0[p]);
                     pu1[p] = fma(kk, ph.y, pu1[p]);
                 }
@@ -182,21 +191,35 @@ __global__ void __launch_bounds__(128) sls_kernel(const SlsArgs a, const Params<
                 }
             }
         }
-        __syncwarp(mask);
-        // beta[k, col, :] = max(rowwise ||[Phi_x; Phi_u]||^2, eps)   (G = [I;-I]: rows i and i+nz coincide)
+        // closed-loop rows  (A + B K)[r, :] -> sm.T (my rows), and beta of the state rows
         {
-            double* bo = a.beta + (((size_t)b * N + k) * N + col) * NI;
-            double n0 = 0.0, n1 = 0.0;
+            const double* Bk = Bb + (size_t)k * NX * NU;
+            double b0[NU], b1[NU];
 #pragma unroll
-            for (int c = 0; c < NX; ++c) {
-                const double p0 = sm.S[r0 * LD + c], p1 = sm.S[r1c * LD + c];
+            for (int p = 0; p < NU; ++p) { b0[p] = __ldg(Bk + r0 * NU + p); b1[p] = __ldg(Bk + r1c * NU + p); }
+            double n0 = 0.0, n1 = 0.0;
+#pragma unroll 1
+            for (int m = 0; m < NX; ++m) {
+                double x0 = sm.T[r0 * LD + m], x1 = sm.T[r1c * LD + m];      // A_k rows (in place -> closed loop rows)
+#pragma unroll
+                for (int p = 0; p < NU; ++p) {
+                    const double kk = sm.K[m * NU + p];
+                    x0 = fma(b0[p], kk, x0);
+                    x1 = fma(b1[p], kk, x1);
+                }
+                sm.T[r0 * LD + m] = x0;
+                if (v1) sm.T[r1 * LD + m] = x1;
+                const double p0 = sm.S[r0 * LD + m], p1 = sm.S[r1c * LD + m];
                 n0 = fma(p0, p0, n0);
                 n1 = fma(p1, p1, n1);
             }
+            // beta[k, col, :] = max(rowwise ||[Phi_x; Phi_u]||^2, eps)   (G = [I;-I]: rows i and i+nz coincide)
+            double* bo = a.beta + (((size_t)b * N + k) * N + col) * NI;
             n0 = fmax(n0, kEpsBackoff);
             n1 = fmax(n1, kEpsBackoff);
             bo[r0] = n0; bo[r0 + NZ] = n0;
             if (v1) { bo[r1] = n1; bo[r1 + NZ] = n1; }
+            __syncwarp(mask);      // PU complete
             for (int p = sl; p < NU; p += LPS) {
                 double nn = 0.0;
 #pragma unroll
@@ -207,28 +230,9 @@ __global__ void __launch_bounds__(128) sls_kernel(const SlsArgs a, const Params<
         }
         // Phi_x[k+1, col] = (A + B K) Phi_x[k, col] : my rows
         double ph0[LD], ph1[LD];
-        {
-            double c0[NX], c1[NX];
-            const double* Ak = Ab + (size_t)k * NX * NX;
-            const double* Bk = Bb + (size_t)k * NX * NU;
-            double b0[NU], b1[NU];
 #pragma unroll
-            for (int p = 0; p < NU; ++p) { b0[p] = __ldg(Bk + r0 * NU + p); b1[p] = __ldg(Bk + r1c * NU + p); }
-#pragma unroll
-            for (int m = 0; m < NX; ++m) {
-                double x0 = __ldg(Ak + r0 * NX + m), x1 = __ldg(Ak + r1c * NX + m);
-#pragma unroll
-                for (int p = 0; p < NU; ++p) {
-                    const double kk = sm.K[p * LD + m];
-                    x0 = fma(b0[p], kk, x0);
-                    x1 = fma(b1[p], kk, x1);
-                }
-                c0[m] = x0; c1[m] = x1;
-            }
-#pragma unroll
-            for (int c = 0; c < LD; ++c) { ph0[c] = 0.0; ph1[c] = 0.0; }
-            rowmm2<NX, LD>(c0, c1, sm.S, ph0, ph1);
-        }
+        for (int c = 0; c < LD; ++c) { ph0[c] = 0.0; ph1[c] = 0.0; }
+        rowmm2<NX, LD>([&](int m) { return make_double2(sm.T[r0 * LD + m], sm.T[r1c * LD + m]); }, sm.S, ph0, ph1);
         __syncwarp(mask);
 #pragma unroll
         for (int c = 0; c < LD; c += 2) {

@@ -117,7 +117,7 @@ def test_qp_vs_oracle_golden(name):
             scale = max(np.abs(g["mu"][i]).max(), 1.0)
             assert np.abs(out["mu"][j] - g["mu"][i]).max() < TOL_TRAJ * scale
             assert np.abs(out["mu_f"][j] - g["mu_f"][i]).max() < TOL_TRAJ * scale
-            assert abs(out["cost"][j] - g["cost"][i]) < 1e-6 * max(1.0, abs(g["cost"][i]))   # dynamics rows: 1e-10 interval midpoint x costates
+            assert abs(out["cost"][j] - g["cost"][i]) < 1e-5 * max(1.0, abs(g["cost"][i]))   # dynamics rows: 1e-10 interval midpoint x costates
             assert out["mu"][j].min() > -1e-12          # dual feasibility
             assert np.abs(out["dX"][j][0] - g["x0"][i] + g["X"][i][0]).max() < 1e-14     # x(0) pinned to the measurement
     s.close()
