@@ -53,17 +53,45 @@ __host__ __device__ constexpr int even_up(int n) { return (n + 1) & ~1; }
 // ncu attributed 27 % of the stall samples to instruction fetch).
 template <int M, int LD, class InFn>
 __device__ __forceinline__ void rowmm2(InFn&& in, const double* __restrict__ Mat, double (&acc0)[LD], double (&acc1)[LD]) {
-#pragma unroll 1
-    for (int m = 0; m < M; ++m) {
-        const double2 iv = in(m);
-        const double* row = Mat + m * LD;
+    // two-stage software pipeline: the LDS of row m+1 are in flight while the 2*LD DFMA of row m issue (ncu: without it the
+    // DFMAs of this loop sat on the short scoreboard waiting for their own iteration's loads)
+    constexpr int H = LD / 2;
+    double2 va[H], vb[H];
+    double2 ia = in(0), ib;
 #pragma unroll
-        for (int c = 0; c < LD; c += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(row + c);
-            acc0[c] = fma(iv.x, v.x, acc0[c]);
-            acc0[c + 1] = fma(iv.x, v.y, acc0[c + 1]);
-            acc1[c] = fma(iv.y, v.x, acc1[c]);
-            acc1[c + 1] = fma(iv.y, v.y, acc1[c + 1]);
+    for (int c = 0; c < H; ++c) va[c] = *reinterpret_cast<const double2*>(Mat + 2 * c);
+#pragma unroll 1
+    for (int m = 0; m + 1 < M; m += 2) {
+        ib = in(m + 1);
+#pragma unroll
+        for (int c = 0; c < H; ++c) vb[c] = *reinterpret_cast<const double2*>(Mat + (m + 1) * LD + 2 * c);
+#pragma unroll
+        for (int c = 0; c < H; ++c) {
+            acc0[2 * c] = fma(ia.x, va[c].x, acc0[2 * c]);
+            acc0[2 * c + 1] = fma(ia.x, va[c].y, acc0[2 * c + 1]);
+            acc1[2 * c] = fma(ia.y, va[c].x, acc1[2 * c]);
+            acc1[2 * c + 1] = fma(ia.y, va[c].y, acc1[2 * c + 1]);
+        }
+        if (m + 2 < M) {
+            ia = in(m + 2);
+#pragma unroll
+            for (int c = 0; c < H; ++c) va[c] = *reinterpret_cast<const double2*>(Mat + (m + 2) * LD + 2 * c);
+        }
+#pragma unroll
+        for (int c = 0; c < H; ++c) {
+            acc0[2 * c] = fma(ib.x, vb[c].x, acc0[2 * c]);
+            acc0[2 * c + 1] = fma(ib.x, vb[c].y, acc0[2 * c + 1]);
+            acc1[2 * c] = fma(ib.y, vb[c].x, acc1[2 * c]);
+            acc1[2 * c + 1] = fma(ib.y, vb[c].y, acc1[2 * c + 1]);
+        }
+    }
+    if (M & 1) {
+#pragma unroll
+        for (int c = 0; c < H; ++c) {
+            acc0[2 * c] = fma(ia.x, va[c].x, acc0[2 * c]);
+            acc0[2 * c + 1] = fma(ia.x, va[c].y, acc0[2 * c + 1]);
+            acc1[2 * c] = fma(ia.y, va[c].x, acc1[2 * c]);
+            acc1[2 * c + 1] = fma(ia.y, va[c].y, acc1[2 * c + 1]);
         }
     }
 }
@@ -112,9 +140,9 @@ __device__ __forceinline__ void chol_solve(const double (&L)[NU][NU], double (&f
     }
 }
 
-// Shared-memory working set of one slot.
+// Shared-memory working set of one slot (see SlotSmem below for the bank-conflict padding).
 template <int NX, int NU>
-struct SlotSmem {
+struct SlotSmemCore {
     static constexpr int LD = Slot<NX>::LD;
     double S[NX * LD];              // current cost-to-go S (backward) / Phi_x (forward), full matrix for broadcast
     double T[NX * LD];              // closed-loop matrix A+BK (backward)
@@ -126,6 +154,17 @@ struct SlotSmem {
         struct { double K[NU * LD]; double PU[NU * LD]; };                               // K_k^T / Phi_u (fast-SLS)
         struct { double vec[4 * LD]; double red[even_up(2 * Slot<NX>::LPS)]; };          // vector / reduction scratch (QP)
     };
+};
+
+// The slots of one warp read the same offset of their own SlotSmem in one LDS (a "broadcast" per slot).  With a slot
+// stride that is a multiple of 128 B those 2-3 addresses fall into the same banks and every LDS.128 replays 3x (ncu:
+// l1tex__data_bank_conflicts_pipe_lsu_mem_shared ~ 1.2e8 per QP launch).  Padding the stride to 16 (mod 128) bytes puts
+// neighbouring slots into different 16-byte bank groups.
+template <int NX, int NU>
+struct SlotSmem : SlotSmemCore<NX, NU> {
+    static constexpr int kCore = (int)sizeof(SlotSmemCore<NX, NU>);
+    static constexpr int kPad = ((16 - kCore % 128) + 128) % 128;
+    double pad_[kPad / 8 > 0 ? kPad / 8 : 1];
 };
 
 // Software prefetch of a global range into L2 (no registers held): issued one stage ahead of use, it turns the DRAM round

@@ -145,12 +145,13 @@ struct Engine : IEngine {
     P* d_prm = nullptr;
     std::map<std::string, std::pair<void*, size_t>> bufs;
     bool phi_enabled = false;
+    int diag_cost = 0;
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     double *X, *U, *A, *Bm, *c, *dX, *dU, *mu, *mu_f, *beta, *beta_f, *backoff, *backoff_f, *K, *cost, *prevX, *prevU;
     double *Phi_x = nullptr, *Phi_u = nullptr;
-    double *wZ, *wSU, *wSL, *wLU, *wLL, *wDZA, *wDZC, *wG, *wSIG, *rp, *Sc, *dff, *Kq, *Lq;
+    double *wZ, *wSU, *wSL, *wLU, *wLL, *wDZA, *wDZC, *wG, *wSIG, *wZN, *wISU, *wISL, *rp, *Sc, *dff, *Kq, *Lq;
     int *flags, *status, *qp_iters, *iters_tmp, *status_tmp;
 
     template <class T>
@@ -178,6 +179,13 @@ struct Engine : IEngine {
         memcpy(hp.uub, cfg->u_ub, sizeof(hp.uub)); memcpy(hp.ulb, cfg->u_lb, sizeof(hp.ulb));
         memcpy(hp.xubf, cfg->xf_ub, sizeof(hp.xubf)); memcpy(hp.xlbf, cfg->xf_lb, sizeof(hp.xlbf));
         hp.h = h;
+        diag_cost = 1;
+        for (int i = 0; i < NX; ++i)
+            for (int j = 0; j < NX; ++j)
+                if (i != j && (hp.Q[i * NX + j] != 0.0 || hp.Qf[i * NX + j] != 0.0)) diag_cost = 0;
+        for (int i = 0; i < NU; ++i)
+            for (int j = 0; j < NU; ++j)
+                if (i != j && hp.R[i * NU + j] != 0.0) diag_cost = 0;
         RN_CUDA(cudaMalloc((void**)&d_prm, sizeof(P)));
         RN_CUDA(cudaMemcpy(d_prm, &hp, sizeof(P), cudaMemcpyHostToDevice));
         const size_t B = cap, n1 = N + 1;
@@ -193,6 +201,7 @@ struct Engine : IEngine {
         rc |= alloc("wZ", wZ, B * n1 * NZ); rc |= alloc("wSU", wSU, B * n1 * NZ); rc |= alloc("wSL", wSL, B * n1 * NZ);
         rc |= alloc("wLU", wLU, B * n1 * NZ); rc |= alloc("wLL", wLL, B * n1 * NZ); rc |= alloc("wDZA", wDZA, B * n1 * NZ);
         rc |= alloc("wDZC", wDZC, B * n1 * NZ); rc |= alloc("wG", wG, B * n1 * NZ); rc |= alloc("wSIG", wSIG, B * n1 * NZ);
+        rc |= alloc("wZN", wZN, B * n1 * NZ); rc |= alloc("wISU", wISU, B * n1 * NZ); rc |= alloc("wISL", wISL, B * n1 * NZ);
         rc |= alloc("rp", rp, B * N * NX); rc |= alloc("Sc", Sc, B * N * NX); rc |= alloc("dff", dff, B * N * NU);
         rc |= alloc("Kq", Kq, B * N * NU * NX); rc |= alloc("Lq", Lq, B * N * NU * NU);
         rc |= alloc("flags", flags, B); rc |= alloc("status", status, B); rc |= alloc("qp_iters", qp_iters, B);
@@ -272,7 +281,7 @@ struct Engine : IEngine {
         a.A = A_; a.Bm = B_; a.c = c_; a.Xnom = X_; a.Unom = U_; a.x0 = x0; a.backoff = bo; a.backoff_f = bof;
         a.flags = fl; a.skip_mask = skip_mask;
         a.dX = dX_; a.dU = dU_; a.mu = mu_; a.mu_f = mu_f_; a.cost = cost_; a.iters = iters_; a.status = status_;
-        a.Z = wZ; a.SU = wSU; a.SL = wSL; a.LU = wLU; a.LL = wLL; a.DZA = wDZA; a.DZC = wDZC; a.G = wG; a.SIG = wSIG; a.rp = rp; a.Sc = Sc;
+        a.Z = wZ; a.SU = wSU; a.SL = wSL; a.LU = wLU; a.LL = wLL; a.DZA = wDZA; a.DZC = wDZC; a.G = wG; a.SIG = wSIG; a.ZN = wZN; a.ISU = wISU; a.ISL = wISL; a.diag_cost = diag_cost; a.rp = rp; a.Sc = Sc;
         a.dff = dff; a.Kq = Kq; a.Lq = Lq;
         const long long warps = ((long long)B + Slot<NX>::SPW - 1) / Slot<NX>::SPW;
         const unsigned grid = (unsigned)((warps + kWarps - 1) / kWarps);

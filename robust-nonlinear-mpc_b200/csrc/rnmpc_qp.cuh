@@ -48,6 +48,10 @@ struct QpArgs {
     double* DZC;            // combined step
     double* G;              // right-hand side of the current KKT solve
     double* SIG;            // barrier Hessian diagonal  LU/SU + LL/SL
+    double* ZN;             // nominal trajectory in entry layout
+    double* ISU;            // 1/SU (0 where there is no bound)
+    double* ISL;            // 1/SL
+    int diag_cost;          // 1: Q, R, Qf are diagonal (all reference drivers) -> element-wise gradient
     double* rp;             // [B][N][nx]     dynamics residual at the initial point
     double* Sc;             // [B][N][nx]     S_{k+1} rp_k
     double* dff;            // [B][N][nu]     feed-forward
@@ -105,6 +109,9 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     double* __restrict__ DZC = a.DZC + eoff;
     double* __restrict__ G = a.G + eoff;
     double* __restrict__ SIG = a.SIG + eoff;
+    double* __restrict__ ZN = a.ZN + eoff;
+    double* __restrict__ ISU = a.ISU + eoff;
+    double* __restrict__ ISL = a.ISL + eoff;
     double* rp = a.rp + (size_t)b * N * NX;
     double* Sc = a.Sc + (size_t)b * N * NX;
     double* dff = a.dff + (size_t)b * N * NU;
@@ -216,6 +223,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     if (hl) { sl_ = z - l_; ll = 1.0; n_box += 1.0; }
                 }
                 Z[idx] = z; SU[idx] = su; SLk[idx] = sl_; LU[idx] = lu; LL[idx] = ll;
+                ZN[idx] = (en < 2) ? Xn[k * NX + i] : (k < N ? Un[k * NU + (i - NX)] : 0.0);
             }
         }
         slot_sum2(bad, n_box);
@@ -273,31 +281,41 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     for (; it < a.max_iter; ++it) {
         if (__all_sync(mask, done)) break;
         __syncwarp(mask);
-        // ---- P1: barrier diagonal SIG and gradient G = 2 H (z + z_nom)
+        // ---- P1: reciprocal slacks, barrier diagonal SIG and gradient G = 2 H (z + z_nom)
         {
-            const double* arr[4] = {SU, SLk, LU, LL};
-            entry_pass(I4{}, arr, [&](int, int idx, const double (&v)[4]) {
-                double sg = 0.0;
-                if (v[0] < kBig) sg += v[2] / v[0];
-                if (v[1] < kBig) sg += v[3] / v[1];
-                SIG[idx] = sg;
-            });
-            for (int k = 0; k <= N; ++k) {
-                const double* Qm = (k < N) ? prm->Q : prm->Qf;
-                double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-                for (int m = 0; m < NX; ++m) {
-                    const double y = Z[k * NZ + m] + Xn[k * NX + m];
-                    acc0 = fma(Qm[r0 * NX + m], y, acc0);
-                    acc1 = fma(Qm[r1c * NX + m], y, acc1);
+            const double* arr[6] = {SU, SLk, LU, LL, Z, ZN};
+            const double qd[3] = {prm->Q[r0 * NX + r0], prm->Q[r1c * NX + r1c], vu ? prm->R[sl * NU + sl] : 0.0};
+            const double qfd[2] = {prm->Qf[r0 * NX + r0], prm->Qf[r1c * NX + r1c]};
+            const bool dg = a.diag_cost != 0;
+            entry_pass(I6{}, arr, [&](int k, int idx, const double (&v)[6]) {
+                double sg = 0.0, iu = 0.0, il = 0.0;
+                if (v[0] < kBig) { iu = 1.0 / v[0]; sg = v[2] * iu; }
+                if (v[1] < kBig) { il = 1.0 / v[1]; sg = fma(v[3], il, sg); }
+                SIG[idx] = sg; ISU[idx] = iu; ISL[idx] = il;
+                if (dg) {
+                    const int i = idx - k * NZ;
+                    const double q = (i >= NX) ? qd[2] : (i == r0 ? (k < N ? qd[0] : qfd[0]) : (k < N ? qd[1] : qfd[1]));
+                    G[idx] = 2.0 * q * (v[4] + v[5]);
                 }
-                G[k * NZ + r0] = 2.0 * acc0;
-                if (v1) G[k * NZ + r1] = 2.0 * acc1;
-                if (vu && k < N) {
-                    double acc = 0.0;
+            });
+            if (!dg) {
+                for (int k = 0; k <= N; ++k) {
+                    const double* Qm = (k < N) ? prm->Q : prm->Qf;
+                    double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-                    for (int m = 0; m < NU; ++m) acc = fma(prm->R[sl * NU + m], Z[k * NZ + NX + m] + Un[k * NU + m], acc);
-                    G[k * NZ + NX + sl] = 2.0 * acc;
+                    for (int m = 0; m < NX; ++m) {
+                        const double y = Z[k * NZ + m] + ZN[k * NZ + m];
+                        acc0 = fma(Qm[r0 * NX + m], y, acc0);
+                        acc1 = fma(Qm[r1c * NX + m], y, acc1);
+                    }
+                    G[k * NZ + r0] = 2.0 * acc0;
+                    if (v1) G[k * NZ + r1] = 2.0 * acc1;
+                    if (vu && k < N) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int m = 0; m < NU; ++m) acc = fma(prm->R[sl * NU + m], Z[k * NZ + NX + m] + ZN[k * NZ + NX + m], acc);
+                        G[k * NZ + NX + sl] = 2.0 * acc;
+                    }
                 }
             }
         }
@@ -428,22 +446,24 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             // ---- forward: dx_0 = 0 ; du_k = K dx_k + d_k ; dx_{k+1} = A dx_k + B du_k + rp_k ; fused ratio test
             double* __restrict__ DZ = pass == 0 ? DZA : DZC;
             const double tau = pass == 0 ? 1.0 : (mu_c > 1e-8 ? 0.995 : 0.9999);
-            double apl = 1.0, adl = 1.0;
-            // ratio test + dual step of one entry: given dz (and the affine step for the corrector)
-            auto ratio_entry = [&](double su, double sl_, double lu, double ll, double dz, double dza) {
-                if (su < kBig) {
+            // largest dz/s and -dlam/lam over the entries: alpha = min(1, tau / max)
+            double rpm = 0.0, rdm = 0.0;
+            auto ratio_entry = [&](double isu, double isl, double lu, double ll, double dz, double dza) {
+                if (isu > 0.0) {
+                    const double ru = lu * isu;
                     double tgt = 0.0;
-                    if (pass == 1) { const double dla = -lu + (lu / su) * dza; tgt = sigma_mu + dza * dla; }
-                    const double dlu = tgt / su - lu + (lu / su) * dz;
-                    if (dz > 0.0) apl = fmin(apl, tau * su / dz);
-                    if (dlu < 0.0) adl = fmin(adl, -tau * lu / dlu);
+                    if (pass == 1) tgt = sigma_mu + dza * (ru * dza - lu);
+                    const double dlu = tgt * isu - lu + ru * dz;
+                    rpm = fmax(rpm, dz * isu);
+                    if (dlu < 0.0) rdm = fmax(rdm, -dlu / lu);
                 }
-                if (sl_ < kBig) {
+                if (isl > 0.0) {
+                    const double rl = ll * isl;
                     double tgt = 0.0;
-                    if (pass == 1) { const double dla = -ll - (ll / sl_) * dza; tgt = sigma_mu - dza * dla; }
-                    const double dll = tgt / sl_ - ll - (ll / sl_) * dz;
-                    if (dz < 0.0) apl = fmin(apl, -tau * sl_ / dz);
-                    if (dll < 0.0) adl = fmin(adl, -tau * ll / dll);
+                    if (pass == 1) tgt = sigma_mu + dza * (rl * dza + ll);
+                    const double dll = tgt * isl - ll - rl * dz;
+                    rpm = fmax(rpm, -dz * isl);
+                    if (dll < 0.0) rdm = fmax(rdm, -dll / ll);
                 }
             };
             __syncwarp(mask);
@@ -456,80 +476,95 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 const double* Ak = Ab + (size_t)k * NX * NX;
                 const double* Bk = Bb + (size_t)k * NX * NU;
                 const double* Kk = Kq + (size_t)k * NU * NX;
+                // stage A_k, B_k, K_k in shared memory (coalesced, all loads in flight together) + this stage's entry data
+                load_matrix_smem<NX, NX, LD, LPS>(sm.T, Ak, sl);
+                load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bk, sl);
+                load_matrix_smem<NU, NX, NX, LPS>(sm.SB, Kk, sl);
                 if (k + 1 < N) {
                     prefetch_l2<LPS>(Ak + NX * NX, NX * NX * 8, sl);
                     prefetch_l2<LPS>(Bk + NX * NU, NX * NU * 8, sl);
                     prefetch_l2<LPS>(Kk + NU * NX, NU * NX * 8, sl);
                 }
-                // loads that do not depend on the sweep: rows of A, B, K, and the entry data of the ratio test
-                double ar0[NX], ar1[NX], br0[NU], br1[NU], kr[NX];
-#pragma unroll
-                for (int m = 0; m < NX; ++m) { ar0[m] = __ldg(Ak + r0 * NX + m); ar1[m] = __ldg(Ak + r1c * NX + m); }
-#pragma unroll
-                for (int p = 0; p < NU; ++p) { br0[p] = __ldg(Bk + r0 * NU + p); br1[p] = __ldg(Bk + r1c * NU + p); }
-                if (vu) {
-#pragma unroll
-                    for (int m = 0; m < NX; ++m) kr[m] = Kk[sl * NX + m];
-                }
                 const int iu = k * NZ + NX + (vu ? sl : 0), ix0 = (k + 1) * NZ + r0, ix1 = (k + 1) * NZ + r1c;
-                const double e_su[3] = {SU[ix0], SU[ix1], SU[iu]}, e_sl[3] = {SLk[ix0], SLk[ix1], SLk[iu]};
+                const double e_iu[3] = {ISU[ix0], ISU[ix1], ISU[iu]}, e_il[3] = {ISL[ix0], ISL[ix1], ISL[iu]};
                 const double e_lu[3] = {LU[ix0], LU[ix1], LU[iu]}, e_ll[3] = {LL[ix0], LL[ix1], LL[iu]};
                 double e_da[3] = {0.0, 0.0, 0.0};
                 if (pass == 1) { e_da[0] = DZA[ix0]; e_da[1] = DZA[ix1]; e_da[2] = DZA[iu]; }
                 double n0 = rp_scale * rp[k * NX + r0], n1 = rp_scale * rp[k * NX + r1c];
+                double u = vu ? dff[k * NU + sl] : 0.0;
+                __syncwarp(mask);
                 if (vu) {
-                    double u = dff[k * NU + sl];
+                    double u2 = 0.0;
 #pragma unroll
-                    for (int m = 0; m < NX; ++m) u = fma(kr[m], sm.vec[m], u);
+                    for (int m = 0; m + 1 < NX; m += 2) {
+                        u = fma(sm.SB[sl * NX + m], sm.vec[m], u);
+                        u2 = fma(sm.SB[sl * NX + m + 1], sm.vec[m + 1], u2);
+                    }
+                    if (NX & 1) u = fma(sm.SB[sl * NX + NX - 1], sm.vec[NX - 1], u);
+                    u += u2;
                     sm.vec[LD + sl] = u;
                     DZ[iu] = u;
-                    ratio_entry(e_su[2], e_sl[2], e_lu[2], e_ll[2], u, e_da[2]);
+                    ratio_entry(e_iu[2], e_il[2], e_lu[2], e_ll[2], u, e_da[2]);
+                }
+                {
+                    double m0 = 0.0, m1 = 0.0;
+#pragma unroll
+                    for (int m = 0; m + 1 < NX; m += 2) {
+                        const double xa = sm.vec[m], xb = sm.vec[m + 1];
+                        n0 = fma(sm.T[r0 * LD + m], xa, n0);
+                        n1 = fma(sm.T[r1c * LD + m], xa, n1);
+                        m0 = fma(sm.T[r0 * LD + m + 1], xb, m0);
+                        m1 = fma(sm.T[r1c * LD + m + 1], xb, m1);
+                    }
+                    if (NX & 1) {
+                        const double xa = sm.vec[NX - 1];
+                        n0 = fma(sm.T[r0 * LD + NX - 1], xa, n0);
+                        n1 = fma(sm.T[r1c * LD + NX - 1], xa, n1);
+                    }
+                    n0 += m0; n1 += m1;
                 }
                 __syncwarp(mask);
 #pragma unroll
-                for (int m = 0; m < NX; ++m) {
-                    const double xm = sm.vec[m];
-                    n0 = fma(ar0[m], xm, n0);
-                    n1 = fma(ar1[m], xm, n1);
-                }
-#pragma unroll
                 for (int p = 0; p < NU; ++p) {
                     const double up = sm.vec[LD + p];
-                    n0 = fma(br0[p], up, n0);
-                    n1 = fma(br1[p], up, n1);
+                    n0 = fma(sm.Bm[r0 * NU + p], up, n0);
+                    n1 = fma(sm.Bm[r1c * NU + p], up, n1);
                 }
                 __syncwarp(mask);
                 sm.vec[r0] = n0;
                 if (v1) sm.vec[r1] = n1;
                 DZ[ix0] = n0;
-                ratio_entry(e_su[0], e_sl[0], e_lu[0], e_ll[0], n0, e_da[0]);
+                ratio_entry(e_iu[0], e_il[0], e_lu[0], e_ll[0], n0, e_da[0]);
                 if (v1) {
                     DZ[ix1] = n1;
-                    ratio_entry(e_su[1], e_sl[1], e_lu[1], e_ll[1], n1, e_da[1]);
+                    ratio_entry(e_iu[1], e_il[1], e_lu[1], e_ll[1], n1, e_da[1]);
                 }
                 __syncwarp(mask);
             }
-            slot_min2(apl, adl);
+            rpm = -rpm; rdm = -rdm;
+            slot_min2(rpm, rdm);
+            double apl = (-rpm > tau) ? tau / (-rpm) : 1.0;
+            double adl = (-rdm > tau) ? tau / (-rdm) : 1.0;
             ap = apl; ad = adl;
             if (pass == 0) {
                 // ---- P2: mu_aff and sigma ; P3: corrector right-hand side G += (sigma mu - corr_u)/su - (sigma mu - corr_l)/sl
                 double acc = 0.0, dmy = 0.0;
                 const double* arr[5] = {SU, SLk, LU, LL, DZA};
-                entry_pass(I5{}, arr, [&](int, int, const double (&v)[5]) {
+                entry_pass(I5{}, arr, [&](int, int idx, const double (&v)[5]) {
                     const double dz = v[4];
-                    if (v[0] < kBig) { const double dl = -v[2] + (v[2] / v[0]) * dz; acc = fma(v[0] - ap * dz, v[2] + ad * dl, acc); }
-                    if (v[1] < kBig) { const double dl = -v[3] - (v[3] / v[1]) * dz; acc = fma(v[1] + ap * dz, v[3] + ad * dl, acc); }
+                    if (v[0] < kBig) { const double dl = v[2] * (ISU[idx] * dz - 1.0); acc = fma(v[0] - ap * dz, v[2] + ad * dl, acc); }
+                    if (v[1] < kBig) { const double dl = -v[3] * (ISL[idx] * dz + 1.0); acc = fma(v[1] + ap * dz, v[3] + ad * dl, acc); }
                 });
                 slot_sum2(acc, dmy);
                 const double mu_aff = n_box > 0.0 ? acc / n_box : 0.0;
                 const double ratio_mu = mu_c > 0.0 ? mu_aff / mu_c : 0.0;
                 sigma_mu = ratio_mu * ratio_mu * ratio_mu * mu_c;
-                const double* arr6[6] = {SU, SLk, LU, LL, DZA, G};
+                const double* arr6[6] = {ISU, ISL, LU, LL, DZA, G};
                 entry_pass(I6{}, arr6, [&](int, int idx, const double (&v)[6]) {
                     const double dz = v[4];
                     double g = v[5];
-                    if (v[0] < kBig) { const double dl = -v[2] + (v[2] / v[0]) * dz; g += (sigma_mu + dz * dl) / v[0]; }
-                    if (v[1] < kBig) { const double dl = -v[3] - (v[3] / v[1]) * dz; g -= (sigma_mu - dz * dl) / v[1]; }
+                    if (v[0] > 0.0) { const double dl = v[2] * (v[0] * dz - 1.0); g = fma(sigma_mu + dz * dl, v[0], g); }
+                    if (v[1] > 0.0) { const double dl = -v[3] * (v[1] * dz + 1.0); g = fma(-(sigma_mu - dz * dl), v[1], g); }
                     G[idx] = g;
                 });
                 __syncwarp(mask);
@@ -545,14 +580,14 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 if (upd) {
                     const double dza = v[4], dz = v[5];
                     if (su < kBig) {
-                        const double dla = -lu + (lu / su) * dza;
-                        const double dlu = (sigma_mu + dza * dla) / su - lu + (lu / su) * dz;
+                        const double iu = ISU[idx], ru = lu * iu;
+                        const double dlu = (sigma_mu + dza * (ru * dza - lu)) * iu - lu + ru * dz;
                         su -= ap * dz; lu += ad * dlu;
                         SU[idx] = su; LU[idx] = lu;
                     }
                     if (sl_ < kBig) {
-                        const double dla = -ll - (ll / sl_) * dza;
-                        const double dll = (sigma_mu - dza * dla) / sl_ - ll - (ll / sl_) * dz;
+                        const double il = ISL[idx], rl = ll * il;
+                        const double dll = (sigma_mu + dza * (rl * dza + ll)) * il - ll - rl * dz;
                         sl_ += ap * dz; ll += ad * dll;
                         SLk[idx] = sl_; LL[idx] = ll;
                     }
