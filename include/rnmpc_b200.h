@@ -50,7 +50,7 @@ typedef struct rnmpc_config {
     const double* xf_ub;     /* [nx]  gf = [xf_ub, -xf_lb] */
     const double* xf_lb;     /* [nx] */
     double h;                /* RK4 step of ddyn (0.05 on the SCP path, dyn/model.py:15) */
-    int qp_max_iter;         /* interior-point iteration cap (default 60 if <= 0) */
+    int qp_max_iter;         /* interior-point iteration cap (default 40 if <= 0) */
     double qp_tol_mu;        /* complementarity tolerance (default 1e-14 if <= 0) */
     double qp_tol_res;       /* dynamics-residual tolerance (default 1e-9 if <= 0) */
 } rnmpc_config;

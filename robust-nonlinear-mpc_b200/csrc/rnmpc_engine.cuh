@@ -60,7 +60,9 @@ IEngine* make_rocket(const rnmpc_config* cfg, int cap, int device);
 // the previous *first-in-step* QP solution, kept across MPC steps; only the primal test is used.
 static __global__ void q3_check_kernel(int B, int nxs, int nus, const double* __restrict__ dX, const double* __restrict__ dU,
                                        double* __restrict__ prevX, double* __restrict__ prevU, int* __restrict__ flags) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per instance: coalesced reads, shuffle max-reduction
+    const int b = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
     if (b >= B) return;
     int f = flags[b];
     if (f & FLAG_FAIL) return;
@@ -69,12 +71,16 @@ static __global__ void q3_check_kernel(int B, int nxs, int nus, const double* __
     double* px = prevX + (size_t)b * nxs;
     double* pu = prevU + (size_t)b * nus;
     double m = 0.0;
-    for (int i = 0; i < nxs; ++i) { m = fmax(m, fabs(x[i] - px[i])); px[i] = x[i]; }
-    for (int i = 0; i < nus; ++i) { m = fmax(m, fabs(u[i] - pu[i])); pu[i] = u[i]; }
-    f &= ~FLAG_Q3;
-    if ((f & FLAG_PREV) && m <= 1e-3) f |= FLAG_Q3;
-    f |= FLAG_PREV;
-    flags[b] = f;
+    for (int i = lane; i < nxs; i += 32) { const double v = x[i]; m = fmax(m, fabs(v - px[i])); px[i] = v; }
+    for (int i = lane; i < nus; i += 32) { const double v = u[i]; m = fmax(m, fabs(v - pu[i])); pu[i] = v; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) {
+        f &= ~FLAG_Q3;
+        if ((f & FLAG_PREV) && m <= 1e-3) f |= FLAG_Q3;
+        f |= FLAG_PREV;
+        flags[b] = f;
+    }
 }
 static __global__ void clear_flag_kernel(int B, int* flags, int bits) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -166,7 +172,7 @@ struct Engine : IEngine {
         device = device_;
         RN_CUDA(cudaSetDevice(device));
         N = cfg->N; cap = cap_; rti = cfg->rti; sls_steps = cfg->sls_steps; h = cfg->h;
-        qp_max_iter = cfg->qp_max_iter > 0 ? cfg->qp_max_iter : 60;
+        qp_max_iter = cfg->qp_max_iter > 0 ? cfg->qp_max_iter : 40;
         qp_tol_mu = cfg->qp_tol_mu > 0 ? cfg->qp_tol_mu : 1e-14;
         qp_tol_res = cfg->qp_tol_res > 0 ? cfg->qp_tol_res : 1e-9;
         P hp;
@@ -354,7 +360,7 @@ struct Engine : IEngine {
             for (int i = 0; i < sls_steps; ++i) {
                 rc = resident_qp(B, -1, x0, st);                        // forward_solve
                 if (rc) return rc;
-                q3_check_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, prevX, prevU, flags);
+                q3_check_kernel<<<(B + 3) / 4, 128, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, prevX, prevU, flags);
                 ++launches;
                 SlsArgs a{};                                            // evaluate_dual_eta + backward_solve + update_tightening
                 a.B = B; a.N = N; a.A = A; a.Bm = Bm; a.mu = mu; a.mu_f = mu_f; a.beta_in = beta; a.beta_f_in = beta_f;

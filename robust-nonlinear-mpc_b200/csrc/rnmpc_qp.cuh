@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
         mu_c = n_box > 0.0 ? acc / n_box : 0.0;
     }
 
-    int it = 0;
+    int it = 0, stalled = 0;
     bool done = (status != 0);
     for (; it < a.max_iter; ++it) {
         if (__all_sync(mask, done)) break;
@@ -610,6 +610,10 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             else {
                 mu_c = mu_new;
                 if (mu_c < a.tol_mu && rp_inf * rp_scale < a.tol_res && it >= 2) done = true;
+                // infeasible / unbounded-dual detection: the iteration makes no progress (steps collapse) while the
+                // dynamics residual or the complementarity stay large -> give up early instead of burning max_iter
+                stalled = (ap < 1e-4 && ad < 1e-4) ? stalled + 1 : 0;
+                if (!done && (stalled >= 3 || mu_c > 1e12)) { status = 2; done = true; }
             }
         }
     }
