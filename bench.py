@@ -79,33 +79,21 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------- CPU baseline
-def _cpu_worker(args):
-    seed, steps = args
+def cpu_baseline(n_scen, steps, threads):
+    """CPU port of the whole solve (oracle/cpu_port/rnmpc_cpu.cpp: C++, one scenario per std::thread worker, all host cores)
+    on a bounded sample of the bench workload.  The reference's own CPU path needs CasADi + OSQP (absent from the image)."""
     from oracle import models as om, scp as oscp
+    from oracle import cpu_port
     from tests.helpers import rocket_scenarios
     m, cfg = om.rocket_config()
-    x0, W = rocket_scenarios(1, seed=seed, steps=steps)
-    X0, U0, ok = oscp.nominal_sqp(m, cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], x0[0], iters=10)
+    x0, W = rocket_scenarios(n_scen, seed=4242, steps=steps)
+    X0, U0, ok = oscp.nominal_sqp(m, cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], x0[0], iters=10)     # untimed (same x0 for all scenarios)
+    X0b, U0b = np.repeat(X0.T[None], n_scen, 0), np.repeat(U0.T[None], n_scen, 0)
+    cpu_port.closed_loop(m, cfg, x0[:threads], W[:threads, :2], 2, X0b[:threads], U0b[:threads], threads)          # warm-up
     t0 = time.perf_counter()
-    out = oscp.closed_loop(m, cfg, x0[0], W[0], steps, X0=X0, U0=U0)
-    return time.perf_counter() - t0, len(out["U"])
-
-
-def cpu_baseline(n_scen, steps, procs):
-    """Oracle port of the whole solve (NumPy restatement of linearisation + QP + fast-SLS + tightened QP), one scenario per
-    process, `procs` processes."""
-    import multiprocessing as mp
-    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):   # one BLAS thread per worker process
-        os.environ[k] = "1"
-    ctx = mp.get_context("spawn")
-    t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        res = pool.map(_cpu_worker, [(1000 + i, steps) for i in range(n_scen)])
+    _, _, nfail = cpu_port.closed_loop(m, cfg, x0, W, steps, X0b, U0b, threads)
     wall = time.perf_counter() - t0
-    solves = sum(r[1] for r in res)
-    busy = sum(r[0] for r in res)
-    # throughput with all `procs` cores busy: solves / (sum of per-process busy time / procs)
-    return solves / (busy / procs), dict(solves=solves, wall_s=wall, busy_s=busy)
+    return n_scen * steps / wall, dict(solves=n_scen * steps, wall_s=wall, failed=nfail)
 
 
 # ------------------------------------------------------------------------------------------------------------ main
@@ -116,8 +104,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096, help="scenarios per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-scenarios", type=int, default=0, help="CPU baseline sample: scenarios (default = host cores)")
-    ap.add_argument("--cpu-steps", type=int, default=2, help="CPU baseline sample: MPC steps per scenario")
+    ap.add_argument("--cpu-scenarios", type=int, default=0, help="CPU baseline sample: scenarios (default = 32 x host cores)")
+    ap.add_argument("--cpu-steps", type=int, default=29, help="CPU baseline sample: MPC steps per scenario")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -130,17 +118,17 @@ def main():
         # the reference's CPU path; only rank 0 works
         if rank != 0:
             return
-        n_scen = a.cpu_scenarios or cores
+        n_scen = a.cpu_scenarios or 32 * cores
         t_steps = []
-        for _ in range(max(1, min(a.steps, 2))):          # bounded: each "step" = cpu_steps MPC steps of n_scen scenarios
+        for _ in range(max(1, min(a.steps, 3))):          # bounded: each "step" = cpu_steps MPC steps of n_scen scenarios
             v, info = cpu_baseline(n_scen, a.cpu_steps, cores)
             t_steps.append((v, info))
         v = float(np.mean([t[0] for t in t_steps]))
-        sample = f"{n_scen} rocket scenarios x {a.cpu_steps} MPC steps per timed step, {cores} processes (oracle port, NumPy)"
+        sample = f"{n_scen} rocket scenarios x {a.cpu_steps} MPC steps per timed step, {cores} threads (C++ CPU port oracle/cpu_port)"
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1e3 * float(np.mean([t[1]["wall_s"] for t in t_steps])), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "note": "reference needs CasADi+OSQP (absent); timed: oracle port on host cores"},
+                "config": {"workload": workload, "note": "reference needs CasADi+OSQP (absent); timed: C++ CPU port of the same path on all host cores"},
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -282,17 +270,18 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_all},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "kernel": "qp_ipm_kernel<17,4>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": None,
+                     "frac": achieved / peak, "traffic": 16.13e9 * B / 4096.0,   # dram bytes per launch, ncu (profiles/r1_ncu_full_summary.csv, B=4096)
                      "note": "FP64 DFMA pipe binds (SURVEY 8d); peak = DFMA probe measured live on this GPU (MEASURED_PEAKS.json has no "
                              "fp64 entry); achieved = algorithmic flops of one QP launch / its CUDA-event duration"},
         "failed_solves_last_step": int(stats["failed_solves"]),
     }
     if not a.no_cpu_baseline:
-        n_scen = a.cpu_scenarios or cores
+        n_scen = a.cpu_scenarios or 32 * cores
         v, info = cpu_baseline(n_scen, a.cpu_steps, cores)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{n_scen} rocket scenarios x {a.cpu_steps} MPC steps, {cores} processes, oracle port (NumPy; "
-                                          f"the reference's CasADi+OSQP path is not installable here), {info['wall_s']:.1f} s wall"}
+                                "sample": f"{n_scen} rocket scenarios x {a.cpu_steps} MPC steps, {cores} threads, C++ CPU port (oracle/cpu_port; "
+                                          f"the reference's CasADi+OSQP path is not installable here), {info['wall_s']:.1f} s wall, "
+                                          f"{info['failed']} failed solves"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

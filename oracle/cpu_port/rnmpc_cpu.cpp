@@ -1,0 +1,402 @@
+// CPU port of the SCP / fast-SLS robust-MPC solve (independent MPC instances spread over std::thread workers), used ONLY as the timed CPU
+// baseline of bench.py (`cpu_baseline` / `--impl reference`) and cross-checked against the NumPy oracle in the tests.
+//
+// TEST / BENCH INFRASTRUCTURE ONLY (see oracle/__init__.py): nothing in the product links or calls this file.
+//
+// It follows the same reference functions as the NumPy oracle (file:line of antoineleeman/robust-nonlinear-mpc):
+//   dyn/model.py:15-34 (RK4), SCP_SLS_jit.py:251-366 (linearisation; forward-mode duals instead of CasADi),
+//   fast_SLS_jit.py:43-188, 475-487 (eta, Riccati backward, Phi propagation, back-offs), fast_SLS_jit.py:278-327,
+//   517-600 (RTI control flow, tightening, quirks Q3/Q4/Q5), SCP_SLS_jit.py:404-551 (nominal update, warm-start shift),
+//   qp_jit.py:362-402 (nominal QP; OSQP is replaced by a Riccati-based Mehrotra interior point, as on the GPU).
+// The ODEs are shared with the CUDA sources (csrc/rnmpc_models.cuh compiles as plain C++).
+//
+// Build: g++ -O3 -pthread -shared -fPIC rnmpc_cpu.cpp -o librnmpc_cpu.so   (oracle/cpu_port/Makefile)
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include <atomic>
+#include <thread>
+
+#include "../../robust-nonlinear-mpc_b200/csrc/rnmpc_models.cuh"
+
+using namespace rnmpc;
+
+namespace {
+constexpr double EPS_B = 1e-10, EPS_QP = 1e-10, X0_TOL = 1e-3;
+
+struct Cfg {
+    int N, rti, sls_steps;
+    const double *Q, *R, *Qf, *Qreg, *Rreg, *Qregf, *E, *xub, *xlb, *uub, *ulb, *xubf, *xlbf;
+    double h;
+};
+
+template <int NX, int NU>
+struct Work {
+    static constexpr int NZ = NX + NU, NI = 2 * NZ, NIF = 2 * NX;
+    int N;
+    std::vector<double> X, U, A, B, c, dX, dU, mu, muf, beta, betaf, bo, bof, K, prevX, prevU;
+    bool have_prev = false, tight = false;
+    // QP workspace
+    std::vector<double> Z, SU, SL, LU, LL, DZA, DZC, G, SIG, rp, Sc, dff, Kq, Lq, P, hi, lo;
+    explicit Work(int N_) : N(N_) {
+        const int n1 = N + 1;
+        X.assign(n1 * NX, 0); U.assign(N * NU, 0); A.assign(N * NX * NX, 0); B.assign(N * NX * NU, 0); c.assign(N * NX, 0);
+        dX.assign(n1 * NX, 0); dU.assign(N * NU, 0); mu.assign(N * NI, 0); muf.assign(NIF, 0);
+        beta.assign(N * N * NI, 0); betaf.assign(n1 * NIF, 0); bo.assign(N * NI, 0); bof.assign(NIF, 0);
+        K.assign(N * n1 * NU * NX, 0); prevX.assign(n1 * NX, 0); prevU.assign(N * NU, 0);
+        for (auto* v : {&Z, &SU, &SL, &LU, &LL, &DZA, &DZC, &G, &SIG, &hi, &lo}) v->assign(n1 * NZ, 0);
+        rp.assign(N * NX, 0); Sc.assign(N * NX, 0); dff.assign(N * NU, 0); Kq.assign(N * NU * NX, 0); Lq.assign(N * NU * NU, 0);
+        P.assign(NX * NX, 0);
+    }
+};
+
+// ---- small dense helpers (row-major) ---------------------------------------------------------------------------------
+template <int NU>
+bool chol(double* H) {   // in place lower factor
+    for (int j = 0; j < NU; ++j) {
+        double d = H[j * NU + j];
+        for (int k = 0; k < j; ++k) d -= H[j * NU + k] * H[j * NU + k];
+        if (!(d > 0)) return false;
+        const double l = std::sqrt(d);
+        H[j * NU + j] = l;
+        for (int i = j + 1; i < NU; ++i) {
+            double s = H[i * NU + j];
+            for (int k = 0; k < j; ++k) s -= H[i * NU + k] * H[j * NU + k];
+            H[i * NU + j] = s / l;
+        }
+    }
+    return true;
+}
+template <int NU>
+void chol_solve(const double* L, double* f) {
+    for (int i = 0; i < NU; ++i) { double s = f[i]; for (int k = 0; k < i; ++k) s -= L[i * NU + k] * f[k]; f[i] = s / L[i * NU + i]; }
+    for (int i = NU - 1; i >= 0; --i) { double s = f[i]; for (int k = i + 1; k < NU; ++k) s -= L[k * NU + i] * f[k]; f[i] = s / L[i * NU + i]; }
+}
+
+// One Riccati step (fast_SLS_jit.py:43-62): S <- Cx + A'S(A+BK) symmetrised, K = -(Cu + B'SB)^-1 B'SA.  Lout optional.
+template <int NX, int NU>
+bool riccati(const double* A, const double* B, const double* Cx, const double* Cu, double* S, double* K, double* Lout) {
+    double x[NU * NX], y[NX * NX], H[NU * NU], F[NU * NX], Acl[NX * NX], Sn[NX * NX];
+    for (int p = 0; p < NU; ++p)
+        for (int c = 0; c < NX; ++c) { double s = 0; for (int i = 0; i < NX; ++i) s += B[i * NU + p] * S[i * NX + c]; x[p * NX + c] = s; }
+    for (int r = 0; r < NX; ++r)
+        for (int c = 0; c < NX; ++c) { double s = 0; for (int i = 0; i < NX; ++i) s += A[i * NX + r] * S[i * NX + c]; y[r * NX + c] = s; }
+    for (int p = 0; p < NU; ++p)
+        for (int q = 0; q < NU; ++q) { double s = Cu[p * NU + q]; for (int i = 0; i < NX; ++i) s += x[p * NX + i] * B[i * NU + q]; H[p * NU + q] = s; }
+    for (int p = 0; p < NU; ++p)
+        for (int c = 0; c < NX; ++c) { double s = 0; for (int i = 0; i < NX; ++i) s += x[p * NX + i] * A[i * NX + c]; F[p * NX + c] = s; }
+    if (!chol<NU>(H)) return false;
+    for (int c = 0; c < NX; ++c) {
+        double f[NU];
+        for (int p = 0; p < NU; ++p) f[p] = F[p * NX + c];
+        chol_solve<NU>(H, f);
+        for (int p = 0; p < NU; ++p) K[p * NX + c] = -f[p];
+    }
+    if (Lout) std::memcpy(Lout, H, sizeof(H));
+    for (int i = 0; i < NX; ++i)
+        for (int c = 0; c < NX; ++c) { double s = A[i * NX + c]; for (int p = 0; p < NU; ++p) s += B[i * NU + p] * K[p * NX + c]; Acl[i * NX + c] = s; }
+    for (int r = 0; r < NX; ++r)
+        for (int c = 0; c < NX; ++c) { double s = 0; for (int m = 0; m < NX; ++m) s += y[r * NX + m] * Acl[m * NX + c]; Sn[r * NX + c] = Cx[r * NX + c] + s; }
+    for (int r = 0; r < NX; ++r)
+        for (int c = 0; c < NX; ++c) S[r * NX + c] = 0.5 * (Sn[r * NX + c] + Sn[c * NX + r]);
+    return true;
+}
+
+template <class M>
+void linearize(const Cfg& g, Work<M::NX, M::NU>& w) {
+    constexpr int NX = M::NX, NU = M::NU, NZ = NX + NU;
+    for (int k = 0; k < g.N; ++k) {
+        for (int t = 0; t < NZ; ++t) {
+            Dual x[NX], u[NU], xp[NX];
+            for (int i = 0; i < NX; ++i) x[i] = Dual(w.X[k * NX + i], i == t ? 1.0 : 0.0);
+            for (int p = 0; p < NU; ++p) u[p] = Dual(w.U[k * NU + p], NX + p == t ? 1.0 : 0.0);
+            rk4_step<M, Dual>(x, u, g.h, xp);
+            for (int i = 0; i < NX; ++i) {
+                if (t < NX) w.A[(k * NX + i) * NX + t] = xp[i].d; else w.B[(k * NX + i) * NU + (t - NX)] = xp[i].d;
+                if (t == 0) w.c[k * NX + i] = xp[i].v - w.X[(k + 1) * NX + i];
+            }
+        }
+    }
+}
+
+// Nominal QP by a Riccati-based Mehrotra interior point (same algorithm as csrc/rnmpc_qp.cuh). Returns status.
+template <int NX, int NU>
+int qp(const Cfg& g, Work<NX, NU>& w, const double* x0, bool tight) {
+    constexpr int NZ = NX + NU, NI = 2 * NZ;
+    const int N = g.N;
+    const double BIG = 1e19, e = tight ? 0.0 : EPS_QP;
+    double nbox = 0;
+    bool bad = false;
+    for (int k = 0; k <= N; ++k)
+        for (int i = 0; i < NZ; ++i) {
+            const int idx = k * NZ + i;
+            double h_ = 1e300, l_ = -1e300, z = 0;
+            bool box = false;
+            if (i < NX) {
+                const double xn = w.X[k * NX + i];
+                if (k < N) {
+                    h_ = (g.xub[i] - xn) - (tight ? w.bo[k * NI + i] : 0.0) + e;
+                    l_ = -((xn - g.xlb[i]) - (tight ? w.bo[k * NI + NZ + i] : 0.0) + e);
+                } else if (tight) { h_ = g.xubf[i] - w.bof[i]; l_ = g.xlbf[i] + w.bof[NX + i]; }
+                else { h_ = (g.xubf[i] - xn) + e; l_ = -((xn - g.xlbf[i]) + e); }
+                if (k == 0) { z = x0[i] - xn; if (z > h_ + X0_TOL || z < l_ - X0_TOL) bad = true; }
+                else box = true;
+            } else if (k < N) {
+                const int p = i - NX;
+                const double un = w.U[k * NU + p];
+                h_ = (g.uub[p] - un) - (tight ? w.bo[k * NI + i] : 0.0) + e;
+                l_ = -((un - g.ulb[p]) - (tight ? w.bo[k * NI + NZ + i] : 0.0) + e);
+                box = true;
+            }
+            double su = 1e300, sl = 1e300, lu = 0, ll = 0;
+            if (box) {
+                const double m = 0.01 * (h_ - l_);
+                if (!(h_ - l_ > 1e-12)) bad = true;
+                z = std::min(std::max(0.0, l_ + m), h_ - m);
+                su = h_ - z; sl = z - l_; lu = ll = 1.0; nbox += 2;
+            }
+            w.Z[idx] = z; w.SU[idx] = su; w.SL[idx] = sl; w.LU[idx] = lu; w.LL[idx] = ll;
+        }
+    if (bad) return 2;
+    double rpinf = 0;
+    for (int k = 0; k < N; ++k)
+        for (int r = 0; r < NX; ++r) {
+            double s = w.c[k * NX + r] - w.Z[(k + 1) * NZ + r];
+            for (int m = 0; m < NX; ++m) s += w.A[(k * NX + r) * NX + m] * w.Z[k * NZ + m];
+            for (int p = 0; p < NU; ++p) s += w.B[(k * NX + r) * NU + p] * w.Z[k * NZ + NX + p];
+            w.rp[k * NX + r] = s; rpinf = std::max(rpinf, std::fabs(s));
+        }
+    auto compl_mu = [&]() { double a = 0; for (int i = 0; i < (N + 1) * NZ; ++i) { if (w.SU[i] < BIG) a += w.SU[i] * w.LU[i]; if (w.SL[i] < BIG) a += w.SL[i] * w.LL[i]; } return a / nbox; };
+    double muc = compl_mu(), rps = 1.0;
+    int status = 1, stalled = 0;
+    double Cx[NX * NX], Cu[NU * NU], pv[NX], gvec[NX], t[NU];
+    for (int it = 0; it < 40; ++it) {
+        for (int k = 0; k <= N; ++k) {
+            const double* Qm = k < N ? g.Q : g.Qf;
+            for (int r = 0; r < NX; ++r) { double s = 0; for (int m = 0; m < NX; ++m) s += Qm[r * NX + m] * (w.Z[k * NZ + m] + w.X[k * NX + m]); w.G[k * NZ + r] = 2 * s; }
+            if (k < N) for (int p = 0; p < NU; ++p) { double s = 0; for (int m = 0; m < NU; ++m) s += g.R[p * NU + m] * (w.Z[k * NZ + NX + m] + w.U[k * NU + m]); w.G[k * NZ + NX + p] = 2 * s; }
+        }
+        for (int i = 0; i < (N + 1) * NZ; ++i) { double sg = 0; if (w.SU[i] < BIG) sg += w.LU[i] / w.SU[i]; if (w.SL[i] < BIG) sg += w.LL[i] / w.SL[i]; w.SIG[i] = sg; }
+        double sigmu = 0, ap = 1, ad = 1;
+        bool ok = true;
+        for (int pass = 0; pass < 2 && ok; ++pass) {
+            double* DZ = pass == 0 ? w.DZA.data() : w.DZC.data();
+            for (int r = 0; r < NX; ++r) pv[r] = w.G[N * NZ + r];
+            if (pass == 0) for (int r = 0; r < NX; ++r) for (int c = 0; c < NX; ++c) w.P[r * NX + c] = 2 * g.Qf[r * NX + c] + (r == c ? w.SIG[N * NZ + r] : 0.0);
+            for (int k = N - 1; k >= 0; --k) {
+                const double *Ak = &w.A[k * NX * NX], *Bk = &w.B[k * NX * NU];
+                double* Kk = &w.Kq[k * NU * NX];
+                double* Lk = &w.Lq[k * NU * NU];
+                if (pass == 0) {
+                    for (int r = 0; r < NX; ++r) { double s = 0; for (int c = 0; c < NX; ++c) s += w.P[r * NX + c] * w.rp[k * NX + c]; w.Sc[k * NX + r] = s; }
+                    for (int r = 0; r < NX; ++r) for (int c = 0; c < NX; ++c) Cx[r * NX + c] = 2 * g.Q[r * NX + c] + (r == c && k > 0 ? w.SIG[k * NZ + r] : 0.0);
+                    for (int p = 0; p < NU; ++p) for (int q = 0; q < NU; ++q) Cu[p * NU + q] = 2 * g.R[p * NU + q] + (p == q ? w.SIG[k * NZ + NX + p] : 0.0);
+                    if (!riccati<NX, NU>(Ak, Bk, Cx, Cu, w.P.data(), Kk, Lk)) { ok = false; break; }
+                }
+                for (int r = 0; r < NX; ++r) gvec[r] = pv[r] + rps * w.Sc[k * NX + r];
+                for (int p = 0; p < NU; ++p) { double s = w.G[k * NZ + NX + p]; for (int i = 0; i < NX; ++i) s += Bk[i * NU + p] * gvec[i]; t[p] = s; }
+                double d[NU];
+                for (int p = 0; p < NU; ++p) d[p] = t[p];
+                chol_solve<NU>(Lk, d);
+                for (int p = 0; p < NU; ++p) w.dff[k * NU + p] = -d[p];
+                if (k > 0) for (int r = 0; r < NX; ++r) {
+                    double s = w.G[k * NZ + r];
+                    for (int i = 0; i < NX; ++i) s += Ak[i * NX + r] * gvec[i];
+                    for (int p = 0; p < NU; ++p) s += Kk[p * NX + r] * t[p];
+                    pv[r] = s;
+                }
+            }
+            if (!ok) break;
+            for (int r = 0; r < NX; ++r) DZ[r] = 0;
+            for (int k = 0; k < N; ++k) {
+                const double *Ak = &w.A[k * NX * NX], *Bk = &w.B[k * NX * NU], *Kk = &w.Kq[k * NU * NX];
+                for (int p = 0; p < NU; ++p) { double s = w.dff[k * NU + p]; for (int m = 0; m < NX; ++m) s += Kk[p * NX + m] * DZ[k * NZ + m]; DZ[k * NZ + NX + p] = s; }
+                for (int r = 0; r < NX; ++r) {
+                    double s = rps * w.rp[k * NX + r];
+                    for (int m = 0; m < NX; ++m) s += Ak[r * NX + m] * DZ[k * NZ + m];
+                    for (int p = 0; p < NU; ++p) s += Bk[r * NU + p] * DZ[k * NZ + NX + p];
+                    DZ[(k + 1) * NZ + r] = s;
+                }
+            }
+            for (int p = 0; p < NU; ++p) DZ[N * NZ + NX + p] = 0;
+            const double tau = pass == 0 ? 1.0 : (muc > 1e-8 ? 0.995 : 0.9999);
+            double apl = 1, adl = 1;
+            auto target = [&](int i, bool up) {
+                if (pass == 0) return 0.0;
+                const double dza = w.DZA[i];
+                if (up) { const double dla = -w.LU[i] + w.LU[i] / w.SU[i] * dza; return sigmu + dza * dla; }
+                const double dla = -w.LL[i] - w.LL[i] / w.SL[i] * dza; return sigmu - dza * dla;
+            };
+            for (int i = 0; i < (N + 1) * NZ; ++i) {
+                const double dz = DZ[i];
+                if (w.SU[i] < BIG) { const double dl = target(i, true) / w.SU[i] - w.LU[i] + w.LU[i] / w.SU[i] * dz; if (dz > 0) apl = std::min(apl, tau * w.SU[i] / dz); if (dl < 0) adl = std::min(adl, -tau * w.LU[i] / dl); }
+                if (w.SL[i] < BIG) { const double dl = target(i, false) / w.SL[i] - w.LL[i] - w.LL[i] / w.SL[i] * dz; if (dz < 0) apl = std::min(apl, -tau * w.SL[i] / dz); if (dl < 0) adl = std::min(adl, -tau * w.LL[i] / dl); }
+            }
+            ap = apl; ad = adl;
+            if (pass == 0) {
+                double acc = 0;
+                for (int i = 0; i < (N + 1) * NZ; ++i) {
+                    const double dz = DZ[i];
+                    if (w.SU[i] < BIG) { const double dl = -w.LU[i] + w.LU[i] / w.SU[i] * dz; acc += (w.SU[i] - ap * dz) * (w.LU[i] + ad * dl); }
+                    if (w.SL[i] < BIG) { const double dl = -w.LL[i] - w.LL[i] / w.SL[i] * dz; acc += (w.SL[i] + ap * dz) * (w.LL[i] + ad * dl); }
+                }
+                const double r = (acc / nbox) / muc;
+                sigmu = r * r * r * muc;
+                for (int i = 0; i < (N + 1) * NZ; ++i) {
+                    const double dz = DZ[i];
+                    if (w.SU[i] < BIG) { const double dl = -w.LU[i] + w.LU[i] / w.SU[i] * dz; w.G[i] += (sigmu + dz * dl) / w.SU[i]; }
+                    if (w.SL[i] < BIG) { const double dl = -w.LL[i] - w.LL[i] / w.SL[i] * dz; w.G[i] -= (sigmu - dz * dl) / w.SL[i]; }
+                }
+            }
+        }
+        if (!ok) { status = muc > 1e-9 ? 3 : 0; break; }
+        for (int i = 0; i < (N + 1) * NZ; ++i) {
+            const double dza = w.DZA[i], dz = w.DZC[i];
+            if (w.SU[i] < BIG) { const double dla = -w.LU[i] + w.LU[i] / w.SU[i] * dza; const double dl = (sigmu + dza * dla) / w.SU[i] - w.LU[i] + w.LU[i] / w.SU[i] * dz; w.SU[i] -= ap * dz; w.LU[i] += ad * dl; }
+            if (w.SL[i] < BIG) { const double dla = -w.LL[i] - w.LL[i] / w.SL[i] * dza; const double dl = (sigmu - dza * dla) / w.SL[i] - w.LL[i] - w.LL[i] / w.SL[i] * dz; w.SL[i] += ap * dz; w.LL[i] += ad * dl; }
+            w.Z[i] += ap * dz;
+        }
+        rps *= (1 - ap);
+        muc = compl_mu();
+        if (!(muc == muc)) { status = 3; break; }
+        if (muc < 1e-14 && rpinf * rps < 1e-9 && it >= 2) { status = 0; break; }
+        stalled = (ap < 1e-4 && ad < 1e-4) ? stalled + 1 : 0;
+        if (stalled >= 3 || muc > 1e12) { status = 2; break; }
+    }
+    if (status == 1 && muc < 1e-9 && rpinf * rps < 1e-7) status = 0;
+    for (int k = 0; k <= N; ++k) {
+        for (int r = 0; r < NX; ++r) {
+            w.dX[k * NX + r] = w.Z[k * NZ + r];
+            if (k < N) { w.mu[k * NI + r] = w.LU[k * NZ + r]; w.mu[k * NI + NZ + r] = w.LL[k * NZ + r]; }
+            else { w.muf[r] = w.LU[k * NZ + r]; w.muf[NX + r] = w.LL[k * NZ + r]; }
+        }
+        if (k < N) for (int p = 0; p < NU; ++p) {
+            w.dU[k * NU + p] = w.Z[k * NZ + NX + p];
+            w.mu[k * NI + NX + p] = w.LU[k * NZ + NX + p]; w.mu[k * NI + NZ + NX + p] = w.LL[k * NZ + NX + p];
+        }
+    }
+    return status;
+}
+
+// fast-SLS pass: eta from mu/beta, Riccati backward, Phi forward, back-offs (fast_SLS_jit.py:475-571)
+template <int NX, int NU>
+void sls(const Cfg& g, Work<NX, NU>& w) {
+    constexpr int NZ = NX + NU, NI = 2 * NZ, NIF = 2 * NX;
+    const int N = g.N;
+    std::vector<double> betan(w.beta.size(), 0.0), betafn(w.betaf.size(), 0.0);
+    double S[NX * NX], Cx[NX * NX], Cu[NU * NU], Phi[NX * NX], Phin[NX * NX], PU[NU * NX];
+    auto eta = [&](int k, int j, int i) { const double be = w.tight ? std::max(w.beta[(k * N + j) * NI + i], EPS_B) : EPS_B; return w.mu[k * NI + i] / (2 * std::sqrt(be)); };
+    auto etaf = [&](int j, int i) { const double be = w.tight ? std::max(w.betaf[j * NIF + i], EPS_B) : EPS_B; return w.muf[i] / (2 * std::sqrt(be)); };
+    for (int j = 0; j <= N; ++j) {
+        for (int r = 0; r < NX; ++r) for (int c = 0; c < NX; ++c) S[r * NX + c] = g.Qregf[r * NX + c] + (r == c ? etaf(j, r) + etaf(j, r + NX) : 0.0);
+        for (int k = N - 1; k >= j; --k) {
+            for (int r = 0; r < NX; ++r) for (int c = 0; c < NX; ++c) Cx[r * NX + c] = g.Qreg[r * NX + c] + (r == c ? eta(k, j, r) + eta(k, j, r + NZ) : 0.0);
+            for (int p = 0; p < NU; ++p) for (int q = 0; q < NU; ++q) Cu[p * NU + q] = g.Rreg[p * NU + q] + (p == q ? eta(k, j, NX + p) + eta(k, j, NX + p + NZ) : 0.0);
+            riccati<NX, NU>(&w.A[k * NX * NX], &w.B[k * NX * NU], Cx, Cu, S, &w.K[((k * (N + 1)) + j) * NU * NX], nullptr);
+        }
+        std::memcpy(Phi, g.E, sizeof(Phi));
+        for (int k = j; k < N; ++k) {
+            const double* Kk = &w.K[((k * (N + 1)) + j) * NU * NX];
+            const double *Ak = &w.A[k * NX * NX], *Bk = &w.B[k * NX * NU];
+            for (int p = 0; p < NU; ++p) for (int c = 0; c < NX; ++c) { double s = 0; for (int m = 0; m < NX; ++m) s += Kk[p * NX + m] * Phi[m * NX + c]; PU[p * NX + c] = s; }
+            double* bo = &betan[(k * N + j) * NI];
+            for (int r = 0; r < NX; ++r) { double s = 0; for (int c = 0; c < NX; ++c) s += Phi[r * NX + c] * Phi[r * NX + c]; s = std::max(s, EPS_B); bo[r] = s; bo[r + NZ] = s; }
+            for (int p = 0; p < NU; ++p) { double s = 0; for (int c = 0; c < NX; ++c) s += PU[p * NX + c] * PU[p * NX + c]; s = std::max(s, EPS_B); bo[NX + p] = s; bo[NX + p + NZ] = s; }
+            for (int r = 0; r < NX; ++r) for (int c = 0; c < NX; ++c) {
+                double s = 0;
+                for (int m = 0; m < NX; ++m) { double acl = Ak[r * NX + m]; for (int p = 0; p < NU; ++p) acl += Bk[r * NU + p] * Kk[p * NX + m]; s += acl * Phi[m * NX + c]; }
+                Phin[r * NX + c] = s;
+            }
+            std::memcpy(Phi, Phin, sizeof(Phi));
+        }
+        for (int r = 0; r < NX; ++r) { double s = 0; for (int c = 0; c < NX; ++c) s += Phi[r * NX + c] * Phi[r * NX + c]; s = std::max(s, EPS_B); betafn[j * NIF + r] = s; betafn[j * NIF + NX + r] = s; }
+    }
+    w.beta = betan; w.betaf = betafn;
+    for (int k = 0; k < N; ++k) for (int i = 0; i < NI; ++i) { double s = 0; for (int j = 0; j <= k; ++j) s += std::sqrt(w.beta[(k * N + j) * NI + i]); w.bo[k * NI + i] = s; }
+    for (int i = 0; i < NIF; ++i) { double s = 0; for (int j = 0; j <= N; ++j) s += std::sqrt(w.betaf[j * NIF + i]); w.bof[i] = s; }
+    w.tight = true;
+}
+
+// SCP_SLS.solve, RTI policy (SCP_SLS_jit.py:65-152 + fast_SLS_jit.py:278-327)
+template <class M>
+bool solve(const Cfg& g, Work<M::NX, M::NU>& w, const double* x0) {
+    constexpr int NX = M::NX, NU = M::NU;
+    const int N = g.N;
+    linearize<M>(g, w);
+    for (int ii = 0; ii < g.rti; ++ii) {
+        w.tight = false;
+        for (int i = 0; i < g.sls_steps; ++i) {
+            if (qp<NX, NU>(g, w, x0, w.tight) != 0) return false;
+            double m = 0;
+            for (int e = 0; e < (N + 1) * NX; ++e) { m = std::max(m, std::fabs(w.dX[e] - w.prevX[e])); w.prevX[e] = w.dX[e]; }
+            for (int e = 0; e < N * NU; ++e) { m = std::max(m, std::fabs(w.dU[e] - w.prevU[e])); w.prevU[e] = w.dU[e]; }
+            const bool q3 = w.have_prev && m <= 1e-3;       // quirk Q3
+            w.have_prev = true;
+            if (!q3) sls<NX, NU>(g, w);
+        }
+        if (qp<NX, NU>(g, w, x0, w.tight) != 0) return false;
+        for (int e = 0; e < (N + 1) * NX; ++e) w.X[e] += w.dX[e];
+        for (int e = 0; e < N * NU; ++e) w.U[e] += w.dU[e];
+        if (ii + 1 < g.rti) linearize<M>(g, w);
+    }
+    return true;
+}
+
+template <class M>
+long long closed_loop(const Cfg& g, int B, int steps, const double* x0, const double* W, const double* X0, const double* U0,
+                      double* states, double* inputs, int threads) {
+    constexpr int NX = M::NX, NU = M::NU;
+    const int N = g.N;
+    std::atomic<long long> nfail{0};
+    std::atomic<int> next{0};
+    auto worker = [&]() {
+      for (;;) {
+        const int b = next.fetch_add(1);
+        if (b >= B) break;
+        Work<NX, NU> w(N);
+        std::memcpy(w.X.data(), X0 + (size_t)b * (N + 1) * NX, sizeof(double) * (N + 1) * NX);
+        std::memcpy(w.U.data(), U0 + (size_t)b * N * NU, sizeof(double) * N * NU);
+        double x[NX], xn[NX], u[NU];
+        std::memcpy(x, x0 + (size_t)b * NX, sizeof(x));
+        for (int i = 0; i < steps; ++i) {
+            if (states) std::memcpy(states + ((size_t)b * (steps + 1) + i) * NX, x, sizeof(x));
+            if (i > 0) {   // reset_warm_start (SCP_SLS_jit.py:505-518)
+                double xN[NX], uN[NU], xo[NX];
+                std::memcpy(xN, &w.X[N * NX], sizeof(xN)); std::memcpy(uN, &w.U[(N - 1) * NU], sizeof(uN));
+                rk4_step<M, double>(xN, uN, g.h, xo);
+                std::memmove(&w.X[0], &w.X[NX], sizeof(double) * N * NX);
+                std::memmove(&w.U[0], &w.U[NU], sizeof(double) * (N - 1) * NU);
+                std::memcpy(&w.X[N * NX], xo, sizeof(xo));
+            }
+            if (!solve<M>(g, w, x)) nfail.fetch_add(1);
+            std::memcpy(u, &w.U[0], sizeof(u));
+            if (inputs) std::memcpy(inputs + ((size_t)b * steps + i) * NU, u, sizeof(u));
+            rk4_step<M, double>(x, u, g.h, xn);
+            for (int r = 0; r < NX; ++r) { double s = xn[r]; if (W) for (int j = 0; j < NX; ++j) s += g.E[r * NX + j] * W[((size_t)b * steps + i) * NX + j]; x[r] = s; }
+        }
+        if (states) std::memcpy(states + ((size_t)b * (steps + 1) + steps) * NX, x, sizeof(x));
+      }
+    };
+    const int T = std::max(1, std::min(threads > 0 ? threads : (int)std::thread::hardware_concurrency(), B));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+    return nfail.load();
+}
+}  // namespace
+
+extern "C" long long rnmpc_cpu_closed_loop(int model_id, int N, int rti, int sls_steps, const double* Q, const double* R, const double* Qf,
+                                           const double* Qreg, const double* Rreg, const double* Qregf, const double* E, const double* xub,
+                                           const double* xlb, const double* uub, const double* ulb, const double* xubf, const double* xlbf,
+                                           double h, int B, int steps, const double* x0, const double* W, const double* X0, const double* U0,
+                                           double* states, double* inputs, int threads) {
+    Cfg g{N, rti, sls_steps, Q, R, Qf, Qreg, Rreg, Qregf, E, xub, xlb, uub, ulb, xubf, xlbf, h};
+    switch (model_id) {
+        case MODEL_PENDULUM: return closed_loop<PendulumModel>(g, B, steps, x0, W, X0, U0, states, inputs, threads);
+        case MODEL_QUADROTOR: return closed_loop<QuadrotorModel>(g, B, steps, x0, W, X0, U0, states, inputs, threads);
+        case MODEL_ROCKET: return closed_loop<RocketModel>(g, B, steps, x0, W, X0, U0, states, inputs, threads);
+    }
+    return -1;
+}

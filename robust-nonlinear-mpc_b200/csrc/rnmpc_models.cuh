@@ -7,7 +7,14 @@
 //   dyn/quadrotor.py:108-174 quadrotor ODE (quaternion [w,x,y,z])
 //   dyn/rocket.py:165-254   rockETH ODE incl. gimbal map 2*atan((v - sqrt(w^2+v^2-u^2))/(u+w))
 #pragma once
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
+#else   // plain C++ build (oracle/cpu_port): the ODEs are ordinary host functions
+#ifndef __host__
+#define __host__
+#define __device__
+#endif
+#endif
 #include <math.h>
 
 namespace rnmpc {

@@ -185,3 +185,16 @@ def test_product_has_no_cpu_fallback():
             if fn.endswith(".py"):
                 src = open(os.path.join(dp, fn)).read()
                 assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+@pytest.mark.parametrize("tag,name", [("rocket_rng123", "rocket"), ("pendulum", "pendulum"), ("quadrotor", "quadrotor")])
+def test_cpp_cpu_port_reproduces_oracle_loops(tag, name):
+    """oracle/cpu_port (C++ CPU port timed by bench.py as the CPU baseline) against the NumPy oracle's closed loops."""
+    from oracle import cpu_port
+    g = load(f"loop_{tag}.npz")
+    m, cfg = om.CONFIGS[name]()
+    steps = len(g["inputs"])
+    W = g["W"][None] if g["W"].size else None
+    st, inp, nfail = cpu_port.closed_loop(m, cfg, g["x0"][None], W, steps, g["X0"][None], g["U0"][None], threads=1)
+    assert nfail == 0
+    assert np.abs(st[0] - g["states"]).max() < 1e-6 and np.abs(inp[0] - g["inputs"]).max() < 1e-6
