@@ -323,7 +323,18 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
 
         double sigma_mu = 0.0, ap = 1.0, ad = 1.0;
         bool chol_ok = true;
+        bool skip_corr = false, corr_skipped = false;
+        double maxp0 = 0.0, maxd0 = 0.0;
         for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1 && __all_sync(mask, skip_corr)) {
+                // every slot of the warp is in the Newton phase (full affine step, complementarity reduced 1000x): take the
+                // predictor step with the fraction-to-boundary rule and skip the corrector's two sweeps
+                corr_skipped = true;
+                const double tau_c = mu_c > 1e-8 ? 0.995 : 0.9999;
+                ap = (maxp0 > tau_c) ? tau_c / maxp0 : 1.0;
+                ad = (maxd0 > tau_c) ? tau_c / maxd0 : 1.0;
+                break;
+            }
             // ---- backward: p_N = G_N ; pass 0 also builds S_N = 2 Qf + SIG_N
             sm.vec[r0] = G[N * NZ + r0];
             if (v1) sm.vec[r1] = G[N * NZ + r1];
@@ -543,6 +554,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             }
             rpm = -rpm; rdm = -rdm;
             slot_min2(rpm, rdm);
+            if (pass == 0) { maxp0 = -rpm; maxd0 = -rdm; }
             double apl = (-rpm > tau) ? tau / (-rpm) : 1.0;
             double adl = (-rdm > tau) ? tau / (-rdm) : 1.0;
             ap = apl; ad = adl;
@@ -557,6 +569,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 });
                 slot_sum2(acc, dmy);
                 const double mu_aff = n_box > 0.0 ? acc / n_box : 0.0;
+                skip_corr = done || (ap >= 0.999 && ad >= 0.999 && mu_aff <= 1e-3 * mu_c);
                 const double ratio_mu = mu_c > 0.0 ? mu_aff / mu_c : 0.0;
                 sigma_mu = ratio_mu * ratio_mu * ratio_mu * mu_c;
                 const double* arr6[6] = {ISU, ISL, LU, LL, DZA, G};
@@ -578,16 +591,17 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             entry_pass(I6{}, arr6, [&](int, int idx, const double (&v)[6]) {
                 double su = v[0], sl_ = v[1], lu = v[2], ll = v[3];
                 if (upd) {
-                    const double dza = v[4], dz = v[5];
+                    const double dza = v[4], dz = corr_skipped ? v[4] : v[5];
+                    const double so = corr_skipped ? 0.0 : 1.0;      // second-order + centring terms only with the corrector
                     if (su < kBig) {
                         const double iu = ISU[idx], ru = lu * iu;
-                        const double dlu = (sigma_mu + dza * (ru * dza - lu)) * iu - lu + ru * dz;
+                        const double dlu = so * (sigma_mu + dza * (ru * dza - lu)) * iu - lu + ru * dz;
                         su -= ap * dz; lu += ad * dlu;
                         SU[idx] = su; LU[idx] = lu;
                     }
                     if (sl_ < kBig) {
                         const double il = ISL[idx], rl = ll * il;
-                        const double dll = (sigma_mu + dza * (rl * dza + ll)) * il - ll - rl * dz;
+                        const double dll = so * (sigma_mu + dza * (rl * dza + ll)) * il - ll - rl * dz;
                         sl_ += ap * dz; ll += ad * dll;
                         SLk[idx] = sl_; LL[idx] = ll;
                     }
