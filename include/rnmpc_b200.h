@@ -35,7 +35,8 @@ typedef struct rnmpc_config {
     int model_id;            /* RNMPC_PENDULUM / RNMPC_QUADROTOR / RNMPC_ROCKET */
     int N;                   /* horizon */
     int rti;                 /* SCP iterations per solve (>0); reference kwarg `rti` */
-    int sls_steps;           /* fast-SLS iterations per SCP iteration (>0); reference kwarg `fast_sls_rti_steps` */
+    int sls_steps;           /* fast-SLS iterations per SCP iteration; reference kwarg `fast_sls_rti_steps`.  0 = iterate until
+                              * check_convergence_socp (cap MAX_ITER = 30, then failure: status 4), fast_SLS_jit.py:298-312 */
     const double* Q;         /* [nx*nx] */
     const double* R;         /* [nu*nu] */
     const double* Qf;        /* [nx*nx] */

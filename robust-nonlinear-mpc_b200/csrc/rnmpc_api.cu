@@ -57,8 +57,8 @@ int rnmpc_model_dims(int model_id, int* nx, int* nu) {
 
 int rnmpc_create(rnmpc_handle** out, const rnmpc_config* cfg, int capacity, int device) {
     if (!out || !cfg) { set_error("null argument"); return -1; }
-    if (cfg->N < 1 || cfg->rti < 1 || cfg->sls_steps < 1 || capacity < 1) {
-        set_error("N, rti, sls_steps and capacity must be >= 1");
+    if (cfg->N < 1 || cfg->rti < 1 || cfg->sls_steps < 0 || capacity < 1) {
+        set_error("N, rti and capacity must be >= 1, sls_steps >= 0");
         return -1;
     }
     int ndev = 0;

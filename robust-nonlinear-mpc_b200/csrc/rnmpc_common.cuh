@@ -21,6 +21,7 @@ constexpr int FLAG_FAIL = 1;    // a QP of this solve failed: the instance is fr
 constexpr int FLAG_Q3 = 2;      // check_convergence_socp returned True: skip backward solve + tightening (Q3)
 constexpr int FLAG_TIGHT = 4;   // tube back-offs were computed in this fast-SLS solve and are in the QP bounds
 constexpr int FLAG_PREV = 8;    // _prev_primal_vec exists (Q3 state)
+constexpr int FLAG_SLSDONE = 32; // converge-to-tolerance mode: this instance's fast-SLS iteration has terminated (fast_SLS_jit.py:305)
 constexpr int FLAG_KVALID = 16; // K / Phi were computed since the last reset_solver_to_zeros (else the reference returns None)
 
 constexpr double kX0Tol = 1e-3;         // tolerated violation of the (redundant) stage-0 state box by the measured state

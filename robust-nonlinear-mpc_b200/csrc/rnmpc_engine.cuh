@@ -59,13 +59,13 @@ IEngine* make_rocket(const rnmpc_config* cfg, int cap, int device);
 // check_convergence_socp (solver/fast_SLS_jit.py:581-600, quirk Q3): per instance max |delta - prev_delta| <= 1e-3 against
 // the previous *first-in-step* QP solution, kept across MPC steps; only the primal test is used.
 static __global__ void q3_check_kernel(int B, int nxs, int nus, const double* __restrict__ dX, const double* __restrict__ dU,
-                                       double* __restrict__ prevX, double* __restrict__ prevU, int* __restrict__ flags) {
+                                       double* __restrict__ prevX, double* __restrict__ prevU, int* __restrict__ flags, int skip_mask) {
     // one warp per instance: coalesced reads, shuffle max-reduction
     const int b = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
     int f = flags[b];
-    if (f & FLAG_FAIL) return;
+    if (f & skip_mask) return;
     const double* x = dX + (size_t)b * nxs;
     const double* u = dU + (size_t)b * nus;
     double* px = prevX + (size_t)b * nxs;
@@ -82,13 +82,30 @@ static __global__ void q3_check_kernel(int B, int nxs, int nus, const double* __
         flags[b] = f;
     }
 }
+// converge-to-tolerance mode of fast_SLS.solve (fast_SLS_jit.py:298-312): an instance whose _step returned True is finished
+static __global__ void mark_sls_done_kernel(int B, int* flags, int* n_open) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int f = flags[b];
+    if ((f & (FLAG_FAIL | FLAG_SLSDONE)) == 0) {
+        if (f & FLAG_Q3) { f |= FLAG_SLSDONE; flags[b] = f; }
+        else atomicAdd(n_open, 1);
+    }
+}
+static __global__ void fail_open_kernel(int B, int* flags, int* status) {
+    // MAX_ITER reached without convergence: the reference reports success False (fast_SLS_jit.py:310-312)
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int f = flags[b];
+    if ((f & (FLAG_FAIL | FLAG_SLSDONE)) == 0) { flags[b] = f | FLAG_FAIL; status[b] = 4; }
+}
 static __global__ void clear_flag_kernel(int B, int* flags, int bits) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) flags[b] &= ~bits;
 }
-static __global__ void set_tight_kernel(int B, int* flags) {
+static __global__ void set_tight_kernel(int B, int* flags, int skip_mask) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < B && (flags[b] & (FLAG_FAIL | FLAG_Q3)) == 0) flags[b] |= FLAG_TIGHT | FLAG_KVALID;
+    if (b < B && (flags[b] & skip_mask) == 0) flags[b] |= FLAG_TIGHT | FLAG_KVALID;
 }
 // socp_step (solver/SCP_SLS_jit.py:426-430): X += dX, U += dU for instances whose fast-SLS solve succeeded
 static __global__ void apply_step_kernel(int B, int nxs, int nus, const double* __restrict__ dX, const double* __restrict__ dU,
@@ -102,10 +119,10 @@ static __global__ void apply_step_kernel(int B, int nxs, int nus, const double* 
     else U[(size_t)b * nus + (e - nxs)] += dU[(size_t)b * nus + (e - nxs)];
 }
 static __global__ void fail_from_status_kernel(int B, const int* __restrict__ st_tmp, int* __restrict__ flags, int* __restrict__ iters_acc,
-                                               const int* __restrict__ iters, int* __restrict__ st_acc) {
+                                               const int* __restrict__ iters, int* __restrict__ st_acc, int skip_mask) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    if (flags[b] & FLAG_FAIL) return;
+    if (flags[b] & skip_mask) return;
     iters_acc[b] += iters[b];
     if (st_tmp[b] != 0) { flags[b] |= FLAG_FAIL; st_acc[b] = st_tmp[b]; }
 }
@@ -158,7 +175,8 @@ struct Engine : IEngine {
     double *X, *U, *A, *Bm, *c, *dX, *dU, *mu, *mu_f, *beta, *beta_f, *backoff, *backoff_f, *K, *cost, *prevX, *prevU;
     double *Phi_x = nullptr, *Phi_u = nullptr;
     double *wZ, *wSU, *wSL, *wLU, *wLL, *wDZA, *wDZC, *wG, *wSIG, *wZN, *wISU, *wISL, *rp, *Sc, *dff, *Kq, *Lq;
-    int *flags, *status, *qp_iters, *iters_tmp, *status_tmp;
+    int *flags, *status, *qp_iters, *iters_tmp, *status_tmp, *n_open;
+    int sls_max_iter = 30;             // fast_SLS.MAX_ITER (fast_SLS_jit.py:206)
 
     template <class T>
     int alloc(const char* name, T*& ptr, size_t count) {
@@ -211,7 +229,7 @@ struct Engine : IEngine {
         rc |= alloc("rp", rp, B * N * NX); rc |= alloc("Sc", Sc, B * N * NX); rc |= alloc("dff", dff, B * N * NU);
         rc |= alloc("Kq", Kq, B * N * NU * NX); rc |= alloc("Lq", Lq, B * N * NU * NU);
         rc |= alloc("flags", flags, B); rc |= alloc("status", status, B); rc |= alloc("qp_iters", qp_iters, B);
-        rc |= alloc("iters_tmp", iters_tmp, B); rc |= alloc("status_tmp", status_tmp, B);
+        rc |= alloc("iters_tmp", iters_tmp, B); rc |= alloc("status_tmp", status_tmp, B); rc |= alloc("n_open", n_open, 1);
         if (rc) return -2;
         const int smem_sls = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * kWarps;
         RN_CUDA(cudaFuncSetAttribute(sls_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
@@ -313,11 +331,11 @@ struct Engine : IEngine {
     }
 
     // one QP on the resident trajectories + failure bookkeeping
-    int resident_qp(int B, int tightened, const double* x0, cudaStream_t st) {
-        int rc = launch_qp(B, tightened, A, Bm, c, X, U, x0, backoff, backoff_f, flags, FLAG_FAIL, dX, dU, mu, mu_f, cost, iters_tmp,
+    int resident_qp(int B, int tightened, const double* x0, cudaStream_t st, int skip_mask = FLAG_FAIL) {
+        int rc = launch_qp(B, tightened, A, Bm, c, X, U, x0, backoff, backoff_f, flags, skip_mask, dX, dU, mu, mu_f, cost, iters_tmp,
                            status_tmp, st);
         if (rc) return rc;
-        fail_from_status_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, status_tmp, flags, qp_iters, iters_tmp, status);
+        fail_from_status_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, status_tmp, flags, qp_iters, iters_tmp, status, skip_mask);
         ++launches;
         RN_CUDA(cudaGetLastError());
         return 0;
@@ -353,31 +371,52 @@ struct Engine : IEngine {
         int rc = linearize(B, X, U, A, Bm, c, st);                      // update_jacobian (SCP_SLS_jit.py:80)
         if (timing) cudaEventRecord(ev[1], st);
         if (rc) return rc;
+        const bool converge_mode = sls_steps <= 0;
+        const int skipf = FLAG_FAIL | FLAG_SLSDONE;
         for (int ii = 0; ii < rti; ++ii) {
-            // fast_SLS.solve (fast_SLS_jit.py:280-296): initialize_backoff, sls_steps x _step, final forward_solve
-            clear_flag_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags, FLAG_Q3 | FLAG_TIGHT);
+            // fast_SLS.solve (fast_SLS_jit.py:278-312): initialize_backoff, then either exactly sls_steps x _step + a final
+            // forward_solve (RTI cap), or _step until check_convergence_socp returns True (cap MAX_ITER, then failure)
+            clear_flag_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags, FLAG_Q3 | FLAG_TIGHT | FLAG_SLSDONE);
             ++launches;
-            for (int i = 0; i < sls_steps; ++i) {
-                rc = resident_qp(B, -1, x0, st);                        // forward_solve
+            const int n_steps = converge_mode ? sls_max_iter : sls_steps;
+            bool all_done = false;
+            for (int i = 0; i < n_steps && !all_done; ++i) {
+                rc = resident_qp(B, -1, x0, st, skipf);                 // forward_solve
                 if (rc) return rc;
-                q3_check_kernel<<<(B + 3) / 4, 128, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, prevX, prevU, flags);
+                q3_check_kernel<<<(B + 3) / 4, 128, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, prevX, prevU, flags, skipf);
                 ++launches;
+                if (converge_mode) {
+                    RN_CUDA(cudaMemsetAsync(n_open, 0, sizeof(int), st));
+                    mark_sls_done_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags, n_open);
+                    ++launches;
+                    int open_host = 0;
+                    RN_CUDA(cudaMemcpyAsync(&open_host, n_open, sizeof(int), cudaMemcpyDeviceToHost, st));
+                    RN_CUDA(cudaStreamSynchronize(st));
+                    if (open_host == 0) { all_done = true; break; }
+                }
                 SlsArgs a{};                                            // evaluate_dual_eta + backward_solve + update_tightening
                 a.B = B; a.N = N; a.A = A; a.Bm = Bm; a.mu = mu; a.mu_f = mu_f; a.beta_in = beta; a.beta_f_in = beta_f;
-                a.flags = flags; a.skip_mask = FLAG_FAIL | FLAG_Q3; a.beta_from_flags = 1;
+                a.flags = flags; a.skip_mask = skipf | FLAG_Q3; a.beta_from_flags = 1;
                 a.K = K; a.Phi_x = phi_enabled ? Phi_x : nullptr; a.Phi_u = phi_enabled ? Phi_u : nullptr;
                 a.beta = beta; a.beta_f = beta_f;
                 if (timing) cudaEventRecord(ev[4], st);
                 rc = launch_sls(B, a, st);
                 if (timing) cudaEventRecord(ev[5], st);
                 if (rc) return rc;
-                rc = launch_backoff(B, beta, beta_f, flags, FLAG_FAIL | FLAG_Q3, backoff, backoff_f, st);
+                rc = launch_backoff(B, beta, beta_f, flags, skipf | FLAG_Q3, backoff, backoff_f, st);
                 if (rc) return rc;
-                set_tight_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags);
+                set_tight_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags, skipf | FLAG_Q3);
                 ++launches;
             }
             if (timing) cudaEventRecord(ev[2], st);
-            rc = resident_qp(B, -1, x0, st);                            // final forward_solve
+            if (!converge_mode) {
+                rc = resident_qp(B, -1, x0, st, FLAG_FAIL);             // final forward_solve
+            } else {
+                // instances still open after MAX_ITER: one last QP with the latest bounds, then failure (fast_SLS_jit.py:310-312)
+                rc = all_done ? 0 : resident_qp(B, -1, x0, st, skipf);
+                fail_open_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags, status);
+                ++launches;
+            }
             if (timing) cudaEventRecord(ev[3], st);
             if (rc) return rc;
             apply_step_kernel<<<(unsigned)(((long long)B * ((N + 1) * NX + N * NU) + 255) / 256), 256, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, X, U, flags);   // socp_step

@@ -63,10 +63,8 @@ class SCP_SLS(OCP):
 
     # ---------------------------------------------------------------------------------------------------- engine
     def _build_engine(self):
-        if self.fast_sls_rti_steps is None or self.fast_sls_rti_steps <= 0:
-            raise NotImplementedError(
-                "fast_sls_rti_steps=None (iterate fast-SLS to convergence, fast_SLS_jit.py:298-312) is not built yet; "
-                "all reference drivers use the RTI cap (fast_sls_rti_steps=1 or 2)")
+        # fast_sls_rti_steps None / <= 0: iterate fast-SLS until its convergence test (fast_SLS_jit.py:298-312) -> sls_steps = 0
+        sls_steps = int(self.fast_sls_rti_steps) if (self.fast_sls_rti_steps is not None and self.fast_sls_rti_steps > 0) else 0
         m = self.m
         if getattr(m, "model_name", None) not in ("pendulum", "quadrotor", "rocket"):
             raise TypeError("model must be one of this package's dyn.Pendulum / dyn.Quadrotor / dyn.Rocket")
@@ -78,7 +76,7 @@ class SCP_SLS(OCP):
         rti = int(self.rti) if (self.rti is not None and self.rti > 0) else 1
         self._engine = BatchSolver(m.model_name, self.N, self.Q, self.R, self.Qf, self.Q_reg, self.R_reg, self.Q_reg_f,
                                    np.asarray(m.E, float), x_ub, x_lb, u_ub, u_lb, xf_ub, xf_lb, rti=rti,
-                                   sls_steps=int(self.fast_sls_rti_steps), capacity=self.batch, device=self.device)
+                                   sls_steps=sls_steps, capacity=self.batch, device=self.device)
         self._engine.enable_timing(True)
         self._has_nominal = False
 
@@ -195,7 +193,7 @@ class SCP_SLS(OCP):
             'backoff': o(backoff), 'backoff_f': o(backoff_f), 'backoff_x': o(backoff_x), 'backoff_u': o(backoff_u),
             'beta': o(beta), 'beta_f': o(beta_f),
             'cost_QP': o(cost_qp), 'cost': o(cost_qp + Qs),
-            'SOCP_steps': o(np.where(tight, int(self.fast_sls_rti_steps), 0)),
+            'SOCP_steps': o(np.where(tight, int(self.fast_sls_rti_steps or 0), 0)),
             'iterations': iterations,
             't_jac_ms': float(tm['t_jac_ms']), 't_qp_ms': float(tm['t_qp_ms']),
             't_backward_ms': float(tm['t_backward_ms']) if tight.all() else float('nan'),

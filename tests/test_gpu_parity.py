@@ -327,3 +327,77 @@ def test_reference_api_drop_in():
     solb = sb.solve(np.stack([g["x0"]] * 3))
     assert solb['success'].all() and solb['primal_x'].shape == (3, 17, 16)
     assert rel(solb['primal_x'][2], g["Xn"][0].T) < TOL_TRAJ
+
+
+@pytest.mark.parametrize("name,N", [("pendulum", 1), ("pendulum", 2), ("pendulum", 6), ("quadrotor", 8), ("rocket", 16), ("rocket", 5)])
+def test_other_horizons(name, N):
+    """Horizons other than 15 (the drivers' --N flag): even N exercises the unpaired middle chain of the fast-SLS kernel,
+    N = 1, 2 the degenerate chains; full solves against the oracle."""
+    m, cfg = om.CONFIGS[name]()
+    cfg = dict(cfg, N=N)
+    from rnmpc_b200.engine import BatchSolver
+    s = BatchSolver(name, N, cfg["Q"], cfg["R"], cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], m.E, m.x_ub, m.x_lb, m.u_ub,
+                    m.u_lb, rti=cfg["rti"], sls_steps=cfg["fast_sls_rti_steps"], capacity=3)
+    nx, nu = m.nx, m.nu
+    rng = np.random.default_rng(N)
+    # fast-SLS kernel on random data
+    A = np.eye(nx) + 0.05 * rng.standard_normal((2, N, nx, nx)); B = 0.05 * rng.standard_normal((2, N, nx, nu))
+    eta = 5e4 * np.abs(rng.standard_normal((2, N, N, m.ni))) * (rng.random((2, N, N, m.ni)) < 0.1)
+    eta_f = 5e4 * np.abs(rng.standard_normal((2, N + 1, m.ni_f))) * (rng.random((2, N + 1, m.ni_f)) < 0.1)
+    out = {k: np_(v) for k, v in s.sls(A, B, eta, eta_f, want_phi=True).items() if v is not None}
+    for b in range(2):
+        S, K = osls.backward_solve(N, nx, nu, A[b], B[b], m.G, m.Gf, eta[b], eta_f[b], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"])
+        Px, Pu = osls.propagate(A[b], B[b], np.stack([m.E] * (N + 1)), K)
+        be, bef, bo, bof = osls.backoff_from_phi(Px, Pu, m.G[:, :nx], m.G[:, nx:], m.Gf, 1e-10)
+        assert rel(out["K"][b], K) < TOL_FP and rel(out["Phi_x"][b], Px) < TOL_FP and rel(out["Phi_u"][b], Pu) < TOL_FP
+        assert rel(out["beta"][b], be) < TOL_FP and rel(out["beta_f"][b], bef) < TOL_FP
+        assert rel(out["backoff"][b], bo) < TOL_FP and rel(out["backoff_f"][b], bof) < TOL_FP
+    # one full solve from a mild initial state
+    x0 = 0.02 * (m.x_ub - m.x_lb) * rng.uniform(-1, 1, nx)
+    if name != "pendulum":
+        x0[6:10] = [1.0, 0.0, 0.0, 0.0] if name == "quadrotor" else x0[6:10]
+    X0 = np.stack([x0 * (1 - k / N) for k in range(N + 1)], axis=1)
+    U0 = np.tile((0.5 * (m.u_lb + m.u_ub))[:, None], (1, N)) if name == "quadrotor" else np.zeros((nu, N))
+    ref = oscp.SCPSLS(N, cfg["Q"], cfg["R"], m, cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], rti=cfg["rti"],
+                      fast_sls_rti_steps=cfg["fast_sls_rti_steps"])
+    ref.set_nominal(X0, U0)
+    sol = ref.solve(x0)
+    s.set_nominal(X0.T[None], U0.T[None])
+    s.solve(x0[None])
+    fl = int(s.buffer("flags", 1)[0])
+    assert bool(sol["success"]) == ((fl & 1) == 0)
+    if sol["success"]:
+        assert relf(s.buffer("X", 1)[0], sol["primal_x"].T, 1e-2) < TOL_TRAJ
+        assert relf(s.buffer("U", 1)[0], sol["primal_u"].T, 1e-2) < TOL_TRAJ
+        if fl & 16:
+            assert rel(s.buffer("K", 1)[0], sol["K"]) < TOL_TRAJ
+    s.close()
+
+
+def test_fast_sls_converge_mode_and_scp_until_convergence():
+    """fast_sls_rti_steps=None (iterate fast-SLS until check_convergence_socp, fast_SLS_jit.py:298-312) and rti=-1 (SCP until
+    max|delta| < epsilon, SCP_SLS_jit.py:108-133) against the oracle, pendulum."""
+    from rnmpc_b200.dyn.pendulum import Pendulum
+    from rnmpc_b200.solver.SCP_SLS_jit import SCP_SLS
+    mo, cfg = om.pendulum_config()
+    N = cfg["N"]
+    m = Pendulum()
+    m.E = mo.E
+    x0 = np.array([0.4, 0.2, 0.1, -0.1])
+    X0 = np.stack([x0 * (1 - k / N) for k in range(N + 1)], axis=1)
+    U0 = np.zeros((1, N))
+    for rti in (2, -1):
+        ref = oscp.SCPSLS(N, cfg["Q"], cfg["R"], mo, cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], rti=rti, fast_sls_rti_steps=None)
+        ref.epsilon_convergence = 1e-7
+        ref.set_nominal(X0, U0)
+        sol_ref = ref.solve(x0)
+        s = SCP_SLS(N, cfg["Q"], cfg["R"], m, cfg["Qf"], Q_reg=cfg["Q_reg"], R_reg=cfg["R_reg"], Q_reg_f=cfg["Q_reg_f"], rti=rti,
+                    fast_sls_rti_steps=None, verbose=False)
+        s.epsilon_convergence = 1e-7
+        s.set_nominal_trajectory(X0, U0)
+        sol = s.solve(x0)
+        assert bool(sol["success"]) == bool(sol_ref["success"])
+        assert sol["iterations"] == sol_ref["iterations"]
+        assert relf(sol["primal_x"], sol_ref["primal_x"], 1e-2) < TOL_TRAJ and relf(sol["primal_u"], sol_ref["primal_u"], 1e-2) < TOL_TRAJ
+        if sol_ref.get("K") is not None and sol["K"] is not None:
+            assert rel(sol["K"], sol_ref["K"]) < TOL_TRAJ
