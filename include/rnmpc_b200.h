@@ -95,6 +95,23 @@ int rnmpc_qp(rnmpc_handle* h, int B, int tightened, const double* d_A, const dou
              double* d_dX, double* d_dU, double* d_mu, double* d_mu_f, double* d_cost, int* d_iters, int* d_status,
              void* stream);
 
+/* The same QP with explicit data, as the reference's QP object holds it after update_dynamics / offset_constraints /
+ * update_ubg / update_q_cost_lin (solver/qp_jit.py:518-628): bounds d_hi, d_lo and linear cost d_q (NULL = 0) in "entry"
+ * layout [B][N+1][nz] (stage k: x_k entries then u_k entries; stage N uses the first nx), dynamics offsets d_c, and the
+ * value d_x0pin [B][nx] the first state is pinned to (QP.solve(x0) pins it to -x0, qp_jit.py:376-379).  The stage-0 state
+ * bounds only serve the feasibility check.  Outputs as rnmpc_qp. */
+int rnmpc_qp_general(rnmpc_handle* h, int B, const double* d_A, const double* d_B, const double* d_c, const double* d_hi,
+                     const double* d_lo, const double* d_q, const double* d_x0pin, double* d_dX, double* d_dU, double* d_mu,
+                     double* d_mu_f, double* d_cost, int* d_iters, int* d_status, void* stream);
+
+/* fast-SLS pass from QP duals: evaluate_dual_eta + backward_solve + update_tightening kernels
+ * (solver/fast_SLS_jit.py:475-571) in one launch.  d_mu [B][N][ni], d_mu_f [B][ni_f]; d_beta_in [B][N][N][ni] /
+ * d_beta_f_in [B][N+1][ni_f] are the previous beta (both NULL = epsilon_backoff, the state after initialize_backoff).
+ * d_beta_in may alias d_beta.  Outputs as rnmpc_sls. */
+int rnmpc_sls_duals(rnmpc_handle* h, int B, const double* d_A, const double* d_B, const double* d_mu, const double* d_mu_f,
+                    const double* d_beta_in, const double* d_beta_f_in, double* d_K, double* d_S, double* d_Phi_x, double* d_Phi_u,
+                    double* d_beta, double* d_beta_f, double* d_backoff, double* d_backoff_f, void* stream);
+
 /* ---- stateful solver on the handle's resident trajectories ----------------------------------------------- */
 
 /* Load the nominal trajectories of B instances (replaces the IPOPT initial guess, SCP_SLS_jit.py:161-188, and is what

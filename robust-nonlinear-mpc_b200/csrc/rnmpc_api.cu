@@ -114,6 +114,21 @@ int rnmpc_qp(rnmpc_handle* h, int B, int tightened, const double* A, const doubl
     if (tightened && (!backoff || !backoff_f)) { set_error("tightened QP needs back-offs"); return -1; }
     return h->e->qp(B, tightened, A, Bm, c, X, U, x0, backoff, backoff_f, dX, dU, mu, mu_f, cost, iters, status, (cudaStream_t)stream);
 }
+int rnmpc_qp_general(rnmpc_handle* h, int B, const double* A, const double* Bm, const double* c, const double* hi, const double* lo,
+                     const double* q, const double* x0pin, double* dX, double* dU, double* mu, double* mu_f, double* cost, int* iters,
+                     int* status, void* stream) {
+    RN_ENTER(h);
+    if (!A || !Bm || !c || !hi || !lo || !x0pin || !dX || !dU || !mu || !mu_f || !cost || !iters || !status) { set_error("null buffer"); return -1; }
+    return h->e->qp_general(B, A, Bm, c, hi, lo, q, x0pin, dX, dU, mu, mu_f, cost, iters, status, (cudaStream_t)stream);
+}
+int rnmpc_sls_duals(rnmpc_handle* h, int B, const double* A, const double* Bm, const double* mu, const double* mu_f, const double* beta_in,
+                    const double* beta_f_in, double* K, double* S, double* Phi_x, double* Phi_u, double* beta, double* beta_f,
+                    double* backoff, double* backoff_f, void* stream) {
+    RN_ENTER(h);
+    if (!A || !Bm || !mu || !mu_f || !K || !beta || !beta_f || !backoff || !backoff_f) { set_error("null buffer"); return -1; }
+    if ((beta_in == nullptr) != (beta_f_in == nullptr)) { set_error("beta_in and beta_f_in go together"); return -1; }
+    return h->e->sls_duals(B, A, Bm, mu, mu_f, beta_in, beta_f_in, K, S, Phi_x, Phi_u, beta, beta_f, backoff, backoff_f, (cudaStream_t)stream);
+}
 int rnmpc_set_nominal(rnmpc_handle* h, int B, const double* X, const double* U, void* stream) {
     RN_ENTER(h);
     return h->e->set_nominal(B, X, U, (cudaStream_t)stream);

@@ -39,6 +39,12 @@ struct IEngine {
     virtual int qp(int B, int tightened, const double* A, const double* Bm, const double* c, const double* X, const double* U,
                    const double* x0, const double* backoff, const double* backoff_f, double* dX, double* dU, double* mu,
                    double* mu_f, double* cost, int* iters, int* status, cudaStream_t st) = 0;
+    virtual int qp_general(int B, const double* A, const double* Bm, const double* c, const double* hi, const double* lo,
+                           const double* q, const double* x0pin, double* dX, double* dU, double* mu, double* mu_f, double* cost,
+                           int* iters, int* status, cudaStream_t st) = 0;
+    virtual int sls_duals(int B, const double* A, const double* Bm, const double* mu, const double* mu_f, const double* beta_in,
+                          const double* beta_f_in, double* K, double* S, double* Phi_x, double* Phi_u, double* beta, double* beta_f,
+                          double* backoff, double* backoff_f, cudaStream_t st) = 0;
     virtual int set_nominal(int B, const double* X, const double* U, cudaStream_t st) = 0;
     virtual int init_nominal(int B, const double* x0, int iters, cudaStream_t st) = 0;
     virtual int solve(int B, const double* x0, cudaStream_t st) = 0;
@@ -299,8 +305,10 @@ struct Engine : IEngine {
     }
     int launch_qp(int B, int tightened, const double* A_, const double* B_, const double* c_, const double* X_, const double* U_,
                   const double* x0, const double* bo, const double* bof, const int* fl, int skip_mask, double* dX_, double* dU_,
-                  double* mu_, double* mu_f_, double* cost_, int* iters_, int* status_, cudaStream_t st) {
+                  double* mu_, double* mu_f_, double* cost_, int* iters_, int* status_, cudaStream_t st, const double* hi_in = nullptr,
+                  const double* lo_in = nullptr, const double* q_lin = nullptr) {
         QpArgs a{};
+        a.hi_in = hi_in; a.lo_in = lo_in; a.q_lin = q_lin;
         a.B = B; a.N = N; a.tightened = tightened; a.max_iter = qp_max_iter; a.tol_mu = qp_tol_mu; a.tol_res = qp_tol_res;
         a.A = A_; a.Bm = B_; a.c = c_; a.Xnom = X_; a.Unom = U_; a.x0 = x0; a.backoff = bo; a.backoff_f = bof;
         a.flags = fl; a.skip_mask = skip_mask;
@@ -322,6 +330,36 @@ struct Engine : IEngine {
         return launch_qp(B, tightened ? 1 : 0, A_, B_, c_, X_, U_, x0, bo, bof, nullptr, 0, dX_, dU_, mu_, mu_f_, cost_, iters_, status_, st);
     }
 
+    int qp_general(int B, const double* A_, const double* B_, const double* c_, const double* hi_, const double* lo_, const double* q_,
+                   const double* x0pin, double* dX_, double* dU_, double* mu_, double* mu_f_, double* cost_, int* iters_, int* status_,
+                   cudaStream_t st) override {
+        if (check_B(B)) return -1;
+        // zero nominal: dX is the decision variable itself, the pinned value is passed as "x0"
+        RN_CUDA(cudaMemsetAsync(dXa_zero(), 0, (size_t)B * ((N + 1) * NX + N * NU) * sizeof(double), st));
+        const double* Xz = dXa_zero();
+        const double* Uz = Xz + (size_t)B * (N + 1) * NX;
+        return launch_qp(B, 0, A_, B_, c_, Xz, Uz, x0pin, nullptr, nullptr, nullptr, 0, dX_, dU_, mu_, mu_f_, cost_, iters_, status_, st,
+                         hi_, lo_, q_);
+    }
+    double* zero_buf = nullptr;
+    double* dXa_zero() {
+        if (zero_buf == nullptr) {
+            cudaMalloc((void**)&zero_buf, (size_t)cap * ((N + 1) * NX + N * NU) * sizeof(double));
+            bufs["zero_buf"] = {(void*)zero_buf, (size_t)cap * ((N + 1) * NX + N * NU) * sizeof(double)};
+        }
+        return zero_buf;
+    }
+    int sls_duals(int B, const double* A_, const double* B_, const double* mu_, const double* mu_f_, const double* beta_in_,
+                  const double* beta_f_in_, double* K_, double* S_, double* Phi_x_, double* Phi_u_, double* beta_, double* beta_f_,
+                  double* backoff_, double* backoff_f_, cudaStream_t st) override {
+        if (B <= 0) return -1;
+        SlsArgs a{};
+        a.B = B; a.N = N; a.A = A_; a.Bm = B_; a.mu = mu_; a.mu_f = mu_f_; a.beta_in = beta_in_; a.beta_f_in = beta_f_in_;
+        a.K = K_; a.S = S_; a.Phi_x = Phi_x_; a.Phi_u = Phi_u_; a.beta = beta_; a.beta_f = beta_f_;
+        int rc = launch_sls(B, a, st);
+        if (rc) return rc;
+        return launch_backoff(B, beta_, beta_f_, nullptr, 0, backoff_, backoff_f_, st);
+    }
     int set_nominal(int B, const double* X_, const double* U_, cudaStream_t st) override {
         if (check_B(B)) return -1;
         RN_CUDA(cudaMemcpyAsync(X, X_, (size_t)B * (N + 1) * NX * sizeof(double), cudaMemcpyDeviceToDevice, st));

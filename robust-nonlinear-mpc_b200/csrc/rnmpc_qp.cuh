@@ -29,6 +29,10 @@ struct QpArgs {
     const double* backoff_f;// [B][ni_f]
     const int* flags;       // [B] or nullptr: instances with (flags & skip_mask) do no work
     int skip_mask;
+    // general mode (QP class drop-in, qp_jit.py): explicit bounds and linear cost in entry layout [B][N+1][nz]; Xnom/Unom are zero
+    const double* hi_in;
+    const double* lo_in;
+    const double* q_lin;
     // outputs
     double* dX;             // [B][N+1][nx]
     double* dU;             // [B][N][nu]
@@ -195,12 +199,8 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                         h_ = (prm->xubf[i] - xn) + e;
                         l_ = -((xn - prm->xlbf[i]) + e);
                     }
-                    if (k == 0) {
-                        // x(0) is pinned to the measurement: its box rows are dropped; a violation beyond kX0Tol (OSQP's
-                        // default eps_abs, which the reference's solver would tolerate) makes the instance infeasible
-                        z = a.x0[(size_t)b * NX + i] - xn;
-                        if (z > h_ + kX0Tol || z < l_ - kX0Tol) bad = 1.0;
-                    } else box = true;
+                    if (k == 0) z = a.x0[(size_t)b * NX + i] - xn;      // x(0) is pinned to the measurement
+                    else box = true;
                 } else if (k < N) {                 // input entry
                     const int p = i - NX;
                     const double un = Un[k * NU + p];
@@ -210,6 +210,10 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     l_ = -((un - prm->ulb[p]) - bl + e);
                     box = true;
                 }
+                if (a.hi_in != nullptr && (en < 2 || k < N)) { h_ = a.hi_in[eoff + idx]; l_ = a.lo_in[eoff + idx]; }
+                // the stage-0 state rows only restate the pinned x(0): they are dropped; a violation beyond kX0Tol (OSQP's default
+                // eps_abs, which the reference's solver would tolerate) makes the instance infeasible
+                if (k == 0 && en < 2 && (z > h_ + kX0Tol || z < l_ - kX0Tol)) bad = 1.0;
                 double su = 1e300, sl_ = 1e300, lu = 0.0, ll = 0.0;
                 if (box) {
                     const bool hu = h_ < kBig, hl = l_ > -kBig;
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 if (dg) {
                     const int i = idx - k * NZ;
                     const double q = (i >= NX) ? qd[2] : (i == r0 ? (k < N ? qd[0] : qfd[0]) : (k < N ? qd[1] : qfd[1]));
-                    G[idx] = 2.0 * q * (v[4] + v[5]);
+                    G[idx] = 2.0 * q * (v[4] + v[5]) + (a.q_lin != nullptr ? a.q_lin[eoff + idx] : 0.0);
                 }
             });
             if (!dg) {
@@ -308,13 +312,13 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                         acc0 = fma(Qm[r0 * NX + m], y, acc0);
                         acc1 = fma(Qm[r1c * NX + m], y, acc1);
                     }
-                    G[k * NZ + r0] = 2.0 * acc0;
-                    if (v1) G[k * NZ + r1] = 2.0 * acc1;
+                    G[k * NZ + r0] = 2.0 * acc0 + (a.q_lin != nullptr ? a.q_lin[eoff + k * NZ + r0] : 0.0);
+                    if (v1) G[k * NZ + r1] = 2.0 * acc1 + (a.q_lin != nullptr ? a.q_lin[eoff + k * NZ + r1] : 0.0);
                     if (vu && k < N) {
                         double acc = 0.0;
 #pragma unroll
                         for (int m = 0; m < NU; ++m) acc = fma(prm->R[sl * NU + m], Z[k * NZ + NX + m] + ZN[k * NZ + NX + m], acc);
-                        G[k * NZ + NX + sl] = 2.0 * acc;
+                        G[k * NZ + NX + sl] = 2.0 * acc + (a.q_lin != nullptr ? a.q_lin[eoff + k * NZ + NX + sl] : 0.0);
                     }
                 }
             }
@@ -655,7 +659,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 if (rr && !v1) continue;
                 const int r = rr ? r1 : r0;
                 const double z = Z[k * NZ + r];
-                acc = fma(z, rr ? q1 : q0, acc);
+                acc = fma(z, (rr ? q1 : q0) + (a.q_lin != nullptr ? a.q_lin[eoff + k * NZ + r] : 0.0), acc);
                 Xo[k * NX + r] = z;
                 const double lu = LU[k * NZ + r], ll = LL[k * NZ + r];
                 if (k < N) { mu[k * NI + r] = lu; mu[k * NI + NZ + r] = ll; }
@@ -666,7 +670,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
 #pragma unroll
                 for (int m = 0; m < NU; ++m) q = fma(prm->R[sl * NU + m], Z[k * NZ + NX + m] + 2.0 * Un[k * NU + m], q);
                 const double z = Z[k * NZ + NX + sl];
-                acc = fma(z, q, acc);
+                acc = fma(z, q + (a.q_lin != nullptr ? a.q_lin[eoff + k * NZ + NX + sl] : 0.0), acc);
                 Uo[k * NU + sl] = z;
                 mu[k * NI + NX + sl] = LU[k * NZ + NX + sl];
                 mu[k * NI + NZ + NX + sl] = LL[k * NZ + NX + sl];

@@ -168,6 +168,34 @@ class BatchSolver:
                                      _ptr(out["cost"]), _ptr(out["iters"]), _ptr(out["status"]), self._stream()))
         return out
 
+    def qp_general(self, A, Bm, c, hi, lo, q, x0pin):
+        """QP with explicit bounds / linear cost in entry layout [B, N+1, nz] (rnmpc_qp_general)."""
+        A, Bm, c, hi, lo, x0pin = (self.dev(t) for t in (A, Bm, c, hi, lo, x0pin))
+        q = None if q is None else self.dev(q)
+        B, N = A.shape[0], self.N
+        out = dict(dX=self.zeros(B, N + 1, self.nx), dU=self.zeros(B, N, self.nu), mu=self.zeros(B, N, self.ni),
+                   mu_f=self.zeros(B, self.ni_f), cost=self.zeros(B), iters=self.zeros(B, dtype=torch.int32),
+                   status=self.zeros(B, dtype=torch.int32))
+        _lib.check(self.lib.rnmpc_qp_general(self._h, B, _ptr(A), _ptr(Bm), _ptr(c), _ptr(hi), _ptr(lo), _ptr(q), _ptr(x0pin),
+                                             _ptr(out["dX"]), _ptr(out["dU"]), _ptr(out["mu"]), _ptr(out["mu_f"]), _ptr(out["cost"]),
+                                             _ptr(out["iters"]), _ptr(out["status"]), self._stream()))
+        return out
+
+    def sls_duals(self, A, Bm, mu, mu_f, beta=None, beta_f=None, want_phi=True):
+        """fast-SLS pass from QP duals (rnmpc_sls_duals); beta/beta_f None = epsilon (state after initialize_backoff)."""
+        A, Bm, mu, mu_f = (self.dev(t) for t in (A, Bm, mu, mu_f))
+        B, N, nx, nu = A.shape[0], self.N, self.nx, self.nu
+        bi = None if beta is None else self.dev(beta)
+        bfi = None if beta_f is None else self.dev(beta_f)
+        out = dict(K=self.zeros(B, N, N + 1, nu, nx), beta=self.zeros(B, N, N, self.ni), beta_f=self.zeros(B, N + 1, self.ni_f),
+                   backoff=self.zeros(B, N, self.ni), backoff_f=self.zeros(B, self.ni_f), S=self.zeros(B, N + 1, N + 1, nx, nx))
+        out["Phi_x"] = self.zeros(B, N + 1, N + 1, nx, nx) if want_phi else None
+        out["Phi_u"] = self.zeros(B, N, N + 1, nu, nx) if want_phi else None
+        _lib.check(self.lib.rnmpc_sls_duals(self._h, B, _ptr(A), _ptr(Bm), _ptr(mu), _ptr(mu_f), _ptr(bi), _ptr(bfi), _ptr(out["K"]),
+                                            _ptr(out["S"]), _ptr(out["Phi_x"]), _ptr(out["Phi_u"]), _ptr(out["beta"]), _ptr(out["beta_f"]),
+                                            _ptr(out["backoff"]), _ptr(out["backoff_f"]), self._stream()))
+        return out
+
     # -- stateful solver ---------------------------------------------------------------------------------------------
     def set_nominal(self, X, U):
         X, U = self.dev(X), self.dev(U)

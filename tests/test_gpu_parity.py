@@ -401,3 +401,40 @@ def test_fast_sls_converge_mode_and_scp_until_convergence():
         assert relf(sol["primal_x"], sol_ref["primal_x"], 1e-2) < TOL_TRAJ and relf(sol["primal_u"], sol_ref["primal_u"], 1e-2) < TOL_TRAJ
         if sol_ref.get("K") is not None and sol["K"] is not None:
             assert rel(sol["K"], sol_ref["K"]) < TOL_TRAJ
+
+
+def test_fast_sls_and_qp_class_drop_ins():
+    """The lower-level drop-ins: ``QP`` (qp_jit.py) and ``fast_SLS`` (fast_SLS_jit.py) with the reference's call sequence
+    (update_dynamics_list -> update_linear_cost -> solve), against the oracle's FastSLS on a rocket linearisation."""
+    from rnmpc_b200.dyn.LTV import LTV
+    from rnmpc_b200.dyn.rocket import Rocket
+    from rnmpc_b200.solver.fast_SLS_jit import fast_SLS
+    g = load("loop_rocket_rng123.npz")
+    mo, cfg = om.rocket_config()
+    N = cfg["N"]
+    m = Rocket(); m.E = mo.E
+    ref = oscp.SCPSLS(N, cfg["Q"], cfg["R"], mo, cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], rti=1, fast_sls_rti_steps=2)
+    ref.set_nominal(g["X0"].T, g["U0"].T)
+    ref.update_jacobian()
+    A, B, c, g_list = ref.cur["A_list"], ref.cur["B_list"], ref.cur["c_offset_list"], ref.cur["g_list"]
+    q = 2 * (ref.H @ ref.cur["primal_vec"])
+    f = fast_SLS(N, cfg["Q"], cfg["R"], LTV(m, N), cfg["Qf"])
+    f.Q_reg, f.R_reg, f.Q_reg_f = cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"]          # as SCP_SLS_jit.py:386-388
+    f.verbose = False
+    f.set_rti_steps(2)
+    f.update_dynamics_list(A, B, [m.E] * (N + 1), g_list, [ci.reshape(-1, 1) for ci in c])
+    f.update_linear_cost(q)
+    x_arg = g["X0"][0] - g["x0"]
+    sol = f.solve(x_arg)
+    sol_ref = ref.fast.solve(x_arg)
+    assert sol["success"] and sol_ref["success"]
+    assert sol["iteration_number"] == sol_ref["iteration_number"] == 2
+    for key in ("primal_x", "primal_u", "dual_mu", "dual_mu_f", "K", "Phi_x", "Phi_u", "beta", "backoff", "backoff_x", "backoff_u", "eta"):
+        assert relf(sol[key], sol_ref[key], 1e-3) < TOL_TRAJ, key
+    assert sol["K_mat"].shape == (N * 4, (N + 1) * 17) and sol["Phi_x_mat"].shape == ((N + 1) * 17, (N + 1) * 17)
+    assert abs(sol["cost_nominal"] - sol_ref["cost_nominal"]) < 1e-5 * abs(sol_ref["cost_nominal"])
+    # QP object alone: the stored bounds follow the reference's bookkeeping
+    qp = f.solver_forward
+    assert np.allclose(qp.ubg, ref.fast.ubg) and np.array_equal(np.isneginf(qp.lbg), np.isneginf(ref.fast.lbg))
+    qp.reset_ubg(); qp.reset_lbg(); qp.reset_q_cost_lin()
+    assert not qp.q_cost_lin.any()
