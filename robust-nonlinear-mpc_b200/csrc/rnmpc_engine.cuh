@@ -181,7 +181,9 @@ struct Engine : IEngine {
     double *X, *U, *A, *Bm, *c, *dX, *dU, *mu, *mu_f, *beta, *beta_f, *backoff, *backoff_f, *K, *cost, *prevX, *prevU;
     double *Phi_x = nullptr, *Phi_u = nullptr;
     double *wZ, *wSU, *wSL, *wLU, *wLL, *wDZA, *wDZC, *wG, *wSIG, *wZN, *wISU, *wISL, *rp, *Sc, *dff, *Kq, *Lq;
-    int *flags, *status, *qp_iters, *iters_tmp, *status_tmp, *n_open;
+    int *flags, *status, *qp_iters, *iters_tmp, *status_tmp, *n_open, *ws_valid;
+    bool have_solution = false, shifted_since_solve = false;   // host-side warm-start bookkeeping
+    int warm_enabled = 1;
     int sls_max_iter = 30;             // fast_SLS.MAX_ITER (fast_SLS_jit.py:206)
 
     template <class T>
@@ -235,7 +237,7 @@ struct Engine : IEngine {
         rc |= alloc("rp", rp, B * N * NX); rc |= alloc("Sc", Sc, B * N * NX); rc |= alloc("dff", dff, B * N * NU);
         rc |= alloc("Kq", Kq, B * N * NU * NX); rc |= alloc("Lq", Lq, B * N * NU * NU);
         rc |= alloc("flags", flags, B); rc |= alloc("status", status, B); rc |= alloc("qp_iters", qp_iters, B);
-        rc |= alloc("iters_tmp", iters_tmp, B); rc |= alloc("status_tmp", status_tmp, B); rc |= alloc("n_open", n_open, 1);
+        rc |= alloc("iters_tmp", iters_tmp, B); rc |= alloc("status_tmp", status_tmp, B); rc |= alloc("n_open", n_open, 1); rc |= alloc("ws_valid", ws_valid, B);
         if (rc) return -2;
         const int smem_sls = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * kWarps;
         RN_CUDA(cudaFuncSetAttribute(sls_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
@@ -306,8 +308,9 @@ struct Engine : IEngine {
     int launch_qp(int B, int tightened, const double* A_, const double* B_, const double* c_, const double* X_, const double* U_,
                   const double* x0, const double* bo, const double* bof, const int* fl, int skip_mask, double* dX_, double* dU_,
                   double* mu_, double* mu_f_, double* cost_, int* iters_, int* status_, cudaStream_t st, const double* hi_in = nullptr,
-                  const double* lo_in = nullptr, const double* q_lin = nullptr) {
+                  const double* lo_in = nullptr, const double* q_lin = nullptr, int warm_mode = 0) {
         QpArgs a{};
+        a.warm = warm_enabled ? warm_mode : 0; a.ws_valid = ws_valid;
         a.hi_in = hi_in; a.lo_in = lo_in; a.q_lin = q_lin;
         a.B = B; a.N = N; a.tightened = tightened; a.max_iter = qp_max_iter; a.tol_mu = qp_tol_mu; a.tol_res = qp_tol_res;
         a.A = A_; a.Bm = B_; a.c = c_; a.Xnom = X_; a.Unom = U_; a.x0 = x0; a.backoff = bo; a.backoff_f = bof;
@@ -327,7 +330,9 @@ struct Engine : IEngine {
            const double* x0, const double* bo, const double* bof, double* dX_, double* dU_, double* mu_, double* mu_f_, double* cost_,
            int* iters_, int* status_, cudaStream_t st) override {
         if (check_B(B)) return -1;
-        return launch_qp(B, tightened ? 1 : 0, A_, B_, c_, X_, U_, x0, bo, bof, nullptr, 0, dX_, dU_, mu_, mu_f_, cost_, iters_, status_, st);
+        int rc = launch_qp(B, tightened ? 1 : 0, A_, B_, c_, X_, U_, x0, bo, bof, nullptr, 0, dX_, dU_, mu_, mu_f_, cost_, iters_, status_, st);
+        if (!rc) RN_CUDA(cudaMemsetAsync(ws_valid, 0, (size_t)B * sizeof(int), st));   // the workspace no longer belongs to the resident solve
+        return rc;
     }
 
     int qp_general(int B, const double* A_, const double* B_, const double* c_, const double* hi_, const double* lo_, const double* q_,
@@ -338,8 +343,10 @@ struct Engine : IEngine {
         RN_CUDA(cudaMemsetAsync(dXa_zero(), 0, (size_t)B * ((N + 1) * NX + N * NU) * sizeof(double), st));
         const double* Xz = dXa_zero();
         const double* Uz = Xz + (size_t)B * (N + 1) * NX;
-        return launch_qp(B, 0, A_, B_, c_, Xz, Uz, x0pin, nullptr, nullptr, nullptr, 0, dX_, dU_, mu_, mu_f_, cost_, iters_, status_, st,
-                         hi_, lo_, q_);
+        int rc = launch_qp(B, 0, A_, B_, c_, Xz, Uz, x0pin, nullptr, nullptr, nullptr, 0, dX_, dU_, mu_, mu_f_, cost_, iters_, status_, st,
+                           hi_, lo_, q_);
+        if (!rc) RN_CUDA(cudaMemsetAsync(ws_valid, 0, (size_t)B * sizeof(int), st));
+        return rc;
     }
     double* zero_buf = nullptr;
     double* dXa_zero() {
@@ -365,13 +372,15 @@ struct Engine : IEngine {
         RN_CUDA(cudaMemcpyAsync(X, X_, (size_t)B * (N + 1) * NX * sizeof(double), cudaMemcpyDeviceToDevice, st));
         RN_CUDA(cudaMemcpyAsync(U, U_, (size_t)B * N * NU * sizeof(double), cudaMemcpyDeviceToDevice, st));
         RN_CUDA(cudaMemsetAsync(flags, 0, (size_t)B * sizeof(int), st));
+        RN_CUDA(cudaMemsetAsync(ws_valid, 0, (size_t)B * sizeof(int), st));
+        have_solution = false; shifted_since_solve = false;
         return 0;
     }
 
     // one QP on the resident trajectories + failure bookkeeping
-    int resident_qp(int B, int tightened, const double* x0, cudaStream_t st, int skip_mask = FLAG_FAIL) {
+    int resident_qp(int B, int tightened, const double* x0, cudaStream_t st, int skip_mask = FLAG_FAIL, int warm_mode = 0) {
         int rc = launch_qp(B, tightened, A, Bm, c, X, U, x0, backoff, backoff_f, flags, skip_mask, dX, dU, mu, mu_f, cost, iters_tmp,
-                           status_tmp, st);
+                           status_tmp, st, nullptr, nullptr, nullptr, warm_mode);
         if (rc) return rc;
         fail_from_status_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, status_tmp, flags, qp_iters, iters_tmp, status, skip_mask);
         ++launches;
@@ -386,10 +395,12 @@ struct Engine : IEngine {
         RN_CUDA(cudaMemsetAsync(flags, 0, (size_t)B * sizeof(int), st));
         RN_CUDA(cudaMemsetAsync(status, 0, (size_t)B * sizeof(int), st));
         RN_CUDA(cudaMemsetAsync(qp_iters, 0, (size_t)B * sizeof(int), st));
+        RN_CUDA(cudaMemsetAsync(ws_valid, 0, (size_t)B * sizeof(int), st));
+        have_solution = false; shifted_since_solve = false;
         for (int it = 0; it < iters; ++it) {
             int rc = linearize(B, X, U, A, Bm, c, st);
             if (rc) return rc;
-            rc = resident_qp(B, 0, x0, st);
+            rc = resident_qp(B, 0, x0, st, FLAG_FAIL, it > 0 ? 1 : 0);   // multipliers of the previous SQP iterate
             if (rc) return rc;
             apply_step_kernel<<<(unsigned)(((long long)B * ((N + 1) * NX + N * NU) + 255) / 256), 256, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, X, U, flags);
             ++launches;
@@ -419,7 +430,10 @@ struct Engine : IEngine {
             const int n_steps = converge_mode ? sls_max_iter : sls_steps;
             bool all_done = false;
             for (int i = 0; i < n_steps && !all_done; ++i) {
-                rc = resident_qp(B, -1, x0, st, skipf);                 // forward_solve
+                // warm start: first QP of a solve <- multipliers of the previous solve (shifted if reset_warm_start ran); later QPs of
+                // the same linearisation <- previous iterate and multipliers (only the bounds moved)
+                const int wm = (i > 0) ? (1 | 4) : (ii > 0 ? 1 : (have_solution ? (shifted_since_solve ? (1 | 2) : 1) : 0));
+                rc = resident_qp(B, -1, x0, st, skipf, wm);            // forward_solve
                 if (rc) return rc;
                 q3_check_kernel<<<(B + 3) / 4, 128, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, prevX, prevU, flags, skipf);
                 ++launches;
@@ -448,10 +462,10 @@ struct Engine : IEngine {
             }
             if (timing) cudaEventRecord(ev[2], st);
             if (!converge_mode) {
-                rc = resident_qp(B, -1, x0, st, FLAG_FAIL);             // final forward_solve
+                rc = resident_qp(B, -1, x0, st, FLAG_FAIL, 1 | 4);      // final forward_solve
             } else {
                 // instances still open after MAX_ITER: one last QP with the latest bounds, then failure (fast_SLS_jit.py:310-312)
-                rc = all_done ? 0 : resident_qp(B, -1, x0, st, skipf);
+                rc = all_done ? 0 : resident_qp(B, -1, x0, st, skipf, 1 | 4);
                 fail_open_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags, status);
                 ++launches;
             }
@@ -464,6 +478,7 @@ struct Engine : IEngine {
                 if (rc) return rc;                                      // the last iteration is dead work and is not run
             }
         }
+        have_solution = true; shifted_since_solve = false;
         RN_CUDA(cudaGetLastError());
         return 0;
     }
@@ -474,6 +489,7 @@ struct Engine : IEngine {
         ++launches;
         clear_flag_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags, FLAG_KVALID);   // fast_SLS.reset_solver_to_zeros drops K / Phi
         ++launches;
+        shifted_since_solve = true;
         RN_CUDA(cudaGetLastError());
         return 0;
     }

@@ -56,6 +56,9 @@ struct QpArgs {
     double* ISU;            // 1/SU (0 where there is no bound)
     double* ISL;            // 1/SL
     int diag_cost;          // 1: Q, R, Qf are diagonal (all reference drivers) -> element-wise gradient
+    int warm;               // warm start from the workspace's previous solution of the same instance: bit0 multipliers, bit1 shifted by one
+                            // stage (previous MPC step), bit2 primal iterate; a failed warm-started solve is repeated from the cold start
+    int* ws_valid;          // [B] workspace holds a converged solution
     double* rp;             // [B][N][nx]     dynamics residual at the initial point
     double* Sc;             // [B][N][nx]     S_{k+1} rp_k
     double* dff;            // [B][N][nu]     feed-forward
@@ -172,6 +175,16 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     int status = 0;
     const bool tight = a.tightened < 0 ? ((a.flags[b] & FLAG_TIGHT) != 0) : (a.tightened != 0);
     double n_box = 0.0;
+    bool warm = (a.warm != 0) && (a.ws_valid != nullptr) && (a.ws_valid[b] != 0);
+    int it = 0, it_total = 0;
+    double rp_scale = 1.0, rp_inf = 0.0, mu_c = 1.0;
+    constexpr double kMuWarm = 1e-2, kFracWarm = 1e-3;
+    constexpr int kWarmCap = 15;
+    bool structural = false;       // infeasible by construction (crossed bounds / x(0) outside its box): no retry
+    bool act = true;               // this slot (re)starts in the current attempt
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (act) { status = 0; rp_scale = 1.0; }
+    double n_box_new = 0.0;
 
     // ------------------------------------------------------------------ bounds, initial point, slacks, duals
     {
@@ -217,21 +230,32 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 double su = 1e300, sl_ = 1e300, lu = 0.0, ll = 0.0;
                 if (box) {
                     const bool hu = h_ < kBig, hl = l_ > -kBig;
+                    double z0 = 0.0, lu0 = 1.0, ll0 = 1.0;
+                    if (warm) {
+                        // previous solution of this instance (same workspace); bit1: the multipliers of the next stage (the
+                        // trajectories were shifted by one stage since); reads run ahead of this lane's own writes
+                        const int ks = (a.warm & 2) ? ((en < 2) ? (k + 1 <= N ? k + 1 : N) : (k + 1 < N ? k + 1 : N - 1)) : k;
+                        lu0 = LU[ks * NZ + i]; ll0 = LL[ks * NZ + i];
+                        if (a.warm & 4) z0 = Z[idx];
+                    }
                     if (hu && hl) {
-                        const double m = 0.01 * (h_ - l_);
+                        const double m = (warm ? kFracWarm : 0.01) * (h_ - l_);
                         if (!(h_ - l_ > 1e-12)) bad = 1.0;
-                        z = fmin(fmax(0.0, l_ + m), h_ - m);
-                    } else if (hu) z = fmin(0.0, h_ - 1.0);
-                    else if (hl) z = fmax(0.0, l_ + 1.0);
-                    if (hu) { su = h_ - z; lu = 1.0; n_box += 1.0; }
-                    if (hl) { sl_ = z - l_; ll = 1.0; n_box += 1.0; }
+                        z = fmin(fmax(z0, l_ + m), h_ - m);
+                    } else if (hu) z = fmin(z0, h_ - 1.0);
+                    else if (hl) z = fmax(z0, l_ + 1.0);
+                    if (hu) { su = h_ - z; lu = warm ? fmax(lu0, kMuWarm / su) : 1.0; n_box_new += 1.0; }
+                    if (hl) { sl_ = z - l_; ll = warm ? fmax(ll0, kMuWarm / sl_) : 1.0; n_box_new += 1.0; }
                 }
-                Z[idx] = z; SU[idx] = su; SLk[idx] = sl_; LU[idx] = lu; LL[idx] = ll;
+                if (act) { Z[idx] = z; SU[idx] = su; SLk[idx] = sl_; LU[idx] = lu; LL[idx] = ll; }
                 ZN[idx] = (en < 2) ? Xn[k * NX + i] : (k < N ? Un[k * NU + (i - NX)] : 0.0);
             }
         }
-        slot_sum2(bad, n_box);
-        if (bad > 0.0) status = 2;
+        slot_sum2(bad, n_box_new);
+        if (act) {
+            n_box = n_box_new;
+            if (bad > 0.0) { status = 2; structural = true; }
+        }
         __syncwarp(mask);
         // dynamics residual at the initial point: rp_k = A x_k + B u_k + c_k - x_{k+1}
         for (int k = 0; k < N; ++k) {
@@ -251,13 +275,14 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 acc0 = fma(__ldg(Bk + r0 * NU + p), up, acc0);
                 acc1 = fma(__ldg(Bk + r1c * NU + p), up, acc1);
             }
-            rp[k * NX + r0] = acc0;
-            if (v1) rp[k * NX + r1] = acc1;
+            if (act) {
+                rp[k * NX + r0] = acc0;
+                if (v1) rp[k * NX + r1] = acc1;
+            }
         }
         __syncwarp(mask);
     }
 
-    double rp_scale = 1.0, rp_inf = 0.0;
     {
         double m0 = 0.0, dmy = 0.0;
         for (int k = 0; k < N; ++k) {
@@ -266,9 +291,8 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
         }
         m0 = -m0;
         slot_min2(m0, dmy);
-        rp_inf = -m0;
+        if (act) rp_inf = -m0;
     }
-    double mu_c = 1.0;     // all complementarity products start at su*1 ... computed below
     {
         double acc = 0.0, dmy = 0.0;
         const double* arr[4] = {SU, SLk, LU, LL};
@@ -277,12 +301,14 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             if (v[1] < kBig) acc = fma(v[1], v[3], acc);
         });
         slot_sum2(acc, dmy);
-        mu_c = n_box > 0.0 ? acc / n_box : 0.0;
+        if (act) mu_c = n_box > 0.0 ? acc / n_box : 0.0;
     }
 
-    int it = 0, stalled = 0;
-    bool done = (status != 0);
-    for (; it < a.max_iter; ++it) {
+    int stalled = 0;
+    bool done = (status != 0) || !act;
+    // a warm-started attempt that has not converged after kWarmCap iterations is abandoned for the cold start
+    const int it_cap = (attempt == 0 && __any_sync(mask, warm)) ? min(a.max_iter, kWarmCap) : a.max_iter;
+    for (it = 0; it < it_cap; ++it) {
         if (__all_sync(mask, done)) break;
         __syncwarp(mask);
         // ---- P1: reciprocal slacks, barrier diagonal SIG and gradient G = 2 H (z + z_nom)
@@ -330,15 +356,8 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
         bool skip_corr = false, corr_skipped = false;
         double maxp0 = 0.0, maxd0 = 0.0;
         for (int pass = 0; pass < 2; ++pass) {
-            if (pass == 1 && __all_sync(mask, skip_corr)) {
-                // every slot of the warp is in the Newton phase (full affine step, complementarity reduced 1000x): take the
-                // predictor step with the fraction-to-boundary rule and skip the corrector's two sweeps
-                corr_skipped = true;
-                const double tau_c = mu_c > 1e-8 ? 0.995 : 0.9999;
-                ap = (maxp0 > tau_c) ? tau_c / maxp0 : 1.0;
-                ad = (maxd0 > tau_c) ? tau_c / maxd0 : 1.0;
-                break;
-            }
+            // the corrector's two sweeps are skipped when every slot of the warp is in the Newton phase (see below)
+            if (pass == 1 && __all_sync(mask, skip_corr)) break;
             // ---- backward: p_N = G_N ; pass 0 also builds S_N = 2 Qf + SIG_N
             sm.vec[r0] = G[N * NZ + r0];
             if (v1) sm.vec[r1] = G[N * NZ + r1];
@@ -587,6 +606,15 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 __syncwarp(mask);
             }
         }
+        if (skip_corr) {
+            // Newton phase of this slot (full affine step, complementarity reduced 1000x): take the predictor step with the
+            // fraction-to-boundary rule.  The decision is per slot -- whether the warp executed the corrector for a neighbour
+            // does not change this instance's iterates (results do not depend on the position in the batch).
+            corr_skipped = true;
+            const double tau_c = mu_c > 1e-8 ? 0.995 : 0.9999;
+            ap = (maxp0 > tau_c) ? tau_c / maxp0 : 1.0;
+            ad = (maxd0 > tau_c) ? tau_c / maxd0 : 1.0;
+        }
         // ---- P4: update (slots still iterating) and new complementarity
         double acc = 0.0, dmy = 0.0;
         {
@@ -636,6 +664,13 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
         }
     }
     if (!done && status == 0) status = (mu_c < 1e-9 && rp_inf * rp_scale < 1e-7) ? 0 : 1;
+    if (act) it_total += it;
+    // a warm start that did not converge is repeated from the cold start (whole warp: the slots run in lock-step)
+    const bool retry = act && status != 0 && !structural && (warm || it_cap < a.max_iter);
+    if (attempt == 1 || !__any_sync(mask, retry)) break;
+    act = retry;                   // converged slots keep their solution and idle through the second attempt
+    warm = false;
+  }
 
     // ---- outputs in the reference layouts + objective  x'Hx + q'x  (qp_jit.py:401, P = 2H, q = 2 H y_nom)
     {
@@ -679,8 +714,9 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
         slot_sum2(acc, dmy);
         if (sl == 0) {
             a.cost[b] = acc;
-            a.iters[b] = it;
+            a.iters[b] = it_total;
             a.status[b] = status;
+            if (a.ws_valid != nullptr) a.ws_valid[b] = (status == 0);
         }
     }
 }
