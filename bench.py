@@ -104,6 +104,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096, help="scenarios per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--groups", type=int, default=1, help="independent scenario groups per GPU, each on its own CUDA stream (the groups' "
+                    "kernels overlap, so a slow interior-point straggler only delays its own group)")
     ap.add_argument("--cpu-scenarios", type=int, default=0, help="CPU baseline sample: scenarios (default = 32 x host cores)")
     ap.add_argument("--cpu-steps", type=int, default=29, help="CPU baseline sample: MPC steps per scenario")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -148,16 +150,23 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, K, Wm = a.batch, a.steps, a.warmup
+    G = max(1, min(a.groups, B))
     total_steps = K + Wm
     m, cfg = om.rocket_config()
-    x0, W = rocket_scenarios(B, seed=2025 + rank, steps=2 * total_steps + 2)
-    s = BatchSolver("rocket", cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], m.E, m.x_ub, m.x_lb,
-                    m.u_ub, m.u_lb, rti=cfg["rti"], sls_steps=cfg["fast_sls_rti_steps"], capacity=B, device=local_rank)
-    s.enable_timing(True)
+    x0, W = rocket_scenarios(B, seed=2025 + rank, steps=2 * total_steps + 4)
+    bounds = [(g * B // G, (g + 1) * B // G) for g in range(G)]
+    solvers, streams, xs, Wds = [], [], [], []
+    for lo, hi in bounds:
+        s = BatchSolver("rocket", cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], m.E, m.x_ub, m.x_lb,
+                        m.u_ub, m.u_lb, rti=cfg["rti"], sls_steps=cfg["fast_sls_rti_steps"], capacity=hi - lo, device=local_rank)
+        s.enable_timing(True)
+        solvers.append(s)
+        streams.append(torch.cuda.Stream(device=dev))
+        Wds.append(s.dev(np.ascontiguousarray(np.swapaxes(W[lo:hi], 0, 1))))     # [steps][b][nx], resident
+        xs.append(s.dev(x0[lo:hi]).clone())
     peak = fp64_peak_tflops(local_rank)
-    Wd = s.dev(np.ascontiguousarray(np.swapaxes(W, 0, 1)))     # [steps][B][nx], resident
-    x = s.dev(x0).clone()
-    s.init_nominal(x, 10)
+    for s, x in zip(solvers, xs):
+        s.init_nominal(x, 10)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -166,63 +175,83 @@ def main():
         torch.cuda.synchronize(dev)
 
     step_idx = [0]
-    t_qp, t_sls, t_jac, qp_iters = [], [], [], []
 
-    def device_step(record):
-        i = step_idx[0]
-        if i > 0:
-            s.reset_warm_start(B)
-        s.solve(x)
-        s.plant_step(x, Wd[i])
-        step_idx[0] += 1
-        if record:
-            tm = s.timings()
-            t_qp.append(tm["t_qp_ms"]); t_sls.append(tm["t_backward_ms"]); t_jac.append(tm["t_jac_ms"])
+    def device_steps(n):
+        """n closed-loop MPC steps of every group; each group's launches go to its own stream, no host synchronisation."""
+        i0 = step_idx[0]
+        for j in range(n):
+            for s, st, x, Wd in zip(solvers, streams, xs, Wds):
+                with torch.cuda.stream(st):
+                    if i0 + j > 0:
+                        s.reset_warm_start(x.shape[0])
+                    s.solve(x)
+                    s.plant_step(x, Wd[i0 + j])
+        step_idx[0] += n
 
-    for _ in range(Wm):
-        device_step(False)
+    barrier()
+    device_steps(Wm)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     barrier()
-    launches0 = s.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        device_step(False)
-    e1.record()
+    launches0 = sum(s.launch_count() for s in solvers)
+    t_wall0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record(torch.cuda.current_stream(dev))
+    for st in streams:
+        st.wait_event(e0)
+    device_steps(K)
+    ends = []
+    for st in streams:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(st)
+        ends.append(e)
     barrier()
-    launches = s.launch_count() - launches0
-    ms = e0.elapsed_time(e1)
-    flags = s.buffer("flags")
+    launches = sum(s.launch_count() for s in solvers) - launches0
+    ms = max(e0.elapsed_time(e) for e in ends)          # device time of the slowest group's stream
+    flags = np.concatenate([s.buffer("flags") for s in solvers])
     n_fail_last = int((flags & 1).sum())
-    # per-kernel times + iteration counters on a few extra (untimed) steps so that get_timings' sync stays outside the timed region
+    # per-kernel times + iteration counters on two extra (untimed) steps of group 0 alone, so that the kernel times are not
+    # inflated by the other groups' kernels sharing the SMs and get_timings' sync stays outside the timed region
+    t_qp, t_sls, t_jac, qp_iters = [], [], [], []
     for _ in range(2):
-        device_step(True)
+        s, x, Wd = solvers[0], xs[0], Wds[0]
+        s.reset_warm_start(x.shape[0])
+        s.solve(x)
+        s.plant_step(x, Wd[step_idx[0]])
+        tm = s.timings()
+        t_qp.append(tm["t_qp_ms"]); t_sls.append(tm["t_backward_ms"]); t_jac.append(tm["t_jac_ms"])
         qp_iters.append(s.buffer("qp_iters").astype(np.float64))
+        for s2, st, x2, Wd2 in list(zip(solvers, streams, xs, Wds))[1:]:
+            s2.reset_warm_start(x2.shape[0]); s2.solve(x2); s2.plant_step(x2, Wd2[step_idx[0]])
+        step_idx[0] += 1
+    B0 = bounds[0][1] - bounds[0][0]
 
     # ---- e2e: same steps through host buffers (pinned host memory in, results out, copies inside the timed region)
     xh = torch.empty((B, m.nx), dtype=torch.float64, pin_memory=True)
     wh = torch.empty((B, m.nx), dtype=torch.float64, pin_memory=True)
     oh = torch.empty((B, m.nx + m.nu), dtype=torch.float64, pin_memory=True)
     fh = torch.empty((B,), dtype=torch.int32, pin_memory=True)
-    xh.copy_(x)
+    for (lo, hi), x in zip(bounds, xs):
+        xh[lo:hi].copy_(x)
     Wpin = torch.as_tensor(np.ascontiguousarray(np.swapaxes(W, 0, 1))).pin_memory()
-    xd, wd = torch.empty_like(x), torch.empty_like(x)
+    xds, wds = [torch.empty_like(x) for x in xs], [torch.empty_like(x) for x in xs]
     n_e2e = max(3, min(K, 10))
 
     def e2e_step():
         i = step_idx[0]
-        wh.copy_(Wpin[i])
-        xd.copy_(xh, non_blocking=True)
-        wd.copy_(wh, non_blocking=True)
-        s.reset_warm_start(B)
-        s.solve(xd)
-        s.plant_step(xd, wd)
-        Uv = torch.as_tensor(s.buffer_view("U", B))
-        oh[:, :m.nx].copy_(xd, non_blocking=True)
-        oh[:, m.nx:].copy_(Uv[:, 0], non_blocking=True)
-        fh.copy_(torch.as_tensor(s.buffer_view("flags", B)), non_blocking=True)
+        wh.copy_(Wpin[i])                                   # this step's disturbance draw arrives from the host
+        for (lo, hi), s, st, xd, wd in zip(bounds, solvers, streams, xds, wds):
+            with torch.cuda.stream(st):
+                xd.copy_(xh[lo:hi], non_blocking=True)
+                wd.copy_(wh[lo:hi], non_blocking=True)
+                s.reset_warm_start(hi - lo)
+                s.solve(xd)
+                s.plant_step(xd, wd)
+                Uv = torch.as_tensor(s.buffer_view("U", hi - lo))
+                oh[lo:hi, :m.nx].copy_(xd, non_blocking=True)
+                oh[lo:hi, m.nx:].copy_(Uv[:, 0], non_blocking=True)
+                fh[lo:hi].copy_(torch.as_tensor(s.buffer_view("flags", hi - lo)), non_blocking=True)
         torch.cuda.synchronize(dev)
         xh.copy_(oh[:, :m.nx])
         step_idx[0] += 1
@@ -241,8 +270,9 @@ def main():
     if world > 1:
         dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
     ms_all, e2e_ms_all = float(tvec[0]), float(tvec[1])
-    bo = s.buffer("backoff")
-    stats, per_rank = gather_statistics(dict(solves=B * K, failed_solves=n_fail_last, violations=0, cost_sum=float(s.buffer("cost").sum()),
+    bo = solvers[0].buffer("backoff")
+    stats, per_rank = gather_statistics(dict(solves=B * K, failed_solves=n_fail_last, violations=0,
+                                             cost_sum=float(sum(s.buffer("cost").sum() for s in solvers)),
                                              max_backoff=float(bo.max()), qp_iters=float(np.mean(qp_iters)) * B, elapsed_ms=ms), device=dev)
     if rank != 0:
         if world > 1:
@@ -252,7 +282,7 @@ def main():
     e2e_value = (B * world) / (e2e_ms_all * 1e-3)
     fm = flops_model()
     iters_per_solve = float(np.mean(qp_iters))                 # interior-point iterations over the 2 QPs of a solve
-    qp_flops_launch = B * (iters_per_solve / 2.0) * (fm["qp_fact"] + 2 * fm["qp_solve"])       # one QP kernel launch
+    qp_flops_launch = B0 * (iters_per_solve / 2.0) * (fm["qp_fact"] + 2 * fm["qp_solve"])      # one QP kernel launch (group 0 alone)
     t_qp_ms = float(np.mean(t_qp))
     flops_per_solve = fm["lin"] + fm["sls"] + iters_per_solve * (fm["qp_fact"] + 2 * fm["qp_solve"])
     achieved = qp_flops_launch / (t_qp_ms * 1e-3) * 1e-12
@@ -261,7 +291,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_all / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "global_batch": B * world, "horizon": cfg["N"], "parallelism": f"scenario-sharded x{world}",
+        "config": {"workload": workload, "global_batch": B * world, "horizon": cfg["N"], "parallelism": f"scenario-sharded x{world} GPUs, {G} stream groups per GPU",
                    "l2": "per-step working set ~%.0f MB per GPU > 126 MB L2 (no flush needed)" % (B * 0.2),
                    "flops_per_solve": flops_per_solve, "qp_ipm_iters_per_solve": iters_per_solve,
                    "whole_solve_fp64_frac": value / world * flops_per_solve / (peak * 1e12),
@@ -270,7 +300,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_all},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "kernel": "qp_ipm_kernel<17,4>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": 16.13e9 * B / 4096.0,   # dram bytes per launch, ncu (profiles/r1_ncu_full_summary.csv, B=4096)
+                     "frac": achieved / peak, "traffic": 16.13e9 * B0 / 4096.0,   # dram bytes per launch, ncu (profiles/r1_ncu_full_summary.csv, B=4096)
                      "note": "FP64 DFMA pipe binds (SURVEY 8d); peak = DFMA probe measured live on this GPU (MEASURED_PEAKS.json has no "
                              "fp64 entry); achieved = algorithmic flops of one QP launch / its CUDA-event duration"},
         "failed_solves_last_step": int(stats["failed_solves"]),
