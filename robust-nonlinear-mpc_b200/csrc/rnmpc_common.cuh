@@ -176,6 +176,20 @@ __device__ __forceinline__ void prefetch_l2(const void* p, const int bytes, cons
     for (int off = sl * 128; off < bytes; off += LPS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
 }
 
+// Asynchronous copy (LDGSTS, no registers) of a global [NX][NX] matrix into an LD-strided shared matrix; completion with
+// cp_async_wait_all() + __syncwarp.  Used to stage A_{k-1} while stage k is still computing.
+template <int NX, int LD, int LPS>
+__device__ __forceinline__ void cp_async_matrix(double* dst, const double* __restrict__ src, const int sl) {
+    const unsigned base = (unsigned)__cvta_generic_to_shared(dst);
+#pragma unroll 4
+    for (int e = sl; e < NX * NX; e += LPS) {
+        const int i = e / NX, c = e - i * NX;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(base + (unsigned)((i * LD + c) * 8)), "l"(src + e));
+    }
+    asm volatile("cp.async.commit_group;");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // Cooperative load of an [R][C] global matrix into a shared LDS-strided matrix (zero pad columns).  All loads of a
 // lane are issued before the first store so that their latencies overlap (one L2 round trip per matrix).
 template <int R, int C, int LDS_, int LPS>
@@ -207,7 +221,8 @@ __device__ __forceinline__ bool riccati_step(SlotSmem<NX, NU>& sm, const int sl,
                                              const double* __restrict__ Cx0, const double* __restrict__ Cu0,
                                              const double cxd0, const double cxd1, double* __restrict__ Kout, Pre&& pre,
                                              Post&& post, const bool need_S = true, const double* __restrict__ Ag_next = nullptr,
-                                             const double* __restrict__ Bg_next = nullptr) {
+                                             const double* __restrict__ Bg_next = nullptr, const bool T_ready = false,
+                                             const double* __restrict__ Ag_async = nullptr) {
     constexpr int LD = Slot<NX>::LD;
     constexpr int LPS = Slot<NX>::LPS;
     const int r0 = 2 * sl, r1 = 2 * sl + 1;
@@ -215,7 +230,9 @@ __device__ __forceinline__ bool riccati_step(SlotSmem<NX, NU>& sm, const int sl,
     const int r1c = v1 ? r1 : NX - 1;
 
     // (0) A_k -> sm.T, B_k -> sm.Bm
-    load_matrix_smem<NX, NX, LD, LPS>(sm.T, Ag, sl);
+    // T_ready: A_k was copied into sm.T asynchronously while the previous stage computed
+    if (T_ready) cp_async_wait_all();
+    else load_matrix_smem<NX, NX, LD, LPS>(sm.T, Ag, sl);
     load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bg, sl);
     if (Ag_next != nullptr) {
         prefetch_l2<LPS>(Ag_next, NX * NX * 8, sl);
@@ -339,6 +356,8 @@ __device__ __forceinline__ bool riccati_step(SlotSmem<NX, NU>& sm, const int sl,
         if (v1) *reinterpret_cast<double2*>(sm.S + r1 * LD + c) = make_double2(s1[c], (c + 1 < NX) ? s1[c + 1] : 0.0);
     }
     __syncwarp(mask);
+    // every lane is done with A_k + B_k K_k: start copying the next stage's A into sm.T (lands during the symmetrisation)
+    if (Ag_async != nullptr) cp_async_matrix<NX, LD, LPS>(sm.T, Ag_async, sl);
 #pragma unroll
     for (int c = 0; c < NX; ++c) {
         const double2 t = *reinterpret_cast<const double2*>(sm.S + c * LD + r0);

@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
 
     int stalled = 0;
     bool done = (status != 0) || !act;
+    int resT = -1, resS = -1;      // stage whose A_k is resident (or in flight, cp.async) in sm.T / sm.S
     // a warm-started attempt that has not converged after kWarmCap iterations is abandoned for the cold start
     const int it_cap = (attempt == 0 && __any_sync(mask, warm)) ? min(a.max_iter, kWarmCap) : a.max_iter;
     for (it = 0; it < it_cap; ++it) {
@@ -362,6 +363,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             sm.vec[r0] = G[N * NZ + r0];
             if (v1) sm.vec[r1] = G[N * NZ + r1];
             if (pass == 0) {
+                resS = -1;
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
                     const int r = rr ? r1 : r0;
@@ -395,6 +397,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     __syncwarp(mask);
                 };
                 // vector recursion of the KKT solve; A_k is in sm.T, B_k in sm.Bm, K columns / factor in registers
+                const double* Abuf = sm.T;
                 auto vec_step = [&](const double (&k0)[NU], const double (&k1)[NU], const double (&L)[NU][NU]) {
                     // g = p_{k+1} + Sc
                     const double g0 = sm.vec[r0] + rp_scale * sc0;
@@ -426,7 +429,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
 #pragma unroll 1
                         for (int i = 0; i < NX; ++i) {
                             const double gi = sm.vec[LD + i];
-                            const double2 av = *reinterpret_cast<const double2*>(sm.T + i * LD + r0);
+                            const double2 av = *reinterpret_cast<const double2*>(Abuf + i * LD + r0);
                             p0 = fma(av.x, gi, p0);
                             p1 = fma(av.y, gi, p1);
                         }
@@ -453,14 +456,22 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                             }
                             vec_step(k0, k1, L);
                         },
-                        k > 0, k > 0 ? Ak - NX * NX : nullptr, k > 0 ? Bk - NX * NU : nullptr);
+                        k > 0, k > 0 ? Ak - NX * NX : nullptr, k > 0 ? Bk - NX * NU : nullptr, resT == k, k > 0 ? Ak - NX * NX : nullptr);
+                    resT = (k > 0) ? k - 1 : 0;
                     chol_ok = chol_ok && ok;
                 } else {
                     double k0[NU], k1[NU], L[NU][NU];
-                    load_matrix_smem<NX, NX, LD, LPS>(sm.T, Ak, sl);
+                    cp_async_wait_all();
+                    if (resT != k && resS != k) { load_matrix_smem<NX, NX, LD, LPS>(sm.T, Ak, sl); resT = k; }
+                    const bool inT = (resT == k);
+                    Abuf = inT ? sm.T : sm.S;
+                    if (k > 0) {       // next stage's A into the other buffer while this stage computes
+                        cp_async_matrix<NX, LD, LPS>(inT ? sm.S : sm.T, Ak - NX * NX, sl);
+                        if (inT) resS = k - 1; else resT = k - 1;
+                    }
                     load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bk, sl);
                     if (k > 0) {
-                        prefetch_l2<LPS>(Ak - NX * NX, NX * NX * 8, sl);
+                        if (k > 1) prefetch_l2<LPS>(Ak - 2 * NX * NX, NX * NX * 8, sl);     // two stages ahead: the cp.async of the next stage hits L2
                         prefetch_l2<LPS>(Bk - NX * NU, NX * NU * 8, sl);
                         prefetch_l2<LPS>(Kq + (size_t)(k - 1) * NU * NX, NU * NX * 8, sl);
                     }
@@ -510,12 +521,19 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 const double* Ak = Ab + (size_t)k * NX * NX;
                 const double* Bk = Bb + (size_t)k * NX * NU;
                 const double* Kk = Kq + (size_t)k * NU * NX;
-                // stage A_k, B_k, K_k in shared memory (coalesced, all loads in flight together) + this stage's entry data
-                load_matrix_smem<NX, NX, LD, LPS>(sm.T, Ak, sl);
+                // stage A_k (already resident / in flight from the previous stage or sweep), B_k, K_k + this stage's entry data
+                cp_async_wait_all();
+                if (resT != k && resS != k) { load_matrix_smem<NX, NX, LD, LPS>(sm.T, Ak, sl); resT = k; }
+                const bool inT = (resT == k);
+                const double* Af = inT ? sm.T : sm.S;
+                if (k + 1 < N) {
+                    cp_async_matrix<NX, LD, LPS>(inT ? sm.S : sm.T, Ak + NX * NX, sl);
+                    if (inT) resS = k + 1; else resT = k + 1;
+                }
                 load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bk, sl);
                 load_matrix_smem<NU, NX, NX, LPS>(sm.SB, Kk, sl);
                 if (k + 1 < N) {
-                    prefetch_l2<LPS>(Ak + NX * NX, NX * NX * 8, sl);
+                    if (k + 2 < N) prefetch_l2<LPS>(Ak + 2 * NX * NX, NX * NX * 8, sl);
                     prefetch_l2<LPS>(Bk + NX * NU, NX * NU * 8, sl);
                     prefetch_l2<LPS>(Kk + NU * NX, NU * NX * 8, sl);
                 }
@@ -545,15 +563,15 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
 #pragma unroll
                     for (int m = 0; m + 1 < NX; m += 2) {
                         const double xa = sm.vec[m], xb = sm.vec[m + 1];
-                        n0 = fma(sm.T[r0 * LD + m], xa, n0);
-                        n1 = fma(sm.T[r1c * LD + m], xa, n1);
-                        m0 = fma(sm.T[r0 * LD + m + 1], xb, m0);
-                        m1 = fma(sm.T[r1c * LD + m + 1], xb, m1);
+                        n0 = fma(Af[r0 * LD + m], xa, n0);
+                        n1 = fma(Af[r1c * LD + m], xa, n1);
+                        m0 = fma(Af[r0 * LD + m + 1], xb, m0);
+                        m1 = fma(Af[r1c * LD + m + 1], xb, m1);
                     }
                     if (NX & 1) {
                         const double xa = sm.vec[NX - 1];
-                        n0 = fma(sm.T[r0 * LD + NX - 1], xa, n0);
-                        n1 = fma(sm.T[r1c * LD + NX - 1], xa, n1);
+                        n0 = fma(Af[r0 * LD + NX - 1], xa, n0);
+                        n1 = fma(Af[r1c * LD + NX - 1], xa, n1);
                     }
                     n0 += m0; n1 += m1;
                 }

@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(160, 2) sls_kernel(const SlsArgs a, const Para
 
     // ---------------- backward: Riccati recursion (solver/fast_SLS_jit.py:65-84) ----------------
     const int n_first = N - s;     // steps of column s
+    bool t_ready = false;
     for (int t = 0; t < N; ++t) {
         const bool first = t < n_first;
         const int col = first ? s : N - s;
@@ -114,9 +115,16 @@ __global__ void __launch_bounds__(160, 2) sls_kernel(const SlsArgs a, const Para
         if (sl < NU) sm.cu[sl] = weight(k, col, NX + sl) + weight(k, col, NX + sl + NZ);
         if (LPS < NU) { for (int p = LPS + sl; p < NU; p += LPS) sm.cu[p] = weight(k, col, NX + p) + weight(k, col, NX + p + NZ); }
         double* Kout = a.K + (((size_t)b * N + k) * (N + 1) + col) * kstride;
+        // stage of the next Riccati step of this chain (same column: k-1; first step of the second column: N-1)
+        const double* a_next = nullptr;
+        if (t + 1 < N) {
+            const int kn = (t + 1 < n_first) ? (k - 1) : ((t + 1 == n_first) ? (N - 1) : (k - 1));
+            a_next = Ab + (size_t)kn * NX * NX;
+        }
         riccati_step<NX, NU>(sm, sl, mask, Ab + (size_t)k * NX * NX, Bb + (size_t)k * NX * NU, prm->Qreg, prm->Rreg, cx0, cx1,
                              Kout, NoPre(), NoPost(), true, k > 0 ? Ab + (size_t)(k - 1) * NX * NX : nullptr,
-                             k > 0 ? Bb + (size_t)(k - 1) * NX * NU : nullptr);
+                             k > 0 ? Bb + (size_t)(k - 1) * NX * NU : nullptr, t_ready, a_next);
+        t_ready = a_next != nullptr;
         if (a.S != nullptr) {
             double* So = a.S + ((((size_t)b * (N + 1) + k) * (N + 1)) + col) * NX * NX;
             for (int c = 0; c < NX; ++c) {
