@@ -106,7 +106,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--groups", type=int, default=1, help="independent scenario groups per GPU, each on its own CUDA stream (the groups' "
                     "kernels overlap, so a slow interior-point straggler only delays its own group)")
-    ap.add_argument("--cpu-scenarios", type=int, default=0, help="CPU baseline sample: scenarios (default = 32 x host cores)")
+    ap.add_argument("--cpu-scenarios", type=int, default=0, help="CPU baseline sample: scenarios (default = 256 x host cores)")
     ap.add_argument("--cpu-steps", type=int, default=29, help="CPU baseline sample: MPC steps per scenario")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -120,7 +120,7 @@ def main():
         # the reference's CPU path; only rank 0 works
         if rank != 0:
             return
-        n_scen = a.cpu_scenarios or 32 * cores
+        n_scen = a.cpu_scenarios or 256 * cores
         t_steps = []
         for _ in range(max(1, min(a.steps, 3))):          # bounded: each "step" = cpu_steps MPC steps of n_scen scenarios
             v, info = cpu_baseline(n_scen, a.cpu_steps, cores)
@@ -160,6 +160,7 @@ def main():
         s = BatchSolver("rocket", cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], m.E, m.x_ub, m.x_lb,
                         m.u_ub, m.u_lb, rti=cfg["rti"], sls_steps=cfg["fast_sls_rti_steps"], capacity=hi - lo, device=local_rank)
         s.enable_timing(True)
+        s.set_option("sticky_fail", 1)      # Monte-Carlo semantics: a scenario whose solve failed is dead (the reference's driver would stop)
         solvers.append(s)
         streams.append(torch.cuda.Stream(device=dev))
         Wds.append(s.dev(np.ascontiguousarray(np.swapaxes(W[lo:hi], 0, 1))))     # [steps][b][nx], resident
@@ -306,7 +307,7 @@ def main():
         "failed_solves_last_step": int(stats["failed_solves"]),
     }
     if not a.no_cpu_baseline:
-        n_scen = a.cpu_scenarios or 32 * cores
+        n_scen = a.cpu_scenarios or 256 * cores
         v, info = cpu_baseline(n_scen, a.cpu_steps, cores)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{n_scen} rocket scenarios x {a.cpu_steps} MPC steps, {cores} threads, C++ CPU port (oracle/cpu_port; "

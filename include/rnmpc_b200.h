@@ -159,6 +159,12 @@ int rnmpc_solve_host(rnmpc_handle* h, int B, const double* h_x0, double* h_X, do
 int rnmpc_closed_loop_host(rnmpc_handle* h, int B, int steps, const double* h_x0, const double* h_W, const double* h_X0,
                            const double* h_U0, int init_iters, double* h_states, double* h_inputs, long long* h_nfail);
 
+/* Solver options: "warm_mask" (bit0: warm-start the first QP of a solve from the previous solve's multipliers, bit1: the later
+ * QPs of a solve from the previous iterate; default 3), "sticky_fail" (1: an instance whose solve failed stays frozen -- skipped
+ * by every kernel -- until rnmpc_set_nominal / rnmpc_init_nominal; default 0 = retried at every solve, as a caller of the
+ * reference would), "qp_max_iter", "qp_tol_mu". */
+int rnmpc_set_option(rnmpc_handle* h, const char* name, double value);
+
 /* Measured FP64 FMA peak of the device (TFLOP/s), for the roofline denominator. */
 int rnmpc_fp64_peak(int device, double* tflops);
 

@@ -175,6 +175,11 @@ int rnmpc_get_timings(rnmpc_handle* h, double* out3) {
     if (!out3) return -1;
     return h->e->get_timings(out3);
 }
+int rnmpc_set_option(rnmpc_handle* h, const char* name, double value) {
+    RN_ENTER(h);
+    if (!name) return -1;
+    return h->e->set_option(name, value);
+}
 long long rnmpc_launch_count(rnmpc_handle* h) { return h ? h->e->launches : -1; }
 
 static int copy_out(rnmpc_handle* h, const char* name, void* dst, size_t bytes, cudaStream_t st) {
@@ -238,6 +243,7 @@ int rnmpc_closed_loop_host(rnmpc_handle* h, int B, int steps, const double* h_x0
     }
     long long nfail = 0;
     std::vector<int> fl(B);
+    h->e->set_option("sticky_fail", 1.0);      // Monte-Carlo semantics: a scenario whose solve failed is dead (the reference's driver would stop)
     void* d_flags; long long nb;
     h->e->get_buffer("flags", &d_flags, &nb);
     const size_t srow = (size_t)(steps + 1) * nx * sizeof(double);
@@ -270,6 +276,7 @@ int rnmpc_closed_loop_host(rnmpc_handle* h, int B, int steps, const double* h_x0
         if (h_states) RN_API_CUDA(cudaMemcpyAsync(h_states, d_states, (size_t)B * srow, cudaMemcpyDeviceToHost, st));
         if (h_inputs) RN_API_CUDA(cudaMemcpyAsync(h_inputs, d_inputs, (size_t)B * steps * nu * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
+    h->e->set_option("sticky_fail", 0.0);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(d_x); cudaFree(d_states); cudaFree(d_inputs);
     if (d_W) cudaFree(d_W);

@@ -52,6 +52,7 @@ struct IEngine {
     virtual int plant_step(int B, double* x, const double* w, double* u0, cudaStream_t st) = 0;
     virtual int get_buffer(const char* name, void** ptr, long long* bytes) = 0;
     virtual int enable_phi(int enable) = 0;
+    virtual int set_option(const char* name, double value) = 0;
     virtual int dims(int* nx, int* nu, int* N, int* cap) = 0;
     long long launches = 0;
     int device = 0;
@@ -184,6 +185,9 @@ struct Engine : IEngine {
     int *flags, *status, *qp_iters, *iters_tmp, *status_tmp, *n_open, *ws_valid;
     bool have_solution = false, shifted_since_solve = false;   // host-side warm-start bookkeeping
     int warm_enabled = 1;
+    int warm_mask = 2;             // measured (tools/iter_stats.py, B = 4096, 29 steps): warm-starting the first QP of a solve across MPC
+                                   // steps lowers the mean iteration count but its cold retries lengthen the slowest warp; off by default
+    bool sticky_fail = false;
     int sls_max_iter = 30;             // fast_SLS.MAX_ITER (fast_SLS_jit.py:206)
 
     template <class T>
@@ -412,9 +416,9 @@ struct Engine : IEngine {
     int solve(int B, const double* x0, cudaStream_t st) override {
         if (check_B(B)) return -1;
         // a new solve: failure flags of the previous solve are cleared, the Q3 history (FLAG_PREV) is kept
-        clear_flag_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags, FLAG_FAIL | FLAG_Q3 | FLAG_TIGHT);
+        clear_flag_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags, (sticky_fail ? 0 : FLAG_FAIL) | FLAG_Q3 | FLAG_TIGHT);
         ++launches;
-        RN_CUDA(cudaMemsetAsync(status, 0, (size_t)B * sizeof(int), st));
+        if (!sticky_fail) RN_CUDA(cudaMemsetAsync(status, 0, (size_t)B * sizeof(int), st));   // frozen instances keep their failure status
         RN_CUDA(cudaMemsetAsync(qp_iters, 0, (size_t)B * sizeof(int), st));
         if (timing) cudaEventRecord(ev[0], st);
         int rc = linearize(B, X, U, A, Bm, c, st);                      // update_jacobian (SCP_SLS_jit.py:80)
@@ -432,7 +436,8 @@ struct Engine : IEngine {
             for (int i = 0; i < n_steps && !all_done; ++i) {
                 // warm start: first QP of a solve <- multipliers of the previous solve (shifted if reset_warm_start ran); later QPs of
                 // the same linearisation <- previous iterate and multipliers (only the bounds moved)
-                const int wm = (i > 0) ? (1 | 4) : (ii > 0 ? 1 : (have_solution ? (shifted_since_solve ? (1 | 2) : 1) : 0));
+                const int wm = (i > 0) ? ((warm_mask & 2) ? (1 | 4) : 0)
+                                       : ((warm_mask & 1) ? (ii > 0 ? 1 : (have_solution ? (shifted_since_solve ? (1 | 2) : 1) : 0)) : 0);
                 rc = resident_qp(B, -1, x0, st, skipf, wm);            // forward_solve
                 if (rc) return rc;
                 q3_check_kernel<<<(B + 3) / 4, 128, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, prevX, prevU, flags, skipf);
@@ -462,10 +467,10 @@ struct Engine : IEngine {
             }
             if (timing) cudaEventRecord(ev[2], st);
             if (!converge_mode) {
-                rc = resident_qp(B, -1, x0, st, FLAG_FAIL, 1 | 4);      // final forward_solve
+                rc = resident_qp(B, -1, x0, st, FLAG_FAIL, (warm_mask & 2) ? (1 | 4) : 0);      // final forward_solve
             } else {
                 // instances still open after MAX_ITER: one last QP with the latest bounds, then failure (fast_SLS_jit.py:310-312)
-                rc = all_done ? 0 : resident_qp(B, -1, x0, st, skipf, 1 | 4);
+                rc = all_done ? 0 : resident_qp(B, -1, x0, st, skipf, (warm_mask & 2) ? (1 | 4) : 0);
                 fail_open_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags, status);
                 ++launches;
             }
@@ -526,6 +531,15 @@ struct Engine : IEngine {
         if (it == bufs.end()) { set_error(std::string("unknown buffer ") + name); return -1; }
         *ptr = it->second.first;
         if (bytes) *bytes = (long long)it->second.second;
+        return 0;
+    }
+    int set_option(const char* name, double value) override {
+        const std::string n(name);
+        if (n == "warm_mask") warm_mask = (int)value;            // bit0: first QP of a solve from the previous solve, bit1: later QPs of a solve
+        else if (n == "sticky_fail") sticky_fail = value != 0;    // failed instances stay frozen until set_nominal / init_nominal
+        else if (n == "qp_max_iter") qp_max_iter = (int)value;
+        else if (n == "qp_tol_mu") qp_tol_mu = value;
+        else { set_error("unknown option " + n); return -1; }
         return 0;
     }
     int enable_phi(int enable) override {

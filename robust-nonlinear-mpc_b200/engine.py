@@ -221,6 +221,9 @@ class BatchSolver:
     def enable_phi(self, enable=True):
         _lib.check(self.lib.rnmpc_enable_phi(self._h, int(bool(enable))))
 
+    def set_option(self, name, value):
+        _lib.check(self.lib.rnmpc_set_option(self._h, name.encode(), float(value)))
+
     def enable_timing(self, enable=True):
         _lib.check(self.lib.rnmpc_enable_timing(self._h, int(bool(enable))))
 
