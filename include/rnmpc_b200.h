@@ -136,7 +136,7 @@ int rnmpc_plant_step(rnmpc_handle* h, int B, double* d_x, const double* d_w, dou
 /* Device pointers of the resident results of the last solve (valid until the handle is destroyed).
  * name in: "X" [cap][N+1][nx], "U" [cap][N][nu], "dX", "dU", "mu" [cap][N][ni], "mu_f" [cap][ni_f], "K"
  * [cap][N][N+1][nu][nx], "beta" [cap][N][N][ni], "beta_f" [cap][N+1][ni_f], "backoff" [cap][N][ni], "backoff_f"
- * [cap][ni_f], "A", "B", "c", "cost" [cap], "Phi_x", "Phi_u" (only after rnmpc_enable_phi), "flags" (int32 [cap]:
+ * [cap][ni_f], "A" (padded rows: [cap][N][nx][nx rounded up to even]), "B", "c", "cost" [cap], "Phi_x", "Phi_u" (only after rnmpc_enable_phi), "flags" (int32 [cap]:
  * bit0 failed, bit1 Q3 early return in the last fast-SLS step, bit2 tube back-offs valid, bit3 Q3 history present,
  * bit4 K/Phi computed since the last warm-start reset), "status" (int32 [cap]),
  * "qp_iters" (int32 [cap], interior-point iterations summed over the QPs of the last solve). */

@@ -176,19 +176,37 @@ __device__ __forceinline__ void prefetch_l2(const void* p, const int bytes, cons
     for (int off = sl * 128; off < bytes; off += LPS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
 }
 
-// Asynchronous copy (LDGSTS, no registers) of a global [NX][NX] matrix into an LD-strided shared matrix; completion with
-// cp_async_wait_all() + __syncwarp.  Used to stage A_{k-1} while stage k is still computing.
+// A_k is stored in global memory in the same LD-strided layout as in shared memory ([NX][LD] doubles, pad column zero; the
+// engine keeps its resident A that way and re-packs caller-provided dense matrices), so staging is a contiguous 16-byte copy.
+// Asynchronous version (LDGSTS, no registers); completion with cp_async_wait_all() + __syncwarp.
 template <int NX, int LD, int LPS>
 __device__ __forceinline__ void cp_async_matrix(double* dst, const double* __restrict__ src, const int sl) {
     const unsigned base = (unsigned)__cvta_generic_to_shared(dst);
+    constexpr int N16 = NX * LD / 2;
 #pragma unroll 4
-    for (int e = sl; e < NX * NX; e += LPS) {
-        const int i = e / NX, c = e - i * NX;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(base + (unsigned)((i * LD + c) * 8)), "l"(src + e));
-    }
+    for (int e = sl; e < N16; e += LPS)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + (unsigned)(e * 16)), "l"(src + 2 * e));
     asm volatile("cp.async.commit_group;");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Synchronous staging of a padded A_k: all 16-byte loads of a lane in flight together.
+template <int NX, int LD, int LPS>
+__device__ __forceinline__ void load_padded_smem(double* __restrict__ dst, const double* __restrict__ src, const int sl) {
+    constexpr int N16 = NX * LD / 2;
+    constexpr int IT = (N16 + LPS - 1) / LPS;
+    double2 v[IT];
+#pragma unroll
+    for (int j = 0; j < IT; ++j) {
+        const int e = sl + j * LPS;
+        v[j] = (e < N16) ? __ldg(reinterpret_cast<const double2*>(src) + e) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int j = 0; j < IT; ++j) {
+        const int e = sl + j * LPS;
+        if (e < N16) reinterpret_cast<double2*>(dst)[e] = v[j];
+    }
+}
 
 // Cooperative load of an [R][C] global matrix into a shared LDS-strided matrix (zero pad columns).  All loads of a
 // lane are issued before the first store so that their latencies overlap (one L2 round trip per matrix).
@@ -232,10 +250,10 @@ __device__ __forceinline__ bool riccati_step(SlotSmem<NX, NU>& sm, const int sl,
     // (0) A_k -> sm.T, B_k -> sm.Bm
     // T_ready: A_k was copied into sm.T asynchronously while the previous stage computed
     if (T_ready) cp_async_wait_all();
-    else load_matrix_smem<NX, NX, LD, LPS>(sm.T, Ag, sl);
+    else load_padded_smem<NX, LD, LPS>(sm.T, Ag, sl);
     load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bg, sl);
     if (Ag_next != nullptr) {
-        prefetch_l2<LPS>(Ag_next, NX * NX * 8, sl);
+        prefetch_l2<LPS>(Ag_next, NX * LD * 8, sl);
         prefetch_l2<LPS>(Bg_next, NX * NU * 8, sl);
     }
     __syncwarp(mask);

@@ -106,6 +106,14 @@ static __global__ void fail_open_kernel(int B, int* flags, int* status) {
     const int f = flags[b];
     if ((f & (FLAG_FAIL | FLAG_SLSDONE)) == 0) { flags[b] = f | FLAG_FAIL; status[b] = 4; }
 }
+// caller-provided dense A [n][nx][nx] -> padded [n][nx][ld] (pad zero)
+static __global__ void pad_rows_kernel(long long n_rows, int nx, int ld, const double* __restrict__ src, double* __restrict__ dst) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_rows * ld) return;
+    const long long r = gid / ld;
+    const int c = (int)(gid - r * ld);
+    dst[gid] = (c < nx) ? src[r * nx + c] : 0.0;
+}
 static __global__ void clear_flag_kernel(int B, int* flags, int bits) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) flags[b] &= ~bits;
@@ -169,6 +177,7 @@ __global__ void shift_kernel(int B, int N, double h, double* __restrict__ X, dou
 template <class M>
 struct Engine : IEngine {
     static constexpr int NX = M::NX, NU = M::NU, NZ = NX + NU, NI = 2 * NZ, NIF = 2 * NX;
+    static constexpr int LDA = Slot<NX>::LD;       // row stride of the resident (padded) A_k
     using P = Params<NX, NU>;
     int N, cap, rti, sls_steps, qp_max_iter;
     double qp_tol_mu, qp_tol_res, h;
@@ -227,7 +236,7 @@ struct Engine : IEngine {
         const size_t B = cap, n1 = N + 1;
         int rc = 0;
         rc |= alloc("X", X, B * n1 * NX); rc |= alloc("U", U, B * N * NU);
-        rc |= alloc("A", A, B * N * NX * NX); rc |= alloc("B", Bm, B * N * NX * NU); rc |= alloc("c", c, B * N * NX);
+        rc |= alloc("A", A, B * N * NX * LDA); rc |= alloc("B", Bm, B * N * NX * NU); rc |= alloc("c", c, B * N * NX);
         rc |= alloc("dX", dX, B * n1 * NX); rc |= alloc("dU", dU, B * N * NU);
         rc |= alloc("mu", mu, B * N * NI); rc |= alloc("mu_f", mu_f, B * NIF);
         rc |= alloc("beta", beta, B * N * N * NI); rc |= alloc("beta_f", beta_f, B * n1 * NIF);
@@ -273,9 +282,12 @@ struct Engine : IEngine {
         return 0;
     }
     int linearize(int B, const double* X_, const double* U_, double* A_, double* B_, double* c_, cudaStream_t st) override {
+        return linearize_ld(B, X_, U_, A_, NX, B_, c_, st);      // caller's dense layout
+    }
+    int linearize_ld(int B, const double* X_, const double* U_, double* A_, int lda, double* B_, double* c_, cudaStream_t st) {
         if (B <= 0) return -1;
         const long long n = (long long)B * N * NZ;
-        linearize_kernel<M><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(B, N, X_, U_, h, A_, B_, c_);
+        linearize_kernel<M><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(B, N, X_, U_, h, A_, lda, B_, c_);
         ++launches;
         RN_CUDA(cudaGetLastError());
         return 0;
@@ -299,9 +311,24 @@ struct Engine : IEngine {
         RN_CUDA(cudaGetLastError());
         return 0;
     }
+    double* Apad = nullptr;
+    // caller-provided dense A -> padded scratch copy (no-op layout-wise when nx is even)
+    const double* padded(int B, const double* A_, cudaStream_t st) {
+        if (LDA == NX) return A_;
+        if (Apad == nullptr) {
+            if (cudaMalloc((void**)&Apad, (size_t)cap * N * NX * LDA * sizeof(double)) != cudaSuccess) return nullptr;
+            bufs["Apad"] = {(void*)Apad, (size_t)cap * N * NX * LDA * sizeof(double)};
+        }
+        const long long n = (long long)B * N * NX * LDA;
+        pad_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((long long)B * N * NX, NX, LDA, A_, Apad);
+        ++launches;
+        return Apad;
+    }
     int sls(int B, const double* A_, const double* B_, const double* eta, const double* eta_f, double* K_, double* S_, double* Phi_x_,
             double* Phi_u_, double* beta_, double* beta_f_, double* backoff_, double* backoff_f_, cudaStream_t st) override {
-        if (B <= 0) return -1;
+        if (check_B(B)) return -1;
+        A_ = padded(B, A_, st);
+        if (A_ == nullptr) { set_error("out of memory"); return -2; }
         SlsArgs a{};
         a.B = B; a.N = N; a.A = A_; a.Bm = B_; a.eta = eta; a.eta_f = eta_f;
         a.K = K_; a.S = S_; a.Phi_x = Phi_x_; a.Phi_u = Phi_u_; a.beta = beta_; a.beta_f = beta_f_;
@@ -334,6 +361,8 @@ struct Engine : IEngine {
            const double* x0, const double* bo, const double* bof, double* dX_, double* dU_, double* mu_, double* mu_f_, double* cost_,
            int* iters_, int* status_, cudaStream_t st) override {
         if (check_B(B)) return -1;
+        A_ = padded(B, A_, st);
+        if (A_ == nullptr) { set_error("out of memory"); return -2; }
         int rc = launch_qp(B, tightened ? 1 : 0, A_, B_, c_, X_, U_, x0, bo, bof, nullptr, 0, dX_, dU_, mu_, mu_f_, cost_, iters_, status_, st);
         if (!rc) RN_CUDA(cudaMemsetAsync(ws_valid, 0, (size_t)B * sizeof(int), st));   // the workspace no longer belongs to the resident solve
         return rc;
@@ -343,6 +372,8 @@ struct Engine : IEngine {
                    const double* x0pin, double* dX_, double* dU_, double* mu_, double* mu_f_, double* cost_, int* iters_, int* status_,
                    cudaStream_t st) override {
         if (check_B(B)) return -1;
+        A_ = padded(B, A_, st);
+        if (A_ == nullptr) { set_error("out of memory"); return -2; }
         // zero nominal: dX is the decision variable itself, the pinned value is passed as "x0"
         RN_CUDA(cudaMemsetAsync(dXa_zero(), 0, (size_t)B * ((N + 1) * NX + N * NU) * sizeof(double), st));
         const double* Xz = dXa_zero();
@@ -363,7 +394,9 @@ struct Engine : IEngine {
     int sls_duals(int B, const double* A_, const double* B_, const double* mu_, const double* mu_f_, const double* beta_in_,
                   const double* beta_f_in_, double* K_, double* S_, double* Phi_x_, double* Phi_u_, double* beta_, double* beta_f_,
                   double* backoff_, double* backoff_f_, cudaStream_t st) override {
-        if (B <= 0) return -1;
+        if (check_B(B)) return -1;
+        A_ = padded(B, A_, st);
+        if (A_ == nullptr) { set_error("out of memory"); return -2; }
         SlsArgs a{};
         a.B = B; a.N = N; a.A = A_; a.Bm = B_; a.mu = mu_; a.mu_f = mu_f_; a.beta_in = beta_in_; a.beta_f_in = beta_f_in_;
         a.K = K_; a.S = S_; a.Phi_x = Phi_x_; a.Phi_u = Phi_u_; a.beta = beta_; a.beta_f = beta_f_;
@@ -402,7 +435,7 @@ struct Engine : IEngine {
         RN_CUDA(cudaMemsetAsync(ws_valid, 0, (size_t)B * sizeof(int), st));
         have_solution = false; shifted_since_solve = false;
         for (int it = 0; it < iters; ++it) {
-            int rc = linearize(B, X, U, A, Bm, c, st);
+            int rc = linearize_ld(B, X, U, A, LDA, Bm, c, st);
             if (rc) return rc;
             rc = resident_qp(B, 0, x0, st, FLAG_FAIL, it > 0 ? 1 : 0);   // multipliers of the previous SQP iterate
             if (rc) return rc;
@@ -421,7 +454,7 @@ struct Engine : IEngine {
         if (!sticky_fail) RN_CUDA(cudaMemsetAsync(status, 0, (size_t)B * sizeof(int), st));   // frozen instances keep their failure status
         RN_CUDA(cudaMemsetAsync(qp_iters, 0, (size_t)B * sizeof(int), st));
         if (timing) cudaEventRecord(ev[0], st);
-        int rc = linearize(B, X, U, A, Bm, c, st);                      // update_jacobian (SCP_SLS_jit.py:80)
+        int rc = linearize_ld(B, X, U, A, LDA, Bm, c, st);             // update_jacobian (SCP_SLS_jit.py:80)
         if (timing) cudaEventRecord(ev[1], st);
         if (rc) return rc;
         const bool converge_mode = sls_steps <= 0;
@@ -479,7 +512,7 @@ struct Engine : IEngine {
             apply_step_kernel<<<(unsigned)(((long long)B * ((N + 1) * NX + N * NU) + 255) / 256), 256, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, X, U, flags);   // socp_step
             ++launches;
             if (ii + 1 < rti) {
-                rc = linearize(B, X, U, A, Bm, c, st);                  // update_jacobian (SCP_SLS_jit.py:139); the one after
+                rc = linearize_ld(B, X, U, A, LDA, Bm, c, st);          // update_jacobian (SCP_SLS_jit.py:139); the one after
                 if (rc) return rc;                                      // the last iteration is dead work and is not run
             }
         }

@@ -10,7 +10,7 @@ namespace rnmpc {
 
 template <class M>
 __global__ void __launch_bounds__(128) linearize_kernel(int B, int N, const double* __restrict__ X, const double* __restrict__ U,
-                                                        double h, double* __restrict__ A, double* __restrict__ Bm,
+                                                        double h, double* __restrict__ A, int lda, double* __restrict__ Bm,
                                                         double* __restrict__ c) {
     constexpr int NX = M::NX, NU = M::NU, NZ = NX + NU;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -28,9 +28,9 @@ __global__ void __launch_bounds__(128) linearize_kernel(int B, int N, const doub
     for (int p = 0; p < NU; ++p) ud[p] = Dual(u[p], (NX + p) == t ? 1.0 : 0.0);
     rk4_step<M, Dual>(xd, ud, h, xp);
     if (t < NX) {
-        double* Ao = A + bk * NX * NX;
+        double* Ao = A + bk * NX * lda;      // lda = NX (caller's dense layout) or Slot<NX>::LD (resident padded layout)
 #pragma unroll
-        for (int i = 0; i < NX; ++i) Ao[i * NX + t] = xp[i].d;
+        for (int i = 0; i < NX; ++i) Ao[i * lda + t] = xp[i].d;
     } else {
         double* Bo = Bm + bk * NX * NU;
 #pragma unroll

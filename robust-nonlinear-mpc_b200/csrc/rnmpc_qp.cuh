@@ -19,7 +19,7 @@ struct QpArgs {
                             // -1: per instance, from flags[b] & FLAG_TIGHT
     int max_iter;
     double tol_mu, tol_res;
-    const double* A;        // [B][N][nx][nx]
+    const double* A;        // [B][N][nx][LD] (padded rows)
     const double* Bm;       // [B][N][nx][nu]
     const double* c;        // [B][N][nx]
     const double* Xnom;     // [B][N+1][nx]
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     const int ei[3] = {r0, r1c, NX + (vu ? sl : 0)};
     const bool ev[3] = {true, v1, vu};
 
-    const double* Ab = a.A + (size_t)b * N * NX * NX;
+    const double* Ab = a.A + (size_t)b * N * NX * LD;
     const double* Bb = a.Bm + (size_t)b * N * NX * NU;
     const double* cb = a.c + (size_t)b * N * NX;
     const double* Xn = a.Xnom + (size_t)b * (N + 1) * NX;
@@ -259,15 +259,15 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
         __syncwarp(mask);
         // dynamics residual at the initial point: rp_k = A x_k + B u_k + c_k - x_{k+1}
         for (int k = 0; k < N; ++k) {
-            const double* Ak = Ab + (size_t)k * NX * NX;
+            const double* Ak = Ab + (size_t)k * NX * LD;
             const double* Bk = Bb + (size_t)k * NX * NU;
             double acc0 = cb[k * NX + r0] - Z[(k + 1) * NZ + r0];
             double acc1 = cb[k * NX + r1c] - Z[(k + 1) * NZ + r1c];
 #pragma unroll
             for (int m = 0; m < NX; ++m) {
                 const double xm = Z[k * NZ + m];
-                acc0 = fma(__ldg(Ak + r0 * NX + m), xm, acc0);
-                acc1 = fma(__ldg(Ak + r1c * NX + m), xm, acc1);
+                acc0 = fma(__ldg(Ak + r0 * LD + m), xm, acc0);
+                acc1 = fma(__ldg(Ak + r1c * LD + m), xm, acc1);
             }
 #pragma unroll
             for (int p = 0; p < NU; ++p) {
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             }
             __syncwarp(mask);
             for (int k = N - 1; k >= 0; --k) {
-                const double* Ak = Ab + (size_t)k * NX * NX;
+                const double* Ak = Ab + (size_t)k * NX * LD;
                 const double* Bk = Bb + (size_t)k * NX * NU;
                 // prefetch this stage's scalars before the (long) matrix work
                 const double gx0 = G[k * NZ + r0], gx1 = G[k * NZ + r1c];
@@ -456,22 +456,22 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                             }
                             vec_step(k0, k1, L);
                         },
-                        k > 0, k > 0 ? Ak - NX * NX : nullptr, k > 0 ? Bk - NX * NU : nullptr, resT == k, k > 0 ? Ak - NX * NX : nullptr);
+                        k > 0, k > 0 ? Ak - NX * LD : nullptr, k > 0 ? Bk - NX * NU : nullptr, resT == k, k > 0 ? Ak - NX * LD : nullptr);
                     resT = (k > 0) ? k - 1 : 0;
                     chol_ok = chol_ok && ok;
                 } else {
                     double k0[NU], k1[NU], L[NU][NU];
                     cp_async_wait_all();
-                    if (resT != k && resS != k) { load_matrix_smem<NX, NX, LD, LPS>(sm.T, Ak, sl); resT = k; }
+                    if (resT != k && resS != k) { load_padded_smem<NX, LD, LPS>(sm.T, Ak, sl); resT = k; }
                     const bool inT = (resT == k);
                     Abuf = inT ? sm.T : sm.S;
                     if (k > 0) {       // next stage's A into the other buffer while this stage computes
-                        cp_async_matrix<NX, LD, LPS>(inT ? sm.S : sm.T, Ak - NX * NX, sl);
+                        cp_async_matrix<NX, LD, LPS>(inT ? sm.S : sm.T, Ak - NX * LD, sl);
                         if (inT) resS = k - 1; else resT = k - 1;
                     }
                     load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bk, sl);
                     if (k > 0) {
-                        if (k > 1) prefetch_l2<LPS>(Ak - 2 * NX * NX, NX * NX * 8, sl);     // two stages ahead: the cp.async of the next stage hits L2
+                        if (k > 1) prefetch_l2<LPS>(Ak - 2 * NX * LD, NX * LD * 8, sl);     // two stages ahead: the cp.async of the next stage hits L2
                         prefetch_l2<LPS>(Bk - NX * NU, NX * NU * 8, sl);
                         prefetch_l2<LPS>(Kq + (size_t)(k - 1) * NU * NX, NU * NX * 8, sl);
                     }
@@ -518,22 +518,22 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             if (v1) DZ[r1] = 0.0;
             __syncwarp(mask);
             for (int k = 0; k < N; ++k) {
-                const double* Ak = Ab + (size_t)k * NX * NX;
+                const double* Ak = Ab + (size_t)k * NX * LD;
                 const double* Bk = Bb + (size_t)k * NX * NU;
                 const double* Kk = Kq + (size_t)k * NU * NX;
                 // stage A_k (already resident / in flight from the previous stage or sweep), B_k, K_k + this stage's entry data
                 cp_async_wait_all();
-                if (resT != k && resS != k) { load_matrix_smem<NX, NX, LD, LPS>(sm.T, Ak, sl); resT = k; }
+                if (resT != k && resS != k) { load_padded_smem<NX, LD, LPS>(sm.T, Ak, sl); resT = k; }
                 const bool inT = (resT == k);
                 const double* Af = inT ? sm.T : sm.S;
                 if (k + 1 < N) {
-                    cp_async_matrix<NX, LD, LPS>(inT ? sm.S : sm.T, Ak + NX * NX, sl);
+                    cp_async_matrix<NX, LD, LPS>(inT ? sm.S : sm.T, Ak + NX * LD, sl);
                     if (inT) resS = k + 1; else resT = k + 1;
                 }
                 load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bk, sl);
                 load_matrix_smem<NU, NX, NX, LPS>(sm.SB, Kk, sl);
                 if (k + 1 < N) {
-                    if (k + 2 < N) prefetch_l2<LPS>(Ak + 2 * NX * NX, NX * NX * 8, sl);
+                    if (k + 2 < N) prefetch_l2<LPS>(Ak + 2 * NX * LD, NX * LD * 8, sl);
                     prefetch_l2<LPS>(Bk + NX * NU, NX * NU * 8, sl);
                     prefetch_l2<LPS>(Kk + NU * NX, NU * NX * 8, sl);
                 }

@@ -7,7 +7,7 @@ namespace rnmpc {
 
 struct SlsArgs {
     int B, N;
-    const double* A;       // [B][N][nx][nx]
+    const double* A;       // [B][N][nx][LD] (padded rows, see Slot<NX>::LD)
     const double* Bm;      // [B][N][nx][nu]
     // weights: either explicit eta/eta_f (reference layout [B][N][N][ni], [B][N+1][ni_f]) or mu/mu_f + beta/beta_f
     const double* eta;
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(160, 2) sls_kernel(const SlsArgs a, const Para
     const bool v1 = r1 < NX;
     const int r1c = v1 ? r1 : NX - 1;
     const bool use_beta = (a.beta_in != nullptr) && (!a.beta_from_flags || (a.flags[b] & FLAG_TIGHT) != 0);
-    const double* Ab = a.A + (size_t)b * N * NX * NX;
+    const double* Ab = a.A + (size_t)b * N * NX * LD;
     const double* Bb = a.Bm + (size_t)b * N * NX * NU;
     const size_t kstride = (size_t)NU * NX;
 
@@ -119,10 +119,10 @@ __global__ void __launch_bounds__(160, 2) sls_kernel(const SlsArgs a, const Para
         const double* a_next = nullptr;
         if (t + 1 < N) {
             const int kn = (t + 1 < n_first) ? (k - 1) : ((t + 1 == n_first) ? (N - 1) : (k - 1));
-            a_next = Ab + (size_t)kn * NX * NX;
+            a_next = Ab + (size_t)kn * NX * LD;
         }
-        riccati_step<NX, NU>(sm, sl, mask, Ab + (size_t)k * NX * NX, Bb + (size_t)k * NX * NU, prm->Qreg, prm->Rreg, cx0, cx1,
-                             Kout, NoPre(), NoPost(), true, k > 0 ? Ab + (size_t)(k - 1) * NX * NX : nullptr,
+        riccati_step<NX, NU>(sm, sl, mask, Ab + (size_t)k * NX * LD, Bb + (size_t)k * NX * NU, prm->Qreg, prm->Rreg, cx0, cx1,
+                             Kout, NoPre(), NoPost(), true, k > 0 ? Ab + (size_t)(k - 1) * NX * LD : nullptr,
                              k > 0 ? Bb + (size_t)(k - 1) * NX * NU : nullptr, t_ready, a_next);
         t_ready = a_next != nullptr;
         if (a.S != nullptr) {
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(160, 2) sls_kernel(const SlsArgs a, const Para
             double kv[ITK];
 #pragma unroll
             for (int j = 0; j < ITK; ++j) { const int e = sl + j * LPS; kv[j] = (e < NU * NX) ? Kin[e] : 0.0; }
-            load_matrix_smem<NX, NX, LD, LPS>(sm.T, Ab + (size_t)k * NX * NX, sl);
+            load_padded_smem<NX, LD, LPS>(sm.T, Ab + (size_t)k * NX * LD, sl);
 #pragma unroll
             for (int j = 0; j < ITK; ++j) {
                 const int e = sl + j * LPS;

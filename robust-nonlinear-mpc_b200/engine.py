@@ -97,7 +97,7 @@ class BatchSolver:
         "X": lambda s: (s.N + 1, s.nx), "U": lambda s: (s.N, s.nu), "dX": lambda s: (s.N + 1, s.nx), "dU": lambda s: (s.N, s.nu),
         "mu": lambda s: (s.N, s.ni), "mu_f": lambda s: (s.ni_f,), "K": lambda s: (s.N, s.N + 1, s.nu, s.nx),
         "beta": lambda s: (s.N, s.N, s.ni), "beta_f": lambda s: (s.N + 1, s.ni_f), "backoff": lambda s: (s.N, s.ni),
-        "backoff_f": lambda s: (s.ni_f,), "A": lambda s: (s.N, s.nx, s.nx), "B": lambda s: (s.N, s.nx, s.nu),
+        "backoff_f": lambda s: (s.ni_f,), "A": lambda s: (s.N, s.nx, (s.nx + 1) & ~1), "B": lambda s: (s.N, s.nx, s.nu),
         "c": lambda s: (s.N, s.nx), "cost": lambda s: (), "Phi_x": lambda s: (s.N + 1, s.N + 1, s.nx, s.nx),
         "Phi_u": lambda s: (s.N, s.N + 1, s.nu, s.nx), "flags": lambda s: (), "status": lambda s: (), "qp_iters": lambda s: (),
     }
