@@ -190,7 +190,7 @@ struct Engine : IEngine {
 
     double *X, *U, *A, *Bm, *c, *dX, *dU, *mu, *mu_f, *beta, *beta_f, *backoff, *backoff_f, *K, *cost, *prevX, *prevU;
     double *Phi_x = nullptr, *Phi_u = nullptr;
-    double *wZ, *wSU, *wSL, *wLU, *wLL, *wDZA, *wDZC, *wG, *wSIG, *wZN, *wISU, *wISL, *rp, *Sc, *dff, *Kq, *Lq;
+    double *wE, *wG, *rp, *Sc, *dff, *Kq, *Lq;
     int *flags, *status, *qp_iters, *iters_tmp, *status_tmp, *n_open, *ws_valid;
     bool have_solution = false, shifted_since_solve = false;   // host-side warm-start bookkeeping
     int warm_enabled = 1;
@@ -243,10 +243,7 @@ struct Engine : IEngine {
         rc |= alloc("backoff", backoff, B * N * NI); rc |= alloc("backoff_f", backoff_f, B * NIF);
         rc |= alloc("K", K, B * N * n1 * NU * NX); rc |= alloc("cost", cost, B);
         rc |= alloc("prevX", prevX, B * n1 * NX); rc |= alloc("prevU", prevU, B * N * NU);
-        rc |= alloc("wZ", wZ, B * n1 * NZ); rc |= alloc("wSU", wSU, B * n1 * NZ); rc |= alloc("wSL", wSL, B * n1 * NZ);
-        rc |= alloc("wLU", wLU, B * n1 * NZ); rc |= alloc("wLL", wLL, B * n1 * NZ); rc |= alloc("wDZA", wDZA, B * n1 * NZ);
-        rc |= alloc("wDZC", wDZC, B * n1 * NZ); rc |= alloc("wG", wG, B * n1 * NZ); rc |= alloc("wSIG", wSIG, B * n1 * NZ);
-        rc |= alloc("wZN", wZN, B * n1 * NZ); rc |= alloc("wISU", wISU, B * n1 * NZ); rc |= alloc("wISL", wISL, B * n1 * NZ);
+        rc |= alloc("wE", wE, B * n1 * NZ * kRec); rc |= alloc("wG", wG, B * n1 * NZ);
         rc |= alloc("rp", rp, B * N * NX); rc |= alloc("Sc", Sc, B * N * NX); rc |= alloc("dff", dff, B * N * NU);
         rc |= alloc("Kq", Kq, B * N * NU * NX); rc |= alloc("Lq", Lq, B * N * NU * NU);
         rc |= alloc("flags", flags, B); rc |= alloc("status", status, B); rc |= alloc("qp_iters", qp_iters, B);
@@ -347,7 +344,7 @@ struct Engine : IEngine {
         a.A = A_; a.Bm = B_; a.c = c_; a.Xnom = X_; a.Unom = U_; a.x0 = x0; a.backoff = bo; a.backoff_f = bof;
         a.flags = fl; a.skip_mask = skip_mask;
         a.dX = dX_; a.dU = dU_; a.mu = mu_; a.mu_f = mu_f_; a.cost = cost_; a.iters = iters_; a.status = status_;
-        a.Z = wZ; a.SU = wSU; a.SL = wSL; a.LU = wLU; a.LL = wLL; a.DZA = wDZA; a.DZC = wDZC; a.G = wG; a.SIG = wSIG; a.ZN = wZN; a.ISU = wISU; a.ISL = wISL; a.diag_cost = diag_cost; a.rp = rp; a.Sc = Sc;
+        a.E = wE; a.G = wG; a.diag_cost = diag_cost; a.rp = rp; a.Sc = Sc;
         a.dff = dff; a.Kq = Kq; a.Lq = Lq;
         const long long warps = ((long long)B + Slot<NX>::SPW - 1) / Slot<NX>::SPW;
         const unsigned grid = (unsigned)((warps + kWarps - 1) / kWarps);

@@ -5,13 +5,25 @@
 //
 // Solved per instance by a Mehrotra predictor-corrector primal-dual interior-point method whose every KKT solve is
 // a Riccati factorisation / sweep over the block-tridiagonal structure (riccati_step of rnmpc_common.cuh: the same
-// device function the fast-SLS kernel runs).  One instance per slot (LPS lanes), SPW instances per warp in
-// lock-step.  Per-instance vectors live in global (L2-resident) workspace in one [N+1][nz] "entry" layout; the
-// element-wise phases load groups of KU stages ahead of the arithmetic so that their latency overlaps.
+// device function the fast-SLS kernel runs).  One instance per slot (LPS lanes), SPW instances per warp in lock-step.
+//
+// Per-instance iterate: one 96-byte record per box entry (stage k, component i) in global (L2-resident) workspace,
+//   { s_up, s_lo, lam_up, lam_lo, 1/s_up, 1/s_lo, z, z_nom, dz_affine, dz_combined, sigma, 2*H_ii }
+// so that the data of an entry arrives with six 16-byte loads from one or two cache lines (the first version kept twelve
+// separate arrays: every entry touched twelve 32-byte sectors).  One interior-point iteration is four sweeps over the stages
+// and one element-wise pass:
+//   bwd0  Riccati factorisation + predictor right-hand side (formed on the fly from the records)
+//   fwd0  predictor step, ratio test and the four sums that give mu_affine for any step lengths
+//   bwd1  corrector right-hand side (on the fly) + backward vector recursion with the stored factors
+//   fwd1  combined step + ratio test
+//   P4    update of z, slacks, multipliers; new reciprocals, barrier diagonal and complementarity
 #pragma once
 #include "rnmpc_common.cuh"
 
 namespace rnmpc {
+
+constexpr int kRec = 12;    // doubles per entry record
+enum { F_SU = 0, F_SL = 1, F_LU = 2, F_LL = 3, F_ISU = 4, F_ISL = 5, F_Z = 6, F_ZN = 7, F_DZA = 8, F_DZC = 9, F_SIG = 10, F_QD = 11 };
 
 struct QpArgs {
     int B, N;
@@ -42,39 +54,26 @@ struct QpArgs {
     int* iters;             // [B]
     int* status;            // [B] 0 ok, 1 not converged, 2 infeasible (measured state outside the stage-0 box by more than
                             //     kX0Tol, or crossed bounds), 3 numerical failure (non-positive pivot / NaN)
-    // workspace, entry layout [B][N+1][nz] unless noted
-    double* Z;              // primal iterate (x_k, u_k)
-    double* SU;             // slack of the upper bound  (>= kBig: no bound)
-    double* SL;             // slack of the lower bound
-    double* LU;             // multiplier of the upper bound
-    double* LL;             // multiplier of the lower bound
-    double* DZA;            // affine (predictor) step
-    double* DZC;            // combined step
-    double* G;              // right-hand side of the current KKT solve
-    double* SIG;            // barrier Hessian diagonal  LU/SU + LL/SL
-    double* ZN;             // nominal trajectory in entry layout
-    double* ISU;            // 1/SU (0 where there is no bound)
-    double* ISL;            // 1/SL
-    int diag_cost;          // 1: Q, R, Qf are diagonal (all reference drivers) -> element-wise gradient
-    int warm;               // warm start from the workspace's previous solution of the same instance: bit0 multipliers, bit1 shifted by one
-                            // stage (previous MPC step), bit2 primal iterate; a failed warm-started solve is repeated from the cold start
-    int* ws_valid;          // [B] workspace holds a converged solution
+    // workspace
+    double* E;              // [B][N+1][nz][kRec] entry records
+    double* G;              // [B][N+1][nz]   gradient 2H(z + z_nom) + q, only for non-diagonal cost matrices
     double* rp;             // [B][N][nx]     dynamics residual at the initial point
     double* Sc;             // [B][N][nx]     S_{k+1} rp_k
     double* dff;            // [B][N][nu]     feed-forward
     double* Kq;             // [B][N][nu][nx]
     double* Lq;             // [B][N][nu*nu]
+    int diag_cost;          // 1: Q, R, Qf are diagonal (all reference drivers) -> gradient formed on the fly from the records
+    int warm;               // warm start from the workspace's previous solution of the same instance: bit0 multipliers, bit1 shifted by one
+                            // stage (previous MPC step), bit2 primal iterate; a failed warm-started solve is repeated from the cold start
+    int* ws_valid;          // [B] workspace holds a converged solution
 };
-
-template <int V>
-struct IntTag { static constexpr int value = V; };
 
 template <int NX, int NU>
 __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Params<NX, NU>* __restrict__ prm) {
     using SL_ = Slot<NX>;
     constexpr int LD = SL_::LD, LPS = SL_::LPS, SPW = SL_::SPW;
     constexpr int NZ = NX + NU, NI = 2 * NZ, NIF = 2 * NX;
-    constexpr int KU = 4;                        // stages loaded ahead in the element-wise passes
+    constexpr int KU = 2;                        // stages loaded ahead in the element-wise pass
     static_assert(LPS >= NU, "one lane per input entry");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SlotSmem<NX, NU>* smem = reinterpret_cast<SlotSmem<NX, NU>*>(smem_raw);
@@ -97,8 +96,9 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     const bool v1 = r1 < NX;
     const int r1c = v1 ? r1 : NX - 1;
     const bool vu = sl < NU;
+    const int iuc = NX + (vu ? sl : 0);
     // the (up to) three entries of every stage this lane owns: x[r0], x[r1], u[sl]
-    const int ei[3] = {r0, r1c, NX + (vu ? sl : 0)};
+    const int ei[3] = {r0, r1c, iuc};
     const bool ev[3] = {true, v1, vu};
 
     const double* Ab = a.A + (size_t)b * N * NX * LD;
@@ -107,24 +107,28 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     const double* Xn = a.Xnom + (size_t)b * (N + 1) * NX;
     const double* Un = a.Unom + (size_t)b * N * NU;
     const size_t eoff = (size_t)b * (N + 1) * NZ;
-    double* __restrict__ Z = a.Z + eoff;
-    double* __restrict__ SU = a.SU + eoff;
-    double* __restrict__ SLk = a.SL + eoff;
-    double* __restrict__ LU = a.LU + eoff;
-    double* __restrict__ LL = a.LL + eoff;
-    double* __restrict__ DZA = a.DZA + eoff;
-    double* __restrict__ DZC = a.DZC + eoff;
+    double* __restrict__ E = a.E + eoff * kRec;
     double* __restrict__ G = a.G + eoff;
-    double* __restrict__ SIG = a.SIG + eoff;
-    double* __restrict__ ZN = a.ZN + eoff;
-    double* __restrict__ ISU = a.ISU + eoff;
-    double* __restrict__ ISL = a.ISL + eoff;
     double* rp = a.rp + (size_t)b * N * NX;
     double* Sc = a.Sc + (size_t)b * N * NX;
     double* dff = a.dff + (size_t)b * N * NU;
     double* Kq = a.Kq + (size_t)b * N * NU * NX;
     double* Lq = a.Lq + (size_t)b * N * NU * NU;
+    const bool dg = a.diag_cost != 0;
 
+    auto ld2 = [&](int idx, int f) -> double2 { return *reinterpret_cast<const double2*>(E + (size_t)idx * kRec + f); };
+    auto st2 = [&](int idx, int f, double x, double y) { *reinterpret_cast<double2*>(E + (size_t)idx * kRec + f) = make_double2(x, y); };
+
+    auto slot_sum4 = [&](double& x, double& y, double& z, double& w) {
+        __syncwarp(mask);
+        sm.red[2 * sl] = x; sm.red[2 * sl + 1] = y;
+        sm.vec[3 * LD + 2 * sl] = z; sm.vec[3 * LD + 2 * sl + 1] = w;
+        __syncwarp(mask);
+        double sx = 0.0, sy = 0.0, sz = 0.0, sw = 0.0;
+#pragma unroll
+        for (int i = 0; i < LPS; ++i) { sx += sm.red[2 * i]; sy += sm.red[2 * i + 1]; sz += sm.vec[3 * LD + 2 * i]; sw += sm.vec[3 * LD + 2 * i + 1]; }
+        x = sx; y = sy; z = sz; w = sw;
+    };
     auto slot_sum2 = [&](double& x, double& y) {
         __syncwarp(mask);
         sm.red[2 * sl] = x; sm.red[2 * sl + 1] = y;
@@ -134,43 +138,15 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
         for (int i = 0; i < LPS; ++i) { sx += sm.red[2 * i]; sy += sm.red[2 * i + 1]; }
         x = sx; y = sy;
     };
-    auto slot_min2 = [&](double& x, double& y) {
+    auto slot_max2 = [&](double& x, double& y) {
         __syncwarp(mask);
         sm.red[2 * sl] = x; sm.red[2 * sl + 1] = y;
         __syncwarp(mask);
         double sx = sm.red[0], sy = sm.red[1];
 #pragma unroll
-        for (int i = 1; i < LPS; ++i) { sx = fmin(sx, sm.red[2 * i]); sy = fmin(sy, sm.red[2 * i + 1]); }
+        for (int i = 1; i < LPS; ++i) { sx = fmax(sx, sm.red[2 * i]); sy = fmax(sy, sm.red[2 * i + 1]); }
         x = sx; y = sy;
     };
-    // element-wise pass over the entries of this lane: NA arrays are loaded for KU stages at a time, then
-    // body(k, idx, vals) runs for every owned entry (idx = k*NZ + i)
-    auto entry_pass = [&](auto na_tag, const double* const* arr, auto&& body) {
-        constexpr int NA = decltype(na_tag)::value;
-        for (int k0 = 0; k0 <= N; k0 += KU) {
-            double v[KU][3][NA];
-#pragma unroll
-            for (int j = 0; j < KU; ++j) {
-                const int k = (k0 + j <= N) ? (k0 + j) : N;
-#pragma unroll
-                for (int e = 0; e < 3; ++e)
-#pragma unroll
-                    for (int q = 0; q < NA; ++q) v[j][e][q] = arr[q][k * NZ + ei[e]];
-            }
-#pragma unroll
-            for (int j = 0; j < KU; ++j) {
-                const int k = k0 + j;
-                if (k <= N) {
-#pragma unroll
-                    for (int e = 0; e < 3; ++e)
-                        if (ev[e]) body(k, k * NZ + ei[e], v[j][e]);
-                }
-            }
-        }
-    };
-    using I4 = IntTag<4>;
-    using I5 = IntTag<5>;
-    using I6 = IntTag<6>;
 
     int status = 0;
     const bool tight = a.tightened < 0 ? ((a.flags[b] & FLAG_TIGHT) != 0) : (a.tightened != 0);
@@ -186,7 +162,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     if (act) { status = 0; rp_scale = 1.0; }
     double n_box_new = 0.0;
 
-    // ------------------------------------------------------------------ bounds, initial point, slacks, duals
+    // ------------------------------------------------------------------ bounds, initial point, slacks, duals -> records
     {
         const double e = tight ? 0.0 : kEpsQP;
         double bad = 0.0;
@@ -196,10 +172,12 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 if (!ev[en]) continue;
                 const int i = ei[en];
                 const int idx = k * NZ + i;
-                double h_ = 1e300, l_ = -1e300, z = 0.0;
+                double h_ = 1e300, l_ = -1e300, z = 0.0, zn = 0.0, qd = 0.0;
                 bool box = false;
                 if (en < 2) {                       // state entry
                     const double xn = Xn[k * NX + i];
+                    zn = xn;
+                    qd = 2.0 * ((k < N) ? prm->Q[i * NX + i] : prm->Qf[i * NX + i]);
                     if (k < N) {
                         const double bu = tight ? a.backoff[((size_t)b * N + k) * NI + i] : 0.0;
                         const double bl = tight ? a.backoff[((size_t)b * N + k) * NI + NZ + i] : 0.0;
@@ -217,6 +195,8 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 } else if (k < N) {                 // input entry
                     const int p = i - NX;
                     const double un = Un[k * NU + p];
+                    zn = un;
+                    qd = 2.0 * prm->R[p * NU + p];
                     const double bu = tight ? a.backoff[((size_t)b * N + k) * NI + i] : 0.0;
                     const double bl = tight ? a.backoff[((size_t)b * N + k) * NI + NZ + i] : 0.0;
                     h_ = (prm->uub[p] - un) - bu + e;
@@ -227,6 +207,8 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 // the stage-0 state rows only restate the pinned x(0): they are dropped; a violation beyond kX0Tol (OSQP's default
                 // eps_abs, which the reference's solver would tolerate) makes the instance infeasible
                 if (k == 0 && en < 2 && (z > h_ + kX0Tol || z < l_ - kX0Tol)) bad = 1.0;
+                // the linear cost of the general mode is folded into the nominal: qd (z + zn) + q = qd (z + zn + q/qd)
+                if (a.q_lin != nullptr && dg && qd != 0.0) zn += a.q_lin[eoff + idx] / qd;
                 double su = 1e300, sl_ = 1e300, lu = 0.0, ll = 0.0;
                 if (box) {
                     const bool hu = h_ < kBig, hl = l_ > -kBig;
@@ -235,8 +217,9 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                         // previous solution of this instance (same workspace); bit1: the multipliers of the next stage (the
                         // trajectories were shifted by one stage since); reads run ahead of this lane's own writes
                         const int ks = (a.warm & 2) ? ((en < 2) ? (k + 1 <= N ? k + 1 : N) : (k + 1 < N ? k + 1 : N - 1)) : k;
-                        lu0 = LU[ks * NZ + i]; ll0 = LL[ks * NZ + i];
-                        if (a.warm & 4) z0 = Z[idx];
+                        const double2 lw = ld2(ks * NZ + i, F_LU);
+                        lu0 = lw.x; ll0 = lw.y;
+                        if (a.warm & 4) z0 = E[(size_t)idx * kRec + F_Z];
                     }
                     if (hu && hl) {
                         const double m = (warm ? kFracWarm : 0.01) * (h_ - l_);
@@ -247,8 +230,15 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     if (hu) { su = h_ - z; lu = warm ? fmax(lu0, kMuWarm / su) : 1.0; n_box_new += 1.0; }
                     if (hl) { sl_ = z - l_; ll = warm ? fmax(ll0, kMuWarm / sl_) : 1.0; n_box_new += 1.0; }
                 }
-                if (act) { Z[idx] = z; SU[idx] = su; SLk[idx] = sl_; LU[idx] = lu; LL[idx] = ll; }
-                ZN[idx] = (en < 2) ? Xn[k * NX + i] : (k < N ? Un[k * NU + (i - NX)] : 0.0);
+                if (act) {
+                    const double iu = (su < kBig) ? 1.0 / su : 0.0, il = (sl_ < kBig) ? 1.0 / sl_ : 0.0;
+                    st2(idx, F_SU, su, sl_);
+                    st2(idx, F_LU, lu, ll);
+                    st2(idx, F_ISU, iu, il);
+                    st2(idx, F_Z, z, zn);
+                    st2(idx, F_DZA, 0.0, 0.0);
+                    st2(idx, F_SIG, lu * iu + ll * il, qd);
+                }
             }
         }
         slot_sum2(bad, n_box_new);
@@ -261,17 +251,17 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
         for (int k = 0; k < N; ++k) {
             const double* Ak = Ab + (size_t)k * NX * LD;
             const double* Bk = Bb + (size_t)k * NX * NU;
-            double acc0 = cb[k * NX + r0] - Z[(k + 1) * NZ + r0];
-            double acc1 = cb[k * NX + r1c] - Z[(k + 1) * NZ + r1c];
+            double acc0 = cb[k * NX + r0] - E[(size_t)((k + 1) * NZ + r0) * kRec + F_Z];
+            double acc1 = cb[k * NX + r1c] - E[(size_t)((k + 1) * NZ + r1c) * kRec + F_Z];
 #pragma unroll
             for (int m = 0; m < NX; ++m) {
-                const double xm = Z[k * NZ + m];
+                const double xm = E[(size_t)(k * NZ + m) * kRec + F_Z];
                 acc0 = fma(__ldg(Ak + r0 * LD + m), xm, acc0);
                 acc1 = fma(__ldg(Ak + r1c * LD + m), xm, acc1);
             }
 #pragma unroll
             for (int p = 0; p < NU; ++p) {
-                const double up = Z[k * NZ + NX + p];
+                const double up = E[(size_t)(k * NZ + NX + p) * kRec + F_Z];
                 acc0 = fma(__ldg(Bk + r0 * NU + p), up, acc0);
                 acc1 = fma(__ldg(Bk + r1c * NU + p), up, acc1);
             }
@@ -282,26 +272,26 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
         }
         __syncwarp(mask);
     }
-
     {
-        double m0 = 0.0, dmy = 0.0;
+        double m0 = 0.0, acc = 0.0;
         for (int k = 0; k < N; ++k) {
             m0 = fmax(m0, fabs(rp[k * NX + r0]));
             if (v1) m0 = fmax(m0, fabs(rp[k * NX + r1]));
         }
-        m0 = -m0;
-        slot_min2(m0, dmy);
-        if (act) rp_inf = -m0;
-    }
-    {
-        double acc = 0.0, dmy = 0.0;
-        const double* arr[4] = {SU, SLk, LU, LL};
-        entry_pass(I4{}, arr, [&](int, int, const double (&v)[4]) {
-            if (v[0] < kBig) acc = fma(v[0], v[2], acc);
-            if (v[1] < kBig) acc = fma(v[1], v[3], acc);
-        });
+        for (int k = 0; k <= N; ++k) {
+#pragma unroll
+            for (int en = 0; en < 3; ++en) {
+                if (!ev[en] || (en == 2 && k == N)) continue;
+                const int idx = k * NZ + ei[en];
+                const double2 s = ld2(idx, F_SU), l = ld2(idx, F_LU);
+                if (s.x < kBig) acc = fma(s.x, l.x, acc);
+                if (s.y < kBig) acc = fma(s.y, l.y, acc);
+            }
+        }
+        double dmy = 0.0;
+        slot_max2(m0, dmy);
         slot_sum2(acc, dmy);
-        if (act) mu_c = n_box > 0.0 ? acc / n_box : 0.0;
+        if (act) { rp_inf = m0; mu_c = n_box > 0.0 ? acc / n_box : 0.0; }
     }
 
     int stalled = 0;
@@ -312,63 +302,63 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     for (it = 0; it < it_cap; ++it) {
         if (__all_sync(mask, done)) break;
         __syncwarp(mask);
-        // ---- P1: reciprocal slacks, barrier diagonal SIG and gradient G = 2 H (z + z_nom)
-        {
-            const double* arr[6] = {SU, SLk, LU, LL, Z, ZN};
-            const double qd[3] = {prm->Q[r0 * NX + r0], prm->Q[r1c * NX + r1c], vu ? prm->R[sl * NU + sl] : 0.0};
-            const double qfd[2] = {prm->Qf[r0 * NX + r0], prm->Qf[r1c * NX + r1c]};
-            const bool dg = a.diag_cost != 0;
-            entry_pass(I6{}, arr, [&](int k, int idx, const double (&v)[6]) {
-                double sg = 0.0, iu = 0.0, il = 0.0;
-                if (v[0] < kBig) { iu = 1.0 / v[0]; sg = v[2] * iu; }
-                if (v[1] < kBig) { il = 1.0 / v[1]; sg = fma(v[3], il, sg); }
-                SIG[idx] = sg; ISU[idx] = iu; ISL[idx] = il;
-                if (dg) {
-                    const int i = idx - k * NZ;
-                    const double q = (i >= NX) ? qd[2] : (i == r0 ? (k < N ? qd[0] : qfd[0]) : (k < N ? qd[1] : qfd[1]));
-                    G[idx] = 2.0 * q * (v[4] + v[5]) + (a.q_lin != nullptr ? a.q_lin[eoff + idx] : 0.0);
+        if (!dg) {
+            // dense cost matrices: gradient G = 2 H (z + z_nom) + q by explicit mat-vecs (not used by any reference driver)
+            for (int k = 0; k <= N; ++k) {
+                const double* Qm = (k < N) ? prm->Q : prm->Qf;
+                double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+                for (int m = 0; m < NX; ++m) {
+                    const double2 zz = ld2(k * NZ + m, F_Z);
+                    acc0 = fma(Qm[r0 * NX + m], zz.x + zz.y, acc0);
+                    acc1 = fma(Qm[r1c * NX + m], zz.x + zz.y, acc1);
                 }
-            });
-            if (!dg) {
-                for (int k = 0; k <= N; ++k) {
-                    const double* Qm = (k < N) ? prm->Q : prm->Qf;
-                    double acc0 = 0.0, acc1 = 0.0;
+                G[k * NZ + r0] = 2.0 * acc0 + (a.q_lin != nullptr ? a.q_lin[eoff + k * NZ + r0] : 0.0);
+                if (v1) G[k * NZ + r1] = 2.0 * acc1 + (a.q_lin != nullptr ? a.q_lin[eoff + k * NZ + r1] : 0.0);
+                if (vu && k < N) {
+                    double acc = 0.0;
 #pragma unroll
-                    for (int m = 0; m < NX; ++m) {
-                        const double y = Z[k * NZ + m] + ZN[k * NZ + m];
-                        acc0 = fma(Qm[r0 * NX + m], y, acc0);
-                        acc1 = fma(Qm[r1c * NX + m], y, acc1);
-                    }
-                    G[k * NZ + r0] = 2.0 * acc0 + (a.q_lin != nullptr ? a.q_lin[eoff + k * NZ + r0] : 0.0);
-                    if (v1) G[k * NZ + r1] = 2.0 * acc1 + (a.q_lin != nullptr ? a.q_lin[eoff + k * NZ + r1] : 0.0);
-                    if (vu && k < N) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int m = 0; m < NU; ++m) acc = fma(prm->R[sl * NU + m], Z[k * NZ + NX + m] + ZN[k * NZ + NX + m], acc);
-                        G[k * NZ + NX + sl] = 2.0 * acc + (a.q_lin != nullptr ? a.q_lin[eoff + k * NZ + NX + sl] : 0.0);
-                    }
+                    for (int m = 0; m < NU; ++m) { const double2 zz = ld2(k * NZ + NX + m, F_Z); acc = fma(prm->R[sl * NU + m], zz.x + zz.y, acc); }
+                    G[k * NZ + NX + sl] = 2.0 * acc + (a.q_lin != nullptr ? a.q_lin[eoff + k * NZ + NX + sl] : 0.0);
                 }
             }
+            __syncwarp(mask);
         }
-        __syncwarp(mask);
 
         double sigma_mu = 0.0, ap = 1.0, ad = 1.0;
         bool chol_ok = true;
         bool skip_corr = false, corr_skipped = false;
         double maxp0 = 0.0, maxd0 = 0.0;
+        // right-hand side of one entry: gradient (+ centring / second-order terms in the corrector pass)
+        auto rhs_entry = [&](int pass, int idx, bool use) -> double {
+            if (!use) return 0.0;
+            const double2 zz = ld2(idx, F_Z);
+            double g = dg ? ld2(idx, F_SIG).y * (zz.x + zz.y) : G[idx];
+            if (pass == 1) {
+                const double2 is = ld2(idx, F_ISU), l = ld2(idx, F_LU);
+                const double dza = E[(size_t)idx * kRec + F_DZA];
+                if (is.x > 0.0) g = fma(sigma_mu + dza * (l.x * is.x * dza - l.x), is.x, g);
+                if (is.y > 0.0) g = fma(-(sigma_mu + dza * (l.y * is.y * dza + l.y)), is.y, g);
+            }
+            return g;
+        };
         for (int pass = 0; pass < 2; ++pass) {
             // the corrector's two sweeps are skipped when every slot of the warp is in the Newton phase (see below)
             if (pass == 1 && __all_sync(mask, skip_corr)) break;
-            // ---- backward: p_N = G_N ; pass 0 also builds S_N = 2 Qf + SIG_N
-            sm.vec[r0] = G[N * NZ + r0];
-            if (v1) sm.vec[r1] = G[N * NZ + r1];
+            // ---- backward: p_N = rhs_N ; pass 0 also builds S_N = 2 Qf + SIG_N
+            {
+                const double gN0 = rhs_entry(pass, N * NZ + r0, true), gN1 = rhs_entry(pass, N * NZ + r1c, v1);
+                sm.vec[r0] = gN0;
+                if (v1) sm.vec[r1] = gN1;
+            }
             if (pass == 0) {
+                cp_async_wait_all();
                 resS = -1;
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
                     const int r = rr ? r1 : r0;
                     if (rr && !v1) continue;
-                    const double sg = SIG[N * NZ + r];
+                    const double sg = E[(size_t)(N * NZ + r) * kRec + F_SIG];
                     for (int c = 0; c < LD; ++c) sm.S[r * LD + c] = (c < NX) ? (2.0 * prm->Qf[r * NX + c] + (c == r ? sg : 0.0)) : 0.0;
                 }
             }
@@ -376,9 +366,10 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             for (int k = N - 1; k >= 0; --k) {
                 const double* Ak = Ab + (size_t)k * NX * LD;
                 const double* Bk = Bb + (size_t)k * NX * NU;
-                // prefetch this stage's scalars before the (long) matrix work
-                const double gx0 = G[k * NZ + r0], gx1 = G[k * NZ + r1c];
-                const double gu_ = vu ? G[k * NZ + NX + sl] : 0.0;
+                // this stage's scalars, fetched ahead of the (long) matrix work
+                const double gx0 = (k > 0) ? rhs_entry(pass, k * NZ + r0, true) : 0.0;
+                const double gx1 = (k > 0) ? rhs_entry(pass, k * NZ + r1c, v1) : 0.0;
+                const double gu_ = rhs_entry(pass, k * NZ + iuc, vu);
                 const double rp0 = rp[k * NX + r0], rp1 = rp[k * NX + r1c];
                 double sc0 = 0.0, sc1 = 0.0;
                 // Sc_k = S_{k+1} rp_k while S_{k+1} is still in shared memory (pass 0); the corrector re-reads it
@@ -396,8 +387,8 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     if (v1) Sc[k * NX + r1] = sc1;
                     __syncwarp(mask);
                 };
-                // vector recursion of the KKT solve; A_k is in sm.T, B_k in sm.Bm, K columns / factor in registers
                 const double* Abuf = sm.T;
+                // vector recursion of the KKT solve; A_k is in Abuf, B_k in sm.Bm, K columns / factor in registers
                 auto vec_step = [&](const double (&k0)[NU], const double (&k1)[NU], const double (&L)[NU][NU]) {
                     // g = p_{k+1} + Sc
                     const double g0 = sm.vec[r0] + rp_scale * sc0;
@@ -442,9 +433,12 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     __syncwarp(mask);
                 };
                 if (pass == 0) {
-                    const double cx0 = (k > 0) ? SIG[k * NZ + r0] : 0.0;
-                    const double cx1 = (k > 0 && v1) ? SIG[k * NZ + r1] : 0.0;
-                    if (vu) sm.cu[sl] = SIG[k * NZ + NX + sl];
+                    double cx0 = 0.0, cx1 = 0.0;
+                    if (k > 0) {
+                        cx0 = E[(size_t)(k * NZ + r0) * kRec + F_SIG];
+                        if (v1) cx1 = E[(size_t)(k * NZ + r1) * kRec + F_SIG];
+                    }
+                    if (vu) sm.cu[sl] = E[(size_t)(k * NZ + NX + sl) * kRec + F_SIG];
                     const bool ok = riccati_step<NX, NU>(
                         sm, sl, mask, Ak, Bk, prm->Q2, prm->R2, cx0, cx1, Kq + (size_t)k * NU * NX, pre_step,
                         [&](const double (&k0)[NU], const double (&k1)[NU], const double (&L)[NU][NU]) {
@@ -488,34 +482,38 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     vec_step(k0, k1, L);
                 }
             }
-            // ---- forward: dx_0 = 0 ; du_k = K dx_k + d_k ; dx_{k+1} = A dx_k + B du_k + rp_k ; fused ratio test
-            double* __restrict__ DZ = pass == 0 ? DZA : DZC;
+            // ---- forward: dx_0 = 0 ; du_k = K dx_k + d_k ; dx_{k+1} = A dx_k + B du_k + rp_k ; fused ratio test (+ mu_aff sums)
             const double tau = pass == 0 ? 1.0 : (mu_c > 1e-8 ? 0.995 : 0.9999);
             // largest dz/s and -dlam/lam over the entries: alpha = min(1, tau / max)
             double rpm = 0.0, rdm = 0.0;
-            auto ratio_entry = [&](double isu, double isl, double lu, double ll, double dz, double dza) {
-                if (isu > 0.0) {
-                    const double ru = lu * isu;
+            // (s + ap ds)(lam + ad dlam) summed over the entries = S1 + ad S2 + ap S3 + ap ad S4 for any step lengths
+            double S2 = 0.0, S3 = 0.0, S4 = 0.0;
+            auto ratio_entry = [&](double2 s, double2 is, double2 l, double dz, double dza) {
+                if (is.x > 0.0) {
+                    const double ru = l.x * is.x;
                     double tgt = 0.0;
-                    if (pass == 1) tgt = sigma_mu + dza * (ru * dza - lu);
-                    const double dlu = tgt * isu - lu + ru * dz;
-                    rpm = fmax(rpm, dz * isu);
-                    if (dlu < 0.0) rdm = fmax(rdm, -dlu / lu);
+                    if (pass == 1) tgt = sigma_mu + dza * (ru * dza - l.x);
+                    const double dlu = tgt * is.x - l.x + ru * dz;
+                    rpm = fmax(rpm, dz * is.x);
+                    if (dlu < 0.0) rdm = fmax(rdm, -dlu / l.x);
+                    if (pass == 0) { S2 = fma(s.x, dlu, S2); S3 = fma(-dz, l.x, S3); S4 = fma(-dz, dlu, S4); }
                 }
-                if (isl > 0.0) {
-                    const double rl = ll * isl;
+                if (is.y > 0.0) {
+                    const double rl = l.y * is.y;
                     double tgt = 0.0;
-                    if (pass == 1) tgt = sigma_mu + dza * (rl * dza + ll);
-                    const double dll = tgt * isl - ll - rl * dz;
-                    rpm = fmax(rpm, -dz * isl);
-                    if (dll < 0.0) rdm = fmax(rdm, -dll / ll);
+                    if (pass == 1) tgt = sigma_mu + dza * (rl * dza + l.y);
+                    const double dll = tgt * is.y - l.y - rl * dz;
+                    rpm = fmax(rpm, -dz * is.y);
+                    if (dll < 0.0) rdm = fmax(rdm, -dll / l.y);
+                    if (pass == 0) { S2 = fma(s.y, dll, S2); S3 = fma(dz, l.y, S3); S4 = fma(dz, dll, S4); }
                 }
             };
+            const int fdz = pass == 0 ? F_DZA : F_DZC;
             __syncwarp(mask);
             sm.vec[r0] = 0.0;
             if (v1) sm.vec[r1] = 0.0;
-            DZ[r0] = 0.0;
-            if (v1) DZ[r1] = 0.0;
+            E[(size_t)r0 * kRec + fdz] = 0.0;
+            if (v1) E[(size_t)r1 * kRec + fdz] = 0.0;
             __syncwarp(mask);
             for (int k = 0; k < N; ++k) {
                 const double* Ak = Ab + (size_t)k * NX * LD;
@@ -537,11 +535,12 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     prefetch_l2<LPS>(Bk + NX * NU, NX * NU * 8, sl);
                     prefetch_l2<LPS>(Kk + NU * NX, NU * NX * 8, sl);
                 }
-                const int iu = k * NZ + NX + (vu ? sl : 0), ix0 = (k + 1) * NZ + r0, ix1 = (k + 1) * NZ + r1c;
-                const double e_iu[3] = {ISU[ix0], ISU[ix1], ISU[iu]}, e_il[3] = {ISL[ix0], ISL[ix1], ISL[iu]};
-                const double e_lu[3] = {LU[ix0], LU[ix1], LU[iu]}, e_ll[3] = {LL[ix0], LL[ix1], LL[iu]};
+                const int iu = k * NZ + iuc, ix0 = (k + 1) * NZ + r0, ix1 = (k + 1) * NZ + r1c;
+                const double2 e_s[3] = {ld2(ix0, F_SU), ld2(ix1, F_SU), ld2(iu, F_SU)};
+                const double2 e_is[3] = {ld2(ix0, F_ISU), ld2(ix1, F_ISU), ld2(iu, F_ISU)};
+                const double2 e_l[3] = {ld2(ix0, F_LU), ld2(ix1, F_LU), ld2(iu, F_LU)};
                 double e_da[3] = {0.0, 0.0, 0.0};
-                if (pass == 1) { e_da[0] = DZA[ix0]; e_da[1] = DZA[ix1]; e_da[2] = DZA[iu]; }
+                if (pass == 1) { e_da[0] = E[(size_t)ix0 * kRec + F_DZA]; e_da[1] = E[(size_t)ix1 * kRec + F_DZA]; e_da[2] = E[(size_t)iu * kRec + F_DZA]; }
                 double n0 = rp_scale * rp[k * NX + r0], n1 = rp_scale * rp[k * NX + r1c];
                 double u = vu ? dff[k * NU + sl] : 0.0;
                 __syncwarp(mask);
@@ -555,8 +554,8 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     if (NX & 1) u = fma(sm.SB[sl * NX + NX - 1], sm.vec[NX - 1], u);
                     u += u2;
                     sm.vec[LD + sl] = u;
-                    DZ[iu] = u;
-                    ratio_entry(e_iu[2], e_il[2], e_lu[2], e_ll[2], u, e_da[2]);
+                    E[(size_t)iu * kRec + fdz] = u;
+                    ratio_entry(e_s[2], e_is[2], e_l[2], u, e_da[2]);
                 }
                 {
                     double m0 = 0.0, m1 = 0.0;
@@ -585,43 +584,26 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 __syncwarp(mask);
                 sm.vec[r0] = n0;
                 if (v1) sm.vec[r1] = n1;
-                DZ[ix0] = n0;
-                ratio_entry(e_iu[0], e_il[0], e_lu[0], e_ll[0], n0, e_da[0]);
+                E[(size_t)ix0 * kRec + fdz] = n0;
+                ratio_entry(e_s[0], e_is[0], e_l[0], n0, e_da[0]);
                 if (v1) {
-                    DZ[ix1] = n1;
-                    ratio_entry(e_iu[1], e_il[1], e_lu[1], e_ll[1], n1, e_da[1]);
+                    E[(size_t)ix1 * kRec + fdz] = n1;
+                    ratio_entry(e_s[1], e_is[1], e_l[1], n1, e_da[1]);
                 }
                 __syncwarp(mask);
             }
-            rpm = -rpm; rdm = -rdm;
-            slot_min2(rpm, rdm);
-            if (pass == 0) { maxp0 = -rpm; maxd0 = -rdm; }
-            double apl = (-rpm > tau) ? tau / (-rpm) : 1.0;
-            double adl = (-rdm > tau) ? tau / (-rdm) : 1.0;
-            ap = apl; ad = adl;
+            slot_max2(rpm, rdm);
+            if (pass == 0) { maxp0 = rpm; maxd0 = rdm; }
+            ap = (rpm > tau) ? tau / rpm : 1.0;
+            ad = (rdm > tau) ? tau / rdm : 1.0;
             if (pass == 0) {
-                // ---- P2: mu_aff and sigma ; P3: corrector right-hand side G += (sigma mu - corr_u)/su - (sigma mu - corr_l)/sl
-                double acc = 0.0, dmy = 0.0;
-                const double* arr[5] = {SU, SLk, LU, LL, DZA};
-                entry_pass(I5{}, arr, [&](int, int idx, const double (&v)[5]) {
-                    const double dz = v[4];
-                    if (v[0] < kBig) { const double dl = v[2] * (ISU[idx] * dz - 1.0); acc = fma(v[0] - ap * dz, v[2] + ad * dl, acc); }
-                    if (v[1] < kBig) { const double dl = -v[3] * (ISL[idx] * dz + 1.0); acc = fma(v[1] + ap * dz, v[3] + ad * dl, acc); }
-                });
-                slot_sum2(acc, dmy);
-                const double mu_aff = n_box > 0.0 ? acc / n_box : 0.0;
+                // mu_aff from the four sums, sigma = (mu_aff/mu)^3
+                double dmy = 0.0;
+                slot_sum4(S2, S3, S4, dmy);
+                const double mu_aff = n_box > 0.0 ? (mu_c * n_box + ad * S2 + ap * S3 + ap * ad * S4) / n_box : 0.0;
                 skip_corr = done || (ap >= 0.999 && ad >= 0.999 && mu_aff <= 1e-3 * mu_c);
                 const double ratio_mu = mu_c > 0.0 ? mu_aff / mu_c : 0.0;
                 sigma_mu = ratio_mu * ratio_mu * ratio_mu * mu_c;
-                const double* arr6[6] = {ISU, ISL, LU, LL, DZA, G};
-                entry_pass(I6{}, arr6, [&](int, int idx, const double (&v)[6]) {
-                    const double dz = v[4];
-                    double g = v[5];
-                    if (v[0] > 0.0) { const double dl = v[2] * (v[0] * dz - 1.0); g = fma(sigma_mu + dz * dl, v[0], g); }
-                    if (v[1] > 0.0) { const double dl = -v[3] * (v[1] * dz + 1.0); g = fma(-(sigma_mu - dz * dl), v[1], g); }
-                    G[idx] = g;
-                });
-                __syncwarp(mask);
             }
         }
         if (skip_corr) {
@@ -633,33 +615,58 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             ap = (maxp0 > tau_c) ? tau_c / maxp0 : 1.0;
             ad = (maxd0 > tau_c) ? tau_c / maxd0 : 1.0;
         }
-        // ---- P4: update (slots still iterating) and new complementarity
+        // ---- P4: update (slots still iterating), new reciprocals / barrier diagonal / complementarity
         double acc = 0.0, dmy = 0.0;
         {
-            const double* arr6[6] = {SU, SLk, LU, LL, DZA, DZC};
             const bool upd = !done && chol_ok;
-            entry_pass(I6{}, arr6, [&](int, int idx, const double (&v)[6]) {
-                double su = v[0], sl_ = v[1], lu = v[2], ll = v[3];
-                if (upd) {
-                    const double dza = v[4], dz = corr_skipped ? v[4] : v[5];
-                    const double so = corr_skipped ? 0.0 : 1.0;      // second-order + centring terms only with the corrector
-                    if (su < kBig) {
-                        const double iu = ISU[idx], ru = lu * iu;
-                        const double dlu = so * (sigma_mu + dza * (ru * dza - lu)) * iu - lu + ru * dz;
-                        su -= ap * dz; lu += ad * dlu;
-                        SU[idx] = su; LU[idx] = lu;
+            const double so = corr_skipped ? 0.0 : 1.0;      // second-order + centring terms only with the corrector
+            for (int k0 = 0; k0 <= N; k0 += KU) {
+                double2 vs[KU][3], vl[KU][3], vi[KU][3], vz[KU][3], vd[KU][3];
+#pragma unroll
+                for (int j = 0; j < KU; ++j) {
+                    const int k = (k0 + j <= N) ? (k0 + j) : N;
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        const int idx = k * NZ + ei[e];
+                        vs[j][e] = ld2(idx, F_SU); vl[j][e] = ld2(idx, F_LU); vi[j][e] = ld2(idx, F_ISU);
+                        vz[j][e] = ld2(idx, F_Z); vd[j][e] = ld2(idx, F_DZA);
                     }
-                    if (sl_ < kBig) {
-                        const double il = ISL[idx], rl = ll * il;
-                        const double dll = so * (sigma_mu + dza * (rl * dza + ll)) * il - ll - rl * dz;
-                        sl_ += ap * dz; ll += ad * dll;
-                        SLk[idx] = sl_; LL[idx] = ll;
-                    }
-                    Z[idx] += ap * dz;
                 }
-                if (su < kBig) acc = fma(su, lu, acc);
-                if (sl_ < kBig) acc = fma(sl_, ll, acc);
-            });
+#pragma unroll
+                for (int j = 0; j < KU; ++j) {
+                    const int k = k0 + j;
+                    if (k > N) continue;
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        if (!ev[e] || (e == 2 && k == N)) continue;
+                        const int idx = k * NZ + ei[e];
+                        double su = vs[j][e].x, sl_ = vs[j][e].y, lu = vl[j][e].x, ll = vl[j][e].y;
+                        if (upd) {
+                            const double dza = vd[j][e].x, dz = corr_skipped ? vd[j][e].x : vd[j][e].y;
+                            double iu = 0.0, il = 0.0;
+                            if (su < kBig) {
+                                const double ru = lu * vi[j][e].x;
+                                const double dlu = so * (sigma_mu + dza * (ru * dza - lu)) * vi[j][e].x - lu + ru * dz;
+                                su -= ap * dz; lu += ad * dlu;
+                                iu = 1.0 / su;
+                            }
+                            if (sl_ < kBig) {
+                                const double rl = ll * vi[j][e].y;
+                                const double dll = so * (sigma_mu + dza * (rl * dza + ll)) * vi[j][e].y - ll - rl * dz;
+                                sl_ += ap * dz; ll += ad * dll;
+                                il = 1.0 / sl_;
+                            }
+                            st2(idx, F_SU, su, sl_);
+                            st2(idx, F_LU, lu, ll);
+                            st2(idx, F_ISU, iu, il);
+                            E[(size_t)idx * kRec + F_Z] = vz[j][e].x + ap * dz;
+                            E[(size_t)idx * kRec + F_SIG] = lu * iu + ll * il;
+                        }
+                        if (su < kBig) acc = fma(su, lu, acc);
+                        if (sl_ < kBig) acc = fma(sl_, ll, acc);
+                    }
+                }
+            }
             if (upd) rp_scale *= (1.0 - ap);
         }
         slot_sum2(acc, dmy);
@@ -681,6 +688,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             }
         }
     }
+    cp_async_wait_all();
     if (!done && status == 0) status = (mu_c < 1e-9 && rp_inf * rp_scale < 1e-7) ? 0 : 1;
     if (act) it_total += it;
     // a warm start that did not converge is repeated from the cold start (whole warp: the slots run in lock-step)
@@ -703,7 +711,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             double q0 = 0.0, q1 = 0.0;
 #pragma unroll
             for (int m = 0; m < NX; ++m) {
-                const double y = Z[k * NZ + m] + 2.0 * Xn[k * NX + m];
+                const double y = E[(size_t)(k * NZ + m) * kRec + F_Z] + 2.0 * Xn[k * NX + m];
                 q0 = fma(Qm[r0 * NX + m], y, q0);
                 q1 = fma(Qm[r1c * NX + m], y, q1);
             }
@@ -711,22 +719,23 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             for (int rr = 0; rr < 2; ++rr) {
                 if (rr && !v1) continue;
                 const int r = rr ? r1 : r0;
-                const double z = Z[k * NZ + r];
+                const double z = E[(size_t)(k * NZ + r) * kRec + F_Z];
                 acc = fma(z, (rr ? q1 : q0) + (a.q_lin != nullptr ? a.q_lin[eoff + k * NZ + r] : 0.0), acc);
                 Xo[k * NX + r] = z;
-                const double lu = LU[k * NZ + r], ll = LL[k * NZ + r];
-                if (k < N) { mu[k * NI + r] = lu; mu[k * NI + NZ + r] = ll; }
-                else { muf[r] = lu; muf[NX + r] = ll; }
+                const double2 l = ld2(k * NZ + r, F_LU);
+                if (k < N) { mu[k * NI + r] = l.x; mu[k * NI + NZ + r] = l.y; }
+                else { muf[r] = l.x; muf[NX + r] = l.y; }
             }
             if (vu && k < N) {
                 double q = 0.0;
 #pragma unroll
-                for (int m = 0; m < NU; ++m) q = fma(prm->R[sl * NU + m], Z[k * NZ + NX + m] + 2.0 * Un[k * NU + m], q);
-                const double z = Z[k * NZ + NX + sl];
+                for (int m = 0; m < NU; ++m) q = fma(prm->R[sl * NU + m], E[(size_t)(k * NZ + NX + m) * kRec + F_Z] + 2.0 * Un[k * NU + m], q);
+                const double z = E[(size_t)(k * NZ + NX + sl) * kRec + F_Z];
                 acc = fma(z, q + (a.q_lin != nullptr ? a.q_lin[eoff + k * NZ + NX + sl] : 0.0), acc);
                 Uo[k * NU + sl] = z;
-                mu[k * NI + NX + sl] = LU[k * NZ + NX + sl];
-                mu[k * NI + NZ + NX + sl] = LL[k * NZ + NX + sl];
+                const double2 l = ld2(k * NZ + NX + sl, F_LU);
+                mu[k * NI + NX + sl] = l.x;
+                mu[k * NI + NZ + NX + sl] = l.y;
             }
         }
         slot_sum2(acc, dmy);
