@@ -96,6 +96,52 @@ def cpu_baseline(n_scen, steps, threads):
     return n_scen * steps / wall, dict(solves=n_scen * steps, wall_s=wall, failed=nfail)
 
 
+def cpu_single_latency(steps=29):
+    """Single-instance solve latency of the CPU port: one scenario, one thread, wall time per MPC step (median over 3 runs)."""
+    from oracle import models as om, scp as oscp
+    from oracle import cpu_port
+    from tests.helpers import rocket_scenarios
+    m, cfg = om.rocket_config()
+    x0, W = rocket_scenarios(1, seed=777, steps=steps)
+    X0, U0, ok = oscp.nominal_sqp(m, cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], x0[0], iters=10)
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        cpu_port.closed_loop(m, cfg, x0, W, steps, X0.T[None].copy(), U0.T[None].copy(), 1)
+        ts.append((time.perf_counter() - t0) / steps)
+    return 1e3 * float(np.median(ts))
+
+
+def gpu_single_latency(m, cfg, device, steps=40):
+    """Single-solve latency (BASELINE.json metric, second half): one rocket MPC instance, batch 1, driven from the host as a
+    controller would (measured state in from host memory, solve, nominal trajectory + back-offs out to host memory); wall
+    clock per rnmpc_solve_host call, percentiles over a disturbed closed loop."""
+    import torch
+    from rnmpc_b200.engine import BatchSolver
+    from tests.helpers import rocket_scenarios
+    s = BatchSolver("rocket", cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], m.E, m.x_ub, m.x_lb,
+                    m.u_ub, m.u_lb, rti=cfg["rti"], sls_steps=cfg["fast_sls_rti_steps"], capacity=1, device=device)
+    x0, W = rocket_scenarios(1, seed=777, steps=steps + 8)
+    x = s.dev(x0).clone()
+    s.init_nominal(x, 10)
+    lat, fails = [], 0
+    for i in range(steps + 8):
+        if i > 0:
+            s.reset_warm_start(1)
+        xh = np.array(torch.as_tensor(x).cpu().numpy())
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        out = s.solve_host(xh)
+        dt = time.perf_counter() - t0
+        fails += int(out["flags"][0] & 1)
+        if i >= 8:
+            lat.append(1e3 * dt)
+        s.plant_step(x, s.dev(W[:, i]))
+    lat = np.sort(np.array(lat))
+    return {"p50_ms": float(np.percentile(lat, 50)), "p90_ms": float(np.percentile(lat, 90)), "min_ms": float(lat[0]), "n": int(lat.size),
+            "failed": fails, "what": "rocket SCP_SLS.solve, batch 1, host buffers in/out (rnmpc_solve_host), wall clock"}
+
+
 # ------------------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -132,6 +178,7 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "note": "reference needs CasADi+OSQP (absent); timed: C++ CPU port of the same path on all host cores"},
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "single_solve_latency": {"p50_ms": cpu_single_latency(), "what": "CPU port, one scenario on one thread, wall per MPC step"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -265,6 +312,7 @@ def main():
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / n_e2e
     clk = clocks.stop() if rank == 0 else None
+    single = gpu_single_latency(m, cfg, local_rank) if rank == 0 else None
 
     # ---- reduce over ranks: max time, summed solves
     tvec = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -305,6 +353,7 @@ def main():
                      "note": "FP64 DFMA pipe binds (SURVEY 8d); peak = DFMA probe measured live on this GPU (MEASURED_PEAKS.json has no "
                              "fp64 entry); achieved = algorithmic flops of one QP launch / its CUDA-event duration"},
         "failed_solves_last_step": int(stats["failed_solves"]),
+        "single_solve_latency": single,
     }
     if not a.no_cpu_baseline:
         n_scen = a.cpu_scenarios or 256 * cores
@@ -313,6 +362,7 @@ def main():
                                 "sample": f"{n_scen} rocket scenarios x {a.cpu_steps} MPC steps, {cores} threads, C++ CPU port (oracle/cpu_port; "
                                           f"the reference's CasADi+OSQP path is not installable here), {info['wall_s']:.1f} s wall, "
                                           f"{info['failed']} failed solves"}
+        line["single_solve_latency"]["cpu_port_p50_ms"] = cpu_single_latency()
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -97,6 +97,18 @@ __device__ __forceinline__ void rowmm2(InFn&& in, const double* __restrict__ Mat
     }
 }
 
+// Reciprocal to ~1 ulp without the IEEE division routine (~30 dependent instructions and a slow-path call): hardware
+// seed (MUFU.RCP64H, 20+ bits) and two Newton steps.  Used where the quotient only scales a step or a barrier weight.
+__device__ __forceinline__ double fast_rcp(const double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
 // Cholesky factor of an SPD NU x NU matrix held in registers (lower triangle, in place; the diagonal is stored
 // as its reciprocal).  Returns false if a pivot is not positive.
 template <int NU>
@@ -108,8 +120,7 @@ __device__ __forceinline__ bool chol_inplace(double (&H)[NU][NU]) {
 #pragma unroll
         for (int k = 0; k < j; ++k) d = fma(-H[j][k], H[j][k], d);
         ok = ok && (d > 0.0);
-        const double l = sqrt(d);
-        const double il = 1.0 / l;
+        const double il = rsqrt(d);
         H[j][j] = il;
 #pragma unroll
         for (int i = j + 1; i < NU; ++i) {
@@ -271,7 +282,7 @@ __device__ __forceinline__ bool riccati_step(SlotSmem<NX, NU>& sm, const int sl,
         double sb0[NU], sb1[NU];
 #pragma unroll
         for (int p = 0; p < NU; ++p) { sb0[p] = 0.0; sb1[p] = 0.0; }
-#pragma unroll 1
+#pragma unroll 4
         for (int c = 0; c < NX; ++c) {
             const double s0 = sm.S[r0 * LD + c], s1 = sm.S[r1c * LD + c];
 #pragma unroll
@@ -294,14 +305,28 @@ __device__ __forceinline__ bool riccati_step(SlotSmem<NX, NU>& sm, const int sl,
         *reinterpret_cast<double2*>(sm.S + r0 * LD + c) = make_double2(y0[c], y0[c + 1]);
         if (v1) *reinterpret_cast<double2*>(sm.S + r1 * LD + c) = make_double2(y1[c], y1[c + 1]);
     }
-    // H = Cu + B'(SB)
-#pragma unroll 1
-    for (int e = sl; e < NU * NU; e += LPS) {
-        const int p = e / NU, q = e - p * NU;
-        double hsum = 0.0;
+    // H = Cu + B'(SB): entry e of lane sl is e = sl + j LPS; the entries of a lane accumulate side by side (independent chains)
+    {
+        constexpr int HE = (NU * NU + LPS - 1) / LPS;
+        double hs[HE], hc[HE];
+        int hp[HE], hq[HE];
 #pragma unroll
-        for (int r = 0; r < NX; ++r) hsum = fma(sm.Bm[r * NU + p], sm.SB[r * NU + q], hsum);
-        sm.H[e] = __ldg(Cu0 + e) + (p == q ? sm.cu[p] : 0.0) + hsum;
+        for (int j = 0; j < HE; ++j) {
+            const int e = sl + j * LPS, ec = e < NU * NU ? e : 0;
+            hp[j] = ec / NU; hq[j] = ec - hp[j] * NU;
+            hc[j] = __ldg(Cu0 + ec);
+            hs[j] = 0.0;
+        }
+#pragma unroll 4
+        for (int r = 0; r < NX; ++r) {
+#pragma unroll
+            for (int j = 0; j < HE; ++j) hs[j] = fma(sm.Bm[r * NU + hp[j]], sm.SB[r * NU + hq[j]], hs[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < HE; ++j) {
+            const int e = sl + j * LPS;
+            if (e < NU * NU) sm.H[e] = hc[j] + (hp[j] == hq[j] ? sm.cu[hp[j]] : 0.0) + hs[j];
+        }
     }
     // (2) F[:, r] = (Y B)[r, :]
 #pragma unroll
@@ -340,7 +365,7 @@ __device__ __forceinline__ bool riccati_step(SlotSmem<NX, NU>& sm, const int sl,
     if (!need_S) return ok;
 
     // (5) closed loop in place:  T[:, r] = A[:, r] + B K[:, r]
-#pragma unroll 1
+#pragma unroll 4
     for (int i = 0; i < NX; ++i) {
         double2 t = *reinterpret_cast<const double2*>(sm.T + i * LD + r0);
 #pragma unroll
@@ -359,10 +384,13 @@ __device__ __forceinline__ bool riccati_step(SlotSmem<NX, NU>& sm, const int sl,
 #pragma unroll
     for (int c = 0; c < LD; ++c) { s0[c] = 0.0; s1[c] = 0.0; }
     rowmm2<NX, LD>([&](int m) { return make_double2(sm.S[r0 * LD + m], sm.S[r1c * LD + m]); }, sm.T, s0, s1);
+    // Cx0 == nullptr: the stage cost is diagonal and already part of cxd0 / cxd1
 #pragma unroll
     for (int c = 0; c < NX; ++c) {
-        s0[c] = __ldg(Cx0 + r0 * NX + c) + s0[c];
-        s1[c] = __ldg(Cx0 + r1c * NX + c) + s1[c];
+        if (Cx0 != nullptr) {
+            s0[c] = __ldg(Cx0 + r0 * NX + c) + s0[c];
+            s1[c] = __ldg(Cx0 + r1c * NX + c) + s1[c];
+        }
         if (c == r0) s0[c] += cxd0;
         if (c == r1) s1[c] += cxd1;
     }

@@ -194,6 +194,7 @@ struct Engine : IEngine {
     int *flags, *status, *qp_iters, *iters_tmp, *status_tmp, *n_open, *ws_valid;
     bool have_solution = false, shifted_since_solve = false;   // host-side warm-start bookkeeping
     int warm_enabled = 1;
+    int qp_warps = 0, sls_warps = 0;   // warps per CTA of the slot kernels (0: automatic, see cta_warps)
     int warm_mask = 2;             // measured (tools/iter_stats.py, B = 4096, 29 steps): warm-starting the first QP of a solve across MPC
                                    // steps lowers the mean iteration count but its cold retries lengthen the slowest warp; off by default
     bool sticky_fail = false;
@@ -289,12 +290,21 @@ struct Engine : IEngine {
         RN_CUDA(cudaGetLastError());
         return 0;
     }
+    // Warps per CTA of the slot kernels.  Every warp is an independent sequential chain (no CTA-level synchronisation), so the
+    // CTA size only decides how the warps spread over the SMs: small CTAs put the warps of a batch that does not fill the
+    // GPU on different SMs / scheduler partitions instead of stacking kWarps of them on a few SMs.
+    int cta_warps(int option, long long warps) const {
+        if (option >= 1 && option <= kWarps) return option;
+        (void)warps;
+        return 1;
+    }
     int launch_sls(int B, const SlsArgs& a, cudaStream_t st) {
         const long long items = (long long)B * (N / 2 + 1);
         const long long warps = (items + Slot<NX>::SPW - 1) / Slot<NX>::SPW;
-        const unsigned grid = (unsigned)((warps + kWarps - 1) / kWarps);
-        const int smem = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * kWarps;
-        sls_kernel<NX, NU><<<grid, kWarps * 32, smem, st>>>(a, d_prm);
+        const int w = cta_warps(sls_warps, warps);
+        const unsigned grid = (unsigned)((warps + w - 1) / w);
+        const int smem = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * w;
+        sls_kernel<NX, NU><<<grid, w * 32, smem, st>>>(a, d_prm);
         ++launches;
         RN_CUDA(cudaGetLastError());
         const long long n = (long long)B * ((long long)N * NI + NIF);
@@ -347,9 +357,10 @@ struct Engine : IEngine {
         a.E = wE; a.G = wG; a.diag_cost = diag_cost; a.rp = rp; a.Sc = Sc;
         a.dff = dff; a.Kq = Kq; a.Lq = Lq;
         const long long warps = ((long long)B + Slot<NX>::SPW - 1) / Slot<NX>::SPW;
-        const unsigned grid = (unsigned)((warps + kWarps - 1) / kWarps);
-        const int smem = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * kWarps;
-        qp_ipm_kernel<NX, NU><<<grid, kWarps * 32, smem, st>>>(a, d_prm);
+        const int w = cta_warps(qp_warps, warps);
+        const unsigned grid = (unsigned)((warps + w - 1) / w);
+        const int smem = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * w;
+        qp_ipm_kernel<NX, NU><<<grid, w * 32, smem, st>>>(a, d_prm);
         ++launches;
         RN_CUDA(cudaGetLastError());
         return 0;
@@ -565,6 +576,8 @@ struct Engine : IEngine {
     }
     int set_option(const char* name, double value) override {
         const std::string n(name);
+        if (n == "qp_warps") { qp_warps = (int)value; return 0; }
+        if (n == "sls_warps") { sls_warps = (int)value; return 0; }
         if (n == "warm_mask") warm_mask = (int)value;            // bit0: first QP of a solve from the previous solve, bit1: later QPs of a solve
         else if (n == "sticky_fail") sticky_fail = value != 0;    // failed instances stay frozen until set_nominal / init_nominal
         else if (n == "qp_max_iter") qp_max_iter = (int)value;

@@ -329,19 +329,28 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
         bool chol_ok = true;
         bool skip_corr = false, corr_skipped = false;
         double maxp0 = 0.0, maxd0 = 0.0;
-        // right-hand side of one entry: gradient (+ centring / second-order terms in the corrector pass)
-        auto rhs_entry = [&](int pass, int idx, bool use) -> double {
-            if (!use) return 0.0;
-            const double2 zz = ld2(idx, F_Z);
-            double g = dg ? ld2(idx, F_SIG).y * (zz.x + zz.y) : G[idx];
+        // right-hand side of one entry: gradient (+ centring / second-order terms in the corrector pass).  Split into the loads
+        // (issued at the head of a stage) and the arithmetic (where the value is consumed, after the stage's matrix work), so that
+        // the global round trip is off the warp's critical path.
+        struct RhsRaw { double2 zz, sq, is, l; double dza; };
+        auto rhs_load = [&](int pass, int idx, bool use) -> RhsRaw {
+            RhsRaw r;
+            r.zz = make_double2(0.0, 0.0); r.sq = r.zz; r.is = r.zz; r.l = r.zz; r.dza = 0.0;
+            if (!use) return r;
+            if (dg) { r.zz = ld2(idx, F_Z); r.sq = ld2(idx, F_SIG); }
+            else r.zz.x = G[idx];
+            if (pass == 1) { r.is = ld2(idx, F_ISU); r.l = ld2(idx, F_LU); r.dza = E[(size_t)idx * kRec + F_DZA]; }
+            return r;
+        };
+        auto rhs_eval = [&](int pass, const RhsRaw& r) -> double {
+            double g = dg ? r.sq.y * (r.zz.x + r.zz.y) : r.zz.x;
             if (pass == 1) {
-                const double2 is = ld2(idx, F_ISU), l = ld2(idx, F_LU);
-                const double dza = E[(size_t)idx * kRec + F_DZA];
-                if (is.x > 0.0) g = fma(sigma_mu + dza * (l.x * is.x * dza - l.x), is.x, g);
-                if (is.y > 0.0) g = fma(-(sigma_mu + dza * (l.y * is.y * dza + l.y)), is.y, g);
+                if (r.is.x > 0.0) g = fma(sigma_mu + r.dza * (r.l.x * r.is.x * r.dza - r.l.x), r.is.x, g);
+                if (r.is.y > 0.0) g = fma(-(sigma_mu + r.dza * (r.l.y * r.is.y * r.dza + r.l.y)), r.is.y, g);
             }
             return g;
         };
+        auto rhs_entry = [&](int pass, int idx, bool use) -> double { return rhs_eval(pass, rhs_load(pass, idx, use)); };
         for (int pass = 0; pass < 2; ++pass) {
             // the corrector's two sweeps are skipped when every slot of the warp is in the Newton phase (see below)
             if (pass == 1 && __all_sync(mask, skip_corr)) break;
@@ -367,9 +376,9 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 const double* Ak = Ab + (size_t)k * NX * LD;
                 const double* Bk = Bb + (size_t)k * NX * NU;
                 // this stage's scalars, fetched ahead of the (long) matrix work
-                const double gx0 = (k > 0) ? rhs_entry(pass, k * NZ + r0, true) : 0.0;
-                const double gx1 = (k > 0) ? rhs_entry(pass, k * NZ + r1c, v1) : 0.0;
-                const double gu_ = rhs_entry(pass, k * NZ + iuc, vu);
+                const RhsRaw raw0 = rhs_load(pass, k * NZ + r0, k > 0), raw1 = rhs_load(pass, k * NZ + r1c, k > 0 && v1);
+                const RhsRaw rawu = rhs_load(pass, k * NZ + iuc, vu);
+                if (k > 0) prefetch_l2<LPS>(E + (size_t)(k - 1) * NZ * kRec, NZ * kRec * 8, sl);      // next stage's records
                 const double rp0 = rp[k * NX + r0], rp1 = rp[k * NX + r1c];
                 double sc0 = 0.0, sc1 = 0.0;
                 // Sc_k = S_{k+1} rp_k while S_{k+1} is still in shared memory (pass 0); the corrector re-reads it
@@ -377,12 +386,21 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     sm.vec[LD + r0] = rp0;
                     if (v1) sm.vec[LD + r1] = rp1;
                     __syncwarp(mask);
-#pragma unroll 1
-                    for (int c = 0; c < NX; ++c) {
-                        const double cv = sm.vec[LD + c];
-                        sc0 = fma(sm.S[r0 * LD + c], cv, sc0);
-                        sc1 = fma(sm.S[r1c * LD + c], cv, sc1);
+                    double sc0b = 0.0, sc1b = 0.0;
+#pragma unroll 4
+                    for (int c = 0; c + 1 < NX; c += 2) {
+                        const double2 cv = *reinterpret_cast<const double2*>(sm.vec + LD + c);
+                        const double2 s0v = *reinterpret_cast<const double2*>(sm.S + r0 * LD + c);
+                        const double2 s1v = *reinterpret_cast<const double2*>(sm.S + r1c * LD + c);
+                        sc0 = fma(s0v.x, cv.x, sc0); sc0b = fma(s0v.y, cv.y, sc0b);
+                        sc1 = fma(s1v.x, cv.x, sc1); sc1b = fma(s1v.y, cv.y, sc1b);
                     }
+                    if (NX & 1) {
+                        const double cv = sm.vec[LD + NX - 1];
+                        sc0 = fma(sm.S[r0 * LD + NX - 1], cv, sc0);
+                        sc1 = fma(sm.S[r1c * LD + NX - 1], cv, sc1);
+                    }
+                    sc0 += sc0b; sc1 += sc1b;
                     Sc[k * NX + r0] = sc0;
                     if (v1) Sc[k * NX + r1] = sc1;
                     __syncwarp(mask);
@@ -398,10 +416,14 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     __syncwarp(mask);
                     // t = ru + B' g
                     if (vu) {
-                        double t = gu_;
+                        double t = rhs_eval(pass, rawu), t2 = 0.0;
 #pragma unroll
-                        for (int i = 0; i < NX; ++i) t = fma(sm.Bm[i * NU + sl], sm.vec[LD + i], t);
-                        sm.vec[2 * LD + sl] = t;
+                        for (int i = 0; i + 1 < NX; i += 2) {
+                            t = fma(sm.Bm[i * NU + sl], sm.vec[LD + i], t);
+                            t2 = fma(sm.Bm[(i + 1) * NU + sl], sm.vec[LD + i + 1], t2);
+                        }
+                        if (NX & 1) t = fma(sm.Bm[(NX - 1) * NU + sl], sm.vec[LD + NX - 1], t);
+                        sm.vec[2 * LD + sl] = t + t2;
                     }
                     __syncwarp(mask);
                     double tt[NU], dd[NU];
@@ -416,14 +438,21 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     }
                     if (k > 0) {
                         // p_k = rx_k + A' g + K' t
-                        double p0 = gx0, p1 = v1 ? gx1 : 0.0;
-#pragma unroll 1
-                        for (int i = 0; i < NX; ++i) {
-                            const double gi = sm.vec[LD + i];
+                        double p0 = rhs_eval(pass, raw0), p1 = v1 ? rhs_eval(pass, raw1) : 0.0, p0b = 0.0, p1b = 0.0;
+#pragma unroll 4
+                        for (int i = 0; i + 1 < NX; i += 2) {
+                            const double2 gi = *reinterpret_cast<const double2*>(sm.vec + LD + i);
                             const double2 av = *reinterpret_cast<const double2*>(Abuf + i * LD + r0);
-                            p0 = fma(av.x, gi, p0);
-                            p1 = fma(av.y, gi, p1);
+                            const double2 aw = *reinterpret_cast<const double2*>(Abuf + (i + 1) * LD + r0);
+                            p0 = fma(av.x, gi.x, p0); p1 = fma(av.y, gi.x, p1);
+                            p0b = fma(aw.x, gi.y, p0b); p1b = fma(aw.y, gi.y, p1b);
                         }
+                        if (NX & 1) {
+                            const double gi = sm.vec[LD + NX - 1];
+                            const double2 av = *reinterpret_cast<const double2*>(Abuf + (NX - 1) * LD + r0);
+                            p0 = fma(av.x, gi, p0); p1 = fma(av.y, gi, p1);
+                        }
+                        p0 += p0b; p1 += p1b;
 #pragma unroll
                         for (int p = 0; p < NU; ++p) { p0 = fma(k0[p], tt[p], p0); p1 = fma(k1[p], tt[p], p1); }
                         __syncwarp(mask);
@@ -435,12 +464,13 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 if (pass == 0) {
                     double cx0 = 0.0, cx1 = 0.0;
                     if (k > 0) {
-                        cx0 = E[(size_t)(k * NZ + r0) * kRec + F_SIG];
-                        if (v1) cx1 = E[(size_t)(k * NZ + r1) * kRec + F_SIG];
+                        cx0 = raw0.sq.x; cx1 = v1 ? raw1.sq.x : 0.0;
+                        if (dg) { cx0 += raw0.sq.y; cx1 += v1 ? raw1.sq.y : 0.0; }       // diagonal stage cost folded in
+                        else { cx0 = E[(size_t)(k * NZ + r0) * kRec + F_SIG]; if (v1) cx1 = E[(size_t)(k * NZ + r1) * kRec + F_SIG]; }
                     }
-                    if (vu) sm.cu[sl] = E[(size_t)(k * NZ + NX + sl) * kRec + F_SIG];
+                    if (vu) sm.cu[sl] = dg ? rawu.sq.x : E[(size_t)(k * NZ + NX + sl) * kRec + F_SIG];
                     const bool ok = riccati_step<NX, NU>(
-                        sm, sl, mask, Ak, Bk, prm->Q2, prm->R2, cx0, cx1, Kq + (size_t)k * NU * NX, pre_step,
+                        sm, sl, mask, Ak, Bk, dg ? nullptr : prm->Q2, prm->R2, cx0, cx1, Kq + (size_t)k * NU * NX, pre_step,
                         [&](const double (&k0)[NU], const double (&k1)[NU], const double (&L)[NU][NU]) {
                             if (sl == 0) {
 #pragma unroll
@@ -495,7 +525,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     if (pass == 1) tgt = sigma_mu + dza * (ru * dza - l.x);
                     const double dlu = tgt * is.x - l.x + ru * dz;
                     rpm = fmax(rpm, dz * is.x);
-                    if (dlu < 0.0) rdm = fmax(rdm, -dlu / l.x);
+                    if (dlu < 0.0) rdm = fmax(rdm, -dlu * fast_rcp(l.x));
                     if (pass == 0) { S2 = fma(s.x, dlu, S2); S3 = fma(-dz, l.x, S3); S4 = fma(-dz, dlu, S4); }
                 }
                 if (is.y > 0.0) {
@@ -504,7 +534,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     if (pass == 1) tgt = sigma_mu + dza * (rl * dza + l.y);
                     const double dll = tgt * is.y - l.y - rl * dz;
                     rpm = fmax(rpm, -dz * is.y);
-                    if (dll < 0.0) rdm = fmax(rdm, -dll / l.y);
+                    if (dll < 0.0) rdm = fmax(rdm, -dll * fast_rcp(l.y));
                     if (pass == 0) { S2 = fma(s.y, dll, S2); S3 = fma(dz, l.y, S3); S4 = fma(dz, dll, S4); }
                 }
             };
@@ -531,6 +561,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bk, sl);
                 load_matrix_smem<NU, NX, NX, LPS>(sm.SB, Kk, sl);
                 if (k + 1 < N) {
+                    prefetch_l2<LPS>(E + ((size_t)(k + 1) * NZ + NX) * kRec, NZ * kRec * 8, sl);      // records u_{k+1}, x_{k+2}
                     if (k + 2 < N) prefetch_l2<LPS>(Ak + 2 * NX * LD, NX * LD * 8, sl);
                     prefetch_l2<LPS>(Bk + NX * NU, NX * NU * 8, sl);
                     prefetch_l2<LPS>(Kk + NU * NX, NU * NX * 8, sl);
@@ -648,13 +679,13 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                                 const double ru = lu * vi[j][e].x;
                                 const double dlu = so * (sigma_mu + dza * (ru * dza - lu)) * vi[j][e].x - lu + ru * dz;
                                 su -= ap * dz; lu += ad * dlu;
-                                iu = 1.0 / su;
+                                iu = fast_rcp(su);
                             }
                             if (sl_ < kBig) {
                                 const double rl = ll * vi[j][e].y;
                                 const double dll = so * (sigma_mu + dza * (rl * dza + ll)) * vi[j][e].y - ll - rl * dz;
                                 sl_ += ap * dz; ll += ad * dll;
-                                il = 1.0 / sl_;
+                                il = fast_rcp(sl_);
                             }
                             st2(idx, F_SU, su, sl_);
                             st2(idx, F_LU, lu, ll);
