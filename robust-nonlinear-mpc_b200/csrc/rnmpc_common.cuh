@@ -200,6 +200,26 @@ __device__ __forceinline__ void cp_async_matrix(double* dst, const double* __res
     asm volatile("cp.async.commit_group;");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+// wait until at most PENDING of the most recently committed groups of this thread are still in flight (groups complete in order)
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+// Stage COUNT contiguous doubles (a dense B_k, K_k or Cholesky factor) into shared memory for a LATER stage: asynchronous
+// 16-byte copies when the block is a multiple of 16 bytes (source 16-byte aligned), a plain copy otherwise.  The caller has
+// made sure (__syncwarp) that no lane still reads dst; completion with cp_async_wait_all() + __syncwarp.
+template <int COUNT, int LPS>
+__device__ __forceinline__ void stage_block_async(double* dst, const double* __restrict__ src, const int sl) {
+    if constexpr ((COUNT % 2) == 0) {
+        const unsigned base = (unsigned)__cvta_generic_to_shared(dst);
+#pragma unroll
+        for (int e = sl; e < COUNT / 2; e += LPS)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + (unsigned)(e * 16)), "l"(src + 2 * e));
+    } else {
+        for (int e = sl; e < COUNT; e += LPS) dst[e] = __ldg(src + e);
+    }
+    cp_async_commit();          // always one group per call (possibly empty): callers count groups
+}
 
 // Synchronous staging of a padded A_k: all 16-byte loads of a lane in flight together.
 template <int NX, int LD, int LPS>
@@ -251,7 +271,8 @@ __device__ __forceinline__ bool riccati_step(SlotSmem<NX, NU>& sm, const int sl,
                                              const double cxd0, const double cxd1, double* __restrict__ Kout, Pre&& pre,
                                              Post&& post, const bool need_S = true, const double* __restrict__ Ag_next = nullptr,
                                              const double* __restrict__ Bg_next = nullptr, const bool T_ready = false,
-                                             const double* __restrict__ Ag_async = nullptr) {
+                                             const double* __restrict__ Ag_async = nullptr, const bool B_ready = false,
+                                             const double* __restrict__ Bg_async = nullptr) {
     constexpr int LD = Slot<NX>::LD;
     constexpr int LPS = Slot<NX>::LPS;
     const int r0 = 2 * sl, r1 = 2 * sl + 1;
@@ -260,9 +281,10 @@ __device__ __forceinline__ bool riccati_step(SlotSmem<NX, NU>& sm, const int sl,
 
     // (0) A_k -> sm.T, B_k -> sm.Bm
     // T_ready: A_k was copied into sm.T asynchronously while the previous stage computed
-    if (T_ready) cp_async_wait_all();
-    else load_padded_smem<NX, LD, LPS>(sm.T, Ag, sl);
-    load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bg, sl);
+    // B_ready: likewise B_k in sm.Bm (Bg_async: the B to fetch for the next call once this one is done with sm.Bm)
+    if (T_ready || B_ready) cp_async_wait_all();
+    if (!T_ready) load_padded_smem<NX, LD, LPS>(sm.T, Ag, sl);
+    if (!B_ready) load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bg, sl);
     if (Ag_next != nullptr) {
         prefetch_l2<LPS>(Ag_next, NX * LD * 8, sl);
         prefetch_l2<LPS>(Bg_next, NX * NU * 8, sl);
@@ -378,6 +400,7 @@ __device__ __forceinline__ bool riccati_step(SlotSmem<NX, NU>& sm, const int sl,
         *reinterpret_cast<double2*>(sm.T + i * LD + r0) = t;
     }
     __syncwarp(mask);
+    if (Bg_async != nullptr) stage_block_async<NX * NU, LPS>(sm.Bm, Bg_async, sl);      // lands during (6)
 
     // (6) S' = Cx + Y Acl   (my rows; Y read back from the S buffer)
     double s0[LD], s1[LD];

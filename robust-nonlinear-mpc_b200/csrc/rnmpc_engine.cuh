@@ -347,6 +347,8 @@ struct Engine : IEngine {
                   const double* x0, const double* bo, const double* bof, const int* fl, int skip_mask, double* dX_, double* dU_,
                   double* mu_, double* mu_f_, double* cost_, int* iters_, int* status_, cudaStream_t st, const double* hi_in = nullptr,
                   const double* lo_in = nullptr, const double* q_lin = nullptr, int warm_mode = 0) {
+        // the kernel stages A_k / B_k with 16-byte asynchronous copies
+        if ((reinterpret_cast<uintptr_t>(A_) | reinterpret_cast<uintptr_t>(B_)) & 15) { set_error("qp: A and B must be 16-byte aligned"); return -1; }
         QpArgs a{};
         a.warm = warm_enabled ? warm_mode : 0; a.ws_valid = ws_valid;
         a.hi_in = hi_in; a.lo_in = lo_in; a.q_lin = q_lin;

@@ -119,16 +119,6 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     auto ld2 = [&](int idx, int f) -> double2 { return *reinterpret_cast<const double2*>(E + (size_t)idx * kRec + f); };
     auto st2 = [&](int idx, int f, double x, double y) { *reinterpret_cast<double2*>(E + (size_t)idx * kRec + f) = make_double2(x, y); };
 
-    auto slot_sum4 = [&](double& x, double& y, double& z, double& w) {
-        __syncwarp(mask);
-        sm.red[2 * sl] = x; sm.red[2 * sl + 1] = y;
-        sm.vec[3 * LD + 2 * sl] = z; sm.vec[3 * LD + 2 * sl + 1] = w;
-        __syncwarp(mask);
-        double sx = 0.0, sy = 0.0, sz = 0.0, sw = 0.0;
-#pragma unroll
-        for (int i = 0; i < LPS; ++i) { sx += sm.red[2 * i]; sy += sm.red[2 * i + 1]; sz += sm.vec[3 * LD + 2 * i]; sw += sm.vec[3 * LD + 2 * i + 1]; }
-        x = sx; y = sy; z = sz; w = sw;
-    };
     auto slot_sum2 = [&](double& x, double& y) {
         __syncwarp(mask);
         sm.red[2 * sl] = x; sm.red[2 * sl + 1] = y;
@@ -297,6 +287,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     int stalled = 0;
     bool done = (status != 0) || !act;
     int resT = -1, resS = -1;      // stage whose A_k is resident (or in flight, cp.async) in sm.T / sm.S
+    int resB = -1, resK = -1, resL = -1;   // likewise B_k in sm.Bm, K_k in sm.SB, the Cholesky factor of stage k in sm.H
     // a warm-started attempt that has not converged after kWarmCap iterations is abandoned for the cold start
     const int it_cap = (attempt == 0 && __any_sync(mask, warm)) ? min(a.max_iter, kWarmCap) : a.max_iter;
     for (it = 0; it < it_cap; ++it) {
@@ -413,6 +404,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     const double g1 = v1 ? (sm.vec[r1] + rp_scale * sc1) : 0.0;
                     sm.vec[LD + r0] = g0;
                     if (v1) sm.vec[LD + r1] = g1;
+                    if (pass == 1) { if (k == N - 1 || k == 0) cp_async_wait_all(); else cp_async_wait<3>(); }     // B_k has landed (A, K, L of the next stage may be in flight)
                     __syncwarp(mask);
                     // t = ru + B' g
                     if (vu) {
@@ -426,6 +418,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                         sm.vec[2 * LD + sl] = t + t2;
                     }
                     __syncwarp(mask);
+                    if (pass == 1 && k > 0) { stage_block_async<NX * NU, LPS>(sm.Bm, Bk - NX * NU, sl); resB = k - 1; }
                     double tt[NU], dd[NU];
 #pragma unroll
                     for (int p = 0; p < NU; ++p) { tt[p] = sm.vec[2 * LD + p]; dd[p] = tt[p]; }
@@ -480,31 +473,42 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                             }
                             vec_step(k0, k1, L);
                         },
-                        k > 0, k > 0 ? Ak - NX * LD : nullptr, k > 0 ? Bk - NX * NU : nullptr, resT == k, k > 0 ? Ak - NX * LD : nullptr);
+                        k > 0, k > 0 ? Ak - NX * LD : nullptr, k > 0 ? Bk - NX * NU : nullptr, resT == k, k > 0 ? Ak - NX * LD : nullptr,
+                        resB == k, k > 0 ? Bk - NX * NU : nullptr);
                     resT = (k > 0) ? k - 1 : 0;
+                    resB = (k > 0) ? k - 1 : 0;
+                    resK = -1; resL = -1;          // sm.SB / sm.H were scratch of the factorisation
                     chol_ok = chol_ok && ok;
                 } else {
                     double k0[NU], k1[NU], L[NU][NU];
-                    cp_async_wait_all();
+                    // steady state: groups committed in the order A_k, K_k, L_k (head of the previous stage), B_k (its middle)
+                    if (k == N - 1) cp_async_wait_all(); else cp_async_wait<1>();
                     if (resT != k && resS != k) { load_padded_smem<NX, LD, LPS>(sm.T, Ak, sl); resT = k; }
                     const bool inT = (resT == k);
                     Abuf = inT ? sm.T : sm.S;
-                    if (k > 0) {       // next stage's A into the other buffer while this stage computes
-                        cp_async_matrix<NX, LD, LPS>(inT ? sm.S : sm.T, Ak - NX * LD, sl);
-                        if (inT) resS = k - 1; else resT = k - 1;
+                    if (resB != k) { load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bk, sl); resB = k; }
+                    if (resK != k) { load_matrix_smem<NU, NX, NX, LPS>(sm.SB, Kq + (size_t)k * NU * NX, sl); resK = k; }
+                    if (resL != k) { load_matrix_smem<NU, NU, NU, LPS>(sm.H, Lq + k * NU * NU, sl); resL = k; }
+                    if (k > 1) {
+                        prefetch_l2<LPS>(Ak - 2 * NX * LD, NX * LD * 8, sl);     // two stages ahead: the asynchronous copies of the next stage hit L2
+                        prefetch_l2<LPS>(Bk - 2 * NX * NU, NX * NU * 8, sl);
+                        prefetch_l2<LPS>(Kq + (size_t)(k - 2) * NU * NX, NU * NX * 8, sl);
                     }
-                    load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bk, sl);
-                    if (k > 0) {
-                        if (k > 1) prefetch_l2<LPS>(Ak - 2 * NX * LD, NX * LD * 8, sl);     // two stages ahead: the cp.async of the next stage hits L2
-                        prefetch_l2<LPS>(Bk - NX * NU, NX * NU * 8, sl);
-                        prefetch_l2<LPS>(Kq + (size_t)(k - 1) * NU * NX, NU * NX * 8, sl);
-                    }
+                    __syncwarp(mask);
 #pragma unroll
                     for (int p = 0; p < NU; ++p) {
-                        k0[p] = Kq[(size_t)k * NU * NX + p * NX + r0];
-                        k1[p] = v1 ? Kq[(size_t)k * NU * NX + p * NX + r1c] : 0.0;
+                        k0[p] = sm.SB[p * NX + r0];
+                        k1[p] = v1 ? sm.SB[p * NX + r1c] : 0.0;
 #pragma unroll
-                        for (int q = 0; q < NU; ++q) L[p][q] = Lq[k * NU * NU + p * NU + q];
+                        for (int q = 0; q < NU; ++q) L[p][q] = sm.H[p * NU + q];
+                    }
+                    __syncwarp(mask);
+                    if (k > 0) {       // next stage's A into the other buffer; the gain and the factor are in registers: fetch the next stage's
+                        cp_async_matrix<NX, LD, LPS>(inT ? sm.S : sm.T, Ak - NX * LD, sl);
+                        if (inT) resS = k - 1; else resT = k - 1;
+                        stage_block_async<NU * NX, LPS>(sm.SB, Kq + (size_t)(k - 1) * NU * NX, sl);
+                        stage_block_async<NU * NU, LPS>(sm.H, Lq + (k - 1) * NU * NU, sl);
+                        resK = k - 1; resL = k - 1;
                     }
                     sc0 = Sc[k * NX + r0];
                     sc1 = Sc[k * NX + r1c];
@@ -516,9 +520,10 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             const double tau = pass == 0 ? 1.0 : (mu_c > 1e-8 ? 0.995 : 0.9999);
             // largest dz/s and -dlam/lam over the entries: alpha = min(1, tau / max)
             double rpm = 0.0, rdm = 0.0;
-            // (s + ap ds)(lam + ad dlam) summed over the entries = S1 + ad S2 + ap S3 + ap ad S4 for any step lengths
-            double S2 = 0.0, S3 = 0.0, S4 = 0.0;
-            auto ratio_entry = [&](double2 s, double2 is, double2 l, double dz, double dza) {
+            // (s + ap ds)(lam + ad dlam) summed over the entries = S1 + ad S2 + ap S3 + ap ad S4 for any step lengths, with
+            // S1 = n mu, S3 = sum ds lam, S4 = sum ds dlam and (predictor: s dlam + lam ds = -s lam) S2 = -S1 - S3
+            double S3 = 0.0, S4 = 0.0;
+            auto ratio_entry = [&](double2 is, double2 l, double dz, double dza) {
                 if (is.x > 0.0) {
                     const double ru = l.x * is.x;
                     double tgt = 0.0;
@@ -526,7 +531,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     const double dlu = tgt * is.x - l.x + ru * dz;
                     rpm = fmax(rpm, dz * is.x);
                     if (dlu < 0.0) rdm = fmax(rdm, -dlu * fast_rcp(l.x));
-                    if (pass == 0) { S2 = fma(s.x, dlu, S2); S3 = fma(-dz, l.x, S3); S4 = fma(-dz, dlu, S4); }
+                    if (pass == 0) { S3 = fma(-dz, l.x, S3); S4 = fma(-dz, dlu, S4); }
                 }
                 if (is.y > 0.0) {
                     const double rl = l.y * is.y;
@@ -535,9 +540,12 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     const double dll = tgt * is.y - l.y - rl * dz;
                     rpm = fmax(rpm, -dz * is.y);
                     if (dll < 0.0) rdm = fmax(rdm, -dll * fast_rcp(l.y));
-                    if (pass == 0) { S2 = fma(s.y, dll, S2); S3 = fma(dz, l.y, S3); S4 = fma(dz, dll, S4); }
+                    if (pass == 0) { S3 = fma(dz, l.y, S3); S4 = fma(dz, dll, S4); }
                 }
             };
+            // entry data {x_{k+1}[r0], x_{k+1}[r1], u_k[sl]} of the current stage
+            double2 q_is[3], q_l[3];
+            double q_da[3] = {0.0, 0.0, 0.0};
             const int fdz = pass == 0 ? F_DZA : F_DZC;
             __syncwarp(mask);
             sm.vec[r0] = 0.0;
@@ -549,31 +557,30 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 const double* Ak = Ab + (size_t)k * NX * LD;
                 const double* Bk = Bb + (size_t)k * NX * NU;
                 const double* Kk = Kq + (size_t)k * NU * NX;
-                // stage A_k (already resident / in flight from the previous stage or sweep), B_k, K_k + this stage's entry data
-                cp_async_wait_all();
+                const int iu = k * NZ + iuc, ix0 = (k + 1) * NZ + r0, ix1 = (k + 1) * NZ + r1c;
+                q_is[0] = ld2(ix0, F_ISU); q_is[1] = ld2(ix1, F_ISU); q_is[2] = ld2(iu, F_ISU);
+                q_l[0] = ld2(ix0, F_LU); q_l[1] = ld2(ix1, F_LU); q_l[2] = ld2(iu, F_LU);
+                if (pass == 1) { q_da[0] = E[(size_t)ix0 * kRec + F_DZA]; q_da[1] = E[(size_t)ix1 * kRec + F_DZA]; q_da[2] = E[(size_t)iu * kRec + F_DZA]; }
+                double n0 = rp_scale * rp[k * NX + r0], n1 = rp_scale * rp[k * NX + r1c];
+                double u = vu ? dff[k * NU + sl] : 0.0;
+                // A_k, B_k, K_k are resident or in flight.  In the steady state the groups were committed in the order A_k, K_k, B_k
+                // (head, middle, end of the previous stage): B_k, needed last, may still be in flight here.
+                if (k == 0) cp_async_wait_all(); else cp_async_wait<1>();
                 if (resT != k && resS != k) { load_padded_smem<NX, LD, LPS>(sm.T, Ak, sl); resT = k; }
                 const bool inT = (resT == k);
                 const double* Af = inT ? sm.T : sm.S;
+                if (resB != k) { load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bk, sl); resB = k; }
+                if (resK != k) { load_matrix_smem<NU, NX, NX, LPS>(sm.SB, Kk, sl); resK = k; }
                 if (k + 1 < N) {
                     cp_async_matrix<NX, LD, LPS>(inT ? sm.S : sm.T, Ak + NX * LD, sl);
                     if (inT) resS = k + 1; else resT = k + 1;
-                }
-                load_matrix_smem<NX, NU, NU, LPS>(sm.Bm, Bk, sl);
-                load_matrix_smem<NU, NX, NX, LPS>(sm.SB, Kk, sl);
-                if (k + 1 < N) {
                     prefetch_l2<LPS>(E + ((size_t)(k + 1) * NZ + NX) * kRec, NZ * kRec * 8, sl);      // records u_{k+1}, x_{k+2}
-                    if (k + 2 < N) prefetch_l2<LPS>(Ak + 2 * NX * LD, NX * LD * 8, sl);
-                    prefetch_l2<LPS>(Bk + NX * NU, NX * NU * 8, sl);
-                    prefetch_l2<LPS>(Kk + NU * NX, NU * NX * 8, sl);
+                    if (k + 2 < N) {
+                        prefetch_l2<LPS>(Ak + 2 * NX * LD, NX * LD * 8, sl);
+                        prefetch_l2<LPS>(Bk + 2 * NX * NU, NX * NU * 8, sl);
+                        prefetch_l2<LPS>(Kk + 2 * NU * NX, NU * NX * 8, sl);
+                    }
                 }
-                const int iu = k * NZ + iuc, ix0 = (k + 1) * NZ + r0, ix1 = (k + 1) * NZ + r1c;
-                const double2 e_s[3] = {ld2(ix0, F_SU), ld2(ix1, F_SU), ld2(iu, F_SU)};
-                const double2 e_is[3] = {ld2(ix0, F_ISU), ld2(ix1, F_ISU), ld2(iu, F_ISU)};
-                const double2 e_l[3] = {ld2(ix0, F_LU), ld2(ix1, F_LU), ld2(iu, F_LU)};
-                double e_da[3] = {0.0, 0.0, 0.0};
-                if (pass == 1) { e_da[0] = E[(size_t)ix0 * kRec + F_DZA]; e_da[1] = E[(size_t)ix1 * kRec + F_DZA]; e_da[2] = E[(size_t)iu * kRec + F_DZA]; }
-                double n0 = rp_scale * rp[k * NX + r0], n1 = rp_scale * rp[k * NX + r1c];
-                double u = vu ? dff[k * NU + sl] : 0.0;
                 __syncwarp(mask);
                 if (vu) {
                     double u2 = 0.0;
@@ -586,7 +593,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     u += u2;
                     sm.vec[LD + sl] = u;
                     E[(size_t)iu * kRec + fdz] = u;
-                    ratio_entry(e_s[2], e_is[2], e_l[2], u, e_da[2]);
+                    ratio_entry(q_is[2], q_l[2], u, q_da[2]);
                 }
                 {
                     double m0 = 0.0, m1 = 0.0;
@@ -605,7 +612,10 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     }
                     n0 += m0; n1 += m1;
                 }
+                if (k == 0) cp_async_wait_all(); else cp_async_wait<1>();      // B_k has landed (A_{k+1} may be in flight)
                 __syncwarp(mask);
+                // every lane is done with K_k (and dx_k): the next stage's gain streams into sm.SB
+                if (k + 1 < N) { stage_block_async<NU * NX, LPS>(sm.SB, Kk + NU * NX, sl); resK = k + 1; }
 #pragma unroll
                 for (int p = 0; p < NU; ++p) {
                     const double up = sm.vec[LD + p];
@@ -613,13 +623,14 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                     n1 = fma(sm.Bm[r1c * NU + p], up, n1);
                 }
                 __syncwarp(mask);
+                if (k + 1 < N) { stage_block_async<NX * NU, LPS>(sm.Bm, Bk + NX * NU, sl); resB = k + 1; }
                 sm.vec[r0] = n0;
                 if (v1) sm.vec[r1] = n1;
                 E[(size_t)ix0 * kRec + fdz] = n0;
-                ratio_entry(e_s[0], e_is[0], e_l[0], n0, e_da[0]);
+                ratio_entry(q_is[0], q_l[0], n0, q_da[0]);
                 if (v1) {
                     E[(size_t)ix1 * kRec + fdz] = n1;
-                    ratio_entry(e_s[1], e_is[1], e_l[1], n1, e_da[1]);
+                    ratio_entry(q_is[1], q_l[1], n1, q_da[1]);
                 }
                 __syncwarp(mask);
             }
@@ -629,9 +640,8 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             ad = (rdm > tau) ? tau / rdm : 1.0;
             if (pass == 0) {
                 // mu_aff from the four sums, sigma = (mu_aff/mu)^3
-                double dmy = 0.0;
-                slot_sum4(S2, S3, S4, dmy);
-                const double mu_aff = n_box > 0.0 ? (mu_c * n_box + ad * S2 + ap * S3 + ap * ad * S4) / n_box : 0.0;
+                slot_sum2(S3, S4);
+                const double mu_aff = n_box > 0.0 ? (mu_c * n_box * (1.0 - ad) + (ap - ad) * S3 + ap * ad * S4) / n_box : 0.0;
                 skip_corr = done || (ap >= 0.999 && ad >= 0.999 && mu_aff <= 1e-3 * mu_c);
                 const double ratio_mu = mu_c > 0.0 ? mu_aff / mu_c : 0.0;
                 sigma_mu = ratio_mu * ratio_mu * ratio_mu * mu_c;

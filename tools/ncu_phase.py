@@ -95,3 +95,14 @@ print("--- by opcode")
 for k, v in ex_op.most_common(25): print("%-10s %6.2f%%" % (k, 100.0 * v / etot))
 print("--- top stacks by instructions")
 for k, v in ex_stack.most_common(40): print("%6.2f%%  %s" % (100.0 * v / etot, k))
+st_phase = collections.Counter()
+for off in instr:
+    chain = table.get(off)
+    own = [c for c in (chain or ()) if repo(c[0])]
+    key = next((c[1] for c in own if c[0] in main), None)
+    ph = "other"
+    if key is not None:
+        ph = next((n for n, lo, hi in phases if lo <= key <= hi), "unphased")
+    st_phase[ph] += 1
+print("--- static instructions per phase (x16 bytes)")
+for k, v in st_phase.most_common(): print("%-14s %6d  %5.1f KB" % (k, v, v * 16 / 1024.0))

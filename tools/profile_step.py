@@ -10,6 +10,8 @@ m, cfg, s = make_solver("rocket", B)
 s.init_nominal(x0, 10)
 x = s.dev(x0).clone()
 s.enable_timing(True)
+for a in sys.argv[3:]:
+    k_, v_ = a.split("="); s.set_option(k_, float(v_))
 import time
 for i in range(steps):
     if i > 0:
