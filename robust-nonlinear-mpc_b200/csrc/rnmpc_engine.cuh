@@ -299,6 +299,8 @@ struct Engine : IEngine {
         return 1;
     }
     int launch_sls(int B, const SlsArgs& a, cudaStream_t st) {
+        // the kernel stages A_k / B_k with 16-byte asynchronous copies
+        if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.Bm)) & 15) { set_error("sls: A and B must be 16-byte aligned"); return -1; }
         const long long items = (long long)B * (N / 2 + 1);
         const long long warps = (items + Slot<NX>::SPW - 1) / Slot<NX>::SPW;
         const int w = cta_warps(sls_warps, warps);

@@ -117,13 +117,15 @@ __global__ void __launch_bounds__(160, 2) sls_kernel(const SlsArgs a, const Para
         double* Kout = a.K + (((size_t)b * N + k) * (N + 1) + col) * kstride;
         // stage of the next Riccati step of this chain (same column: k-1; first step of the second column: N-1)
         const double* a_next = nullptr;
+        const double* b_next = nullptr;
         if (t + 1 < N) {
             const int kn = (t + 1 < n_first) ? (k - 1) : ((t + 1 == n_first) ? (N - 1) : (k - 1));
             a_next = Ab + (size_t)kn * NX * LD;
+            b_next = Bb + (size_t)kn * NX * NU;
         }
         riccati_step<NX, NU>(sm, sl, mask, Ab + (size_t)k * NX * LD, Bb + (size_t)k * NX * NU, prm->Qreg, prm->Rreg, cx0, cx1,
                              Kout, NoPre(), NoPost(), true, k > 0 ? Ab + (size_t)(k - 1) * NX * LD : nullptr,
-                             k > 0 ? Bb + (size_t)(k - 1) * NX * NU : nullptr, t_ready, a_next);
+                             k > 0 ? Bb + (size_t)(k - 1) * NX * NU : nullptr, t_ready, a_next, t_ready, b_next);
         t_ready = a_next != nullptr;
         if (a.S != nullptr) {
             double* So = a.S + ((((size_t)b * (N + 1) + k) * (N + 1)) + col) * NX * NX;
