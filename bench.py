@@ -349,9 +349,16 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_all},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "kernel": "qp_ipm_kernel<17,4>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": 16.13e9 * B0 / 4096.0,   # dram bytes per launch, ncu (profiles/r1_ncu_full_summary.csv, B=4096)
-                     "note": "FP64 DFMA pipe binds (SURVEY 8d); peak = DFMA probe measured live on this GPU (MEASURED_PEAKS.json has no "
-                             "fp64 entry); achieved = algorithmic flops of one QP launch / its CUDA-event duration"},
+                     "frac": achieved / peak,
+                     # dram__bytes_read + dram__bytes_write of ONE launch of this kernel at batch 4096 from the committed ncu capture
+                     # (profiles/r1c_ncu_full_summary.csv: the tightened QP of a fresh step, 4.75 ms under ncu); scaled to this batch
+                     "traffic": 11.83e9 * B0 / 4096.0,
+                     "traffic_note": "static figure from the ncu capture, not measured in this run; 2.49 TB/s inside that capture = 39 % of the "
+                                     "measured HBM copy bandwidth; the launch's inputs + outputs are only 0.26 GB (re-streamed working set)",
+                     "note": "algorithmic flops of one QP launch (batch-mean interior-point iterations) / its CUDA-event duration vs the DFMA "
+                             "peak measured live on this GPU (MEASURED_PEAKS.json has no fp64 entry).  The timed launch is the last QP of "
+                             "two extra steps after the loop and includes the straggler tail.  Neither the FP64 nor the HBM roof is near: "
+                             "the kernel is latency bound (DESIGN.md section 5)"},
         "failed_solves_last_step": int(stats["failed_solves"]),
         "single_solve_latency": single,
     }
