@@ -183,6 +183,14 @@ def main():
         print(json.dumps(line))
         return
 
+    # The contract is ONE JSON line on stdout.  Native libraries write there too (with NCCL_DEBUG=VERSION, as on the GPU boxes,
+    # NCCL printf()s its version banner to stdout; NCCL_DEBUG_FILE does not redirect that line -- tried), so file descriptor 1 is
+    # pointed at stderr for the whole run and the result line goes to a private duplicate of the original stdout.
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+    result_out = os.fdopen(result_fd, "w")
+
     import torch
     import torch.distributed as dist
     from oracle import models as om            # model constants only (no oracle compute on this path)
@@ -370,7 +378,8 @@ def main():
                                           f"the reference's CasADi+OSQP path is not installable here), {info['wall_s']:.1f} s wall, "
                                           f"{info['failed']} failed solves"}
         line["single_solve_latency"]["cpu_port_p50_ms"] = cpu_single_latency()
-    print(json.dumps(line))
+    result_out.write(json.dumps(line) + "\n")
+    result_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
