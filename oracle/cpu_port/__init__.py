@@ -26,8 +26,10 @@ def load():
     return _lib
 
 
-def closed_loop(m, cfg, x0, W, steps, X0, U0, threads=0):
-    """B closed loops on the host: x0 [B,nx], W [B,steps,nx] or None, X0 [B,N+1,nx], U0 [B,N,nu] -> states, inputs, n_failed."""
+def closed_loop(m, cfg, x0, W, steps, X0, U0, threads=0, return_ok=False):
+    """B closed loops on the host: x0 [B,nx], W [B,steps,nx] or None, X0 [B,N+1,nx], U0 [B,N,nu] -> states, inputs, n_failed
+    (+ ok [B,steps] int32 with return_ok: 1 where the solve of that scenario and step succeeded; the port keeps stepping a
+    scenario after a failed solve with the stale input, it does not freeze it)."""
     lib = load()
     d = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64))
     p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
@@ -37,7 +39,10 @@ def closed_loop(m, cfg, x0, W, steps, X0, U0, threads=0):
     keep = [d(cfg[k]) for k in ("Q", "R", "Qf", "Q_reg", "R_reg", "Q_reg_f")] + [d(m.E), d(m.x_ub), d(m.x_lb), d(m.u_ub), d(m.u_lb),
                                                                             d(m.x_ub), d(m.x_lb)]
     states, inputs = np.empty((B, steps + 1, m.nx)), np.empty((B, steps, m.nu))
+    ok = np.ones((B, steps), dtype=np.int32) if return_ok else None
     nfail = lib.rnmpc_cpu_closed_loop(C.c_int(m.model_id), C.c_int(cfg["N"]), C.c_int(cfg["rti"]), C.c_int(cfg["fast_sls_rti_steps"]),
                                       *[p(a) for a in keep], C.c_double(0.05), C.c_int(B), C.c_int(steps), p(x0), p(Wc), p(X0), p(U0),
-                                      p(states), p(inputs), C.c_int(threads))
+                                      p(states), p(inputs), C.c_int(threads), p(ok))
+    if return_ok:
+        return states, inputs, int(nfail), ok
     return states, inputs, int(nfail)

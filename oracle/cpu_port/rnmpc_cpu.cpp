@@ -345,7 +345,7 @@ bool solve(const Cfg& g, Work<M::NX, M::NU>& w, const double* x0) {
 
 template <class M>
 long long closed_loop(const Cfg& g, int B, int steps, const double* x0, const double* W, const double* X0, const double* U0,
-                      double* states, double* inputs, int threads) {
+                      double* states, double* inputs, int threads, int* solve_ok) {
     constexpr int NX = M::NX, NU = M::NU;
     const int N = g.N;
     std::atomic<long long> nfail{0};
@@ -369,7 +369,9 @@ long long closed_loop(const Cfg& g, int B, int steps, const double* x0, const do
                 std::memmove(&w.U[0], &w.U[NU], sizeof(double) * (N - 1) * NU);
                 std::memcpy(&w.X[N * NX], xo, sizeof(xo));
             }
-            if (!solve<M>(g, w, x)) nfail.fetch_add(1);
+            const bool ok = solve<M>(g, w, x);
+            if (!ok) nfail.fetch_add(1);
+            if (solve_ok) solve_ok[(size_t)b * steps + i] = ok ? 1 : 0;      // per scenario and step (the loop goes on after a failure)
             std::memcpy(u, &w.U[0], sizeof(u));
             if (inputs) std::memcpy(inputs + ((size_t)b * steps + i) * NU, u, sizeof(u));
             rk4_step<M, double>(x, u, g.h, xn);
@@ -391,12 +393,12 @@ extern "C" long long rnmpc_cpu_closed_loop(int model_id, int N, int rti, int sls
                                            const double* Qreg, const double* Rreg, const double* Qregf, const double* E, const double* xub,
                                            const double* xlb, const double* uub, const double* ulb, const double* xubf, const double* xlbf,
                                            double h, int B, int steps, const double* x0, const double* W, const double* X0, const double* U0,
-                                           double* states, double* inputs, int threads) {
+                                           double* states, double* inputs, int threads, int* solve_ok) {
     Cfg g{N, rti, sls_steps, Q, R, Qf, Qreg, Rreg, Qregf, E, xub, xlb, uub, ulb, xubf, xlbf, h};
     switch (model_id) {
-        case MODEL_PENDULUM: return closed_loop<PendulumModel>(g, B, steps, x0, W, X0, U0, states, inputs, threads);
-        case MODEL_QUADROTOR: return closed_loop<QuadrotorModel>(g, B, steps, x0, W, X0, U0, states, inputs, threads);
-        case MODEL_ROCKET: return closed_loop<RocketModel>(g, B, steps, x0, W, X0, U0, states, inputs, threads);
+        case MODEL_PENDULUM: return closed_loop<PendulumModel>(g, B, steps, x0, W, X0, U0, states, inputs, threads, solve_ok);
+        case MODEL_QUADROTOR: return closed_loop<QuadrotorModel>(g, B, steps, x0, W, X0, U0, states, inputs, threads, solve_ok);
+        case MODEL_ROCKET: return closed_loop<RocketModel>(g, B, steps, x0, W, X0, U0, states, inputs, threads, solve_ok);
     }
     return -1;
 }

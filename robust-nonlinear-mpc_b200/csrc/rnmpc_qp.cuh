@@ -288,9 +288,11 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     bool done = (status != 0) || !act;
     int resT = -1, resS = -1;      // stage whose A_k is resident (or in flight, cp.async) in sm.T / sm.S
     int resB = -1, resK = -1, resL = -1;   // likewise B_k in sm.Bm, K_k in sm.SB, the Cholesky factor of stage k in sm.H
-    // a warm-started attempt that has not converged after kWarmCap iterations is abandoned for the cold start
-    const int it_cap = (attempt == 0 && __any_sync(mask, warm)) ? min(a.max_iter, kWarmCap) : a.max_iter;
-    for (it = 0; it < it_cap; ++it) {
+    for (it = 0; it < a.max_iter; ++it) {
+        // A warm-started slot that is not even at working precision after kWarmCap iterations is abandoned for the cold start; one
+        // that is (mu < 1e-9) keeps iterating to the full tolerance.  (Accepting it at the cap, as an earlier version did, left
+        // single solves accurate to ~1e-6 only: tools/failure_parity.py, profiles/r1_notes.md.)
+        if (warm && it == kWarmCap && !done && !(mu_c < 1e-9 && rp_inf * rp_scale < 1e-7)) { status = 1; done = true; }
         if (__all_sync(mask, done)) break;
         __syncwarp(mask);
         if (!dg) {
@@ -730,10 +732,11 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
         }
     }
     cp_async_wait_all();
+    // out of iterations (the full budget): accepted at working precision
     if (!done && status == 0) status = (mu_c < 1e-9 && rp_inf * rp_scale < 1e-7) ? 0 : 1;
     if (act) it_total += it;
     // a warm start that did not converge is repeated from the cold start (whole warp: the slots run in lock-step)
-    const bool retry = act && status != 0 && !structural && (warm || it_cap < a.max_iter);
+    const bool retry = act && status != 0 && !structural && warm;
     if (attempt == 1 || !__any_sync(mask, retry)) break;
     act = retry;                   // converged slots keep their solution and idle through the second attempt
     warm = false;
