@@ -8,19 +8,28 @@ from tests.helpers import make_solver, rocket_scenarios
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 2025
-opts = [a.split("=") for a in sys.argv[3:]]          # key=value solver options (rnmpc_set_option)
-steps = 29
-m, cfg = om.rocket_config()
-x0, W = rocket_scenarios(B, seed=seed, steps=steps)
-X0, U0, ok = oscp.nominal_sqp(m, cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], x0[0], iters=10)
-X0b, U0b = np.repeat(X0.T[None], B, 0), np.repeat(U0.T[None], B, 0)
-st_c, in_c, nf_c, ok_c = cpu_port.closed_loop(m, cfg, x0, W, steps, X0b, U0b, 0, return_ok=True)
-ff_c = np.where((ok_c == 0).any(1), (ok_c == 0).argmax(1), steps)
-
-_, _, s = make_solver("rocket", B)
+name = next((a for a in sys.argv[3:] if "=" not in a), "rocket")
+opts = [a.split("=") for a in sys.argv[3:] if "=" in a]          # key=value solver options (rnmpc_set_option)
+steps = {"rocket": 29, "pendulum": 60, "quadrotor": 30}[name]     # lengths of the reference drivers' loops
+m, cfg = om.CONFIGS[name]()
+_, _, s = make_solver(name, B)
 s.set_option("sticky_fail", 1)
 for k_, v_ in opts: s.set_option(k_, float(v_))
-s.set_nominal(X0b, U0b)
+rng = np.random.default_rng(seed)
+if name == "rocket":
+    x0, W = rocket_scenarios(B, seed=seed, steps=steps)
+    X0, U0, ok = oscp.nominal_sqp(m, cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], x0[0], iters=10)
+    X0b, U0b = np.repeat(X0.T[None], B, 0), np.repeat(U0.T[None], B, 0)
+    s.set_nominal(X0b, U0b)
+else:
+    # pendulum: the driver's x0, disturbance draws U[-1,1]^nx through E; quadrotor: seeded x0 draws of the driver + disturbances.
+    # The nominal initialiser is not the subject: the GPU's is used and handed to the CPU port.
+    x0 = np.repeat(om.PENDULUM_X0[None], B, 0) if name == "pendulum" else np.stack([om.quadrotor_x0(seed + b) for b in range(B)])
+    W = rng.uniform(-1, 1, size=(B, steps, m.nx))
+    s.init_nominal(x0, 10)
+    X0b, U0b = s.buffer("X", B).copy(), s.buffer("U", B).copy()
+st_c, in_c, nf_c, ok_c = cpu_port.closed_loop(m, cfg, x0, W, steps, X0b, U0b, 0, return_ok=True)
+ff_c = np.where((ok_c == 0).any(1), (ok_c == 0).argmax(1), steps)
 x = s.dev(x0).clone()
 st_g = np.empty((B, steps + 1, m.nx)); ff_g = np.full(B, steps); its_g = np.zeros((B, steps), dtype=int)
 for i in range(steps):
