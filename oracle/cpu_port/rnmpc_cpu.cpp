@@ -159,6 +159,12 @@ int qp(const Cfg& g, Work<NX, NU>& w, const double* x0, bool tight) {
             w.Z[idx] = z; w.SU[idx] = su; w.SL[idx] = sl; w.LU[idx] = lu; w.LL[idx] = ll;
         }
     if (bad) return 2;
+    {   // centred cold start (same as the CUDA kernel, rnmpc_qp.cuh): multipliers mu_bar / slack, mu_bar = 0.3 x mean slack
+        double ssum = 0;
+        for (int i = 0; i < (N + 1) * NZ; ++i) { if (w.SU[i] < BIG) ssum += w.SU[i]; if (w.SL[i] < BIG) ssum += w.SL[i]; }
+        const double mu_bar = nbox > 0 ? 0.3 * ssum / nbox : 1.0;
+        for (int i = 0; i < (N + 1) * NZ; ++i) { if (w.SU[i] < BIG) w.LU[i] = mu_bar / w.SU[i]; if (w.SL[i] < BIG) w.LL[i] = mu_bar / w.SL[i]; }
+    }
     double rpinf = 0;
     for (int k = 0; k < N; ++k)
         for (int r = 0; r < NX; ++r) {

@@ -181,6 +181,7 @@ struct Engine : IEngine {
     using P = Params<NX, NU>;
     int N, cap, rti, sls_steps, qp_max_iter;
     double qp_tol_mu, qp_tol_res, h;
+    double qp_mu0 = -0.3;          // cold start of the interior point: centred, multipliers = 0.3 x mean slack / slack (see QpArgs::mu0)
     P* d_prm = nullptr;
     std::map<std::string, std::pair<void*, size_t>> bufs;
     bool phi_enabled = false;
@@ -354,7 +355,7 @@ struct Engine : IEngine {
         QpArgs a{};
         a.warm = warm_enabled ? warm_mode : 0; a.ws_valid = ws_valid;
         a.hi_in = hi_in; a.lo_in = lo_in; a.q_lin = q_lin;
-        a.B = B; a.N = N; a.tightened = tightened; a.max_iter = qp_max_iter; a.tol_mu = qp_tol_mu; a.tol_res = qp_tol_res;
+        a.B = B; a.N = N; a.tightened = tightened; a.max_iter = qp_max_iter; a.tol_mu = qp_tol_mu; a.tol_res = qp_tol_res; a.mu0 = qp_mu0;
         a.A = A_; a.Bm = B_; a.c = c_; a.Xnom = X_; a.Unom = U_; a.x0 = x0; a.backoff = bo; a.backoff_f = bof;
         a.flags = fl; a.skip_mask = skip_mask;
         a.dX = dX_; a.dU = dU_; a.mu = mu_; a.mu_f = mu_f_; a.cost = cost_; a.iters = iters_; a.status = status_;
@@ -586,6 +587,7 @@ struct Engine : IEngine {
         else if (n == "sticky_fail") sticky_fail = value != 0;    // failed instances stay frozen until set_nominal / init_nominal
         else if (n == "qp_max_iter") qp_max_iter = (int)value;
         else if (n == "qp_tol_mu") qp_tol_mu = value;
+        else if (n == "qp_mu0") qp_mu0 = value;
         else { set_error("unknown option " + n); return -1; }
         return 0;
     }

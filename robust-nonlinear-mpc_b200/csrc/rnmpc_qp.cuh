@@ -31,6 +31,10 @@ struct QpArgs {
                             // -1: per instance, from flags[b] & FLAG_TIGHT
     int max_iter;
     double tol_mu, tol_res;
+    double mu0;             // cold start: 0 -> multipliers 1 (uncentred: s_i lam_i = s_i spreads over the box widths); > 0 -> centred,
+                            // multipliers mu0 / slack; < 0 -> centred and scale-adaptive, multipliers |mu0| x mean slack / slack (default -0.3;
+                            // -1 is the average complementarity of the uncentred start).  Rocket loop: 13.2 -> 9.6-10.1 iterations of the first QP
+                            // for any centred variant with mu0 >= 1 or the adaptive one; mu0 <= 0.1 is worse than uncentred.
     const double* A;        // [B][N][nx][LD] (padded rows)
     const double* Bm;       // [B][N][nx][nu]
     const double* c;        // [B][N][nx]
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     bool act = true;               // this slot (re)starts in the current attempt
   for (int attempt = 0; attempt < 2; ++attempt) {
     if (act) { status = 0; rp_scale = 1.0; }
-    double n_box_new = 0.0;
+    double n_box_new = 0.0, s_sum = 0.0;
 
     // ------------------------------------------------------------------ bounds, initial point, slacks, duals -> records
     {
@@ -217,8 +221,8 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                         z = fmin(fmax(z0, l_ + m), h_ - m);
                     } else if (hu) z = fmin(z0, h_ - 1.0);
                     else if (hl) z = fmax(z0, l_ + 1.0);
-                    if (hu) { su = h_ - z; lu = warm ? fmax(lu0, kMuWarm / su) : 1.0; n_box_new += 1.0; }
-                    if (hl) { sl_ = z - l_; ll = warm ? fmax(ll0, kMuWarm / sl_) : 1.0; n_box_new += 1.0; }
+                    if (hu) { su = h_ - z; lu = warm ? fmax(lu0, kMuWarm / su) : (a.mu0 > 0.0 ? a.mu0 / su : 1.0); n_box_new += 1.0; s_sum += su; }
+                    if (hl) { sl_ = z - l_; ll = warm ? fmax(ll0, kMuWarm / sl_) : (a.mu0 > 0.0 ? a.mu0 / sl_ : 1.0); n_box_new += 1.0; s_sum += sl_; }
                 }
                 if (act) {
                     const double iu = (su < kBig) ? 1.0 / su : 0.0, il = (sl_ < kBig) ? 1.0 / sl_ : 0.0;
@@ -237,6 +241,26 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             if (bad > 0.0) { status = 2; structural = true; }
         }
         __syncwarp(mask);
+        if (a.mu0 < 0.0) {
+            // scale-adaptive centred cold start: multipliers mu_bar / slack with mu_bar = |mu0| x the mean slack
+            double dmy = 0.0;
+            slot_sum2(s_sum, dmy);
+            const double mu_bar = n_box_new > 0.0 ? -a.mu0 * s_sum / n_box_new : 1.0;
+            if (act && !warm) {
+                for (int k = 0; k <= N; ++k) {
+#pragma unroll
+                    for (int en = 0; en < 3; ++en) {
+                        if (!ev[en] || (en == 2 && k == N)) continue;
+                        const int idx = k * NZ + ei[en];
+                        const double2 is = ld2(idx, F_ISU);
+                        const double lu = mu_bar * is.x, ll = mu_bar * is.y;       // 1/slack is 0 for an absent bound
+                        st2(idx, F_LU, lu, ll);
+                        E[(size_t)idx * kRec + F_SIG] = lu * is.x + ll * is.y;
+                    }
+                }
+            }
+            __syncwarp(mask);
+        }
         // dynamics residual at the initial point: rp_k = A x_k + B u_k + c_k - x_{k+1}
         for (int k = 0; k < N; ++k) {
             const double* Ak = Ab + (size_t)k * NX * LD;
