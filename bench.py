@@ -214,7 +214,7 @@ def main():
     for lo, hi in bounds:
         s = BatchSolver("rocket", cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], m.E, m.x_ub, m.x_lb,
                         m.u_ub, m.u_lb, rti=cfg["rti"], sls_steps=cfg["fast_sls_rti_steps"], capacity=hi - lo, device=local_rank)
-        s.enable_timing(True)
+        s.enable_timing(2)                  # event pair around every hot-kernel launch, summed after the timed region (no sync inside)
         s.set_option("sticky_fail", 1)      # Monte-Carlo semantics: a scenario whose solve failed is dead (the reference's driver would stop)
         solvers.append(s)
         streams.append(torch.cuda.Stream(device=dev))
@@ -251,6 +251,10 @@ def main():
         clocks.start()
     barrier()
     launches0 = sum(s.launch_count() for s in solvers)
+    for s in solvers:
+        for kname in ("linearize", "qp", "sls"):
+            s.kernel_time(kname)                    # forget the warm-up launches
+    ipm0 = sum(s.ipm_iterations() for s in solvers)
     t_wall0 = time.perf_counter()
     e0 = torch.cuda.Event(enable_timing=True)
     e0.record(torch.cuda.current_stream(dev))
@@ -264,6 +268,11 @@ def main():
         ends.append(e)
     barrier()
     launches = sum(s.launch_count() for s in solvers) - launches0
+    # hot kernels over the timed region: summed launch durations (CUDA events on the launching streams) and launch counts
+    region = {kname: [sum(v) for v in zip(*[s.kernel_time(kname) for s in solvers])] for kname in ("linearize", "qp", "sls")}
+    ipm_region = sum(s.ipm_iterations() for s in solvers) - ipm0
+    for s in solvers:
+        s.enable_timing(1)
     ms = max(e0.elapsed_time(e) for e in ends)          # device time of the slowest group's stream
     flags = np.concatenate([s.buffer("flags") for s in solvers])
     n_fail_last = int((flags & 1).sum())
@@ -338,11 +347,15 @@ def main():
     value = stats["solves"] / (ms_all * 1e-3)
     e2e_value = (B * world) / (e2e_ms_all * 1e-3)
     fm = flops_model()
-    iters_per_solve = float(np.mean(qp_iters))                 # interior-point iterations over the 2 QPs of a solve
-    qp_flops_launch = B0 * (iters_per_solve / 2.0) * (fm["qp_fact"] + 2 * fm["qp_solve"])      # one QP kernel launch (group 0 alone)
-    t_qp_ms = float(np.mean(t_qp))
-    flops_per_solve = fm["lin"] + fm["sls"] + iters_per_solve * (fm["qp_fact"] + 2 * fm["qp_solve"])
-    achieved = qp_flops_launch / (t_qp_ms * 1e-3) * 1e-12
+    # roofline of the dominant kernel over the TIMED REGION (this rank): every QP launch of the region is bracketed by CUDA events
+    # on its stream; the interior-point iterations of all instances are counted on the device
+    per_it = fm["qp_fact"] + 2 * fm["qp_solve"]                # algorithmic flops of one interior-point iteration of one instance
+    qp_ms_total, qp_launches = region["qp"]
+    iters_per_solve = ipm_region / float(B * K)                # over the 2 QPs of a solve, frozen scenarios count as 0
+    t_qp_ms = qp_ms_total / max(qp_launches, 1)                # average launch duration
+    qp_flops_launch = ipm_region * per_it / max(qp_launches, 1)
+    flops_per_solve = fm["lin"] + fm["sls"] + iters_per_solve * per_it
+    achieved = ipm_region * per_it / (qp_ms_total * 1e-3) * 1e-12
     h2d = 2 * B * m.nx * 8
     d2h = B * (m.nx + m.nu) * 8 + B * 4
     line = {
@@ -352,7 +365,10 @@ def main():
                    "l2": "per-step working set ~%.0f MB per GPU > 126 MB L2 (no flush needed)" % (B * 0.2),
                    "flops_per_solve": flops_per_solve, "qp_ipm_iters_per_solve": iters_per_solve,
                    "whole_solve_fp64_frac": value / world * flops_per_solve / (peak * 1e12),
-                   "kernel_ms": {"linearize": float(np.mean(t_jac)), "qp_last": t_qp_ms, "fast_sls": float(np.mean(t_sls))}},
+                   "kernel_ms_avg_over_region": {k_: (v_[0] / max(v_[1], 1)) for k_, v_ in region.items()},
+                   "kernel_launches_in_region": {k_: int(v_[1]) for k_, v_ in region.items()},
+                   "kernel_share_of_step": {k_: v_[0] / ms for k_, v_ in region.items()},
+                   "kernel_ms_after_region": {"linearize": float(np.mean(t_jac)), "qp_last": float(np.mean(t_qp)), "fast_sls": float(np.mean(t_sls))}},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_all},
         "gpu_launches": int(launches),
@@ -363,10 +379,11 @@ def main():
                      "traffic": 11.83e9 * B0 / 4096.0,
                      "traffic_note": "static figure from the ncu capture, not measured in this run; 2.49 TB/s inside that capture = 39 % of the "
                                      "measured HBM copy bandwidth; the launch's inputs + outputs are only 0.26 GB (re-streamed working set)",
-                     "note": "algorithmic flops of one QP launch (batch-mean interior-point iterations) / its CUDA-event duration vs the DFMA "
-                             "peak measured live on this GPU (MEASURED_PEAKS.json has no fp64 entry).  The timed launch is the last QP of "
-                             "two extra steps after the loop and includes the straggler tail.  Neither the FP64 nor the HBM roof is near: "
-                             "the kernel is latency bound (DESIGN.md section 5)"},
+                     "launch_ms_avg": t_qp_ms, "launches": int(qp_launches), "flops_per_launch": qp_flops_launch,
+                     "note": "all QP launches of the timed region on rank 0: algorithmic flops (interior-point iterations counted on the "
+                             "device x 0.49 MFLOP) / summed CUDA-event durations, vs the DFMA peak measured live on this GPU "
+                             "(MEASURED_PEAKS.json has no fp64 entry).  Neither the FP64 nor the HBM roof is near: the kernel is latency "
+                             "bound (DESIGN.md section 5)"},
         "failed_solves_last_step": int(stats["failed_solves"]),
         "single_solve_latency": single,
     }

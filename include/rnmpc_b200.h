@@ -180,6 +180,12 @@ int rnmpc_fp64_peak(int device, double* tflops);
 int rnmpc_enable_timing(rnmpc_handle* h, int enable);
 int rnmpc_get_timings(rnmpc_handle* h, double* out3);
 
+/* rnmpc_enable_timing(h, 2): an event pair around EVERY launch of the three hot kernels, without any host synchronisation.
+ * rnmpc_kernel_time sums (and forgets) the pairs recorded since its last call for kernel = "linearize" | "qp" | "sls":
+ * total device time in ms and the number of launches.  Synchronises.  (bench.py: average launch duration of the QP kernel
+ * over the timed region, for the roofline.) */
+int rnmpc_kernel_time(rnmpc_handle* h, const char* kernel, double* total_ms, long long* launches);
+
 /* Number of kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
 long long rnmpc_launch_count(rnmpc_handle* h);
 

@@ -58,6 +58,7 @@ SYMBOLS = {
     "rnmpc_set_option": (_I, [_VP, C.c_char_p, _D]),
     "rnmpc_enable_timing": (_I, [_VP, _I]),
     "rnmpc_get_timings": (_I, [_VP, C.POINTER(_D)]),
+    "rnmpc_kernel_time": (_I, [_VP, C.c_char_p, C.POINTER(_D), C.POINTER(C.c_longlong)]),
     "rnmpc_launch_count": (_LL, [_VP]),
 }
 

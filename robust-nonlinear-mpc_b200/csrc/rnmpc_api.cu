@@ -175,6 +175,11 @@ int rnmpc_get_timings(rnmpc_handle* h, double* out3) {
     if (!out3) return -1;
     return h->e->get_timings(out3);
 }
+int rnmpc_kernel_time(rnmpc_handle* h, const char* kernel, double* total_ms, long long* launches) {
+    RN_ENTER(h);
+    if (!kernel || !total_ms || !launches) return -1;
+    return h->e->kernel_time(kernel, total_ms, launches);
+}
 int rnmpc_set_option(rnmpc_handle* h, const char* name, double value) {
     RN_ENTER(h);
     if (!name) return -1;

@@ -32,6 +32,7 @@ struct IEngine {
     virtual int ddyn(int B, const double* x, const double* u, const double* w, double step, double* xp, cudaStream_t st) = 0;
     virtual int enable_timing(int enable) = 0;
     virtual int get_timings(double* out3) = 0;
+    virtual int kernel_time(const char* kernel, double* total_ms, long long* count) = 0;
     virtual int linearize(int B, const double* X, const double* U, double* A, double* Bm, double* c, cudaStream_t st) = 0;
     virtual int sls(int B, const double* A, const double* Bm, const double* eta, const double* eta_f, double* K, double* S,
                     double* Phi_x, double* Phi_u, double* beta, double* beta_f, double* backoff, double* backoff_f,
@@ -134,11 +135,13 @@ static __global__ void apply_step_kernel(int B, int nxs, int nus, const double* 
     else U[(size_t)b * nus + (e - nxs)] += dU[(size_t)b * nus + (e - nxs)];
 }
 static __global__ void fail_from_status_kernel(int B, const int* __restrict__ st_tmp, int* __restrict__ flags, int* __restrict__ iters_acc,
-                                               const int* __restrict__ iters, int* __restrict__ st_acc, int skip_mask) {
+                                               const int* __restrict__ iters, int* __restrict__ st_acc, int skip_mask,
+                                               unsigned long long* __restrict__ iters_sum) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     if (flags[b] & skip_mask) return;
     iters_acc[b] += iters[b];
+    atomicAdd(iters_sum, (unsigned long long)iters[b]);      // interior-point iterations of all instances and launches since creation
     if (st_tmp[b] != 0) { flags[b] |= FLAG_FAIL; st_acc[b] = st_tmp[b]; }
 }
 static __global__ void interp_nominal_kernel(int B, int N, int nx, int nu, const double* __restrict__ x0, double* __restrict__ X,
@@ -188,11 +191,28 @@ struct Engine : IEngine {
     int diag_cost = 0;
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // timing mode 2: an event pair around EVERY launch of the three hot kernels, kept until kernel_time() sums them -- no host
+    // synchronisation while a region is being timed
+    int timing_mode = 0;
+    struct EvPair { cudaEvent_t a, b; };
+    std::vector<EvPair> ev_log[3];      // 0 linearise, 1 QP, 2 fast-SLS
+    std::vector<EvPair> ev_pool;
+    cudaEvent_t region_begin(int which, cudaStream_t st) {
+        if (timing_mode != 2) return nullptr;
+        EvPair p;
+        if (!ev_pool.empty()) { p = ev_pool.back(); ev_pool.pop_back(); }
+        else if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return nullptr;
+        ev_log[which].push_back(p);
+        cudaEventRecord(p.a, st);
+        return p.b;
+    }
+    static void region_end(cudaEvent_t e, cudaStream_t st) { if (e) cudaEventRecord(e, st); }
 
     double *X, *U, *A, *Bm, *c, *dX, *dU, *mu, *mu_f, *beta, *beta_f, *backoff, *backoff_f, *K, *cost, *prevX, *prevU;
     double *Phi_x = nullptr, *Phi_u = nullptr;
     double *wE, *wG, *rp, *Sc, *dff, *Kq, *Lq;
     int *flags, *status, *qp_iters, *iters_tmp, *status_tmp, *n_open, *ws_valid;
+    unsigned long long* iters_sum;
     bool have_solution = false, shifted_since_solve = false;   // host-side warm-start bookkeeping
     int warm_enabled = 1;
     int qp_warps = 0, sls_warps = 0;   // warps per CTA of the slot kernels (0: automatic, see cta_warps)
@@ -249,7 +269,7 @@ struct Engine : IEngine {
         rc |= alloc("rp", rp, B * N * NX); rc |= alloc("Sc", Sc, B * N * NX); rc |= alloc("dff", dff, B * N * NU);
         rc |= alloc("Kq", Kq, B * N * NU * NX); rc |= alloc("Lq", Lq, B * N * NU * NU);
         rc |= alloc("flags", flags, B); rc |= alloc("status", status, B); rc |= alloc("qp_iters", qp_iters, B);
-        rc |= alloc("iters_tmp", iters_tmp, B); rc |= alloc("status_tmp", status_tmp, B); rc |= alloc("n_open", n_open, 1); rc |= alloc("ws_valid", ws_valid, B);
+        rc |= alloc("iters_tmp", iters_tmp, B); rc |= alloc("status_tmp", status_tmp, B); rc |= alloc("n_open", n_open, 1); rc |= alloc("iters_sum", iters_sum, 1); rc |= alloc("ws_valid", ws_valid, B);
         if (rc) return -2;
         const int smem_sls = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * kWarps;
         RN_CUDA(cudaFuncSetAttribute(sls_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
@@ -260,6 +280,9 @@ struct Engine : IEngine {
         cudaSetDevice(device);
         for (auto& kv : bufs) cudaFree(kv.second.first);
         if (d_prm) cudaFree(d_prm);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (auto& log : ev_log) for (auto& p : log) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+        for (auto& p : ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     }
 
     static constexpr int kWarps = 5;   // warps per CTA of the slot kernels (160 threads; 2 CTAs = 10 warps per SM by shared memory)
@@ -286,7 +309,9 @@ struct Engine : IEngine {
     int linearize_ld(int B, const double* X_, const double* U_, double* A_, int lda, double* B_, double* c_, cudaStream_t st) {
         if (B <= 0) return -1;
         const long long n = (long long)B * N * NZ;
+        cudaEvent_t te = region_begin(0, st);
         linearize_kernel<M><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(B, N, X_, U_, h, A_, lda, B_, c_);
+        region_end(te, st);
         ++launches;
         RN_CUDA(cudaGetLastError());
         return 0;
@@ -307,7 +332,9 @@ struct Engine : IEngine {
         const int w = cta_warps(sls_warps, warps);
         const unsigned grid = (unsigned)((warps + w - 1) / w);
         const int smem = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * w;
+        cudaEvent_t te = region_begin(2, st);
         sls_kernel<NX, NU><<<grid, w * 32, smem, st>>>(a, d_prm);
+        region_end(te, st);
         ++launches;
         RN_CUDA(cudaGetLastError());
         const long long n = (long long)B * ((long long)N * NI + NIF);
@@ -365,7 +392,9 @@ struct Engine : IEngine {
         const int w = cta_warps(qp_warps, warps);
         const unsigned grid = (unsigned)((warps + w - 1) / w);
         const int smem = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * w;
+        cudaEvent_t te = region_begin(1, st);
         qp_ipm_kernel<NX, NU><<<grid, w * 32, smem, st>>>(a, d_prm);
+        region_end(te, st);
         ++launches;
         RN_CUDA(cudaGetLastError());
         return 0;
@@ -432,7 +461,7 @@ struct Engine : IEngine {
         int rc = launch_qp(B, tightened, A, Bm, c, X, U, x0, backoff, backoff_f, flags, skip_mask, dX, dU, mu, mu_f, cost, iters_tmp,
                            status_tmp, st, nullptr, nullptr, nullptr, warm_mode);
         if (rc) return rc;
-        fail_from_status_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, status_tmp, flags, qp_iters, iters_tmp, status, skip_mask);
+        fail_from_status_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, status_tmp, flags, qp_iters, iters_tmp, status, skip_mask, iters_sum);
         ++launches;
         RN_CUDA(cudaGetLastError());
         return 0;
@@ -558,6 +587,23 @@ struct Engine : IEngine {
         if (enable && ev[0] == nullptr)
             for (auto& e : ev) RN_CUDA(cudaEventCreate(&e));
         timing = enable != 0;
+        timing_mode = enable;
+        return 0;
+    }
+    int kernel_time(const char* kernel, double* total_ms, long long* count) override {
+        const std::string n(kernel);
+        const int which = n == "linearize" ? 0 : n == "qp" ? 1 : n == "sls" ? 2 : -1;
+        if (which < 0) { set_error("kernel_time: unknown kernel " + n); return -1; }
+        double tot = 0.0;
+        long long cnt = 0;
+        for (auto& p : ev_log[which]) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { tot += ms; ++cnt; }
+            ev_pool.push_back(p);
+        }
+        ev_log[which].clear();
+        cudaGetLastError();
+        *total_ms = tot; *count = cnt;
         return 0;
     }
     int get_timings(double* out3) override {

@@ -226,12 +226,26 @@ class BatchSolver:
         _lib.check(self.lib.rnmpc_set_option(self._h, name.encode(), float(value)))
 
     def enable_timing(self, enable=True):
-        _lib.check(self.lib.rnmpc_enable_timing(self._h, int(bool(enable))))
+        """True / 1: events around the phases of the last solve (timings()); 2: an event pair around every launch of the hot
+        kernels, summed by kernel_time() (no synchronisation in between)."""
+        _lib.check(self.lib.rnmpc_enable_timing(self._h, int(enable)))
 
     def timings(self):
         out = (C.c_double * 3)()
         _lib.check(self.lib.rnmpc_get_timings(self._h, out))
         return dict(t_jac_ms=out[0], t_qp_ms=out[1], t_backward_ms=out[2])
+
+    def kernel_time(self, kernel):
+        """(total ms, launches) of every launch of `kernel` ("linearize" | "qp" | "sls") since the last call; needs enable_timing(2)."""
+        tot, cnt = C.c_double(), C.c_longlong()
+        _lib.check(self.lib.rnmpc_kernel_time(self._h, kernel.encode(), C.byref(tot), C.byref(cnt)))
+        return float(tot.value), int(cnt.value)
+
+    def ipm_iterations(self):
+        """Interior-point iterations of all instances and QP launches of this handle since creation (device counter)."""
+        v = np.zeros(1, dtype=np.uint64)
+        _lib.check(self.lib.rnmpc_copy_buffer(self._h, b"iters_sum", C.c_void_p(v.ctypes.data), 8))
+        return int(v[0])
 
     def launch_count(self):
         return int(self.lib.rnmpc_launch_count(self._h))
