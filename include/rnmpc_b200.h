@@ -160,8 +160,9 @@ int rnmpc_closed_loop_host(rnmpc_handle* h, int B, int steps, const double* h_x0
                            const double* h_U0, int init_iters, double* h_states, double* h_inputs, long long* h_nfail);
 
 /* Solver options: "warm_mask" (bit0: warm-start the first QP of a solve from the previous solve's multipliers, bit1: the later
- * QPs of a solve from the previous iterate; default 2 -- bit0 lowers the mean iteration count but measured 4 % slower on the
- * 29-step rocket loop, its cold restarts lengthen the slowest warp), "sticky_fail" (1: an instance whose solve failed stays
+ * QPs of a solve from the previous iterate; default 0 = every QP starts cold: with the centred cold start a cold QP needs 9-10
+ * iterations with a maximum of 15-18, a warm-started one 10 with a tail to 30, and a launch lasts as long as its slowest
+ * instance -- bit1 measured 8 % slower on the 29-step rocket loop, bit0 slower still), "sticky_fail" (1: an instance whose solve failed stays
  * frozen -- skipped by every kernel -- until rnmpc_set_nominal / rnmpc_init_nominal; default 0 = retried at every solve, as a
  * caller of the reference would), "qp_max_iter" (default 40), "qp_tol_mu" (default 1e-14), "qp_mu0" (cold start of the interior
  * point: 0 = multipliers 1; > 0 = centred, multipliers qp_mu0 / slack; < 0 = centred and scale-adaptive, multipliers

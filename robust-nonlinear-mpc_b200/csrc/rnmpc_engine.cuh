@@ -216,8 +216,10 @@ struct Engine : IEngine {
     bool have_solution = false, shifted_since_solve = false;   // host-side warm-start bookkeeping
     int warm_enabled = 1;
     int qp_warps = 0, sls_warps = 0;   // warps per CTA of the slot kernels (0: automatic, see cta_warps)
-    int warm_mask = 2;             // measured (tools/iter_stats.py, B = 4096, 29 steps): warm-starting the first QP of a solve across MPC
-                                   // steps lowers the mean iteration count but its cold retries lengthen the slowest warp; off by default
+    int warm_mask = 0;             // warm starts are OFF by default.  Measured (tools/iter_stats.py / iter_tail.py, B = 4096, 29 steps): with the
+                                   // centred cold start every QP needs 9-10 iterations (max 15-18); a warm-started tightened QP needs 10.1 on
+                                   // average with a tail to 30 (slow or restarted warm starts), and a launch lasts as long as its slowest
+                                   // instance: 572.8 ms with bit1, 530.6 ms with none.  Bit0 (across MPC steps) was slower still.
     bool sticky_fail = false;
     int sls_max_iter = 30;             // fast_SLS.MAX_ITER (fast_SLS_jit.py:206)
 
