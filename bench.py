@@ -275,7 +275,8 @@ def main():
         s.enable_timing(1)
     ms = max(e0.elapsed_time(e) for e in ends)          # device time of the slowest group's stream
     flags = np.concatenate([s.buffer("flags") for s in solvers])
-    n_fail_last = int((flags & 1).sum())
+    n_fail_last = int((flags & 1).sum())                   # scenarios dead after W + K steps of the device-resident loop
+    dev_x_checksum = float(sum(np.abs(x.cpu().numpy()).sum() for x in xs))
     # per-kernel times + iteration counters on two extra (untimed) steps of group 0 alone, so that the kernel times are not
     # inflated by the other groups' kernels sharing the SMs and get_timings' sync stays outside the timed region
     t_qp, t_sls, t_jac, qp_iters = [], [], [], []
@@ -301,8 +302,6 @@ def main():
         xh[lo:hi].copy_(x)
     Wpin = torch.as_tensor(np.ascontiguousarray(np.swapaxes(W, 0, 1))).pin_memory()
     xds, wds = [torch.empty_like(x) for x in xs], [torch.empty_like(x) for x in xs]
-    n_e2e = max(3, min(K, 10))
-
     def e2e_step():
         i = step_idx[0]
         wh.copy_(Wpin[i])                                   # this step's disturbance draw arrives from the host
@@ -310,7 +309,8 @@ def main():
             with torch.cuda.stream(st):
                 xd.copy_(xh[lo:hi], non_blocking=True)
                 wd.copy_(wh[lo:hi], non_blocking=True)
-                s.reset_warm_start(hi - lo)
+                if i > 0:
+                    s.reset_warm_start(hi - lo)
                 s.solve(xd)
                 s.plant_step(xd, wd)
                 Uv = torch.as_tensor(s.buffer_view("U", hi - lo))
@@ -321,13 +321,24 @@ def main():
         xh.copy_(oh[:, :m.nx])
         step_idx[0] += 1
 
-    e2e_step()
+    # the SAME scenarios and the SAME MPC steps as the device-resident measurement: state and nominal trajectory are
+    # re-initialised (untimed), W warm-up steps and then K timed steps run through the host-buffer path
+    xh.copy_(torch.as_tensor(x0))
+    for (lo, hi), s in zip(bounds, solvers):
+        s.init_nominal(s.dev(x0[lo:hi]), 10)
+    barrier()                                               # the initialiser ran on the default stream, the steps run on the groups' streams
+    step_idx[0] = 0
+    n_e2e = K
+    for _ in range(Wm):
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(n_e2e):
         e2e_step()
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / n_e2e
+    e2e_failed = int((fh.numpy() & 1).sum())               # scenarios dead after W + K steps of the host-buffer loop
+    e2e_x_checksum = float(np.abs(xh.numpy()).sum())
     clk = clocks.stop() if rank == 0 else None
     single = gpu_single_latency(m, cfg, local_rank) if rank == 0 else None
 
@@ -346,6 +357,14 @@ def main():
         return
     value = stats["solves"] / (ms_all * 1e-3)
     e2e_value = (B * world) / (e2e_ms_all * 1e-3)
+    # the host-buffer loop ran the same scenarios and steps as the device-resident loop: it must end in the same place.  A loop
+    # that diverged (dead scenarios cost nothing) would report a meaningless throughput, so it is not reported at all.
+    e2e_invalid = None
+    if e2e_failed != n_fail_last or not (abs(e2e_x_checksum - dev_x_checksum) <= 1e-6 * abs(dev_x_checksum)):
+        e2e_invalid = "host-buffer loop ended with %d dead scenarios / state checksum %r, device-resident loop with %d / %r" % (
+            e2e_failed, e2e_x_checksum, n_fail_last, dev_x_checksum)
+        print("bench.py: e2e measurement INVALID: " + e2e_invalid, file=sys.stderr)
+        e2e_value = None
     fm = flops_model()
     # roofline of the dominant kernel over the TIMED REGION (this rank): every QP launch of the region is bracketed by CUDA events
     # on its stream; the interior-point iterations of all instances are counted on the device
@@ -370,7 +389,9 @@ def main():
                    "kernel_share_of_step": {k_: v_[0] / ms for k_, v_ in region.items()},
                    "kernel_ms_after_region": {"linearize": float(np.mean(t_jac)), "qp_last": float(np.mean(t_qp)), "fast_sls": float(np.mean(t_sls))}},
         "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_all},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_all,
+                "steps": n_e2e, "dead_scenarios_after_loop": e2e_failed, "state_checksum": e2e_x_checksum, "invalid": e2e_invalid},
+        "device_loop": {"dead_scenarios_after_loop": n_fail_last, "state_checksum": dev_x_checksum},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "kernel": "qp_ipm_kernel<17,4>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak,
