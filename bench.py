@@ -343,10 +343,19 @@ def main():
     single = gpu_single_latency(m, cfg, local_rank) if rank == 0 else None
 
     # ---- reduce over ranks: max time, summed solves
-    tvec = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    # the host-buffer loop ran the same scenarios and steps as the device-resident loop: on EVERY rank it must end in the same
+    # place.  A loop that diverged (dead scenarios cost nothing) would report a meaningless throughput, so it is not reported.
+    e2e_invalid = None
+    if e2e_failed != n_fail_last or not (abs(e2e_x_checksum - dev_x_checksum) <= 1e-6 * abs(dev_x_checksum)):
+        e2e_invalid = "rank %d: host-buffer loop ended with %d dead scenarios / state checksum %r, device-resident loop with %d / %r" % (
+            rank, e2e_failed, e2e_x_checksum, n_fail_last, dev_x_checksum)
+        print("bench.py: e2e measurement INVALID: " + e2e_invalid, file=sys.stderr)
+    tvec = torch.tensor([ms, e2e_ms, 1.0 if e2e_invalid else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
     ms_all, e2e_ms_all = float(tvec[0]), float(tvec[1])
+    if float(tvec[2]) > 0.0 and e2e_invalid is None:
+        e2e_invalid = "the host-buffer loop diverged from the device-resident loop on another rank (see stderr)"
     bo = solvers[0].buffer("backoff")
     stats, per_rank = gather_statistics(dict(solves=B * K, failed_solves=n_fail_last, violations=0,
                                              cost_sum=float(sum(s.buffer("cost").sum() for s in solvers)),
@@ -356,15 +365,8 @@ def main():
             dist.destroy_process_group()
         return
     value = stats["solves"] / (ms_all * 1e-3)
-    e2e_value = (B * world) / (e2e_ms_all * 1e-3)
-    # the host-buffer loop ran the same scenarios and steps as the device-resident loop: it must end in the same place.  A loop
-    # that diverged (dead scenarios cost nothing) would report a meaningless throughput, so it is not reported at all.
-    e2e_invalid = None
-    if e2e_failed != n_fail_last or not (abs(e2e_x_checksum - dev_x_checksum) <= 1e-6 * abs(dev_x_checksum)):
-        e2e_invalid = "host-buffer loop ended with %d dead scenarios / state checksum %r, device-resident loop with %d / %r" % (
-            e2e_failed, e2e_x_checksum, n_fail_last, dev_x_checksum)
-        print("bench.py: e2e measurement INVALID: " + e2e_invalid, file=sys.stderr)
-        e2e_value = None
+    e2e_value = None if e2e_invalid else (B * world) / (e2e_ms_all * 1e-3)
+
     fm = flops_model()
     # roofline of the dominant kernel over the TIMED REGION (this rank): every QP launch of the region is bracketed by CUDA events
     # on its stream; the interior-point iterations of all instances are counted on the device
