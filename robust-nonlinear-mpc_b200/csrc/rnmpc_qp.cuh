@@ -72,7 +72,9 @@ struct QpArgs {
     int* ws_valid;          // [B] workspace holds a converged solution
 };
 
-template <int NX, int NU>
+// DG: the cost matrices are diagonal (all reference drivers): the dense-cost code is compiled out of that instantiation, which
+// keeps it out of the iteration loop's instruction footprint.
+template <int NX, int NU, bool DG>
 __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Params<NX, NU>* __restrict__ prm) {
     using SL_ = Slot<NX>;
     constexpr int LD = SL_::LD, LPS = SL_::LPS, SPW = SL_::SPW;
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     double* dff = a.dff + (size_t)b * N * NU;
     double* Kq = a.Kq + (size_t)b * N * NU * NX;
     double* Lq = a.Lq + (size_t)b * N * NU * NU;
-    const bool dg = a.diag_cost != 0;
+    constexpr bool dg = DG;
 
     auto ld2 = [&](int idx, int f) -> double2 { return *reinterpret_cast<const double2*>(E + (size_t)idx * kRec + f); };
     auto st2 = [&](int idx, int f, double x, double y) { *reinterpret_cast<double2*>(E + (size_t)idx * kRec + f) = make_double2(x, y); };

@@ -440,6 +440,52 @@ def test_fast_sls_and_qp_class_drop_ins():
     assert not qp.q_cost_lin.any()
 
 
+@pytest.mark.parametrize("name", ["pendulum", "quadrotor"])
+def test_dense_cost_matrices_vs_oracle(name):
+    """Non-diagonal Q, R, Qf (the reference's API accepts any SPD matrices; its drivers only use diagonal ones, for which the QP
+    kernel has its own instantiation): SQP initialiser and two MPC steps against the NumPy oracle."""
+    from rnmpc_b200.engine import BatchSolver
+    m, cfg = om.CONFIGS[name]()
+    rng = np.random.default_rng(3)
+
+    def dense(M):       # SPD, visibly non-diagonal: M + 0.3 v v' with v = +-sqrt(diag M)
+        v = np.sqrt(np.diag(M)) * rng.choice([-1.0, 1.0], size=M.shape[0])
+        return M + 0.3 * np.outer(v, v)
+
+    Q, R, Qf = dense(cfg["Q"]), dense(cfg["R"]) if m.nu > 1 else cfg["R"], dense(cfg["Qf"])
+    assert np.abs(Q - np.diag(np.diag(Q))).max() > 0
+    cfg2 = dict(cfg, Q=Q, R=R, Qf=Qf)
+    s = BatchSolver(name, cfg["N"], Q, R, Qf, cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], m.E, m.x_ub, m.x_lb, m.u_ub, m.u_lb,
+                    rti=cfg["rti"], sls_steps=cfg["fast_sls_rti_steps"], capacity=2)
+    x0 = np.stack([om.PENDULUM_X0, 0.8 * om.PENDULUM_X0]) if name == "pendulum" else np.stack([om.quadrotor_x0(0), om.quadrotor_x0(1)])
+    W = rng.uniform(-1, 1, size=(2, 2, m.nx))
+    N, nx = cfg["N"], m.nx
+    s.init_nominal(x0, 10)
+    Xg, Ug = s.buffer("X", 2), s.buffer("U", 2)
+    x = s.dev(x0).clone()
+    res = []
+    for i in range(2):
+        if i > 0:
+            s.reset_warm_start(2)
+        s.solve(x)
+        res.append((s.buffer("X", 2), s.buffer("U", 2), s.buffer("K", 2), s.buffer("backoff", 2), s.buffer("flags", 2)))
+        s.plant_step(x, W[:, i])
+    for b in range(2):
+        X0, U0, ok = oscp.nominal_sqp(m, N, Q, R, Qf, x0[b], iters=10)
+        assert ok and rel(Xg[b], X0.T) < TOL_TRAJ and relf(Ug[b], U0.T) < TOL_TRAJ
+        ref = oscp.closed_loop(m, cfg2, x0[b], W[b], 2, X0=X0, U0=U0)
+        for i in range(2):
+            Xn, Un, K, bo, fl = (r[b] for r in res[i])
+            assert fl & 1 == 0
+            assert rel(Xn, ref["Xn"][i].T) < TOL_TRAJ and relf(Un, ref["Un"][i].T) < TOL_TRAJ
+            skipped = (fl & 4) == 0                 # Q3 early return: the reference reports no back-offs for that solve
+            assert skipped == bool(ref["skipped"][i]), f"scenario {b} step {i}: Q3 early return differs"
+            if not skipped:
+                assert rel(K, ref["K"][i]) < TOL_TRAJ
+                assert rel(bo[:, :nx], ref["backoff_x"][i][:N]) < TOL_TRAJ
+    s.close()
+
+
 @pytest.mark.parametrize("name,B,seed,warm_mask", [("rocket", 2048, 2025, 0), ("rocket", 2048, 2025, 2), ("quadrotor", 512, 5, 0),
                                                    ("pendulum", 256, 5, 0)])
 def test_monte_carlo_population_vs_cpu_port(name, B, seed, warm_mask):
