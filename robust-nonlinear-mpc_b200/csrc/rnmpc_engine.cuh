@@ -275,8 +275,10 @@ struct Engine : IEngine {
         if (rc) return -2;
         const int smem_sls = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * kWarps;
         RN_CUDA(cudaFuncSetAttribute(sls_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
-        RN_CUDA(cudaFuncSetAttribute(qp_ipm_kernel<NX, NU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
-        RN_CUDA(cudaFuncSetAttribute(qp_ipm_kernel<NX, NU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
+        RN_CUDA(cudaFuncSetAttribute(qp_ipm_kernel<NX, NU, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
+        RN_CUDA(cudaFuncSetAttribute(qp_ipm_kernel<NX, NU, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
+        RN_CUDA(cudaFuncSetAttribute(qp_ipm_kernel<NX, NU, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
+        RN_CUDA(cudaFuncSetAttribute(qp_ipm_kernel<NX, NU, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
         return 0;
     }
     ~Engine() override {
@@ -396,8 +398,14 @@ struct Engine : IEngine {
         const unsigned grid = (unsigned)((warps + w - 1) / w);
         const int smem = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * w;
         cudaEvent_t te = region_begin(1, st);
-        if (diag_cost) qp_ipm_kernel<NX, NU, true><<<grid, w * 32, smem, st>>>(a, d_prm);
-        else qp_ipm_kernel<NX, NU, false><<<grid, w * 32, smem, st>>>(a, d_prm);
+        const bool may_warm = a.warm != 0;
+        if (diag_cost) {
+            if (may_warm) qp_ipm_kernel<NX, NU, true, true><<<grid, w * 32, smem, st>>>(a, d_prm);
+            else qp_ipm_kernel<NX, NU, true, false><<<grid, w * 32, smem, st>>>(a, d_prm);
+        } else {
+            if (may_warm) qp_ipm_kernel<NX, NU, false, true><<<grid, w * 32, smem, st>>>(a, d_prm);
+            else qp_ipm_kernel<NX, NU, false, false><<<grid, w * 32, smem, st>>>(a, d_prm);
+        }
         region_end(te, st);
         ++launches;
         RN_CUDA(cudaGetLastError());

@@ -74,7 +74,9 @@ struct QpArgs {
 
 // DG: the cost matrices are diagonal (all reference drivers): the dense-cost code is compiled out of that instantiation, which
 // keeps it out of the iteration loop's instruction footprint.
-template <int NX, int NU, bool DG>
+// WARM: the launch may warm-start (QpArgs::warm != 0); without it the second attempt, the warm branches of the initialisation and
+// the checkpoints of the iteration are compiled out.
+template <int NX, int NU, bool DG, bool WARM>
 __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Params<NX, NU>* __restrict__ prm) {
     using SL_ = Slot<NX>;
     constexpr int LD = SL_::LD, LPS = SL_::LPS, SPW = SL_::SPW;
@@ -147,14 +149,14 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     int status = 0;
     const bool tight = a.tightened < 0 ? ((a.flags[b] & FLAG_TIGHT) != 0) : (a.tightened != 0);
     double n_box = 0.0;
-    bool warm = (a.warm != 0) && (a.ws_valid != nullptr) && (a.ws_valid[b] != 0);
+    bool warm = WARM && (a.warm != 0) && (a.ws_valid != nullptr) && (a.ws_valid[b] != 0);
     int it = 0, it_total = 0;
     double rp_scale = 1.0, rp_inf = 0.0, mu_c = 1.0;
     constexpr double kMuWarm = 1e-2, kFracWarm = 1e-3;
     constexpr int kWarmCap = 15, kWarmChk = 5;
     bool structural = false;       // infeasible by construction (crossed bounds / x(0) outside its box): no retry
     bool act = true;               // this slot (re)starts in the current attempt
-  for (int attempt = 0; attempt < 2; ++attempt) {
+  for (int attempt = 0; attempt < (WARM ? 2 : 1); ++attempt) {
     if (act) { status = 0; rp_scale = 1.0; }
     double n_box_new = 0.0, s_sum = 0.0;
 
@@ -769,7 +771,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     if (act) it_total += it;
     // a warm start that did not converge is repeated from the cold start (whole warp: the slots run in lock-step)
     const bool retry = act && status != 0 && !structural && warm;
-    if (attempt == 1 || !__any_sync(mask, retry)) break;
+    if (!WARM || attempt == 1 || !__any_sync(mask, retry)) break;
     act = retry;                   // converged slots keep their solution and idle through the second attempt
     warm = false;
   }
