@@ -398,9 +398,9 @@ def main():
         "roofline": {"bound": "fp64", "kernel": "qp_ipm_kernel<17,4>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak,
                      # dram__bytes_read + dram__bytes_write of ONE launch of this kernel at batch 4096 from the committed ncu capture
-                     # (profiles/r1c_ncu_full_summary.csv: the tightened QP of a fresh step, 4.75 ms under ncu); scaled to this batch
-                     "traffic": 11.83e9 * B0 / 4096.0,
-                     "traffic_note": "static figure from the ncu capture, not measured in this run; 2.49 TB/s inside that capture = 39 % of the "
+                     # (profiles/r1f_ncu_full_summary.csv: the tightened QP of a fresh step, 4.57 ms under ncu); scaled to this batch
+                     "traffic": 11.80e9 * B0 / 4096.0,
+                     "traffic_note": "static figure from the ncu capture, not measured in this run; 2.58 TB/s inside that capture = 40 % of the "
                                      "measured HBM copy bandwidth; the launch's inputs + outputs are only 0.26 GB (re-streamed working set)",
                      "launch_ms_avg": t_qp_ms, "launches": int(qp_launches), "flops_per_launch": qp_flops_launch,
                      "note": "all QP launches of the timed region on rank 0: algorithmic flops (interior-point iterations counted on the "
