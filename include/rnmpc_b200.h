@@ -183,7 +183,7 @@ int rnmpc_get_timings(rnmpc_handle* h, double* out3);
 
 /* rnmpc_enable_timing(h, 2): an event pair around EVERY launch of the three hot kernels, without any host synchronisation.
  * rnmpc_kernel_time sums (and forgets) the pairs recorded since its last call for kernel = "linearize" | "qp" | "sls":
- * total device time in ms and the number of launches.  Synchronises.  (bench.py: average launch duration of the QP kernel
+ * total device time in ms and the number of launches (at most 65536 launches per kernel are kept between two calls).  Synchronises.  (bench.py: average launch duration of the QP kernel
  * over the timed region, for the roofline.) */
 int rnmpc_kernel_time(rnmpc_handle* h, const char* kernel, double* total_ms, long long* launches);
 

@@ -197,8 +197,9 @@ struct Engine : IEngine {
     struct EvPair { cudaEvent_t a, b; };
     std::vector<EvPair> ev_log[3];      // 0 linearise, 1 QP, 2 fast-SLS
     std::vector<EvPair> ev_pool;
+    static constexpr size_t kMaxLoggedLaunches = 1 << 16;
     cudaEvent_t region_begin(int which, cudaStream_t st) {
-        if (timing_mode != 2) return nullptr;
+        if (timing_mode != 2 || ev_log[which].size() >= kMaxLoggedLaunches) return nullptr;      // bounded: nobody may be collecting
         EvPair p;
         if (!ev_pool.empty()) { p = ev_pool.back(); ev_pool.pop_back(); }
         else if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return nullptr;
