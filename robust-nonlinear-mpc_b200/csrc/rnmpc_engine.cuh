@@ -11,6 +11,7 @@
 #include "rnmpc_common.cuh"
 #include "rnmpc_lin.cuh"
 #include "rnmpc_qp.cuh"
+#include "rnmpc_qp_block.cuh"
 #include "rnmpc_sls.cuh"
 
 namespace rnmpc {
@@ -184,6 +185,10 @@ struct Engine : IEngine {
     using P = Params<NX, NU>;
     int N, cap, rti, sls_steps, qp_max_iter;
     double qp_tol_mu, qp_tol_res, h;
+    int qp_block_max = 512;        // batches up to this size use the one-CTA-per-instance QP kernel (rnmpc_qp_block.cuh); 0: never.  Measured
+                                   // crossover against qp_ipm_kernel: about 1000 instances (tools/latency_probe.py)
+    size_t qp_block_smem = 0;
+    bool qp_block_ok = false;
     double qp_mu0 = -0.3;          // cold start of the interior point: centred, multipliers = 0.3 x mean slack / slack (see QpArgs::mu0)
     P* d_prm = nullptr;
     std::map<std::string, std::pair<void*, size_t>> bufs;
@@ -276,6 +281,11 @@ struct Engine : IEngine {
         if (rc) return -2;
         const int smem_sls = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * kWarps;
         RN_CUDA(cudaFuncSetAttribute(sls_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
+        qp_block_smem = qp_block_smem_doubles<NX, NU>(N) * sizeof(double);
+        // the attribute belongs to the kernel, not to this handle (handles with different horizons share it): always the maximum
+        qp_block_ok = qp_block_smem <= 227 * 1024 &&
+                      cudaFuncSetAttribute(qp_block_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+        cudaGetLastError();
         RN_CUDA(cudaFuncSetAttribute(qp_ipm_kernel<NX, NU, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
         RN_CUDA(cudaFuncSetAttribute(qp_ipm_kernel<NX, NU, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
         RN_CUDA(cudaFuncSetAttribute(qp_ipm_kernel<NX, NU, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
@@ -400,7 +410,10 @@ struct Engine : IEngine {
         const int smem = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * w;
         cudaEvent_t te = region_begin(1, st);
         const bool may_warm = a.warm != 0;
-        if (diag_cost) {
+        if (qp_block_ok && B <= qp_block_max && diag_cost && !may_warm && hi_in == nullptr && lo_in == nullptr && q_lin == nullptr) {
+            // small batch: one CTA per instance, working set in shared memory (rnmpc_qp_block.cuh)
+            qp_block_kernel<NX, NU><<<(unsigned)B, kBlockThreads, qp_block_smem, st>>>(a, d_prm);
+        } else if (diag_cost) {
             if (may_warm) qp_ipm_kernel<NX, NU, true, true><<<grid, w * 32, smem, st>>>(a, d_prm);
             else qp_ipm_kernel<NX, NU, true, false><<<grid, w * 32, smem, st>>>(a, d_prm);
         } else {
@@ -647,6 +660,7 @@ struct Engine : IEngine {
         else if (n == "qp_max_iter") qp_max_iter = (int)value;
         else if (n == "qp_tol_mu") qp_tol_mu = value;
         else if (n == "qp_mu0") qp_mu0 = value;
+        else if (n == "qp_block_max") qp_block_max = (int)value;
         else { set_error("unknown option " + n); return -1; }
         return 0;
     }

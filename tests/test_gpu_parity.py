@@ -95,11 +95,14 @@ def test_sls_ragged_batch_and_zero_duals(name):
     s.close()
 
 
+@pytest.mark.parametrize("block", [0, 64], ids=["batch_kernel", "block_kernel"])
 @pytest.mark.parametrize("name", MODELS)
-def test_qp_vs_oracle_golden(name):
-    """CUDA interior-point QP vs the oracle's exact solutions (un-tightened and tightened bounds, quirk Q4)."""
+def test_qp_vs_oracle_golden(name, block):
+    """CUDA interior-point QP vs the oracle's exact solutions (un-tightened and tightened bounds, quirk Q4); both the
+    instance-per-slot kernel and the one-CTA-per-instance kernel for small batches (`qp_block_max`)."""
     g = load(f"qp_{name}.npz")
     m, cfg, s = make_solver(name, 8)
+    s.set_option("qp_block_max", block)
     n = len(g["X"])
     A, B, c = s.linearize(g["X"], g["U"])
     for tight in (False, True):
@@ -141,8 +144,9 @@ def test_qp_infeasible_instance_does_not_poison_batch():
     s.close()
 
 
-def _run_loop_gpu(name, g, steps):
+def _run_loop_gpu(name, g, steps, block=0):
     m, cfg, s = make_solver(name, 1)
+    s.set_option("qp_block_max", block)
     s.set_nominal(g["X0"][None], g["U0"][None])
     x = s.dev(g["x0"][None]).clone()
     W = g["W"] if g["W"].size else None
@@ -161,13 +165,15 @@ def _run_loop_gpu(name, g, steps):
     return m, cfg, out
 
 
+@pytest.mark.parametrize("block", [0, 64], ids=["batch_kernel", "block_kernel"])
 @pytest.mark.parametrize("tag,name,steps", [("rocket_w08", "rocket", 29), ("rocket_rng123", "rocket", 29),
                                             ("pendulum", "pendulum", 60), ("quadrotor", "quadrotor", 30)])
-def test_closed_loop_vs_oracle_golden(tag, name, steps):
-    """Whole closed loops of the reference drivers (configs 1-4 of BASELINE.json) against the oracle's trajectories."""
+def test_closed_loop_vs_oracle_golden(tag, name, steps, block):
+    """Whole closed loops of the reference drivers (configs 1-4 of BASELINE.json) against the oracle's trajectories, with either
+    QP kernel."""
     g = load(f"loop_{tag}.npz")
     assert g["success"].all() and len(g["inputs"]) == steps
-    m, cfg, out = _run_loop_gpu(name, g, steps)
+    m, cfg, out = _run_loop_gpu(name, g, steps, block)
     nx, nu, N = m.nx, m.nu, cfg["N"]
     for i in range(steps):
         skipped = (out["flags"][i] & 4) == 0
@@ -242,12 +248,21 @@ def test_batch_properties_at_bench_size():
     # identical scenarios give identical results wherever they sit in the batch (slot / warp independence)
     xs = np.stack([x0s[0]] * 7)
     _, _, s2 = make_solver("rocket", 7)
+    s2.set_option("qp_block_max", 0)           # the instance-per-slot QP kernel also for this small batch
     s2.init_nominal(xs, 10)
     s2.solve(xs)
     X7, K7 = s2.buffer("X"), s2.buffer("K")
     assert all(np.array_equal(X7[0], X7[i]) and np.array_equal(K7[0], K7[i]) for i in range(1, 7))
     assert np.array_equal(X7[0], s.buffer("X", 1)[0])
-    s.close(); s2.close()
+    # the one-CTA-per-instance QP kernel (default for small batches): deterministic per instance; against the other kernel the
+    # same algorithm with different summation orders -> equal to rounding, not bit for bit
+    _, _, s3 = make_solver("rocket", 7)
+    s3.init_nominal(xs, 10)
+    s3.solve(xs)
+    Xb, Kb = s3.buffer("X"), s3.buffer("K")
+    assert all(np.array_equal(Xb[0], Xb[i]) and np.array_equal(Kb[0], Kb[i]) for i in range(1, 7))
+    assert rel(Xb[0], X7[0]) < 1e-9 and rel(Kb[0], K7[0]) < 1e-9
+    s.close(); s2.close(); s3.close()
 
 
 def test_host_entry_points_match_device_path():

@@ -3,10 +3,12 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from tests.helpers import make_solver, rocket_scenarios
-for B in [int(a) for a in sys.argv[1:]] or [1, 9, 456, 4096]:
+opts = [a.split("=") for a in sys.argv[1:] if "=" in a]
+for B in [int(a) for a in sys.argv[1:] if "=" not in a] or [1, 9, 456, 4096]:
     x0, W = rocket_scenarios(B, steps=8)
     m, cfg, s = make_solver("rocket", B)
     s.enable_timing(True)
+    for k_, v_ in opts: s.set_option(k_, float(v_))
     s.init_nominal(x0, 10)
     x = s.dev(x0).clone()
     for i in range(6):

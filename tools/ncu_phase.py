@@ -60,7 +60,7 @@ for f in os.listdir(tmp):
     if table: break
 tot = sum(samples.values())
 ex_phase = collections.Counter(); ex_stack = collections.Counter(); ex_op = collections.Counter(); by_stack = collections.Counter(); by_line = collections.Counter(); by_phase = collections.Counter(); by_func = collections.Counter()
-main = ("rnmpc_qp.cuh", "rnmpc_sls.cuh")
+main = ("rnmpc_qp.cuh", "rnmpc_sls.cuh", "rnmpc_qp_block.cuh")
 repo = lambda f: f.startswith("rnmpc_")
 for off, n in samples.items():
     chain = table.get(off)
