@@ -3,7 +3,7 @@
 // Mehrotra predictor-corrector, every KKT solve a Riccati factorisation / sweep, centred cold start, same termination tests and
 // status codes -- but parallel over the ENTRIES of the small matrices instead of over instances:
 //   * the factorisation sweep runs on all 128 threads, one output entry of each matrix product per thread and round
-//     (6 block barriers per stage);
+//     (4 block barriers per stage; the Cholesky factorisation of the 4 x 4 block runs beside the largest product);
 //   * the vector sweeps (predictor / corrector forward, corrector backward) run on warp 0 with one lane per vector entry;
 //   * A_k, B_k, K_k, the Cholesky factors and the per-entry iterate (slacks, multipliers, steps) never leave shared memory.
 // qp_ipm_kernel gives every instance 9 lanes and streams its ~100 KB working set from L2/HBM four times per iteration: right for
@@ -31,10 +31,32 @@ __host__ __device__ inline size_t qp_block_smem_doubles(int N) {
          + 4 * ev(NX) + 3 * ev(NU) + ev(NX + NU) + 64;                                                               // p, pn, g, xc, tt, dd, uc, rhs, red
 }
 
+// One output entry of a small matrix product as a strided dot product: *out = add + sum_m a[m sa] b[m sb].
+struct Dot { const double* a; const double* b; int sa, sb; double* out; double add; };
+
+// The dot tasks e = t, t + TW, ... < count of thread t run side by side (R tasks, two accumulators each, loop over m unrolled): the
+// loads of all of them are in flight together instead of one dependent load-FMA pair at a time.
+template <int LEN, int R, int TW, class Decode>
+__device__ __forceinline__ void run_dots_t(const int t, const int count, Decode&& dec) {
+    Dot d[R];
+    bool on[R];
+    double acc[R][2];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { const int e = t + r * TW; on[r] = e < count; d[r] = dec(on[r] ? e : 0); acc[r][0] = 0.0; acc[r][1] = 0.0; }
+#pragma unroll
+    for (int m = 0; m < LEN; ++m)
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r][m & 1] = fma(d[r].a[m * d[r].sa], d[r].b[m * d[r].sb], acc[r][m & 1]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) if (on[r]) *d[r].out = d[r].add + (acc[r][0] + acc[r][1]);
+}
+template <int LEN, int R, class Decode>
+__device__ __forceinline__ void run_dots(const int t, const int count, Decode&& dec) { run_dots_t<LEN, R, kBlockThreads>(t, count, dec); }
+
 template <int NX, int NU>
 __global__ void __launch_bounds__(kBlockThreads, 2) qp_block_kernel(const QpArgs a, const Params<NX, NU>* __restrict__ prm) {
     constexpr int NZ = NX + NU, NI = 2 * NZ, NIF = 2 * NX, LD = Slot<NX>::LD, T = kBlockThreads;
-    static_assert(NX + NU <= 32, "one lane of warp 0 per vector entry");
+    static_assert(NX + NU <= 32 && NX <= 31, "one lane of warp 0 per vector entry, lane 31 free");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = a.N;
@@ -215,55 +237,28 @@ __global__ void __launch_bounds__(kBlockThreads, 2) qp_block_kernel(const QpArgs
             const double* Ak = A + (size_t)k * NX * NX;
             const double* Bk = Bm + (size_t)k * NX * NU;
             double* Kk = Kq + (size_t)k * NU * NX;
-            // phase 1: Y = A'S, SB = S B, Sc_k = S rp_k, stage right-hand sides
-            for (int e = tid; e < NX * NX + NX * NU + NX + NZ; e += T) {
-                if (e < NX * NX) {
-                    const int i = e / NX, j = e - i * NX;
-                    double acc = 0.0, acc2 = 0.0;
-#pragma unroll 4
-                    for (int m = 0; m + 1 < NX; m += 2) { acc = fma(Ak[m * NX + i], S[m * NX + j], acc); acc2 = fma(Ak[(m + 1) * NX + i], S[(m + 1) * NX + j], acc2); }
-                    if (NX & 1) acc = fma(Ak[(NX - 1) * NX + i], S[(NX - 1) * NX + j], acc);
-                    Y[e] = acc + acc2;
-                } else if (e < NX * NX + NX * NU) {
-                    const int f = e - NX * NX, i = f / NU, p = f - i * NU;
-                    double acc = 0.0;
-#pragma unroll 4
-                    for (int m = 0; m < NX; ++m) acc = fma(S[i * NX + m], Bk[m * NU + p], acc);
-                    SB[f] = acc;
-                } else if (e < NX * NX + NX * NU + NX) {
-                    const int i = e - NX * NX - NX * NU;
-                    double acc = 0.0;
-#pragma unroll 4
-                    for (int m = 0; m < NX; ++m) acc = fma(S[i * NX + m], rp[k * NX + m], acc);
-                    Sc[k * NX + i] = acc;
-                } else {
-                    const int i = e - NX * NX - NX * NU - NX;      // entry i of stage k: rx (k > 0) and ru
-                    rhs[i] = (i < NX && k == 0) ? 0.0 : rhs_entry(0, k * NZ + i);
-                }
-            }
+            // phase 1: Y = A'S, SB = S B, Sc_k = S rp_k (dot tasks), stage right-hand sides
+            run_dots<NX, (NX * NX + NX * NU + NX + T - 1) / T>(tid, NX * NX + NX * NU + NX, [&](int e) -> Dot {
+                if (e < NX * NX) { const int i = e / NX, j = e - i * NX; return Dot{Ak + i, S + j, NX, NX, Y + e, 0.0}; }
+                if (e < NX * NX + NX * NU) { const int f = e - NX * NX, i = f / NU, p = f - i * NU; return Dot{S + i * NX, Bk + p, 1, NU, SB + f, 0.0}; }
+                const int i = e - NX * NX - NX * NU;
+                return Dot{S + i * NX, rp + k * NX, 1, 1, Sc + k * NX + i, 0.0};
+            });
+            if (tid >= T - NZ) { const int i = tid - (T - NZ); rhs[i] = (i < NX && k == 0) ? 0.0 : rhs_entry(0, k * NZ + i); }
             __syncthreads();
-            // phase 2: H = R2 + diag(sig_u) + B'SB, Ft = Y B (= (B'SA)'), g = p + rp_scale Sc
-            for (int e = tid; e < NU * NU + NX * NU + NX; e += T) {
-                if (e < NU * NU) {
-                    const int p = e / NU, q = e - p * NU;
-                    double acc = 0.0;
-#pragma unroll 4
-                    for (int m = 0; m < NX; ++m) acc = fma(Bk[m * NU + p], SB[m * NU + q], acc);
-                    H[e] = prm->R2[e] + (p == q ? e_sg[k * NZ + NX + p] : 0.0) + acc;
-                } else if (e < NU * NU + NX * NU) {
-                    const int f = e - NU * NU, j = f / NU, p = f - j * NU;
-                    double acc = 0.0;
-#pragma unroll 4
-                    for (int m = 0; m < NX; ++m) acc = fma(Y[j * NX + m], Bk[m * NU + p], acc);
-                    Ft[f] = acc;
-                } else {
-                    const int i = e - NU * NU - NX * NU;
-                    gv[i] = pv[i] + rp_scale * Sc[k * NX + i];
-                }
-            }
+            // phase 2: H = R2 + diag(sig_u) + B'SB, Ft = Y B (= (B'SA)'), B'p and B'Sc (for t = ru + B'(p + rp_scale Sc)), g = p + rp_scale Sc
+            run_dots<NX, (NU * NU + NX * NU + 2 * NU + T - 1) / T>(tid, NU * NU + NX * NU + 2 * NU, [&](int e) -> Dot {
+                if (e < NU * NU) { const int p = e / NU, q = e - p * NU; return Dot{Bk + p, SB + q, NU, NU, H + e, prm->R2[e] + (p == q ? e_sg[k * NZ + NX + p] : 0.0)}; }
+                if (e < NU * NU + NX * NU) { const int f = e - NU * NU, j = f / NU, p = f - j * NU; return Dot{Y + j * NX, Bk + p, 1, NU, Ft + f, 0.0}; }
+                const int f = e - NU * NU - NX * NU;
+                if (f < NU) return Dot{Bk + f, pv, NU, 1, tt + f, 0.0};
+                return Dot{Bk + (f - NU), Sc + k * NX, NU, 1, dd + (f - NU), 0.0};
+            });
+            if (tid >= T - NX) { const int i = tid - (T - NX); gv[i] = pv[i] + rp_scale * Sc[k * NX + i]; }
             __syncthreads();
-            // phase 3: Cholesky of H (every participating thread factors its own copy), K = -H^{-1} F column by column, t = ru + B'g
-            if (tid < NX + NU + 1) {
+            // phase 3: threads 0 .. NX+1 factor H (each its own copy): K = -H^{-1} F column by column, t and d = -H^{-1} t, stored factor;
+            // the other threads meanwhile form the part of S' that does not need K:  Sn = Y A
+            if (tid < NX + 2) {
                 double L[NU][NU];
 #pragma unroll
                 for (int p = 0; p < NU; ++p)
@@ -277,13 +272,13 @@ __global__ void __launch_bounds__(kBlockThreads, 2) qp_block_kernel(const QpArgs
                     chol_solve<NU>(L, f);
 #pragma unroll
                     for (int p = 0; p < NU; ++p) Kk[p * NX + tid] = -f[p];
-                } else if (tid < NX + NU) {
-                    const int p = tid - NX;
-                    double t = rhs[NX + p], t2 = 0.0;
-#pragma unroll 4
-                    for (int i = 0; i + 1 < NX; i += 2) { t = fma(Bk[i * NU + p], gv[i], t); t2 = fma(Bk[(i + 1) * NU + p], gv[i + 1], t2); }
-                    if (NX & 1) t = fma(Bk[(NX - 1) * NU + p], gv[NX - 1], t);
-                    tt[p] = t + t2;
+                } else if (tid == NX) {
+                    double d[NU];
+#pragma unroll
+                    for (int p = 0; p < NU; ++p) { d[p] = rhs[NX + p] + tt[p] + rp_scale * dd[p]; uc[p] = d[p]; }      // t (kept in uc for p')
+                    chol_solve<NU>(L, d);
+#pragma unroll
+                    for (int p = 0; p < NU; ++p) dff[k * NU + p] = -d[p];
                 } else {
 #pragma unroll
                     for (int p = 0; p < NU; ++p)
@@ -291,58 +286,32 @@ __global__ void __launch_bounds__(kBlockThreads, 2) qp_block_kernel(const QpArgs
                         for (int q = 0; q < NU; ++q) Lq[k * NU * NU + p * NU + q] = L[p][q];
                     if (!ok) red[32] = 1.0;
                 }
-            }
-            __syncthreads();
-            // phase 4: closed loop T = A + B K; feed-forward d = -H^{-1} t
-            for (int e = tid; e < NX * NX + 1; e += T) {
-                if (e < NX * NX) {
+            } else if (k > 0) {
+                constexpr int TW = T - (NX + 2);
+                run_dots_t<NX, (NX * NX + TW - 1) / TW, TW>(tid - (NX + 2), NX * NX, [&](int e) -> Dot {
                     const int i = e / NX, j = e - i * NX;
-                    double acc = Ak[e];
-#pragma unroll
-                    for (int p = 0; p < NU; ++p) acc = fma(Bk[i * NU + p], Kk[p * NX + j], acc);
-                    Tm[e] = acc;
-                } else {
-                    double L[NU][NU], d[NU];
-#pragma unroll
-                    for (int p = 0; p < NU; ++p) {
-                        d[p] = tt[p];
-#pragma unroll
-                        for (int q = 0; q < NU; ++q) L[p][q] = Lq[k * NU * NU + p * NU + q];
-                    }
-                    chol_solve<NU>(L, d);
-#pragma unroll
-                    for (int p = 0; p < NU; ++p) dff[k * NU + p] = -d[p];
-                }
+                    return Dot{Y + i * NX, Ak + j, 1, NX, Sn + e, 0.0};
+                });
             }
             __syncthreads();
             if (k > 0) {
-                // phase 5: S' = Y (A + B K) (stage cost added on the diagonal below), p' = rx + A'g + K't
-                for (int e = tid; e < NX * NX + NX; e += T) {
-                    if (e < NX * NX) {
-                        const int i = e / NX, j = e - i * NX;
-                        double acc = 0.0, acc2 = 0.0;
-#pragma unroll 4
-                        for (int m = 0; m + 1 < NX; m += 2) { acc = fma(Y[i * NX + m], Tm[m * NX + j], acc); acc2 = fma(Y[i * NX + m + 1], Tm[(m + 1) * NX + j], acc2); }
-                        if (NX & 1) acc = fma(Y[i * NX + NX - 1], Tm[(NX - 1) * NX + j], acc);
-                        Sn[e] = acc + acc2;
-                    } else {
-                        const int i = e - NX * NX;
-                        double acc = rhs[i], acc2 = 0.0;
-#pragma unroll 4
-                        for (int m = 0; m + 1 < NX; m += 2) { acc = fma(Ak[m * NX + i], gv[m], acc); acc2 = fma(Ak[(m + 1) * NX + i], gv[m + 1], acc2); }
-                        if (NX & 1) acc = fma(Ak[(NX - 1) * NX + i], gv[NX - 1], acc);
+                // phase 4: S = sym(Sn + Ft K) + diagonal stage cost (2Q + barrier weights), p = rx + A'g + K't
+                for (int e = tid; e < NX * NX; e += T) {
+                    const int i = e / NX, j = e - i * NX;
+                    double acc = Sn[e] + Sn[j * NX + i];
 #pragma unroll
-                        for (int p = 0; p < NU; ++p) acc = fma(Kk[p * NX + i], tt[p], acc);
-                        pn[i] = acc + acc2;
-                    }
+                    for (int p = 0; p < NU; ++p) acc = fma(Ft[i * NU + p], Kk[p * NX + j], fma(Ft[j * NU + p], Kk[p * NX + i], acc));
+                    S[e] = 0.5 * acc + (i == j ? (e_qd[k * NZ + i] + e_sg[k * NZ + i]) : 0.0);
                 }
-                __syncthreads();
-                // phase 6: symmetrise, add the (diagonal) stage cost 2Q + barrier weights
-                for (int e = tid; e < NX * NX + NX; e += T) {
-                    if (e < NX * NX) {
-                        const int i = e / NX, j = e - i * NX;
-                        S[e] = 0.5 * (Sn[e] + Sn[j * NX + i]) + (i == j ? (e_qd[k * NZ + i] + e_sg[k * NZ + i]) : 0.0);
-                    } else pv[e - NX * NX] = pn[e - NX * NX];
+                if (tid >= T - NX) {
+                    const int i = tid - (T - NX);
+                    double acc = rhs[i], acc2 = 0.0;
+#pragma unroll
+                    for (int m = 0; m + 1 < NX; m += 2) { acc = fma(Ak[m * NX + i], gv[m], acc); acc2 = fma(Ak[(m + 1) * NX + i], gv[m + 1], acc2); }
+                    if (NX & 1) acc = fma(Ak[(NX - 1) * NX + i], gv[NX - 1], acc);
+#pragma unroll
+                    for (int p = 0; p < NU; ++p) acc = fma(Kk[p * NX + i], uc[p], acc);
+                    pv[i] = acc + acc2;
                 }
                 __syncthreads();
             }
@@ -351,45 +320,47 @@ __global__ void __launch_bounds__(kBlockThreads, 2) qp_block_kernel(const QpArgs
 
         // ================================================================ vector sweeps on warp 0 (one lane per vector entry)
         // forward: dx_0 = 0 ; du_k = K dx_k + d_k ; dx_{k+1} = A dx_k + B du_k + rp_scale rp_k ; ratio test (+ sums for mu_affine)
+        // NU-vector results (u = K x + d, t = ru + B'g) are split over LPO lanes per output and combined with shuffles
+        constexpr int LPO = NU >= 3 ? 8 : (NU == 2 ? 16 : 32);
         auto forward = [&](const int pass) {
             const double tau = pass == 0 ? 1.0 : (mu_c > 1e-8 ? 0.995 : 0.9999);
             double rpm = 0.0, rdm = 0.0, S3 = 0.0, S4 = 0.0;
             double* e_dz = pass == 0 ? e_da : e_dc;
+            const int up = lane / LPO, uj = lane - up * LPO;          // this lane's share of u[up]: terms m = uj, uj + LPO, ...
             if (lane < NX) { xc[lane] = 0.0; e_dz[lane] = 0.0; }
             __syncwarp();
             for (int k = 0; k < N; ++k) {
                 const double* Ak = A + (size_t)k * NX * NX;
                 const double* Bk = Bm + (size_t)k * NX * NU;
                 const double* Kk = Kq + (size_t)k * NU * NX;
-                if (lane >= NX && lane < NZ) {
-                    const int p = lane - NX;
-                    double u = dff[k * NU + p], u2 = 0.0;
-#pragma unroll 4
-                    for (int m = 0; m + 1 < NX; m += 2) { u = fma(Kk[p * NX + m], xc[m], u); u2 = fma(Kk[p * NX + m + 1], xc[m + 1], u2); }
-                    if (NX & 1) u = fma(Kk[p * NX + NX - 1], xc[NX - 1], u);
-                    uc[p] = u + u2;
+                // entry data of this stage's entries (x_{k+1}[lane] / u_k[lane - NX]) -- in flight during the products
+                const int idx = lane < NX ? (k + 1) * NZ + lane : k * NZ + lane;
+                double iu = 0.0, il = 0.0, lu = 0.0, ll = 0.0, dza = 0.0;
+                if (lane < NZ) { iu = e_iu[idx]; il = e_il[idx]; lu = e_lu[idx]; ll = e_ll[idx]; dza = e_da[idx]; }
+                double upart = 0.0;
+                if (up < NU) {
+#pragma unroll
+                    for (int m = uj; m < NX; m += LPO) upart = fma(Kk[up * NX + m], xc[m], upart);
                 }
+                double n[4] = {0.0, 0.0, 0.0, 0.0};
+                if (lane < NX) {
+                    n[0] = rp_scale * rp[k * NX + lane];
+#pragma unroll
+                    for (int m = 0; m < NX; ++m) n[m & 3] = fma(Ak[lane * NX + m], xc[m], n[m & 3]);
+                }
+#pragma unroll
+                for (int o = LPO / 2; o > 0; o >>= 1) upart += __shfl_xor_sync(0xffffffffu, upart, o);
+                if (up < NU && uj == 0) uc[up] = upart + dff[k * NU + up];
                 __syncwarp();
                 double dz = 0.0;
-                int idx = 0;
                 if (lane < NX) {
-                    double n0 = rp_scale * rp[k * NX + lane], n1 = 0.0;
-#pragma unroll 4
-                    for (int m = 0; m + 1 < NX; m += 2) { n0 = fma(Ak[lane * NX + m], xc[m], n0); n1 = fma(Ak[lane * NX + m + 1], xc[m + 1], n1); }
-                    if (NX & 1) n0 = fma(Ak[lane * NX + NX - 1], xc[NX - 1], n0);
 #pragma unroll
-                    for (int p = 0; p < NU; ++p) n0 = fma(Bk[lane * NU + p], uc[p], n0);
-                    dz = n0 + n1;
-                    idx = (k + 1) * NZ + lane;
-                } else if (lane < NZ) {
-                    dz = uc[lane - NX];
-                    idx = k * NZ + lane;
-                }
-                __syncwarp();
-                if (lane < NX) xc[lane] = dz;
+                    for (int p = 0; p < NU; ++p) n[p & 3] = fma(Bk[lane * NU + p], uc[p], n[p & 3]);
+                    dz = (n[0] + n[1]) + (n[2] + n[3]);
+                    xc[lane] = dz;
+                } else if (lane < NZ) dz = uc[lane - NX];
                 if (lane < NZ) {
                     e_dz[idx] = dz;
-                    const double iu = e_iu[idx], il = e_il[idx], lu = e_lu[idx], ll = e_ll[idx], dza = e_da[idx];
                     if (iu > 0.0) {
                         const double ru = lu * iu;
                         const double tgt = pass == 1 ? sigma_mu + dza * (ru * dza - lu) : 0.0;
@@ -417,30 +388,36 @@ __global__ void __launch_bounds__(kBlockThreads, 2) qp_block_kernel(const QpArgs
             if (lane == 0) { red[40] = rpm; red[41] = rdm; red[42] = S3; red[43] = S4; red[44] = tau; }
         };
         // corrector backward sweep with the stored factors: p_N = rhs_N ; g = p + rp_scale Sc ; t = ru + B'g ; d = -H^{-1} t ;
-        // p_k = rx + A'g + K't
+        // p_k = rx + A'g + K't.  p[i] only ever belongs to lane i: it lives in a register.
         auto backward_corrector = [&]() {
-            if (lane < NX) pv[lane] = rhs_entry(1, N * NZ + lane);
-            __syncwarp();
+            const int up = lane / LPO, uj = lane - up * LPO;
+            double pl = lane < NX ? rhs_entry(1, N * NZ + lane) : 0.0;
             for (int k = N - 1; k >= 0; --k) {
                 const double* Ak = A + (size_t)k * NX * NX;
                 const double* Bk = Bm + (size_t)k * NX * NU;
                 const double* Kk = Kq + (size_t)k * NU * NX;
                 double r = 0.0;
                 if (lane < NX) {
-                    gv[lane] = pv[lane] + rp_scale * Sc[k * NX + lane];
+                    gv[lane] = pl + rp_scale * Sc[k * NX + lane];
                     r = k > 0 ? rhs_entry(1, k * NZ + lane) : 0.0;
-                } else if (lane < NZ) r = rhs_entry(1, k * NZ + lane);
-                __syncwarp();
-                if (lane >= NX && lane < NZ) {
-                    const int p = lane - NX;
-                    double t = r, t2 = 0.0;
-#pragma unroll 4
-                    for (int i = 0; i + 1 < NX; i += 2) { t = fma(Bk[i * NU + p], gv[i], t); t2 = fma(Bk[(i + 1) * NU + p], gv[i + 1], t2); }
-                    if (NX & 1) t = fma(Bk[(NX - 1) * NU + p], gv[NX - 1], t);
-                    tt[p] = t + t2;
                 }
+                const double ru = up < NU && uj == 0 ? rhs_entry(1, k * NZ + NX + up) : 0.0;
                 __syncwarp();
-                if (lane == NZ || (NZ == 32 && lane == 0)) {
+                double tpart = 0.0;
+                if (up < NU) {
+#pragma unroll
+                    for (int i = uj; i < NX; i += LPO) tpart = fma(Bk[i * NU + up], gv[i], tpart);
+                }
+                double acc[4] = {r, 0.0, 0.0, 0.0};
+                if (lane < NX && k > 0) {
+#pragma unroll
+                    for (int m = 0; m < NX; ++m) acc[m & 3] = fma(Ak[m * NX + lane], gv[m], acc[m & 3]);
+                }
+#pragma unroll
+                for (int o = LPO / 2; o > 0; o >>= 1) tpart += __shfl_xor_sync(0xffffffffu, tpart, o);
+                if (up < NU && uj == 0) tt[up] = tpart + ru;
+                __syncwarp();
+                if (lane == 31) {          // a lane without a p-entry (NX <= 31) solves for the feed-forward meanwhile
                     double L[NU][NU], d[NU];
 #pragma unroll
                     for (int p = 0; p < NU; ++p) {
@@ -452,19 +429,12 @@ __global__ void __launch_bounds__(kBlockThreads, 2) qp_block_kernel(const QpArgs
 #pragma unroll
                     for (int p = 0; p < NU; ++p) dff[k * NU + p] = -d[p];
                 }
-                double pnew = 0.0;
                 if (lane < NX && k > 0) {
-                    double acc = r, acc2 = 0.0;
-#pragma unroll 4
-                    for (int m = 0; m + 1 < NX; m += 2) { acc = fma(Ak[m * NX + lane], gv[m], acc); acc2 = fma(Ak[(m + 1) * NX + lane], gv[m + 1], acc2); }
-                    if (NX & 1) acc = fma(Ak[(NX - 1) * NX + lane], gv[NX - 1], acc);
 #pragma unroll
-                    for (int p = 0; p < NU; ++p) acc = fma(Kk[p * NX + lane], tt[p], acc);
-                    pnew = acc + acc2;
+                    for (int p = 0; p < NU; ++p) acc[p & 3] = fma(Kk[p * NX + lane], tt[p], acc[p & 3]);
+                    pl = (acc[0] + acc[1]) + (acc[2] + acc[3]);
                 }
-                __syncwarp();
-                if (lane < NX && k > 0) pv[lane] = pnew;
-                __syncwarp();
+                __syncwarp();              // gv / tt are rewritten by the next stage
             }
         };
 
