@@ -167,8 +167,8 @@ int rnmpc_closed_loop_host(rnmpc_handle* h, int B, int steps, const double* h_x0
  * caller of the reference would), "qp_max_iter" (default 40), "qp_tol_mu" (default 1e-14), "qp_mu0" (cold start of the interior
  * point: 0 = multipliers 1; > 0 = centred, multipliers qp_mu0 / slack; < 0 = centred and scale-adaptive, multipliers
  * |qp_mu0| x mean slack / slack; default -0.3), "qp_block_max" (batches up to this size are solved by the one-CTA-per-instance QP
- * kernel with the working set in shared memory, rnmpc_qp_block.cuh: 2.2 x faster for one instance, crossover against the
- * instance-per-slot kernel near 1000 instances; default 512, 0 = never; the two kernels agree to rounding, not bit for bit),
+ * kernel with the working set in shared memory, rnmpc_qp_block.cuh: 2.9 x faster for one instance, crossover against the
+ * instance-per-slot kernel near 1500 instances; default 1024, 0 = never; the two kernels agree to rounding, not bit for bit),
  * "qp_warps" / "sls_warps" (warps per
  * CTA of the QP / fast-SLS kernel, 1..5; default 0 = automatic, currently 1: the warps are independent chains and small CTAs
  * fill the SMs evenly; 3 and 4 measured 20 % slower at batch 4096 because the grid no longer fits one wave).

@@ -185,8 +185,9 @@ struct Engine : IEngine {
     using P = Params<NX, NU>;
     int N, cap, rti, sls_steps, qp_max_iter;
     double qp_tol_mu, qp_tol_res, h;
-    int qp_block_max = 512;        // batches up to this size use the one-CTA-per-instance QP kernel (rnmpc_qp_block.cuh); 0: never.  Measured
-                                   // crossover against qp_ipm_kernel: about 1000 instances (tools/latency_probe.py)
+    int qp_block_max = 1024;       // batches up to this size use the one-CTA-per-instance QP kernel (rnmpc_qp_block.cuh); 0: never.  Measured
+                                   // (tools/latency_probe.py, rocket, whole solve): 1024 instances 6.96 ms vs 8.81 ms with qp_ipm_kernel,
+                                   // 1536: 9.83 vs 10.06, 2048: 12.36 vs 11.33
     size_t qp_block_smem = 0;
     bool qp_block_ok = false;
     double qp_mu0 = -0.3;          // cold start of the interior point: centred, multipliers = 0.3 x mean slack / slack (see QpArgs::mu0)
