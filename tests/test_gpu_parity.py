@@ -501,12 +501,13 @@ def test_dense_cost_matrices_vs_oracle(name):
     s.close()
 
 
-@pytest.mark.parametrize("name,B,seed,warm_mask", [("rocket", 2048, 2025, 0), ("rocket", 2048, 2025, 2), ("quadrotor", 512, 5, 0),
-                                                   ("pendulum", 256, 5, 0)])
+@pytest.mark.parametrize("name,B,seed,warm_mask", [("rocket", 2048, 2025, 0), ("rocket", 2048, 2025, 2), ("rocket", 1024, 99, 0),
+                                                   ("quadrotor", 512, 5, 0), ("pendulum", 256, 5, 0)])
 def test_monte_carlo_population_vs_cpu_port(name, B, seed, warm_mask):
     """Disturbed closed loops of a whole population (lengths of the reference drivers' loops; default solver options = every QP
     cold, and once with the optional warm start of the tightened QP, `warm_mask` = 2, so that this path stays covered)
-    against the C++ CPU port of the same path on identical scenarios and nominal trajectory:
+    against the C++ CPU port of the same path on identical scenarios and nominal trajectory (batches of 2048 run the
+    instance-per-slot QP kernel, batches up to 1024 the one-CTA-per-instance kernel):
     the same scenarios must fail, at the same step, and the closed-loop states produced by successful solves must agree.
     rocket: BASELINE configs[3] distribution (fixed x0, disturbance draws); quadrotor: seeded x0 draws of its driver plus
     disturbances; pendulum: the driver's x0 plus disturbances.
