@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     }
 
     int stalled = 0;
+    int it_slot = 0;               // iterations THIS slot took part in (the warp goes on until its slowest slot is done)
     double mu_chk = 1e300;         // complementarity at the last warm-start checkpoint
     bool done = (status != 0) || !act;
     int resT = -1, resS = -1;      // stage whose A_k is resident (or in flight, cp.async) in sm.T / sm.S
@@ -328,6 +329,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
             mu_chk = mu_c;
         }
         if (__all_sync(mask, done)) break;
+        if (!done) ++it_slot;
         __syncwarp(mask);
         if (!dg) {
             // dense cost matrices: gradient G = 2 H (z + z_nom) + q by explicit mat-vecs (not used by any reference driver)
@@ -768,7 +770,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     cp_async_wait_all();
     // out of iterations (the full budget): accepted at working precision
     if (!done && status == 0) status = (mu_c < 1e-9 && rp_inf * rp_scale < 1e-7) ? 0 : 1;
-    if (act) it_total += it;
+    if (act) it_total += it_slot;
     // a warm start that did not converge is repeated from the cold start (whole warp: the slots run in lock-step)
     const bool retry = act && status != 0 && !structural && warm;
     if (!WARM || attempt == 1 || !__any_sync(mask, retry)) break;
