@@ -169,6 +169,9 @@ int rnmpc_closed_loop_host(rnmpc_handle* h, int B, int steps, const double* h_x0
  * |qp_mu0| x mean slack / slack; default -0.3), "qp_block_max" (batches up to this size are solved by the one-CTA-per-instance QP
  * kernel with the working set in shared memory, rnmpc_qp_block.cuh: 2.9 x faster for one instance, crossover against the
  * instance-per-slot kernel near 1500 instances; default 1024, 0 = never; the two kernels agree to rounding, not bit for bit),
+ * "qp_handoff_iter" (batches above qp_block_max: the instance-per-slot kernel stops after this many iterations and the instances
+ * that are not done -- a launch lasts as long as its slowest instance -- are finished by the one-CTA-per-instance kernel from
+ * the same iterate; default 9 = -5 % on the 29-step rocket loop, 0 = off),
  * "qp_warps" / "sls_warps" (warps per
  * CTA of the QP / fast-SLS kernel, 1..5; default 0 = automatic, currently 1: the warps are independent chains and small CTAs
  * fill the SMs evenly; 3 and 4 measured 20 % slower at batch 4096 because the grid no longer fits one wave).

@@ -189,6 +189,12 @@ struct Engine : IEngine {
                                    // (tools/latency_probe.py, rocket, whole solve): 1024 instances 6.96 ms vs 8.81 ms with qp_ipm_kernel,
                                    // 1536: 9.83 vs 10.06, 2048: 12.36 vs 11.33
     size_t qp_block_smem = 0;
+    int qp_handoff_iter = 9;       // large batches: qp_ipm_kernel stops after this many iterations and hands the unfinished instances to
+                                   // qp_block_kernel (QpArgs::handoff_iter); 0: off.  29-step rocket loop at batch 4096 (ms): off 499.6,
+                                   // 14: 501.3, 12: 497.3, 11: 487.2, 10: 479.3, 9: 473.1, 8: 483.3, 7: 503.9, 6: 529.0 (the mean iteration
+                                   // count there is 9; tuned on that loop only)
+    int *handoff_count = nullptr, *handoff_list = nullptr;
+    double* handoff_state = nullptr;
     bool qp_block_ok = false;
     double qp_mu0 = -0.3;          // cold start of the interior point: centred, multipliers = 0.3 x mean slack / slack (see QpArgs::mu0)
     P* d_prm = nullptr;
@@ -278,7 +284,8 @@ struct Engine : IEngine {
         rc |= alloc("rp", rp, B * N * NX); rc |= alloc("Sc", Sc, B * N * NX); rc |= alloc("dff", dff, B * N * NU);
         rc |= alloc("Kq", Kq, B * N * NU * NX); rc |= alloc("Lq", Lq, B * N * NU * NU);
         rc |= alloc("flags", flags, B); rc |= alloc("status", status, B); rc |= alloc("qp_iters", qp_iters, B);
-        rc |= alloc("iters_tmp", iters_tmp, B); rc |= alloc("status_tmp", status_tmp, B); rc |= alloc("n_open", n_open, 1); rc |= alloc("iters_sum", iters_sum, 1); rc |= alloc("ws_valid", ws_valid, B);
+        rc |= alloc("iters_tmp", iters_tmp, B); rc |= alloc("status_tmp", status_tmp, B); rc |= alloc("n_open", n_open, 1); rc |= alloc("iters_sum", iters_sum, 1);
+        rc |= alloc("handoff_count", handoff_count, 1); rc |= alloc("handoff_list", handoff_list, B); rc |= alloc("handoff_state", handoff_state, B * 4); rc |= alloc("ws_valid", ws_valid, B);
         if (rc) return -2;
         const int smem_sls = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * kWarps;
         RN_CUDA(cudaFuncSetAttribute(sls_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
@@ -416,7 +423,15 @@ struct Engine : IEngine {
             qp_block_kernel<NX, NU><<<(unsigned)B, kBlockThreads, qp_block_smem, st>>>(a, d_prm);
         } else if (diag_cost) {
             if (may_warm) qp_ipm_kernel<NX, NU, true, true><<<grid, w * 32, smem, st>>>(a, d_prm);
-            else qp_ipm_kernel<NX, NU, true, false><<<grid, w * 32, smem, st>>>(a, d_prm);
+            else if (qp_block_ok && qp_handoff_iter > 0 && hi_in == nullptr && lo_in == nullptr && q_lin == nullptr) {
+                // instance-per-slot kernel up to qp_handoff_iter iterations, then the stragglers on one CTA each (resume mode)
+                cudaMemsetAsync(handoff_count, 0, sizeof(int), st);
+                a.handoff_iter = qp_handoff_iter; a.handoff_count = handoff_count; a.handoff_list = handoff_list; a.handoff_state = handoff_state;
+                qp_ipm_kernel<NX, NU, true, false><<<grid, w * 32, smem, st>>>(a, d_prm);
+                a.resume = 1;
+                qp_block_kernel<NX, NU><<<(unsigned)B, kBlockThreads, qp_block_smem, st>>>(a, d_prm);
+                ++launches;
+            } else qp_ipm_kernel<NX, NU, true, false><<<grid, w * 32, smem, st>>>(a, d_prm);
         } else {
             if (may_warm) qp_ipm_kernel<NX, NU, false, true><<<grid, w * 32, smem, st>>>(a, d_prm);
             else qp_ipm_kernel<NX, NU, false, false><<<grid, w * 32, smem, st>>>(a, d_prm);
@@ -662,6 +677,7 @@ struct Engine : IEngine {
         else if (n == "qp_tol_mu") qp_tol_mu = value;
         else if (n == "qp_mu0") qp_mu0 = value;
         else if (n == "qp_block_max") qp_block_max = (int)value;
+        else if (n == "qp_handoff_iter") qp_handoff_iter = (int)value;
         else { set_error("unknown option " + n); return -1; }
         return 0;
     }

@@ -23,6 +23,7 @@
 namespace rnmpc {
 
 constexpr int kRec = 12;    // doubles per entry record
+constexpr int kStatusHandoff = 5;   // transient: handed to qp_block_kernel (never visible to callers)
 enum { F_SU = 0, F_SL = 1, F_LU = 2, F_LL = 3, F_ISU = 4, F_ISL = 5, F_Z = 6, F_ZN = 7, F_DZA = 8, F_DZC = 9, F_SIG = 10, F_QD = 11 };
 
 struct QpArgs {
@@ -70,6 +71,14 @@ struct QpArgs {
     int warm;               // warm start from the workspace's previous solution of the same instance: bit0 multipliers, bit1 shifted by one
                             // stage (previous MPC step), bit2 primal iterate; a failed warm-started solve is repeated from the cold start
     int* ws_valid;          // [B] workspace holds a converged solution
+    // straggler hand-off (large batches): an instance that is not done after `handoff_iter` iterations stops here with its iterate
+    // in the record workspace; qp_block_kernel (resume mode, one CTA per instance) finishes it.  A launch lasts as long as its
+    // slowest instance, and the slowest 2-3 % need 12-18 iterations where the mean is 9.
+    int handoff_iter;       // 0: off
+    int* handoff_count;     // [1] number of instances handed off (zeroed by the caller)
+    int* handoff_list;      // [B] their indices
+    double* handoff_state;  // [B][4] rp_scale, mu, rp_inf, n_box
+    int resume;             // qp_block_kernel only: 1 = finish the instances of handoff_list
 };
 
 // DG: the cost matrices are diagonal (all reference drivers): the dense-cost code is compiled out of that instantiation, which
@@ -764,6 +773,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
                 // dynamics residual or the complementarity stay large -> give up early instead of burning max_iter
                 stalled = (ap < 1e-4 && ad < 1e-4) ? stalled + 1 : 0;
                 if (!done && (stalled >= 3 || mu_c > 1e12)) { status = 2; done = true; }
+                if (!WARM && !done && a.handoff_iter > 0 && it + 1 >= a.handoff_iter) { status = kStatusHandoff; done = true; }
             }
         }
     }
@@ -771,6 +781,16 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
     // out of iterations (the full budget): accepted at working precision
     if (!done && status == 0) status = (mu_c < 1e-9 && rp_inf * rp_scale < 1e-7) ? 0 : 1;
     if (act) it_total += it_slot;
+    if (!WARM && status == kStatusHandoff) {
+        // the iterate of this instance (records, rp) is complete in the workspace; the scalars of the iteration go with it
+        __syncwarp(mask);
+        if (sl == 0) {
+            const int pos = atomicAdd(a.handoff_count, 1);
+            a.handoff_list[pos] = b;
+            double* hs = a.handoff_state + (size_t)b * 4;
+            hs[0] = rp_scale; hs[1] = mu_c; hs[2] = rp_inf; hs[3] = n_box;
+        }
+    }
     // a warm start that did not converge is repeated from the cold start (whole warp: the slots run in lock-step)
     const bool retry = act && status != 0 && !structural && warm;
     if (!WARM || attempt == 1 || !__any_sync(mask, retry)) break;

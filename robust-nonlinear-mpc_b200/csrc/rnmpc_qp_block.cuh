@@ -58,10 +58,17 @@ __global__ void __launch_bounds__(kBlockThreads, 2) qp_block_kernel(const QpArgs
     constexpr int NZ = NX + NU, NI = 2 * NZ, NIF = 2 * NX, LD = Slot<NX>::LD, T = kBlockThreads;
     static_assert(NX + NU <= 32 && NX <= 31, "one lane of warp 0 per vector entry, lane 31 free");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = a.N;
-    if (b >= a.B) return;
-    if (a.flags != nullptr && (a.flags[b] & a.skip_mask) != 0) return;
+    const bool resume = a.resume != 0;
+    int b = blockIdx.x;
+    if (resume) {                   // finish the instances the instance-per-slot kernel handed off (QpArgs::handoff_*)
+        if (b >= *a.handoff_count) return;
+        b = a.handoff_list[b];
+    } else {
+        if (b >= a.B) return;
+        if (a.flags != nullptr && (a.flags[b] & a.skip_mask) != 0) return;
+    }
 
     double* sp = reinterpret_cast<double*>(smem_raw);
     auto take = [&](size_t n) { double* p = sp; sp += (n + 1) & ~(size_t)1; return p; };
@@ -117,7 +124,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) qp_block_kernel(const QpArgs
     // ------------------------------------------------------------------ bounds, initial point, slacks (rnmpc_qp.cuh, cold start)
     const bool tight = a.tightened < 0 ? ((a.flags[b] & FLAG_TIGHT) != 0) : (a.tightened != 0);
     double bad = 0.0, n_box = 0.0, s_sum = 0.0;
-    {
+    if (!resume) {
         const double eps = tight ? 0.0 : kEpsQP;
         for (int idx = tid; idx < NE; idx += T) {
             const int k = idx / NZ, i = idx - k * NZ;
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) qp_block_kernel(const QpArgs
     n_box = block_sum(n_box);
     s_sum = block_sum(s_sum);
     int status = bad > 0.0 ? 2 : 0;
-    {   // centred cold start: multipliers mu_bar / slack (QpArgs::mu0)
+    if (!resume) {   // centred cold start: multipliers mu_bar / slack (QpArgs::mu0)
         const double mu_bar = a.mu0 < 0.0 ? (n_box > 0.0 ? -a.mu0 * s_sum / n_box : 1.0) : a.mu0;
         for (int idx = tid; idx < NE; idx += T) {
             double lu, ll;
@@ -189,6 +196,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) qp_block_kernel(const QpArgs
     __syncthreads();
     // dynamics residual at the initial point: rp_k = A x_k + B u_k + c_k - x_{k+1}
     double rp_inf = 0.0;
+    if (!resume)
     for (int e = tid; e < N * NX; e += T) {
         const int k = e / NX, r = e - k * NX;
         double acc = cg[e] - e_z[(k + 1) * NZ + r];
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) qp_block_kernel(const QpArgs
     }
     rp_inf = block_max(rp_inf);
     double mu_c;
-    {
+    if (!resume) {
         double acc = 0.0;
         for (int idx = tid; idx < NE; idx += T) {
             if (e_su[idx] < kBig) acc = fma(e_su[idx], e_lu[idx], acc);
@@ -207,6 +215,23 @@ __global__ void __launch_bounds__(kBlockThreads, 2) qp_block_kernel(const QpArgs
         }
         acc = block_sum(acc);
         mu_c = n_box > 0.0 ? acc / n_box : 0.0;
+    }
+    double rp_scale = 1.0;
+    int it0 = 0;                    // iterations already done by qp_ipm_kernel
+    if (resume) {
+        // iterate of the handed-off instance: entry records and dynamics residual from qp_ipm_kernel's workspace
+        const double* E = a.E + (size_t)b * NE * kRec;
+        for (int idx = tid; idx < NE; idx += T) {
+            const double* r = E + (size_t)idx * kRec;
+            e_su[idx] = r[F_SU]; e_sl[idx] = r[F_SL]; e_lu[idx] = r[F_LU]; e_ll[idx] = r[F_LL]; e_iu[idx] = r[F_ISU]; e_il[idx] = r[F_ISL];
+            e_z[idx] = r[F_Z]; e_zn[idx] = r[F_ZN]; e_da[idx] = 0.0; e_dc[idx] = 0.0; e_sg[idx] = r[F_SIG]; e_qd[idx] = r[F_QD];
+        }
+        for (int e = tid; e < N * NX; e += T) rp[e] = a.rp[(size_t)b * N * NX + e];
+        const double* hs = a.handoff_state + (size_t)b * 4;
+        rp_scale = hs[0]; mu_c = hs[1]; rp_inf = hs[2]; n_box = hs[3];
+        it0 = a.iters[b];
+        status = 0;
+        __syncthreads();
     }
 
     // right-hand side of one entry (rnmpc_qp.cuh rhs_eval): gradient (+ centring / second-order terms in the corrector pass)
@@ -221,10 +246,9 @@ __global__ void __launch_bounds__(kBlockThreads, 2) qp_block_kernel(const QpArgs
         return g;
     };
 
-    double rp_scale = 1.0;
     int stalled = 0, it = 0;
     bool done = status != 0;
-    for (it = 0; it < a.max_iter && !done; ++it) {
+    for (it = it0; it < a.max_iter && !done; ++it) {
         bool chol_ok = true;
         double ap = 1.0, ad = 1.0, maxp0 = 0.0, maxd0 = 0.0;
         bool skip_corr = false;
