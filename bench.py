@@ -403,7 +403,7 @@ def main():
                      "traffic_note": "static figure from the ncu capture, not measured in this run; 2.58 TB/s inside that capture = 40 % of the "
                                      "measured HBM copy bandwidth; the launch's inputs + outputs are only 0.26 GB (re-streamed working set)",
                      "launch_ms_avg": t_qp_ms, "launches": int(qp_launches), "flops_per_launch": qp_flops_launch,
-                     "note": "all QP launches of the timed region on rank 0: algorithmic flops (interior-point iterations counted on the "
+                     "note": "all QP solves of the timed region on rank 0 (qp_ipm_kernel + its hand-off launch to qp_block_kernel): algorithmic flops (interior-point iterations counted on the "
                              "device x 0.49 MFLOP) / summed CUDA-event durations, vs the DFMA peak measured live on this GPU "
                              "(MEASURED_PEAKS.json has no fp64 entry).  Neither the FP64 nor the HBM roof is near: the kernel is latency "
                              "bound (DESIGN.md section 5)"},
