@@ -68,7 +68,8 @@ IEngine* make_rocket(const rnmpc_config* cfg, int cap, int device);
 // check_convergence_socp (solver/fast_SLS_jit.py:581-600, quirk Q3): per instance max |delta - prev_delta| <= 1e-3 against
 // the previous *first-in-step* QP solution, kept across MPC steps; only the primal test is used.
 static __global__ void q3_check_kernel(int B, int nxs, int nus, const double* __restrict__ dX, const double* __restrict__ dU,
-                                       double* __restrict__ prevX, double* __restrict__ prevU, int* __restrict__ flags, int skip_mask) {
+                                       double* __restrict__ prevX, double* __restrict__ prevU, int* __restrict__ flags, int skip_mask,
+                                       double conv_eps, double* __restrict__ margin) {
     // one warp per instance: coalesced reads, shuffle max-reduction
     const int b = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -86,7 +87,10 @@ static __global__ void q3_check_kernel(int B, int nxs, int nus, const double* __
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) {
         f &= ~FLAG_Q3;
-        if ((f & FLAG_PREV) && m <= 1e-3) f |= FLAG_Q3;
+        if ((f & FLAG_PREV) && m <= conv_eps) f |= FLAG_Q3;
+        // closest approach of the tested quantity to its threshold since the last reset (diagnostic: a decision taken within
+        // rounding of the threshold is not reproducible across implementations)
+        if ((f & FLAG_PREV) && margin != nullptr) margin[b] = fmin(margin[b], fabs(m - conv_eps));
         f |= FLAG_PREV;
         flags[b] = f;
     }
@@ -189,6 +193,9 @@ struct Engine : IEngine {
                                    // (tools/latency_probe.py, rocket, whole solve): 1024 instances 6.96 ms vs 8.81 ms with qp_ipm_kernel,
                                    // 1536: 9.83 vs 10.06, 2048: 12.36 vs 11.33
     size_t qp_block_smem = 0;
+    double q3_eps = 1e-3;          // CONV_EPS of check_convergence_socp (fast_SLS_jit.py): the Q3 early return fires when the nominal QP solution
+                                   // moved by less than this since the previous forward solve
+    double* q3_margin = nullptr;   // [B] diagnostic: min |tested quantity - q3_eps| since "q3_margin_reset"
     int qp_handoff_iter = 9;       // large batches: qp_ipm_kernel stops after this many iterations and hands the unfinished instances to
                                    // qp_block_kernel (QpArgs::handoff_iter); 0: off.  29-step rocket loop at batch 4096 (ms): off 499.6,
                                    // 14: 501.3, 12: 497.3, 11: 487.2, 10: 479.3, 9: 473.1, 8: 483.3, 7: 503.9, 6: 529.0 (the mean iteration
@@ -285,7 +292,7 @@ struct Engine : IEngine {
         rc |= alloc("Kq", Kq, B * N * NU * NX); rc |= alloc("Lq", Lq, B * N * NU * NU);
         rc |= alloc("flags", flags, B); rc |= alloc("status", status, B); rc |= alloc("qp_iters", qp_iters, B);
         rc |= alloc("iters_tmp", iters_tmp, B); rc |= alloc("status_tmp", status_tmp, B); rc |= alloc("n_open", n_open, 1); rc |= alloc("iters_sum", iters_sum, 1);
-        rc |= alloc("handoff_count", handoff_count, 1); rc |= alloc("handoff_list", handoff_list, B); rc |= alloc("handoff_state", handoff_state, B * 4); rc |= alloc("ws_valid", ws_valid, B);
+        rc |= alloc("q3_margin", q3_margin, B); rc |= alloc("handoff_count", handoff_count, 1); rc |= alloc("handoff_list", handoff_list, B); rc |= alloc("handoff_state", handoff_state, B * 4); rc |= alloc("ws_valid", ws_valid, B);
         if (rc) return -2;
         const int smem_sls = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * kWarps;
         RN_CUDA(cudaFuncSetAttribute(sls_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
@@ -557,7 +564,7 @@ struct Engine : IEngine {
                                        : ((warm_mask & 1) ? (ii > 0 ? 1 : (have_solution ? (shifted_since_solve ? (1 | 2) : 1) : 0)) : 0);
                 rc = resident_qp(B, -1, x0, st, skipf, wm);            // forward_solve
                 if (rc) return rc;
-                q3_check_kernel<<<(B + 3) / 4, 128, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, prevX, prevU, flags, skipf);
+                q3_check_kernel<<<(B + 3) / 4, 128, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, prevX, prevU, flags, skipf, q3_eps, q3_margin);
                 ++launches;
                 if (converge_mode) {
                     RN_CUDA(cudaMemsetAsync(n_open, 0, sizeof(int), st));
@@ -677,6 +684,8 @@ struct Engine : IEngine {
         else if (n == "qp_tol_mu") qp_tol_mu = value;
         else if (n == "qp_mu0") qp_mu0 = value;
         else if (n == "qp_block_max") qp_block_max = (int)value;
+        else if (n == "q3_eps") q3_eps = value;
+        else if (n == "q3_margin_reset") { if (q3_margin) { std::vector<double> big((size_t)cap, 1e300); cudaMemcpy(q3_margin, big.data(), big.size() * sizeof(double), cudaMemcpyHostToDevice); } }
         else if (n == "qp_handoff_iter") qp_handoff_iter = (int)value;
         else { set_error("unknown option " + n); return -1; }
         return 0;

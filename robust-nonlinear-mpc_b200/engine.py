@@ -100,7 +100,7 @@ class BatchSolver:
         "backoff_f": lambda s: (s.ni_f,), "A": lambda s: (s.N, s.nx, (s.nx + 1) & ~1), "B": lambda s: (s.N, s.nx, s.nu),
         "c": lambda s: (s.N, s.nx), "cost": lambda s: (), "Phi_x": lambda s: (s.N + 1, s.N + 1, s.nx, s.nx),
         "Phi_u": lambda s: (s.N, s.N + 1, s.nu, s.nx), "flags": lambda s: (), "status": lambda s: (), "qp_iters": lambda s: (),
-        "iters_tmp": lambda s: (), "ws_valid": lambda s: (),      # last QP launch's iteration count per instance; workspace-valid flag
+        "q3_margin": lambda s: (), "iters_tmp": lambda s: (), "ws_valid": lambda s: (),      # last QP launch's iteration count per instance; workspace-valid flag
     }
     _INT = {"flags", "status", "qp_iters", "iters_tmp", "ws_valid"}
 
