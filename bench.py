@@ -118,9 +118,10 @@ def gpu_single_latency(m, cfg, device, steps=40):
     clock per rnmpc_solve_host call, percentiles over a disturbed closed loop."""
     import torch
     from rnmpc_b200.engine import BatchSolver
-    from tests.helpers import rocket_scenarios
-    s = BatchSolver("rocket", cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], m.E, m.x_ub, m.x_lb,
-                    m.u_ub, m.u_lb, rti=cfg["rti"], sls_steps=cfg["fast_sls_rti_steps"], capacity=1, device=device)
+    from rnmpc_b200.workloads import rocket_scenarios
+    x_ub, x_lb, u_ub, u_lb, _, _ = m.box()
+    s = BatchSolver("rocket", cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], m.E, x_ub, x_lb,
+                    u_ub, u_lb, rti=cfg["rti"], sls_steps=cfg["fast_sls_rti_steps"], capacity=1, device=device)
     x0, W = rocket_scenarios(1, seed=777, steps=steps + 8)
     x = s.dev(x0).clone()
     s.init_nominal(x, 10)
@@ -193,10 +194,10 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from oracle import models as om            # model constants only (no oracle compute on this path)
+    # this arm imports the product only: nothing under oracle/ (the checker) is loaded here
     from rnmpc_b200.engine import BatchSolver, fp64_peak_tflops
     from rnmpc_b200.sharding import gather_statistics
-    from tests.helpers import rocket_scenarios
+    from rnmpc_b200.workloads import rocket_config, rocket_scenarios
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU fallback); use --impl reference for the CPU arm")
@@ -207,13 +208,14 @@ def main():
     B, K, Wm = a.batch, a.steps, a.warmup
     G = max(1, min(a.groups, B))
     total_steps = K + Wm
-    m, cfg = om.rocket_config()
+    m, cfg = rocket_config()
+    x_ub, x_lb, u_ub, u_lb, _, _ = m.box()
     x0, W = rocket_scenarios(B, seed=2025 + rank, steps=2 * total_steps + 4)
     bounds = [(g * B // G, (g + 1) * B // G) for g in range(G)]
     solvers, streams, xs, Wds = [], [], [], []
     for lo, hi in bounds:
-        s = BatchSolver("rocket", cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], m.E, m.x_ub, m.x_lb,
-                        m.u_ub, m.u_lb, rti=cfg["rti"], sls_steps=cfg["fast_sls_rti_steps"], capacity=hi - lo, device=local_rank)
+        s = BatchSolver("rocket", cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], m.E, x_ub, x_lb,
+                        u_ub, u_lb, rti=cfg["rti"], sls_steps=cfg["fast_sls_rti_steps"], capacity=hi - lo, device=local_rank)
         s.enable_timing(2)                  # event pair around every hot-kernel launch, summed after the timed region (no sync inside)
         s.set_option("sticky_fail", 1)      # Monte-Carlo semantics: a scenario whose solve failed is dead (the reference's driver would stop)
         solvers.append(s)

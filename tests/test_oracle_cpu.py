@@ -170,6 +170,36 @@ def test_c_abi_exports_every_declared_symbol():
     assert b"unknown model" in lib.rnmpc_last_error()
 
 
+def test_bench_gpu_arm_does_not_import_the_oracle():
+    """bench.py may touch oracle/ only in its CPU-baseline leg (cpu_baseline, cpu_single_latency); the measured arm imports the
+    product alone, and the product-side workload is the same as the oracle-side one the tests and the CPU arm use."""
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    allowed = {"cpu_baseline", "cpu_single_latency"}
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            mod = node.module if isinstance(node, ast.ImportFrom) else None
+            names = [a.name for a in node.names] if isinstance(node, ast.Import) else []
+            if (mod and (mod.split(".")[0] in ("oracle", "tests"))) or any(n.split(".")[0] in ("oracle", "tests") for n in names):
+                assert fn.name in allowed, f"bench.py:{node.lineno} imports {mod or names} inside {fn.name}()"
+    for node in tree.body:      # module level
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            mod = getattr(node, "module", None) or ""
+            assert mod.split(".")[0] not in ("oracle", "tests")
+    from oracle import models as om
+    from tests.helpers import rocket_scenarios as rs_o
+    from rnmpc_b200.workloads import ROCKET_X0, rocket_config, rocket_scenarios as rs_p
+    m_o, c_o = om.rocket_config()
+    m_p, c_p = rocket_config()
+    assert np.array_equal(ROCKET_X0, om.ROCKET_X0) and np.array_equal(m_o.E, m_p.E)
+    assert all(np.array_equal(np.asarray(c_o[k]), np.asarray(c_p[k])) for k in c_o)
+    xu, xl, uu, ul, _, _ = m_p.box()
+    assert np.array_equal(xu, m_o.x_ub) and np.array_equal(xl, m_o.x_lb) and np.array_equal(uu, m_o.u_ub) and np.array_equal(ul, m_o.u_lb)
+    for args in ((64, 2025, 29, 0.0), (16, 7, 5, 0.002)):
+        a, b = rs_o(*args), rs_p(*args)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
 def test_product_has_no_cpu_fallback():
     """Without a CUDA device the product must refuse to run instead of falling back to the oracle / NumPy."""
     import torch
