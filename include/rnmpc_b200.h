@@ -175,7 +175,7 @@ int rnmpc_closed_loop_host(rnmpc_handle* h, int B, int steps, const double* h_x0
  * "qp_warps" / "sls_warps" (warps per
  * CTA of the QP / fast-SLS kernel, 1..5; default 0 = automatic, currently 1: the warps are independent chains and small CTAs
  * fill the SMs evenly; 3 and 4 measured 20 % slower at batch 4096 because the grid no longer fits one wave).
- * Diagnostics: "q3_eps" (CONV_EPS of the reference's check_convergence_socp, default 1e-3), "q3_margin_reset" (resets the buffer
+ * Diagnostics: "q3_eps" (threshold of the reference's check_convergence_socp, which hard-codes 1e-3, fast_SLS_jit.py:594), "q3_margin_reset" (resets the buffer
  * "q3_margin": per instance the closest the tested quantity came to that threshold since the reset).
  * Unknown names return -1. */
 int rnmpc_set_option(rnmpc_handle* h, const char* name, double value);

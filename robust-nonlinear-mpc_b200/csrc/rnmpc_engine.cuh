@@ -193,8 +193,8 @@ struct Engine : IEngine {
                                    // (tools/latency_probe.py, rocket, whole solve): 1024 instances 6.96 ms vs 8.81 ms with qp_ipm_kernel,
                                    // 1536: 9.83 vs 10.06, 2048: 12.36 vs 11.33
     size_t qp_block_smem = 0;
-    double q3_eps = 1e-3;          // CONV_EPS of check_convergence_socp (fast_SLS_jit.py): the Q3 early return fires when the nominal QP solution
-                                   // moved by less than this since the previous forward solve
+    double q3_eps = 1e-3;          // threshold of check_convergence_socp (fast_SLS_jit.py:594 hard-codes 1e-3; the drivers' CONV_EPS is not used
+                                   // there): the Q3 early return fires when the nominal QP solution moved by less since the previous forward solve
     double* q3_margin = nullptr;   // [B] diagnostic: min |tested quantity - q3_eps| since "q3_margin_reset"
     int qp_handoff_iter = 9;       // large batches: qp_ipm_kernel stops after this many iterations and hands the unfinished instances to
                                    // qp_block_kernel (QpArgs::handoff_iter); 0: off.  29-step rocket loop at batch 4096 (ms): off 499.6,

@@ -558,3 +558,41 @@ def test_monte_carlo_population_vs_cpu_port(name, B, seed, warm_mask):
         assert np.quantile(err, 0.995) < 1e-6 and err.max() < 1e-3, (np.quantile(err, 0.995), err.max())
     else:
         assert err.max() < 1e-6, err.max()
+
+
+def test_rocket_driver_schema_and_loop(tmp_path):
+    """The package's counterpart of expe/main_rocket_robust_closed_loop.py --run: the .npz has the reference driver's key set and
+    shapes (:189-206), every solve succeeds, the saved trajectory obeys x+ = f(x, u0) + E w with the driver's disturbance stream
+    (np.random.seed(0); w = 2 rand(nx) - 1, :30,180), and it equals the device-path loop (BatchSolver) on the same stream."""
+    from rnmpc_b200.expe.main_rocket_robust_closed_loop import generate
+    fn, ok = generate(N=15, out_dir=str(tmp_path), verbose=False)
+    assert ok
+    d = np.load(fn)
+    m, cfg = om.rocket_config()
+    T, N, nx, nu = 30, 15, m.nx, m.nu
+    shapes = dict(state_trajectory=(nx, T), input_trajectory=(nu, T - 1), nominal_trajectory_x=(nx, N + 1, T),
+                  nominal_trajectory_u=(nu, N, T), backoff_trajectory_x=(nx, N + 1, T), backoff_trajectory_u=(nu, N, T),
+                  t_jac=(T, 1), t_qp=(T, 1), t_riccati=(T, 1), g=(2 * (nx + nu),))
+    assert set(d.files) == set(shapes) | {"dt", "nx", "nu", "simulation_time_steps", "N"}
+    for k, shp in shapes.items():
+        assert d[k].shape == shp, (k, d[k].shape)
+    assert int(d["N"]) == N and int(d["nx"]) == nx and int(d["simulation_time_steps"]) == T and float(d["dt"]) == 0.05
+    assert np.isfinite(d["t_qp"]).all() and (d["t_qp"] > 0).all()
+    # the disturbance stream of the driver
+    np.random.seed(0)
+    W = np.stack([2 * np.random.rand(nx) - 1 for _ in range(T)])
+    _, _, s = make_solver("rocket", 1)
+    x = s.dev(om.ROCKET_X0[None]).clone()
+    s.init_nominal(x, 10)
+    for i in range(T):
+        assert np.abs(x.cpu().numpy()[0] - d["state_trajectory"][:, i]).max() < 1e-10, i
+        if i > 0:
+            s.reset_warm_start(1)
+        s.solve(x)
+        assert (s.buffer("flags", 1)[0] & 1) == 0
+        Xn, Un = s.buffer("X", 1)[0], s.buffer("U", 1)[0]
+        assert rel(Xn.T, d["nominal_trajectory_x"][:, :, i]) < 1e-10 and relf(Un.T, d["nominal_trajectory_u"][:, :, i]) < 1e-10
+        bo = s.buffer("backoff", 1)[0]
+        assert rel(bo[:, :nx].T, d["backoff_trajectory_x"][:, :N, i]) < 1e-10
+        s.plant_step(x, W[i][None])
+    s.close()
