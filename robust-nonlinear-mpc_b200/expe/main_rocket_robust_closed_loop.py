@@ -6,15 +6,12 @@
 
 Differences from the reference driver: the first-step nominal trajectory comes from the package's tube-free SQP initialiser
 instead of IPOPT; plotting is left to the reference (`plot()` there needs matplotlib only)."""
-import argparse
-import os
-from datetime import datetime
-
 import numpy as np
 
 from ..dyn.rocket import Rocket
 from ..solver.SCP_SLS_jit import SCP_SLS
 from ..workloads import ROCKET_X0
+from ._closed_loop import cli, rollout_and_save
 
 folder_name = "rockETH_robust_closed_loop"
 
@@ -41,62 +38,10 @@ def generate(N=None, out_dir=None, seed=0, simulation_time_steps=30, verbose=Tru
     solver.fast_SLS_solver.CONV_EPS = 1e-4
     solver.epsilon_convergence = 1e-3
 
-    x0 = ROCKET_X0.copy()
-    state_trajectory = np.zeros((m.nx, simulation_time_steps))
-    state_trajectory[:, 0] = x0
-    input_trajectory = np.zeros((m.nu, simulation_time_steps - 1))
-    backoff_trajectory_x = np.zeros((m.nx, N + 1, simulation_time_steps))
-    backoff_trajectory_u = np.zeros((m.nu, N, simulation_time_steps))
-    nominal_trajectory_x = np.zeros((m.nx, N + 1, simulation_time_steps))
-    nominal_trajectory_u = np.zeros((m.nu, N, simulation_time_steps))
-    t_jac = np.zeros((simulation_time_steps, 1))
-    t_qp = np.zeros((simulation_time_steps, 1))
-    t_riccati = np.zeros((simulation_time_steps, 1))
-    success = np.ones(simulation_time_steps, dtype=bool)
-
-    for i in range(simulation_time_steps):
-        if i > 0:
-            solver.reset_warm_start()
-        solution = solver.solve(x0)
-        if not solution.get("success", True):
-            success[i:] = False
-            print(f"[Rocket] Step {i + 1}/{simulation_time_steps}: solver failed, stopping")
-            break
-        t_jac[i] = float(solution.get("t_jac_ms", np.nan))
-        t_qp[i] = float(solution.get("t_qp_ms", np.nan))
-        t_riccati[i] = float(solution.get("t_backward_ms", np.nan))
-        if verbose:
-            print(f"[Rocket] Step {i + 1}/{simulation_time_steps}: jac={t_jac[i, 0]:.2f} ms, qp={t_qp[i, 0]:.2f} ms, "
-                  f"riccati={t_riccati[i, 0]:.2f} ms")
-        backoff_trajectory_x[:, :, i] = solution["backoff_x"].T
-        backoff_trajectory_u[:, :, i] = solution["backoff_u"].T
-        nominal_trajectory_x[:, :, i] = solution["primal_x"]
-        nominal_trajectory_u[:, :, i] = solution["primal_u"]
-        state_trajectory[:, i] = solution["primal_x"][:, 0]
-        if i < simulation_time_steps - 1:
-            input_trajectory[:, i] = solution["primal_u"][:, 0]
-        w = 2 * np.random.rand(m.nx) - 1
-        x0 = np.asarray(m.ddyn(x0, solution["primal_u"][:, 0])).reshape(-1) + m.E @ w
-
-    out_dir = out_dir or folder_name
-    os.makedirs(out_dir, exist_ok=True)
-    filename = os.path.join(out_dir, f"rockETH_robust_closed_loop_{datetime.now().strftime('%Y-%m-%d_%H-%M-%S')}.npz")
-    np.savez(filename, state_trajectory=state_trajectory, input_trajectory=input_trajectory,
-             nominal_trajectory_x=nominal_trajectory_x, nominal_trajectory_u=nominal_trajectory_u,
-             backoff_trajectory_x=backoff_trajectory_x, backoff_trajectory_u=backoff_trajectory_u,
-             dt=m.dt, g=m.g, nx=m.nx, nu=m.nu, simulation_time_steps=simulation_time_steps, N=N,
-             t_jac=t_jac, t_qp=t_qp, t_riccati=t_riccati)
-    print(f"Results saved to {filename}")
-    return filename, bool(success.all())
+    noise = lambda i: 2 * np.random.rand(m.nx) - 1          # main_rocket_robust_closed_loop.py:180
+    return rollout_and_save("Rocket", solver, m, N, ROCKET_X0.copy(), simulation_time_steps, noise, out_dir, folder_name,
+                            "rockETH_robust_closed_loop", verbose)
 
 
 if __name__ == "__main__":
-    parser = argparse.ArgumentParser(description="Rocket robust closed-loop experiment (GPU path)")
-    parser.add_argument("--run", action="store_true", help="Run the closed-loop simulation (generate data)")
-    parser.add_argument("--N", type=int, default=None, help="Horizon length (overrides default if provided)")
-    parser.add_argument("--out", default=None, help="output directory (default: rockETH_robust_closed_loop/)")
-    args = parser.parse_args()
-    if args.run:
-        generate(args.N, args.out)
-    else:
-        print("plotting is the reference's: run its expe/main_rocket_robust_closed_loop.py without --run on the saved file")
+    cli("Rocket robust closed-loop experiment (GPU path)", generate)

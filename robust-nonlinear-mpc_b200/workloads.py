@@ -5,6 +5,7 @@ rocket: expe/main_rocket_robust_closed_loop.py:33-85,110-126 / expe/main_rocket_
 BASELINE.json configs[3] / [4] (disturbance draws U[-1,1]^nx per step, optionally perturbed initial states)."""
 import numpy as np
 
+from .dyn.quadrotor import Quadrotor
 from .dyn.rocket import Rocket
 
 ROCKET_X0 = np.array([1.75729, 4.15951, 4.72757, -0.18913, -0.38367, -0.08697, -0.79487, 0.00768, -0.21110,
@@ -33,3 +34,15 @@ def rocket_scenarios(B, seed=2025, steps=29, x0_scale=0.0):
     x0[:, 6:10] *= (qn / np.linalg.norm(x0[:, 6:10], axis=1))[:, None]
     W = rng.uniform(-1, 1, size=(B, steps, m.nx))
     return x0, W
+
+
+def quadrotor_x0(seed=0):
+    """Seeded form of the unseeded draw at expe/main_quadrotor_robust_closed_loop.py:82-90: uniform in the half range of the
+    state box, quaternion slots 6:10 <- a normalised normal(4) draw."""
+    m = Quadrotor()
+    x_ub, x_lb, _, _, _, _ = m.box()
+    rng = np.random.default_rng(seed)
+    x0 = rng.uniform(x_lb / 2, x_ub / 2)
+    q = rng.normal(size=4)
+    x0[6:10] = q / np.linalg.norm(q)
+    return x0

@@ -616,3 +616,27 @@ def test_long_horizon_uses_the_slot_kernel():
     assert X.shape == (B, N + 1, m.nx) and np.abs(X[ok, 0] - x0[ok]).max() < 1e-12
     assert (bo[ok] > 0).all()
     s.close()
+
+
+@pytest.mark.parametrize("name,tag,T", [("pendulum", "pendulum", 60), ("quadrotor", "quadrotor", 30)])
+def test_pendulum_and_quadrotor_drivers_vs_golden_loops(tmp_path, name, tag, T):
+    """The package's counterparts of expe/main_pendulum_robust_closed_loop.py / main_quadrotor_robust_closed_loop.py --run
+    (BASELINE.json configs[0], configs[1]): reference key set and shapes, and the saved closed loop against the oracle's golden
+    loop of the same configuration (the driver starts from the package's nominal initialiser, the golden loop from the
+    oracle's: they agree to ~1e-9, the loops to the closed-loop tolerance)."""
+    import importlib
+    gen = importlib.import_module(f"rnmpc_b200.expe.main_{name}_robust_closed_loop").generate
+    fn, ok = gen(N=15, out_dir=str(tmp_path), verbose=False)
+    assert ok
+    d, g = np.load(fn), load(f"loop_{tag}.npz")
+    m, cfg = om.CONFIGS[name]()
+    nx, nu, N = m.nx, m.nu, 15
+    assert set(d.files) == {"state_trajectory", "input_trajectory", "nominal_trajectory_x", "nominal_trajectory_u", "backoff_trajectory_x",
+                            "backoff_trajectory_u", "dt", "g", "nx", "nu", "simulation_time_steps", "N", "t_jac", "t_qp", "t_riccati"}
+    assert d["state_trajectory"].shape == (nx, T) and d["input_trajectory"].shape == (nu, T - 1)
+    assert d["nominal_trajectory_x"].shape == (nx, N + 1, T) and d["backoff_trajectory_u"].shape == (nu, N, T)
+    assert np.array_equal(d["g"], m.g)
+    assert rel(d["state_trajectory"].T, g["states"][:T]) < TOL_STATE
+    assert relf(d["input_trajectory"].T, g["inputs"][:T - 1]) < TOL_STATE
+    for i in (0, 1, T // 2, T - 1):
+        assert relf(d["nominal_trajectory_x"][:, :, i].T, g["Xn"][i], 1e-2) < 1e-5, i
