@@ -640,3 +640,25 @@ def test_pendulum_and_quadrotor_drivers_vs_golden_loops(tmp_path, name, tag, T):
     assert relf(d["input_trajectory"].T, g["inputs"][:T - 1]) < TOL_STATE
     for i in (0, 1, T // 2, T - 1):
         assert relf(d["nominal_trajectory_x"][:, :, i].T, g["Xn"][i], 1e-2) < 1e-5, i
+
+
+def test_rocket_compare_driver_robust_arm(tmp_path):
+    """Robust arm of expe/main_rocket_compare_closed_loop.py batched over disturbance sequences (BASELINE.json configs[3]): scenario 0 is
+    the driver's own W = -0.8 sequence = the golden loop `rocket_w08`; key set of the reference with a leading scenario axis."""
+    from rnmpc_b200.expe.main_rocket_compare_closed_loop import closed_loop_cost, generate
+    fn = generate(batch=64, keep=2, out_dir=str(tmp_path))
+    d, g = np.load(fn), load("loop_rocket_w08.npz")
+    m, cfg = om.rocket_config()
+    B, T, N, nx, nu = 64, 30, 15, m.nx, m.nu
+    assert {"r_state_trajectory", "r_input_trajectory", "r_nominal_trajectory_x", "r_nominal_trajectory_u", "r_backoff_trajectory_x",
+            "r_backoff_trajectory_u", "dt", "g", "nx", "nu", "simulation_time_steps", "N", "x0", "W", "Jr_stage", "Jr_terminal",
+            "Jr_total"} <= set(d.files)
+    assert d["r_state_trajectory"].shape == (B, nx, T) and d["r_input_trajectory"].shape == (B, nu, T - 1)
+    assert d["r_nominal_trajectory_x"].shape == (2, nx, N + 1, T - 1) and d["W"].shape == (B, T - 1, nx) and (d["W"][0] == -0.8).all()
+    assert d["r_success"][0]
+    assert rel(d["r_state_trajectory"][0].T, g["states"]) < TOL_STATE and relf(d["r_input_trajectory"][0].T, g["inputs"]) < TOL_STATE
+    assert relf(d["r_nominal_trajectory_x"][0][:, :, 5].T, g["Xn"][5], 1e-2) < 1e-5
+    # cost bookkeeping of the reference (:94-101) on scenario 0
+    X, U = d["r_state_trajectory"][0], d["r_input_trajectory"][0]
+    J = sum(X[:, t] @ cfg["Q"] @ X[:, t] + U[:, t] @ cfg["R"] @ U[:, t] for t in range(T - 1)) + X[:, -1] @ cfg["Qf"] @ X[:, -1]
+    assert abs(d["Jr_total"][0] - J) < 1e-9 * abs(J)
