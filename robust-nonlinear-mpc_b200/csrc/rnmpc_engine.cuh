@@ -190,8 +190,8 @@ struct Engine : IEngine {
     int N, cap, rti, sls_steps, qp_max_iter;
     double qp_tol_mu, qp_tol_res, h;
     int qp_block_max = 1024;       // batches up to this size use the one-CTA-per-instance QP kernel (rnmpc_qp_block.cuh); 0: never.  Measured
-                                   // (tools/latency_probe.py, rocket, whole solve): 1024 instances 6.96 ms vs 8.81 ms with qp_ipm_kernel,
-                                   // 1536: 9.83 vs 10.06, 2048: 12.36 vs 11.33
+                                   // (tools/iter_stats.py, 29-step rocket loop, ms; block kernel vs qp_ipm_kernel with its hand-off):
+                                   // 768 instances 157.4 vs 199.5, 1024: 198.3 vs 216.5, 1536: 276.5 vs 256.2
     size_t qp_block_smem = 0;
     double q3_eps = 1e-3;          // threshold of check_convergence_socp (fast_SLS_jit.py:594 hard-codes 1e-3; the drivers' CONV_EPS is not used
                                    // there): the Q3 early return fires when the nominal QP solution moved by less since the previous forward solve
