@@ -18,5 +18,9 @@ Parity pinning:
   * The nominal QP is solved in the reference by OSQP 1.0.4 (absent here, un-vendored) with default
     tolerances plus polish: PARITY UNPINNED at that boundary.  The QP is strictly convex, so its primal
     solution is unique; the oracle solves it to KKT residual <= 1e-9 with an independent dense primal-dual
-    interior-point method plus exact active-set refinement.
+    interior-point method plus exact active-set refinement.  The MULTIPLIERS, which the algorithm also consumes
+    (eta = mu / (2 sqrt(beta))), are unique only where the active-constraint gradients are linearly independent:
+    on degenerate instances (about one in a thousand random-x0 quadrotor scenarios, tools/degeneracy_check.py)
+    different solvers -- OSQP included -- return different multipliers, and closed-loop parity at 1e-5 is not well
+    defined there.
 """
