@@ -2,6 +2,7 @@
 oracle QP, the host-side layout logic, and the exported C ABI.  No GPU compute."""
 import ctypes
 import os
+import sys
 import re
 
 import numpy as np
@@ -228,3 +229,20 @@ def test_cpp_cpu_port_reproduces_oracle_loops(tag, name):
     st, inp, nfail = cpu_port.closed_loop(m, cfg, g["x0"][None], W, steps, g["X0"][None], g["U0"][None], threads=1)
     assert nfail == 0
     assert np.abs(st[0] - g["states"]).max() < 1e-6 and np.abs(inp[0] - g["inputs"]).max() < 1e-6
+
+
+def test_driver_modules_import_and_mirror_the_reference_command_line(capsys, monkeypatch):
+    """The package's counterparts of the reference's expe/main_*.py import without a GPU, expose generate() and accept the
+    reference's command line (--run / --N); without --run they do not compute."""
+    import importlib
+    import inspect
+    import runpy
+    for name in ("rocket_robust", "pendulum_robust", "quadrotor_robust", "rocket_compare"):
+        mod = importlib.import_module(f"rnmpc_b200.expe.main_{name}_closed_loop")
+        assert callable(mod.generate) and isinstance(mod.folder_name, str)
+        if name != "rocket_compare":
+            assert list(inspect.signature(mod.generate).parameters)[:2] == ["N", "out_dir"]
+        monkeypatch.setattr("sys.argv", [f"main_{name}_closed_loop.py"])
+        sys.modules.pop(f"rnmpc_b200.expe.main_{name}_closed_loop", None)        # run it as a script, not as the imported module
+        runpy.run_module(f"rnmpc_b200.expe.main_{name}_closed_loop", run_name="__main__")
+        assert "plot" in capsys.readouterr().out
