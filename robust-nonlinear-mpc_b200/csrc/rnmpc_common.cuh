@@ -9,7 +9,11 @@
 // with `in` in registers and M broadcast from shared memory as 128-bit loads: 4 DFMA per LDS.128, which the
 // microbenchmark in tools/fp64_microbench.cu measured at 83 % of the DFMA peak on B200 (1 row per lane: 54 %).
 #pragma once
+#ifdef RNMPC_EMU
+#include "simt_emu.h"      // tools/simt_emu: host-side SIMT emulator (test infrastructure; never defined in the product build)
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace rnmpc {
@@ -99,6 +103,7 @@ __device__ __forceinline__ void rowmm2(InFn&& in, const double* __restrict__ Mat
 
 // Reciprocal to ~1 ulp without the IEEE division routine (~30 dependent instructions and a slow-path call): hardware
 // seed (MUFU.RCP64H, 20+ bits) and two Newton steps.  Used where the quotient only scales a step or a barrier weight.
+#ifndef RNMPC_EMU
 __device__ __forceinline__ double fast_rcp(const double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
@@ -108,6 +113,7 @@ __device__ __forceinline__ double fast_rcp(const double x) {
     r = fma(r, e, r);
     return r;
 }
+#endif
 
 // Cholesky factor of an SPD NU x NU matrix held in registers (lower triangle, in place; the diagonal is stored
 // as its reciprocal).  Returns false if a pivot is not positive.
@@ -152,6 +158,7 @@ __device__ __forceinline__ void chol_solve(const double (&L)[NU][NU], double (&f
     }
 }
 
+#ifndef RNMPC_EMU      // the slot machinery below stages with cp.async: not emulated
 // Shared-memory working set of one slot (see SlotSmem below for the bank-conflict padding).
 template <int NX, int NU>
 struct SlotSmemCore {
@@ -450,5 +457,7 @@ struct NoPost {
     template <class K, class L>
     __device__ __forceinline__ void operator()(const K&, const K&, const L&) const {}
 };
+
+#endif  // RNMPC_EMU
 
 }  // namespace rnmpc

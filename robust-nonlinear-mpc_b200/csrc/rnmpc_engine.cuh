@@ -12,6 +12,7 @@
 #include "rnmpc_lin.cuh"
 #include "rnmpc_qp.cuh"
 #include "rnmpc_qp_block.cuh"
+#include "rnmpc_qp_mma.cuh"
 #include "rnmpc_sls.cuh"
 
 namespace rnmpc {
@@ -203,6 +204,13 @@ struct Engine : IEngine {
     int *handoff_count = nullptr, *handoff_list = nullptr;
     double* handoff_state = nullptr;
     bool qp_block_ok = false;
+    // QP kernel selection ("qp_kernel"): 0 automatic = the tensor-pipe kernel (rnmpc_qp_mma.cuh, one CTA per instance) whenever it applies
+    // (diagonal cost, cold start, reference bounds, working set fits shared memory), at every batch size; 1 = instance-per-slot kernel
+    // (with its hand-off), 2 = the round-1 one-CTA-per-instance kernel (rnmpc_qp_block.cuh), 3 = as 0.  1 and 2 remain for comparison.
+    int qp_kernel = 0;
+    long long* qp_prof = nullptr;  // "qp_profile": per-phase cycle counters of instance 0 in qp_mma_kernel (buffer "qp_prof", 16 x int64)
+    bool qp_mma_ok = false;
+    size_t qp_mma_smem = 0;
     double qp_mu0 = -0.3;          // cold start of the interior point: centred, multipliers = 0.3 x mean slack / slack (see QpArgs::mu0)
     P* d_prm = nullptr;
     std::map<std::string, std::pair<void*, size_t>> bufs;
@@ -301,6 +309,11 @@ struct Engine : IEngine {
         qp_block_ok = qp_block_smem <= 227 * 1024 &&
                       cudaFuncSetAttribute(qp_block_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
         cudaGetLastError();
+        qp_mma_smem = qp_mma_smem_doubles<NX, NU>(N) * sizeof(double);
+        qp_mma_ok = qp_mma_smem <= 227 * 1024 &&
+                    cudaFuncSetAttribute(qp_mma_kernel<NX, NU, kHorizonFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
+                    cudaFuncSetAttribute(qp_mma_kernel<NX, NU, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+        cudaGetLastError();
         RN_CUDA(cudaFuncSetAttribute(qp_ipm_kernel<NX, NU, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
         RN_CUDA(cudaFuncSetAttribute(qp_ipm_kernel<NX, NU, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
         RN_CUDA(cudaFuncSetAttribute(qp_ipm_kernel<NX, NU, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
@@ -316,6 +329,7 @@ struct Engine : IEngine {
         for (auto& p : ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     }
 
+    static constexpr int kHorizonFast = 15;   // N of every reference driver (expe/main_*: N = 15): kernels instantiated with it as a constant
     static constexpr int kWarps = 5;   // warps per CTA of the slot kernels (160 threads; 2 CTAs = 10 warps per SM by shared memory)
 
     int dims(int* nx, int* nu, int* N_, int* cap_) override {
@@ -418,14 +432,20 @@ struct Engine : IEngine {
         a.flags = fl; a.skip_mask = skip_mask;
         a.dX = dX_; a.dU = dU_; a.mu = mu_; a.mu_f = mu_f_; a.cost = cost_; a.iters = iters_; a.status = status_;
         a.E = wE; a.G = wG; a.diag_cost = diag_cost; a.rp = rp; a.Sc = Sc;
-        a.dff = dff; a.Kq = Kq; a.Lq = Lq;
+        a.dff = dff; a.Kq = Kq; a.Lq = Lq; a.prof = qp_prof;
         const long long warps = ((long long)B + Slot<NX>::SPW - 1) / Slot<NX>::SPW;
         const int w = cta_warps(qp_warps, warps);
         const unsigned grid = (unsigned)((warps + w - 1) / w);
         const int smem = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * w;
         cudaEvent_t te = region_begin(1, st);
         const bool may_warm = a.warm != 0;
-        if (qp_block_ok && B <= qp_block_max && diag_cost && !may_warm && hi_in == nullptr && lo_in == nullptr && q_lin == nullptr) {
+        const bool plain = diag_cost && !may_warm && hi_in == nullptr && lo_in == nullptr && q_lin == nullptr;
+        if (plain && qp_mma_ok && (qp_kernel == 0 || qp_kernel == 3)) {
+            // one CTA per instance, factorisation on the FP64 tensor pipe, iterate resident in shared memory (rnmpc_qp_mma.cuh)
+            // (the horizon of all reference drivers is a compile-time constant of the fast instantiation; any other horizon runs the generic one)
+            if (N == kHorizonFast) qp_mma_kernel<NX, NU, kHorizonFast><<<(unsigned)B, kMmaThreads, qp_mma_smem, st>>>(a, d_prm);
+            else qp_mma_kernel<NX, NU, 0><<<(unsigned)B, kMmaThreads, qp_mma_smem, st>>>(a, d_prm);
+        } else if (qp_block_ok && (B <= qp_block_max || qp_kernel == 2) && qp_kernel != 1 && diag_cost && !may_warm && hi_in == nullptr && lo_in == nullptr && q_lin == nullptr) {
             // small batch: one CTA per instance, working set in shared memory (rnmpc_qp_block.cuh)
             qp_block_kernel<NX, NU><<<(unsigned)B, kBlockThreads, qp_block_smem, st>>>(a, d_prm);
         } else if (diag_cost) {
@@ -684,6 +704,12 @@ struct Engine : IEngine {
         else if (n == "qp_tol_mu") qp_tol_mu = value;
         else if (n == "qp_mu0") qp_mu0 = value;
         else if (n == "qp_block_max") qp_block_max = (int)value;
+        else if (n == "qp_kernel") qp_kernel = (int)value;
+        else if (n == "qp_profile") {
+            if (value != 0 && qp_prof == nullptr) { if (alloc("qp_prof", qp_prof, 16)) return -2; }
+            else if (qp_prof != nullptr) cudaMemset(qp_prof, 0, 16 * sizeof(long long));
+            if (value == 0) qp_prof = nullptr;
+        }
         else if (n == "q3_eps") q3_eps = value;
         else if (n == "q3_margin_reset") { if (q3_margin) { std::vector<double> big((size_t)cap, 1e300); cudaMemcpy(q3_margin, big.data(), big.size() * sizeof(double), cudaMemcpyHostToDevice); } }
         else if (n == "qp_handoff_iter") qp_handoff_iter = (int)value;

@@ -79,8 +79,10 @@ struct QpArgs {
     int* handoff_list;      // [B] their indices
     double* handoff_state;  // [B][4] rp_scale, mu, rp_inf, n_box
     int resume;             // qp_block_kernel only: 1 = finish the instances of handoff_list
+    long long* prof;        // qp_mma_kernel only, diagnostic ("qp_profile"): [16] cycles of instance 0 per phase, summed over the launches
 };
 
+#ifndef RNMPC_EMU
 // DG: the cost matrices are diagonal (all reference drivers): the dense-cost code is compiled out of that instantiation, which
 // keeps it out of the iteration loop's instruction footprint.
 // WARM: the launch may warm-start (QpArgs::warm != 0); without it the second attempt, the warm branches of the initialisation and
@@ -847,5 +849,7 @@ __global__ void __launch_bounds__(160, 2) qp_ipm_kernel(const QpArgs a, const Pa
         }
     }
 }
+
+#endif  // RNMPC_EMU
 
 }  // namespace rnmpc

@@ -1,0 +1,694 @@
+// Nominal QP, tensor-pipe variant: ONE CTA (4 warps) PER INSTANCE, the Riccati factorisation of every interior-point iteration on
+// the FP64 tensor pipe (mma.sync.m8n8k4.f64 -> DMMA), the three vector sweeps as chains of (NX x NX) matrix-vector products with the
+// closed-loop matrices A_k + B_k K_k kept in shared memory.  Same problem, same algorithm, same formulas and status codes as
+// qp_ipm_kernel / qp_block_kernel (rnmpc_qp.cuh, rnmpc_qp_block.cuh; reference: solver/qp_jit.py:77-273, 362-402, 487-513).
+//
+// Why (measured, profiles/r1i_ncu_full_summary.csv, profiles/r2_dmma_probe.txt):
+//   * qp_ipm_kernel keeps all instances of a batch in flight (4096 x ~100 KB = 3 x the L2) and re-streams that working set four
+//     times per iteration: 11.8 GB of HBM traffic per launch for 0.26 GB of inputs + outputs, 80 % of the time on the long scoreboard.
+//     One CTA per instance bounds the number of instances in flight to 2 per SM (30 MB of inputs: L2 resident) and keeps the
+//     iterate on chip: HBM traffic is the compulsory traffic.
+//   * qp_block_kernel does that already, but with one dot product per thread (2 shared-memory loads per DFMA, 4036 cycles per
+//     Riccati stage).  Here a stage is two tile products on the tensor pipe:
+//         W = S_{k+1} [A_k B_k rp_k]                       (M = NX, N = NX + NU + 1, K = NX)
+//         M = [A_k B_k]^T [W  p_{k+1}]                     (upper triangle of tiles only: the result is symmetric)
+//     which yield A'SA, A'SB, B'SB and, in the spare columns, every vector product of the predictor's backward recursion
+//     (S rp, A'S rp, B'S rp, A'p, B'p).  A DMMA is 256 FMA per warp instruction, 16 cycles of the pipe, 26 cycles dependent latency.
+//   * The operand fragments of [A_k B_k] are the same registers in both products (B operand of the first, A operand of the second:
+//     Z[4s + t][8n + g]); they come straight from global memory (L2 resident), one stage ahead.
+//   * The rank-NU updates S_k = A'SA + (A'SB) K and A + B K are one more k-step each on the same pipe (accumulator initialised with
+//     the tile of A'SA / A).
+//   * Instruction footprint: a first version of this kernel was 118 KB of SASS (every shared-memory array address recomputed from
+//     the run-time horizon at each use, predictor and corrector code duplicated) and ran an interior-point iteration in 124 k cycles,
+//     no faster than qp_block_kernel.  The horizon is a template parameter now (NC; 0 = run-time fallback), predictor and corrector
+//     share one copy of the sweep code, loops over stages / entries are not unrolled.
+// Padding: NX = 17 -> tiles of 8 rows / columns, K in steps of 4; padded rows and columns are kept at zero in shared memory.
+#pragma once
+#include "rnmpc_common.cuh"
+#include "rnmpc_qp.cuh"
+
+namespace rnmpc {
+
+constexpr int kMmaThreads = 128;
+
+// D (8 x 8) += A (8 x 4) B (4 x 8); lane (g = lane / 4, t = lane % 4) holds A[g][t], B[t][g], D[g][2t], D[g][2t + 1]
+// (checked on the device: tools/dmma_probe.cu)
+#ifndef RNMPC_EMU
+__device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+#endif
+
+template <int NX, int NU>
+struct QpMma {
+    static constexpr int NZ = NX + NU;
+    static constexpr int KP = (NX + 3) / 4 * 4, KS = KP / 4;      // inner dimension padded to k-steps of 4
+    static constexpr int CB = (NX + 1) & ~1;                      // columns of Z = [A | B | rp]: A at 0, B at CB, rp at CRP
+    static constexpr int CRP = CB + NU;
+    static constexpr int CP = CRP + 1;                            // column of W that carries p_{k+1} (virtual: read from the vector)
+    static constexpr int NT = (CP + 8) / 8;                       // column tiles covering 0 .. CP
+    static constexpr int MTS = (NX + 7) / 8;                      // row tiles of S (first product)
+    static constexpr int MTM = (CB + NU + 7) / 8;                 // row tiles of M (second product): rows = columns of [A | B]
+    static constexpr int ld4(int n) { return n + ((4 - n % 8) + 8) % 8; }   // smallest L >= n with L = 4 (mod 8): fragment loads of a
+                                                                            // row-major matrix with that stride are bank-conflict free
+    static constexpr int LDS = ld4(KP), LDW = ld4(8 * NT);
+    static constexpr int SROWS = 8 * MTS, WROWS = (8 * MTS > KP ? 8 * MTS : KP), MROWS = 8 * MTM;
+    static constexpr int LDA = (NX + 1) & ~1;                     // row stride of the stored closed-loop matrices and gains
+    static_assert(MTS <= 3, "one warp per row tile of S, one warp left for the stage scalars");
+    static_assert(NU <= 4, "the rank-NU updates of a stage (S + (A'SB) K, A + B K) are one k-step of the tensor pipe");
+    static_assert(MTM <= NT, "fragments of Z are shared by the two products");
+};
+
+__host__ __device__ inline size_t mma_ev(size_t n) { return (n + 1) & ~(size_t)1; }
+
+// shared-memory footprint in doubles
+template <int NX, int NU>
+__host__ __device__ inline size_t qp_mma_smem_doubles(int N) {
+    using D = QpMma<NX, NU>;
+    const size_t NE = (size_t)(N + 1) * D::NZ;
+    return mma_ev((size_t)N * NX * D::LDA) + mma_ev((size_t)N * NU * D::LDA) + mma_ev((size_t)N * NU * NU)      // Acl, K, L
+         + 11 * mma_ev(NE)                                                                                     // entry arrays
+         + 3 * mma_ev((size_t)N * NX) + mma_ev((size_t)(N + 1) * NX) + 2 * mma_ev((size_t)N * NU)              // rp, Sc, gv, wv, dff, tu
+         + mma_ev(D::SROWS * D::LDS) + mma_ev(D::WROWS * D::LDW) + mma_ev(D::MROWS * D::LDW)                   // S, W, M
+         + mma_ev(D::KP) + 3 * mma_ev(D::NZ) + mma_ev(NU) + 64;                                                // pv, rhs, dgn, xq, uc, red
+}
+
+template <int NX, int NU, int NC>
+__global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, const Params<NX, NU>* __restrict__ prm) {
+    using D = QpMma<NX, NU>;
+    constexpr int NZ = D::NZ, NI = 2 * NZ, NIF = 2 * NX, T = kMmaThreads, LDG = Slot<NX>::LD;
+    constexpr int KP = D::KP, KS = D::KS, CB = D::CB, CRP = D::CRP, CP = D::CP, NT = D::NT, MTS = D::MTS, MTM = D::MTM;
+    constexpr int LDS = D::LDS, LDW = D::LDW, LDA = D::LDA;
+    static_assert(NX <= 32 && NU <= 32, "one lane per vector entry in the sweeps");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x;
+    if (b >= a.B) return;
+    if (a.flags != nullptr && (a.flags[b] & a.skip_mask) != 0) return;
+    // The warps' roles rotate with the instance index so that the DMMA-heavy roles of the CTAs sharing an SM land on
+    // different scheduler partitions (warp w of every CTA sits on partition w).
+    const int lane = threadIdx.x & 31;
+    const int role = ((threadIdx.x >> 5) + b) & 3;
+    const int rt = role * 32 + lane;               // logical thread index: work is distributed by rt, not threadIdx.x
+    const int g = lane >> 2, t4 = lane & 3;
+    const int N = NC > 0 ? NC : a.N;               // compile-time horizon: every shared-memory address below is a constant
+
+    double* sp = reinterpret_cast<double*>(smem_raw);
+    auto take = [&](size_t n) { double* p = sp; sp += mma_ev(n); return p; };
+    const int NE = (N + 1) * NZ;
+    double* Acl = take((size_t)N * NX * LDA); double* Kq = take((size_t)N * NU * LDA); double* Lq = take((size_t)N * NU * NU);
+    double* e_su = take(NE); double* e_sl = take(NE); double* e_lu = take(NE); double* e_ll = take(NE);
+    double* e_iu = take(NE); double* e_il = take(NE); double* e_z = take(NE); double* e_zn = take(NE);
+    double* e_da = take(NE); double* e_dc = take(NE); double* e_qd = take(NE);
+    double* rp = take((size_t)N * NX); double* Sc = take((size_t)N * NX); double* gv = take((size_t)N * NX);
+    double* wv = take((size_t)(N + 1) * NX); double* dff = take((size_t)N * NU); double* tu = take((size_t)N * NU);
+    double* S = take(D::SROWS * LDS); double* W = take(D::WROWS * LDW); double* M = take(D::MROWS * LDW);
+    double* pv = take(KP); double* rhs = take(NZ); double* dgn = take(NZ); double* xq = take(NZ); double* uc = take(NU);
+    double* red = take(64);
+    (void)xq;
+
+    const double* Ag = a.A + (size_t)b * N * NX * LDG;
+    const double* Bg = a.Bm + (size_t)b * N * NX * NU;
+    const double* cg = a.c + (size_t)b * N * NX;
+    const double* Xn = a.Xnom + (size_t)b * (N + 1) * NX;
+    const double* Un = a.Unom + (size_t)b * N * NU;
+
+    // block-wide reduction of four values at once: v0, v1 by maximum, v2, v3 by sum (two barriers).  The partial results are
+    // combined in the order of the roles: the same value in every thread, independent of the role rotation.
+    auto block_reduce4 = [&](double& v0, double& v1, double& v2, double& v3) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 = fmax(v0, __shfl_xor_sync(0xffffffffu, v0, o)); v1 = fmax(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+            v2 += __shfl_xor_sync(0xffffffffu, v2, o); v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+        }
+        __syncthreads();
+        if (lane == 0) { red[4 * role] = v0; red[4 * role + 1] = v1; red[4 * role + 2] = v2; red[4 * role + 3] = v3; }
+        __syncthreads();
+        v0 = fmax(fmax(red[0], red[4]), fmax(red[8], red[12]));
+        v1 = fmax(fmax(red[1], red[5]), fmax(red[9], red[13]));
+        v2 = ((red[2] + red[6]) + red[10]) + red[14];
+        v3 = ((red[3] + red[7]) + red[11]) + red[15];
+    };
+
+    // diagnostic phase timer (option "qp_profile"): cycles of the logical thread 0 of instance 0 between consecutive marks
+    const bool prof_on = a.prof != nullptr && b == 0 && rt == 0;
+    long long* pacc = reinterpret_cast<long long*>(red + 40);
+    long long t_last = 0;
+    if (prof_on) {
+        for (int i = 0; i < 16; ++i) pacc[i] = 0;
+        t_last = clock64();
+    }
+    auto mark = [&](const int slot) {
+        if (prof_on) { const long long t = clock64(); pacc[slot] += t - t_last; t_last = t; }
+    };
+
+    // ------------------------------------------------------------------ zero the padded tile buffers once
+    for (int e = rt; e < D::SROWS * LDS; e += T) S[e] = 0.0;
+    for (int e = rt; e < D::WROWS * LDW; e += T) W[e] = 0.0;
+    for (int e = rt; e < D::MROWS * LDW; e += T) M[e] = 0.0;
+    for (int e = rt; e < N * NX * LDA; e += T) Acl[e] = 0.0;
+    if (rt < KP) pv[rt] = 0.0;
+    if (rt == 0) red[32] = 0.0;        // "a pivot of the factorisation was not positive" flag of the current iteration
+
+    // ------------------------------------------------------------------ bounds, initial point, slacks (rnmpc_qp.cuh, cold start)
+    const bool tight = a.tightened < 0 ? ((a.flags[b] & FLAG_TIGHT) != 0) : (a.tightened != 0);
+    double bad = 0.0, n_box = 0.0, s_sum = 0.0, dmy = 0.0;
+    {
+        const double eps = tight ? 0.0 : kEpsQP;
+#pragma unroll 1
+        for (int idx = rt; idx < NE; idx += T) {
+            const int k = idx / NZ, i = idx - k * NZ;
+            double h_ = 1e300, l_ = -1e300, z = 0.0, zn = 0.0, qd = 0.0;
+            bool box = false;
+            if (i < NX) {
+                const double xn = Xn[k * NX + i];
+                zn = xn;
+                qd = 2.0 * ((k < N) ? prm->Q[i * NX + i] : prm->Qf[i * NX + i]);
+                if (k < N) {
+                    const double bu = tight ? a.backoff[((size_t)b * N + k) * NI + i] : 0.0;
+                    const double bl = tight ? a.backoff[((size_t)b * N + k) * NI + NZ + i] : 0.0;
+                    h_ = (prm->xub[i] - xn) - bu + eps;
+                    l_ = -((xn - prm->xlb[i]) - bl + eps);
+                } else if (tight) {
+                    h_ = prm->xubf[i] - a.backoff_f[(size_t)b * NIF + i];              // Q4: terminal bound not shifted by x_N
+                    l_ = -(-prm->xlbf[i] - a.backoff_f[(size_t)b * NIF + NX + i]);
+                } else {
+                    h_ = (prm->xubf[i] - xn) + eps;
+                    l_ = -((xn - prm->xlbf[i]) + eps);
+                }
+                if (k == 0) {
+                    z = a.x0[(size_t)b * NX + i] - xn;                                  // x(0) is pinned to the measurement
+                    if (z > h_ + kX0Tol || z < l_ - kX0Tol) bad = 1.0;
+                } else box = true;
+            } else if (k < N) {
+                const int p = i - NX;
+                const double un = Un[k * NU + p];
+                zn = un;
+                qd = 2.0 * prm->R[p * NU + p];
+                const double bu = tight ? a.backoff[((size_t)b * N + k) * NI + i] : 0.0;
+                const double bl = tight ? a.backoff[((size_t)b * N + k) * NI + NZ + i] : 0.0;
+                h_ = (prm->uub[p] - un) - bu + eps;
+                l_ = -((un - prm->ulb[p]) - bl + eps);
+                box = true;
+            }
+            double su = 1e300, sl = 1e300;
+            if (box) {
+                const bool hu = h_ < kBig, hl = l_ > -kBig;
+                if (hu && hl) {
+                    const double m = 0.01 * (h_ - l_);
+                    if (!(h_ - l_ > 1e-12)) bad = 1.0;
+                    z = fmin(fmax(0.0, l_ + m), h_ - m);
+                } else if (hu) z = fmin(0.0, h_ - 1.0);
+                else if (hl) z = fmax(0.0, l_ + 1.0);
+                if (hu) { su = h_ - z; n_box += 1.0; s_sum += su; }
+                if (hl) { sl = z - l_; n_box += 1.0; s_sum += sl; }
+            }
+            e_su[idx] = su; e_sl[idx] = sl;
+            e_iu[idx] = (su < kBig) ? 1.0 / su : 0.0; e_il[idx] = (sl < kBig) ? 1.0 / sl : 0.0;
+            e_z[idx] = z; e_zn[idx] = zn; e_da[idx] = 0.0; e_dc[idx] = 0.0; e_qd[idx] = qd;
+        }
+    }
+    block_reduce4(bad, dmy, n_box, s_sum);
+    int status = bad > 0.0 ? 2 : 0;
+    {   // centred cold start: multipliers mu_bar / slack (QpArgs::mu0)
+        const double mu_bar = a.mu0 < 0.0 ? (n_box > 0.0 ? -a.mu0 * s_sum / n_box : 1.0) : a.mu0;
+#pragma unroll 1
+        for (int idx = rt; idx < NE; idx += T) {
+            double lu, ll;
+            if (a.mu0 != 0.0) { lu = mu_bar * e_iu[idx]; ll = mu_bar * e_il[idx]; }
+            else { lu = e_iu[idx] > 0.0 ? 1.0 : 0.0; ll = e_il[idx] > 0.0 ? 1.0 : 0.0; }
+            e_lu[idx] = lu; e_ll[idx] = ll;
+        }
+    }
+    __syncthreads();
+    // dynamics residual at the initial point: rp_k = A x_k + B u_k + c_k - x_{k+1}
+    double rp_inf = 0.0, mu_acc = 0.0;
+#pragma unroll 1
+    for (int e = rt; e < N * NX; e += T) {
+        const int k = e / NX, r = e - k * NX;
+        const double* Ar = Ag + ((size_t)k * NX + r) * LDG;
+        const double* Br = Bg + ((size_t)k * NX + r) * NU;
+        double acc = cg[e] - e_z[(k + 1) * NZ + r], acc2 = 0.0;
+#pragma unroll
+        for (int m = 0; m + 1 < NX; m += 2) { acc = fma(__ldg(Ar + m), e_z[k * NZ + m], acc); acc2 = fma(__ldg(Ar + m + 1), e_z[k * NZ + m + 1], acc2); }
+        if (NX & 1) acc = fma(__ldg(Ar + NX - 1), e_z[k * NZ + NX - 1], acc);
+#pragma unroll
+        for (int p = 0; p < NU; ++p) acc = fma(__ldg(Br + p), e_z[k * NZ + NX + p], acc);
+        acc += acc2;
+        rp[e] = acc;
+        rp_inf = fmax(rp_inf, fabs(acc));
+    }
+#pragma unroll 1
+    for (int idx = rt; idx < NE; idx += T) {
+        if (e_su[idx] < kBig) mu_acc = fma(e_su[idx], e_lu[idx], mu_acc);
+        if (e_sl[idx] < kBig) mu_acc = fma(e_sl[idx], e_ll[idx], mu_acc);
+    }
+    {
+        double d1 = 0.0, d3 = 0.0;
+        block_reduce4(rp_inf, d1, mu_acc, d3);
+    }
+    double mu_c = n_box > 0.0 ? mu_acc / n_box : 0.0;
+    double rp_scale = 1.0;
+
+    auto sg_of = [&](int idx) -> double { return e_lu[idx] * e_iu[idx] + e_ll[idx] * e_il[idx]; };
+    // right-hand side of one entry (rnmpc_qp.cuh rhs_eval): gradient (+ centring / second-order terms in the corrector pass)
+    double sigma_mu = 0.0;
+    auto rhs_entry = [&](const int pass, const int idx) -> double {
+        double gq = e_qd[idx] * (e_z[idx] + e_zn[idx]);
+        if (pass == 1) {
+            const double iu = e_iu[idx], il = e_il[idx], lu = e_lu[idx], ll = e_ll[idx], dza = e_da[idx];
+            if (iu > 0.0) gq = fma(sigma_mu + dza * (lu * iu * dza - lu), iu, gq);
+            if (il > 0.0) gq = fma(-(sigma_mu + dza * (ll * il * dza + ll)), il, gq);
+        }
+        return gq;
+    };
+    // fragments of Z_k = [A_k | B_k | rp_k] (rows padded to KP with zeros): zf[s][n] = Z[4s + t][8n + g]
+    auto load_z = [&](const int k, double (&zf)[KS][NT]) {
+        const double* Ak = Ag + (size_t)k * NX * LDG;
+        const double* Bk = Bg + (size_t)k * NX * NU;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const int r = 4 * s + t4;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                const int c = 8 * n + g;
+                double v = 0.0;
+                if (r < NX) {
+                    if (c < NX) v = __ldg(Ak + r * LDG + c);
+                    else if (c >= CB && c < CB + NU) v = __ldg(Bk + r * NU + (c - CB));
+                    else if (c == CRP) v = rp[k * NX + r];
+                }
+                zf[s][n] = v;
+            }
+        }
+    };
+
+    mark(0);
+    int stalled = 0, it = 0;
+    bool done = status != 0;
+#pragma unroll 1
+    for (it = 0; it < a.max_iter && !done; ++it) {
+        bool chol_ok = true;
+        double ap = 1.0, ad = 1.0, maxp0 = 0.0, maxd0 = 0.0;
+        bool skip_corr = false;
+        __syncthreads();
+        // ================================================================ factorisation sweep + predictor backward recursion
+#pragma unroll 1
+        for (int e = rt; e < NX * NX; e += T) { const int i = e / NX, j = e - i * NX; S[i * LDS + j] = (i == j) ? (e_qd[N * NZ + i] + sg_of(N * NZ + i)) : 0.0; }
+        if (rt < NX) pv[rt] = rhs_entry(0, N * NZ + rt);
+        double zf[KS][NT];
+        load_z(N - 1, zf);
+        __syncthreads();
+        mark(1);
+#pragma unroll 1
+        for (int k = N - 1; k >= 0; --k) {
+            double* Kk = Kq + (size_t)k * NU * LDA;
+            double zn_[KS][NT];
+            if (k > 0) load_z(k - 1, zn_);           // next stage's fragments: in flight during this stage
+            // ---- phase A: W = S [A B rp]  (one warp per row tile of S); the free warp prepares the stage scalars
+            if (role < MTS) {
+                double sa[KS];
+#pragma unroll
+                for (int s = 0; s < KS; ++s) sa[s] = S[(8 * role + g) * LDS + 4 * s + t4];
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int s = 0; s < KS; ++s) dmma884(c0, c1, sa[s], zf[s][n]);
+                    *reinterpret_cast<double2*>(W + (8 * role + g) * LDW + 8 * n + 2 * t4) = make_double2(c0, c1);
+                }
+            } else if (role == 3 && lane < NZ) {
+                const int idx = k * NZ + lane;
+                rhs[lane] = (lane < NX && k == 0) ? 0.0 : rhs_entry(0, idx);
+                dgn[lane] = (lane < NX ? e_qd[idx] : 0.0) + sg_of(idx);      // barrier weights (+ diagonal state cost); R2 is added to H below
+            }
+            __syncthreads();
+            mark(2);
+            // ---- phase B: M = [A B]^T [W p]  (upper triangle of tiles, round robin over the warps)
+            {
+                int ti = 0;
+#pragma unroll
+                for (int mt = 0; mt < MTM; ++mt) {
+#pragma unroll
+                    for (int n = mt; n < NT; ++n, ++ti) {
+                        if ((ti & 3) != role) continue;
+                        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                        for (int s = 0; s < KS; ++s) {
+                            const double bv = (8 * n + g == CP) ? pv[4 * s + t4] : W[(4 * s + t4) * LDW + 8 * n + g];
+                            dmma884(c0, c1, zf[s][mt], bv);
+                        }
+                        *reinterpret_cast<double2*>(M + (8 * mt + g) * LDW + 8 * n + 2 * t4) = make_double2(c0, c1);
+                    }
+                }
+            }
+            __syncthreads();
+            mark(3);
+            // ---- phase C: H = R2 + diag + B'SB -> Cholesky; K = -H^{-1} (A'SB)' column by column; t = ru + B'(p + rp_scale S rp), d = -H^{-1} t
+            if (rt < NX + 2) {
+                double L[NU][NU];
+#pragma unroll
+                for (int p = 0; p < NU; ++p)
+#pragma unroll
+                    for (int q = 0; q < NU; ++q) {
+                        const int lo = p < q ? p : q, hi = p < q ? q : p;
+                        L[p][q] = M[(CB + lo) * LDW + CB + hi] + prm->R2[p * NU + q] + (p == q ? dgn[NX + p] : 0.0);
+                    }
+                const bool ok = chol_inplace<NU>(L);
+                if (rt < NX) {
+                    double f[NU];
+#pragma unroll
+                    for (int p = 0; p < NU; ++p) f[p] = M[rt * LDW + CB + p];
+                    chol_solve<NU>(L, f);
+#pragma unroll
+                    for (int p = 0; p < NU; ++p) Kk[p * LDA + rt] = -f[p];
+                } else if (rt == NX) {
+                    double d[NU];
+#pragma unroll
+                    for (int p = 0; p < NU; ++p) { d[p] = rhs[NX + p] + M[(CB + p) * LDW + CP] + rp_scale * M[(CB + p) * LDW + CRP]; uc[p] = d[p]; }
+                    chol_solve<NU>(L, d);
+#pragma unroll
+                    for (int p = 0; p < NU; ++p) dff[k * NU + p] = -d[p];
+                } else {
+#pragma unroll
+                    for (int p = 0; p < NU; ++p)
+#pragma unroll
+                        for (int q = 0; q < NU; ++q) Lq[k * NU * NU + p * NU + q] = L[p][q];
+                    if (!ok) red[32] = 1.0;
+                }
+            }
+            __syncthreads();
+            mark(4);
+            // ---- phase D: one more k-step per tile: S_k = A'SA + (A'SB) K + diag (upper triangle, mirrored: exactly symmetric) and
+            //      A + B K (kept for the three vector sweeps); p_k = rx + A'g + K't and S rp_k on the last threads
+            {
+                const double* Ak = Ag + (size_t)k * NX * LDG;
+                const double* Bk = Bg + (size_t)k * NX * NU;
+                double* Ac = Acl + (size_t)k * NX * LDA;
+                double kf[MTS];                               // B operand: K[t][8n + g]
+#pragma unroll
+                for (int n = 0; n < MTS; ++n) kf[n] = (t4 < NU && 8 * n + g < NX) ? Kk[t4 * LDA + 8 * n + g] : 0.0;
+                int ti = 0;
+#pragma unroll
+                for (int mt = 0; mt < MTS; ++mt) {
+                    const int r = 8 * mt + g;
+#pragma unroll
+                    for (int n = 0; n < MTS; ++n) {
+                        const int c = 8 * n + 2 * t4;
+                        // closed loop tile (mt, n): accumulator = A tile, A operand = B_k[r][t]
+                        if ((ti & 3) == role) {
+                            double c0 = 0.0, c1 = 0.0;
+                            if (r < NX && c < NX) { c0 = __ldg(Ak + r * LDG + c); if (c + 1 < NX) c1 = __ldg(Ak + r * LDG + c + 1); }
+                            const double bf = (t4 < NU && r < NX) ? __ldg(Bk + r * NU + t4) : 0.0;
+                            dmma884(c0, c1, bf, kf[n]);
+                            if (r < NX && c < NX) { Ac[r * LDA + c] = c0; if (c + 1 < NX) Ac[r * LDA + c + 1] = c1; }
+                        }
+                        ++ti;
+                        // cost-to-go tile (mt <= n): accumulator = A'SA tile, A operand = (A'SB)[r][t]
+                        if (n >= mt) {
+                            if ((ti & 3) == role && k > 0) {
+                                const double2 mv = *reinterpret_cast<const double2*>(M + r * LDW + c);
+                                double c0 = mv.x, c1 = mv.y;
+                                const double gf = (t4 < NU) ? M[r * LDW + CB + t4] : 0.0;
+                                dmma884(c0, c1, gf, kf[n]);
+                                if (r < NX) {
+                                    if (c < NX && r <= c) { const double v = c0 + (r == c ? dgn[r] : 0.0); S[r * LDS + c] = v; S[c * LDS + r] = v; }
+                                    if (c + 1 < NX && r <= c + 1) { const double v = c1 + (r == c + 1 ? dgn[r] : 0.0); S[r * LDS + c + 1] = v; S[(c + 1) * LDS + r] = v; }
+                                }
+                            }
+                            ++ti;
+                        }
+                    }
+                }
+                if (rt >= T - NX) {
+                    const int i = rt - (T - NX);
+                    Sc[k * NX + i] = W[i * LDW + CRP];
+                    if (k > 0) {
+                        double acc = rhs[i] + M[i * LDW + CP] + rp_scale * M[i * LDW + CRP];
+#pragma unroll
+                        for (int p = 0; p < NU; ++p) acc = fma(Kk[p * LDA + i], uc[p], acc);
+                        pv[i] = acc;                     // p_k: the p column of the next stage's second product (nobody reads pv in this phase)
+                    }
+                }
+            }
+            __syncthreads();
+            mark(5);
+#pragma unroll
+            for (int s = 0; s < KS; ++s)
+#pragma unroll
+                for (int n = 0; n < NT; ++n) zf[s][n] = zn_[s][n];
+        }
+        chol_ok = red[32] == 0.0;
+
+        // ================================================================ predictor (pass 0) and corrector (pass 1): one copy of the sweep code
+        const double tau_c = mu_c > 1e-8 ? 0.995 : 0.9999;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            double* e_dz = pass ? e_dc : e_da;
+            if (pass == 1) {
+                // ---- corrector right-hand sides: r'_k = rx_k + K_k' ru_k (k >= 1), ru_k kept for the feed-forward; p_N = rx_N
+#pragma unroll 1
+                for (int idx = rt; idx < NE; idx += T) e_dc[idx] = rhs_entry(1, idx);      // e_dc doubles as scratch until the forward chain
+                __syncthreads();
+#pragma unroll 1
+                for (int e = rt; e < (N + 1) * NX; e += T) {
+                    const int k = e / NX, i = e - k * NX;
+                    double acc = e_dc[k * NZ + i];
+                    if (k < N) {
+#pragma unroll
+                        for (int p = 0; p < NU; ++p) acc = fma(Kq[((size_t)k * NU + p) * LDA + i], e_dc[k * NZ + NX + p], acc);
+                    }
+                    wv[e] = acc;
+                }
+#pragma unroll 1
+                for (int e = rt; e < N * NU; e += T) { const int k = e / NU, p = e - k * NU; tu[e] = e_dc[k * NZ + NX + p]; }
+                __syncthreads();
+                mark(6);
+                if (role == 0) {
+                    // p_k = r'_k + (A_k + B_k K_k)' (p_{k+1} + rp_scale Sc_k) on one warp; g_k = p_{k+1} + rp_scale Sc_k is kept for every stage
+                    const int r = lane < NX ? lane : NX - 1;
+                    double pl = wv[N * NX + r];
+#pragma unroll 1
+                    for (int k = N - 1; k >= 0; --k) {
+                        if (lane < NX) gv[k * NX + lane] = pl + rp_scale * Sc[k * NX + lane];
+                        __syncwarp();
+                        if (k > 0) {
+                            const double* gk = gv + k * NX;
+                            const double* col = Acl + (size_t)k * NX * LDA + r;
+                            double a0 = wv[k * NX + r], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                            for (int m = 0; m + 3 < NX; m += 4) {
+                                a0 = fma(col[m * LDA], gk[m], a0); a1 = fma(col[(m + 1) * LDA], gk[m + 1], a1);
+                                a2 = fma(col[(m + 2) * LDA], gk[m + 2], a2); a3 = fma(col[(m + 3) * LDA], gk[m + 3], a3);
+                            }
+#pragma unroll
+                            for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(col[m * LDA], gk[m], a0);
+                            pl = (a0 + a1) + (a2 + a3);
+                        }
+                    }
+                }
+                __syncthreads();
+                mark(7);
+                // ---- t_k = ru_k + B_k' g_k ; d_k = -H_k^{-1} t_k   (one thread per stage)
+                if (rt < N) {
+                    const int k = rt;
+                    const double* Bk = Bg + (size_t)k * NX * NU;
+                    double d[NU], L[NU][NU];
+#pragma unroll
+                    for (int p = 0; p < NU; ++p) {
+                        d[p] = tu[k * NU + p];
+#pragma unroll
+                        for (int q = 0; q < NU; ++q) L[p][q] = Lq[k * NU * NU + p * NU + q];
+                    }
+#pragma unroll 1
+                    for (int i = 0; i < NX; ++i) {
+                        const double gi = gv[k * NX + i];
+#pragma unroll
+                        for (int p = 0; p < NU; ++p) d[p] = fma(__ldg(Bk + i * NU + p), gi, d[p]);
+                    }
+                    chol_solve<NU>(L, d);
+#pragma unroll
+                    for (int p = 0; p < NU; ++p) dff[k * NU + p] = -d[p];
+                }
+                __syncthreads();
+                mark(8);
+            }
+            // ---- w_k = B_k d_k + rp_scale rp_k (right-hand side of the forward recursion)
+#pragma unroll 1
+            for (int e = rt; e < N * NX; e += T) {
+                const int k = e / NX;
+                const double* Br = Bg + (size_t)e * NU;
+                double acc = rp_scale * rp[e];
+#pragma unroll
+                for (int p = 0; p < NU; ++p) acc = fma(__ldg(Br + p), dff[k * NU + p], acc);
+                wv[e] = acc;
+            }
+            __syncthreads();
+            mark(9);
+            // ---- forward recursion dx_{k+1} = (A_k + B_k K_k) dx_k + w_k, dx_0 = 0, on one warp (lane r owns row r); dx_k is left in
+            //      the x-entries of e_dz
+            if (role == 0) {
+                const int r = lane < NX ? lane : NX - 1;
+                if (lane < NX) { e_dz[lane] = 0.0; e_dz[NZ + lane] = wv[lane]; }      // dx_0 = 0, dx_1 = w_0
+                __syncwarp();
+#pragma unroll 1
+                for (int k = 1; k < N; ++k) {
+                    const double* xk = e_dz + k * NZ;
+                    const double* row = Acl + ((size_t)k * NX + r) * LDA;
+                    double a0 = wv[k * NX + r], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                    for (int m = 0; m + 3 < NX; m += 4) {
+                        const double2 r01 = *reinterpret_cast<const double2*>(row + m), r23 = *reinterpret_cast<const double2*>(row + m + 2);
+                        a0 = fma(r01.x, xk[m], a0); a1 = fma(r01.y, xk[m + 1], a1);
+                        a2 = fma(r23.x, xk[m + 2], a2); a3 = fma(r23.y, xk[m + 3], a3);
+                    }
+#pragma unroll
+                    for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(row[m], xk[m], a0);
+                    if (lane < NX) e_dz[(k + 1) * NZ + lane] = (a0 + a1) + (a2 + a3);
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            mark(10);
+            // ---- du_k = K_k dx_k + d_k for the input entries, then the ratio test over all entries (rnmpc_qp.cuh ratio_entry)
+            double rpm = 0.0, rdm = 0.0, S3 = 0.0, S4 = 0.0;
+#pragma unroll 1
+            for (int idx = rt; idx < NE; idx += T) {
+                const int k = idx / NZ, i = idx - k * NZ;
+                double dz;
+                if (i >= NX) {
+                    if (k == N) continue;
+                    const double* Kr = Kq + ((size_t)k * NU + (i - NX)) * LDA;
+                    const double* xk = e_dz + k * NZ;
+                    double u0 = dff[k * NU + i - NX], u1 = 0.0;
+#pragma unroll
+                    for (int m = 0; m + 1 < NX; m += 2) { u0 = fma(Kr[m], xk[m], u0); u1 = fma(Kr[m + 1], xk[m + 1], u1); }
+                    if (NX & 1) u0 = fma(Kr[NX - 1], xk[NX - 1], u0);
+                    dz = u0 + u1;
+                    e_dz[idx] = dz;
+                } else dz = e_dz[idx];
+                const double iu = e_iu[idx], il = e_il[idx], lu = e_lu[idx], ll = e_ll[idx];
+                const double dza = pass == 1 ? e_da[idx] : 0.0;
+                const double smu = pass == 1 ? sigma_mu : 0.0;
+                if (iu > 0.0) {
+                    const double ru = lu * iu;
+                    const double tgt = pass == 1 ? smu + dza * (ru * dza - lu) : 0.0;
+                    const double dlu = tgt * iu - lu + ru * dz;
+                    rpm = fmax(rpm, dz * iu);
+                    if (dlu < 0.0) rdm = fmax(rdm, -dlu * fast_rcp(lu));
+                    if (pass == 0) { S3 = fma(-dz, lu, S3); S4 = fma(-dz, dlu, S4); }
+                }
+                if (il > 0.0) {
+                    const double rl = ll * il;
+                    const double tgt = pass == 1 ? smu + dza * (rl * dza + ll) : 0.0;
+                    const double dll = tgt * il - ll - rl * dz;
+                    rpm = fmax(rpm, -dz * il);
+                    if (dll < 0.0) rdm = fmax(rdm, -dll * fast_rcp(ll));
+                    if (pass == 0) { S3 = fma(dz, ll, S3); S4 = fma(dz, dll, S4); }
+                }
+            }
+            block_reduce4(rpm, rdm, S3, S4);
+            mark(11);
+            if (pass == 0) {
+                maxp0 = rpm; maxd0 = rdm;
+                ap = (rpm > 1.0) ? 1.0 / rpm : 1.0;
+                ad = (rdm > 1.0) ? 1.0 / rdm : 1.0;
+                const double mu_aff = n_box > 0.0 ? (mu_c * n_box * (1.0 - ad) + (ap - ad) * S3 + ap * ad * S4) / n_box : 0.0;
+                skip_corr = (ap >= 0.999 && ad >= 0.999 && mu_aff <= 1e-3 * mu_c);
+                const double ratio_mu = mu_c > 0.0 ? mu_aff / mu_c : 0.0;
+                sigma_mu = ratio_mu * ratio_mu * ratio_mu * mu_c;
+                if (skip_corr) {
+                    // Newton phase: the predictor step with the fraction-to-boundary rule (rnmpc_qp.cuh)
+                    ap = (maxp0 > tau_c) ? tau_c / maxp0 : 1.0;
+                    ad = (maxd0 > tau_c) ? tau_c / maxd0 : 1.0;
+                    break;
+                }
+            } else {
+                ap = (rpm > tau_c) ? tau_c / rpm : 1.0;
+                ad = (rdm > tau_c) ? tau_c / rdm : 1.0;
+            }
+        }
+        // ================================================================ update, new reciprocals / complementarity
+        double acc = 0.0;
+        {
+            const bool upd = chol_ok;
+            const double so = skip_corr ? 0.0 : 1.0;
+            const double* e_dz = skip_corr ? e_da : e_dc;
+#pragma unroll 1
+            for (int idx = rt; idx < NE; idx += T) {
+                double su = e_su[idx], sl = e_sl[idx], lu = e_lu[idx], ll = e_ll[idx];
+                if (upd) {
+                    const double dza = e_da[idx], dz = e_dz[idx];
+                    double iu = 0.0, il = 0.0;
+                    if (su < kBig) {
+                        const double ru = lu * e_iu[idx];
+                        const double dlu = so * (sigma_mu + dza * (ru * dza - lu)) * e_iu[idx] - lu + ru * dz;
+                        su -= ap * dz; lu += ad * dlu;
+                        iu = fast_rcp(su);
+                    }
+                    if (sl < kBig) {
+                        const double rl = ll * e_il[idx];
+                        const double dll = so * (sigma_mu + dza * (rl * dza + ll)) * e_il[idx] - ll - rl * dz;
+                        sl += ap * dz; ll += ad * dll;
+                        il = fast_rcp(sl);
+                    }
+                    e_su[idx] = su; e_sl[idx] = sl; e_lu[idx] = lu; e_ll[idx] = ll; e_iu[idx] = iu; e_il[idx] = il;
+                    e_z[idx] += ap * dz;
+                }
+                if (su < kBig) acc = fma(su, lu, acc);
+                if (sl < kBig) acc = fma(sl, ll, acc);
+            }
+            if (upd) rp_scale *= (1.0 - ap);
+        }
+        {
+            double d0 = 0.0, d1 = 0.0, d3 = 0.0;
+            block_reduce4(d0, d1, acc, d3);
+        }
+        if (rt == 0) red[32] = 0.0;
+        mark(12);
+        const double mu_new = n_box > 0.0 ? acc / n_box : 0.0;
+        if (!chol_ok) {
+            if (mu_c > 1e-9) status = 3;           // a non-positive pivot at mu ~ 1e-14 means converged to working precision
+            done = true;
+        } else if (!(mu_new == mu_new)) { status = 3; done = true; }
+        else {
+            mu_c = mu_new;
+            if (mu_c < a.tol_mu && rp_inf * rp_scale < a.tol_res && it >= 2) done = true;
+            stalled = (ap < 1e-4 && ad < 1e-4) ? stalled + 1 : 0;
+            if (!done && (stalled >= 3 || mu_c > 1e12)) { status = 2; done = true; }
+        }
+        if (done) { ++it; break; }
+    }
+    if (!done && status == 0) status = (mu_c < 1e-9 && rp_inf * rp_scale < 1e-7) ? 0 : 1;
+    __syncthreads();
+
+    // ---- outputs in the reference layouts + objective x'Hx + q'x (qp_jit.py:401, P = 2H, q = 2 H y_nom; diagonal H)
+    {
+        double* Xo = a.dX + (size_t)b * (N + 1) * NX;
+        double* Uo = a.dU + (size_t)b * N * NU;
+        double* mu = a.mu + (size_t)b * N * NI;
+        double* muf = a.mu_f + (size_t)b * NIF;
+        double acc = 0.0;
+#pragma unroll 1
+        for (int idx = rt; idx < NE; idx += T) {
+            const int k = idx / NZ, i = idx - k * NZ;
+            if (i >= NX && k == N) continue;
+            const double z = e_z[idx];
+            acc = fma(z, 0.5 * e_qd[idx] * (z + 2.0 * e_zn[idx]), acc);
+            if (i < NX) Xo[k * NX + i] = z; else Uo[k * NU + i - NX] = z;
+            if (k < N) { mu[k * NI + i] = e_lu[idx]; mu[k * NI + NZ + i] = e_ll[idx]; }
+            else { muf[i] = e_lu[idx]; muf[NX + i] = e_ll[idx]; }
+        }
+        double d0 = 0.0, d1 = 0.0, d3 = 0.0;
+        block_reduce4(d0, d1, acc, d3);
+        mark(13);
+        if (prof_on) { for (int i = 0; i < 16; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + i, (unsigned long long)pacc[i]); }
+        if (rt == 0) {
+            a.cost[b] = acc;
+            a.iters[b] = it;
+            a.status[b] = status;
+            if (a.ws_valid != nullptr) a.ws_valid[b] = 0;          // the records of qp_ipm_kernel's workspace were not written
+        }
+    }
+}
+
+}  // namespace rnmpc

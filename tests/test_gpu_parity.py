@@ -26,6 +26,21 @@ def np_(t):
     return t.detach().cpu().numpy()
 
 
+QP_KERNELS = ["mma", "slot", "block"]
+
+
+def set_qp_kernel(s, which):
+    """mma: the tensor-pipe kernel (rnmpc_qp_mma.cuh, default at every batch size); slot: the instance-per-slot kernel
+    (rnmpc_qp.cuh); block: the round-1 one-CTA-per-instance kernel (rnmpc_qp_block.cuh)."""
+    if which == "mma":
+        s.set_option("qp_kernel", 0)
+    elif which == "slot":
+        s.set_option("qp_kernel", 1)
+        s.set_option("qp_block_max", 0)
+    else:
+        s.set_option("qp_kernel", 2)
+
+
 @pytest.mark.parametrize("name", MODELS)
 def test_linearize_and_ddyn_vs_sympy_golden(name):
     g = load(f"jac_{name}.npz")
@@ -95,14 +110,14 @@ def test_sls_ragged_batch_and_zero_duals(name):
     s.close()
 
 
-@pytest.mark.parametrize("block", [0, 64], ids=["batch_kernel", "block_kernel"])
+@pytest.mark.parametrize("kernel", QP_KERNELS)
 @pytest.mark.parametrize("name", MODELS)
-def test_qp_vs_oracle_golden(name, block):
-    """CUDA interior-point QP vs the oracle's exact solutions (un-tightened and tightened bounds, quirk Q4); both the
-    instance-per-slot kernel and the one-CTA-per-instance kernel for small batches (`qp_block_max`)."""
+def test_qp_vs_oracle_golden(name, kernel):
+    """CUDA interior-point QP vs the oracle's exact solutions (un-tightened and tightened bounds, quirk Q4); all three QP
+    kernels (option `qp_kernel`)."""
     g = load(f"qp_{name}.npz")
     m, cfg, s = make_solver(name, 8)
-    s.set_option("qp_block_max", block)
+    set_qp_kernel(s, kernel)
     n = len(g["X"])
     A, B, c = s.linearize(g["X"], g["U"])
     for tight in (False, True):
@@ -144,9 +159,9 @@ def test_qp_infeasible_instance_does_not_poison_batch():
     s.close()
 
 
-def _run_loop_gpu(name, g, steps, block=0):
+def _run_loop_gpu(name, g, steps, kernel="mma"):
     m, cfg, s = make_solver(name, 1)
-    s.set_option("qp_block_max", block)
+    set_qp_kernel(s, kernel)
     s.set_nominal(g["X0"][None], g["U0"][None])
     x = s.dev(g["x0"][None]).clone()
     W = g["W"] if g["W"].size else None
@@ -165,15 +180,15 @@ def _run_loop_gpu(name, g, steps, block=0):
     return m, cfg, out
 
 
-@pytest.mark.parametrize("block", [0, 64], ids=["batch_kernel", "block_kernel"])
+@pytest.mark.parametrize("kernel", QP_KERNELS)
 @pytest.mark.parametrize("tag,name,steps", [("rocket_w08", "rocket", 29), ("rocket_rng123", "rocket", 29),
                                             ("pendulum", "pendulum", 60), ("quadrotor", "quadrotor", 30)])
-def test_closed_loop_vs_oracle_golden(tag, name, steps, block):
+def test_closed_loop_vs_oracle_golden(tag, name, steps, kernel):
     """Whole closed loops of the reference drivers (configs 1-4 of BASELINE.json) against the oracle's trajectories, with either
     QP kernel."""
     g = load(f"loop_{tag}.npz")
     assert g["success"].all() and len(g["inputs"]) == steps
-    m, cfg, out = _run_loop_gpu(name, g, steps, block)
+    m, cfg, out = _run_loop_gpu(name, g, steps, kernel)
     nx, nu, N = m.nx, m.nu, cfg["N"]
     for i in range(steps):
         skipped = (out["flags"][i] & 4) == 0
@@ -248,20 +263,22 @@ def test_batch_properties_at_bench_size():
     # identical scenarios give identical results wherever they sit in the batch (slot / warp independence)
     xs = np.stack([x0s[0]] * 7)
     _, _, s2 = make_solver("rocket", 7)
-    s2.set_option("qp_block_max", 0)           # the instance-per-slot QP kernel also for this small batch
+    set_qp_kernel(s2, "slot")                  # the instance-per-slot QP kernel also for this small batch
     s2.init_nominal(xs, 10)
     s2.solve(xs)
     X7, K7 = s2.buffer("X"), s2.buffer("K")
     assert all(np.array_equal(X7[0], X7[i]) and np.array_equal(K7[0], K7[i]) for i in range(1, 7))
-    assert np.array_equal(X7[0], s.buffer("X", 1)[0])
-    # the one-CTA-per-instance QP kernel (default for small batches): deterministic per instance; against the other kernel the
-    # same algorithm with different summation orders -> equal to rounding, not bit for bit
+    assert rel(X7[0], s.buffer("X", 1)[0]) < 1e-9
+    # the one-CTA-per-instance QP kernels: deterministic per instance (the tensor-pipe kernel rotates its warps' roles with the
+    # instance index: the results must not depend on it); against the slot kernel the same algorithm with different summation
+    # orders -> equal to rounding, not bit for bit
     _, _, s3 = make_solver("rocket", 7)
     s3.init_nominal(xs, 10)
     s3.solve(xs)
     Xb, Kb = s3.buffer("X"), s3.buffer("K")
     assert all(np.array_equal(Xb[0], Xb[i]) and np.array_equal(Kb[0], Kb[i]) for i in range(1, 7))
     assert rel(Xb[0], X7[0]) < 1e-9 and rel(Kb[0], K7[0]) < 1e-9
+    assert np.array_equal(Xb[0], s.buffer("X", 1)[0])                    # same kernel in the batch of 4096: bit for bit
     s.close(); s2.close(); s3.close()
 
 

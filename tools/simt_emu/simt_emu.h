@@ -1,0 +1,129 @@
+// Minimal SIMT emulator (host, test infrastructure only): runs ONE thread block of an unmodified CUDA kernel source on the CPU,
+// one fiber (ucontext) per thread, so that the kernels of csrc/ can be checked against the oracle where no GPU exists (the
+// build container).  Supported: threadIdx / blockIdx / blockDim / gridDim, __syncthreads, __syncwarp, __shfl_xor_sync,
+// __shfl_sync, __ballot_sync, __all_sync, __any_sync, atomicAdd, extern __shared__ (one block at a time), the warp-collective
+// mma.sync.m8n8k4.f64 through the wrapper rnmpc::dmma884, the usual math functions.  Not supported: cp.async, static __shared__.
+// Threads of a warp that call a collective block until every lane of the mask has arrived (two-phase exchange), so divergent
+// control flow around a collective is detected as a deadlock instead of being silently accepted.
+// The product never includes this file: csrc/*.cuh see it only under -DRNMPC_EMU (tools/simt_emu/Makefile).
+#pragma once
+#include <ucontext.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __restrict__
+#define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
+#define __shared__
+
+struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+struct double2 { double x, y; } __attribute__((aligned(16)));
+static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+typedef void* cudaStream_t;
+
+namespace simt {
+struct Thread {
+    ucontext_t ctx;
+    std::vector<unsigned char> stack;
+    bool done = false;
+    int wait_kind = 0;            // 0 runnable, 1 block barrier, 2 warp barrier
+    unsigned wait_mask = 0;
+};
+struct Block {
+    std::vector<Thread> th;
+    ucontext_t sched;
+    int cur = 0;
+    int nthreads = 0;
+    // warp exchange slots
+    struct Slot { double d[4]; unsigned u; int pred; };
+    std::vector<Slot> slots;
+    std::function<void()> body;
+};
+extern Block* g_blk;
+extern dim3 g_blockIdx, g_gridDim, g_blockDim;
+extern int g_order;
+
+inline int tid() { return g_blk->cur; }
+void yield_block_barrier();
+void yield_warp_barrier(unsigned mask);
+void run_block(int nthreads, dim3 bidx, dim3 gdim, const std::function<void()>& body, size_t stack_bytes = (size_t)1 << 20);
+}  // namespace simt
+
+// threadIdx.x etc. as objects with implicit conversion
+struct EmuThreadIdx { struct { operator unsigned() const { return (unsigned)simt::tid(); } } x; unsigned y = 0, z = 0; };
+struct EmuBlockIdx { struct { operator unsigned() const { return simt::g_blockIdx.x; } } x; unsigned y = 0, z = 0; };
+struct EmuBlockDim { struct { operator unsigned() const { return simt::g_blockDim.x; } } x; unsigned y = 1, z = 1; };
+struct EmuGridDim { struct { operator unsigned() const { return simt::g_gridDim.x; } } x; unsigned y = 1, z = 1; };
+static EmuThreadIdx threadIdx;
+static EmuBlockIdx blockIdx;
+static EmuBlockDim blockDim;
+static EmuGridDim gridDim;
+
+// the kernels declare `extern __shared__ unsigned char smem_raw[];` at block scope inside namespace rnmpc: the driver defines
+// rnmpc::smem_raw (one block runs at a time)
+
+static inline void __syncthreads() { simt::yield_block_barrier(); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { simt::yield_warp_barrier(mask); }
+
+template <class T>
+static inline T emu_exchange(unsigned mask, T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "");
+    simt::Block* b = simt::g_blk;
+    const int me = b->cur, w0 = me & ~31;
+    std::memcpy(&b->slots[me].d[0], &v, sizeof(T));
+    simt::yield_warp_barrier(mask);
+    T r;
+    std::memcpy(&r, &b->slots[w0 + (src_lane & 31)].d[0], sizeof(T));
+    simt::yield_warp_barrier(mask);
+    return r;
+}
+template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int o) { return emu_exchange(mask, v, (simt::tid() & 31) ^ o); }
+template <class T> static inline T __shfl_sync(unsigned mask, T v, int src) { return emu_exchange(mask, v, src); }
+static inline unsigned __ballot_sync(unsigned mask, int pred) {
+    simt::Block* b = simt::g_blk;
+    const int me = b->cur, w0 = me & ~31;
+    b->slots[me].pred = pred ? 1 : 0;
+    simt::yield_warp_barrier(mask);
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l)
+        if ((mask >> l) & 1u) { if (w0 + l < b->nthreads && !b->th[w0 + l].done && b->slots[w0 + l].pred) r |= 1u << l; }
+    simt::yield_warp_barrier(mask);
+    return r;
+}
+static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == (mask & __ballot_sync(mask, 1)); }
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline long long clock64() { return 0; }
+static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+using std::fma; using std::fmax; using std::fmin; using std::fabs; using std::sqrt;
+
+namespace rnmpc {
+// D (8x8) += A (8x4) B (4x8) across the 32 lanes of the calling warp (fragment layout of mma.sync.m8n8k4.f64)
+static inline void dmma884(double& c0, double& c1, const double a, const double bb) {
+    simt::Block* b = simt::g_blk;
+    const int me = b->cur, w0 = me & ~31, lane = me & 31, g = lane >> 2, t = lane & 3;
+    b->slots[me].d[0] = a; b->slots[me].d[1] = bb;
+    simt::yield_warp_barrier(0xffffffffu);
+    double r0 = c0, r1 = c1;
+    for (int k = 0; k < 4; ++k) {
+        const double av = b->slots[w0 + g * 4 + k].d[0];                 // A[g][k]
+        r0 = std::fma(av, b->slots[w0 + (2 * t) * 4 + k].d[1], r0);      // B[k][2t]
+        r1 = std::fma(av, b->slots[w0 + (2 * t + 1) * 4 + k].d[1], r1);  // B[k][2t+1]
+    }
+    simt::yield_warp_barrier(0xffffffffu);
+    c0 = r0; c1 = r1;
+}
+static inline double fast_rcp(const double x) { return 1.0 / x; }
+}  // namespace rnmpc
