@@ -14,6 +14,7 @@
 #include "rnmpc_qp_block.cuh"
 #include "rnmpc_qp_mma.cuh"
 #include "rnmpc_sls.cuh"
+#include "rnmpc_sls_mma.cuh"
 
 namespace rnmpc {
 
@@ -208,6 +209,9 @@ struct Engine : IEngine {
     // (diagonal cost, cold start, reference bounds, working set fits shared memory), at every batch size; 1 = instance-per-slot kernel
     // (with its hand-off), 2 = the round-1 one-CTA-per-instance kernel (rnmpc_qp_block.cuh), 3 = as 0.  1 and 2 remain for comparison.
     int qp_kernel = 0;
+    int sls_kernel_sel = 0;        // "sls_kernel": 0 = tensor-pipe fast-SLS kernel (rnmpc_sls_mma.cuh, one warp per chain), 1 = round-1 slot kernel
+    int sls_mma_warps = 7;         // warps (chains) per CTA of the tensor-pipe fast-SLS kernel ("sls_mma_warps")
+    int dense_reg = 0;             // Q_reg has off-diagonal entries
     long long* qp_prof = nullptr;  // "qp_profile": per-phase cycle counters of instance 0 in qp_mma_kernel (buffer "qp_prof", 16 x int64)
     bool qp_mma_ok = false;
     size_t qp_mma_smem = 0;
@@ -283,6 +287,9 @@ struct Engine : IEngine {
         for (int i = 0; i < NU; ++i)
             for (int j = 0; j < NU; ++j)
                 if (i != j && hp.R[i * NU + j] != 0.0) diag_cost = 0;
+        for (int i = 0; i < NX; ++i)
+            for (int j = 0; j < NX; ++j)
+                if (i != j && hp.Qreg[i * NX + j] != 0.0) dense_reg = 1;
         RN_CUDA(cudaMalloc((void**)&d_prm, sizeof(P)));
         RN_CUDA(cudaMemcpy(d_prm, &hp, sizeof(P), cudaMemcpyHostToDevice));
         const size_t B = cap, n1 = N + 1;
@@ -304,6 +311,7 @@ struct Engine : IEngine {
         if (rc) return -2;
         const int smem_sls = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * kWarps;
         RN_CUDA(cudaFuncSetAttribute(sls_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
+        RN_CUDA(cudaFuncSetAttribute(sls_mma_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * SlsMma<NX, NU>::PER_WARP * (int)sizeof(double)));
         qp_block_smem = qp_block_smem_doubles<NX, NU>(N) * sizeof(double);
         // the attribute belongs to the kernel, not to this handle (handles with different horizons share it): always the maximum
         qp_block_ok = qp_block_smem <= 227 * 1024 &&
@@ -378,7 +386,12 @@ struct Engine : IEngine {
         const unsigned grid = (unsigned)((warps + w - 1) / w);
         const int smem = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * w;
         cudaEvent_t te = region_begin(2, st);
-        sls_kernel<NX, NU><<<grid, w * 32, smem, st>>>(a, d_prm);
+        if (sls_kernel_sel == 0) {
+            // one warp per chain, every product of a stage on the FP64 tensor pipe (rnmpc_sls_mma.cuh)
+            const int wpc = sls_mma_warps < 1 ? 1 : (sls_mma_warps > 7 ? 7 : sls_mma_warps);
+            const unsigned gridm = (unsigned)((items + wpc - 1) / wpc);
+            sls_mma_kernel<NX, NU><<<gridm, wpc * 32, wpc * SlsMma<NX, NU>::PER_WARP * sizeof(double), st>>>(a, d_prm, dense_reg);
+        } else sls_kernel<NX, NU><<<grid, w * 32, smem, st>>>(a, d_prm);
         region_end(te, st);
         ++launches;
         RN_CUDA(cudaGetLastError());
@@ -705,6 +718,8 @@ struct Engine : IEngine {
         else if (n == "qp_mu0") qp_mu0 = value;
         else if (n == "qp_block_max") qp_block_max = (int)value;
         else if (n == "qp_kernel") qp_kernel = (int)value;
+        else if (n == "sls_kernel") sls_kernel_sel = (int)value;
+        else if (n == "sls_mma_warps") sls_mma_warps = (int)value;
         else if (n == "qp_profile") {
             if (value != 0 && qp_prof == nullptr) { if (alloc("qp_prof", qp_prof, 16)) return -2; }
             else if (qp_prof != nullptr) cudaMemset(qp_prof, 0, 16 * sizeof(long long));

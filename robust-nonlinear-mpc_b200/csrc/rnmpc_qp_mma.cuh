@@ -1,6 +1,6 @@
 // Nominal QP, tensor-pipe variant: ONE CTA (4 warps) PER INSTANCE, the Riccati factorisation of every interior-point iteration on
-// the FP64 tensor pipe (mma.sync.m8n8k4.f64 -> DMMA), the three vector sweeps as chains of (NX x NX) matrix-vector products with the
-// closed-loop matrices A_k + B_k K_k kept in shared memory.  Same problem, same algorithm, same formulas and status codes as
+// the FP64 tensor pipe (mma.sync.m8n8k4.f64 -> DMMA), the three vector sweeps as chains of small matrix-vector products on one warp,
+// A_k, B_k, K_k, the Cholesky factors and the whole iterate resident in shared memory: NO global-memory access inside the iteration.  Same problem, same algorithm, same formulas and status codes as
 // qp_ipm_kernel / qp_block_kernel (rnmpc_qp.cuh, rnmpc_qp_block.cuh; reference: solver/qp_jit.py:77-273, 362-402, 487-513).
 //
 // Why (measured, profiles/r1i_ncu_full_summary.csv, profiles/r2_dmma_probe.txt):
@@ -16,8 +16,11 @@
 //     (S rp, A'S rp, B'S rp, A'p, B'p).  A DMMA is 256 FMA per warp instruction, 16 cycles of the pipe, 26 cycles dependent latency.
 //   * The operand fragments of [A_k B_k] are the same registers in both products (B operand of the first, A operand of the second:
 //     Z[4s + t][8n + g]); they come straight from global memory (L2 resident), one stage ahead.
-//   * The rank-NU updates S_k = A'SA + (A'SB) K and A + B K are one more k-step each on the same pipe (accumulator initialised with
-//     the tile of A'SA / A).
+//   * The rank-NU update S_k = A'SA + (A'SB) K is one more k-step on the same pipe (accumulator initialised with the tile of A'SA).
+//   * With 2 x 106 KB of shared memory per SM the L1 carve-out is nil: a global load inside the iteration costs an L2 round trip
+//     (second version of this kernel, profiles/r2_qp_mma_v2_phases.txt: 1200-1600 cycles per phase of a stage where 200-450 were
+//     expected).  A_k and B_k are therefore copied to shared memory once per QP (the launch's compulsory traffic) and every
+//     fragment, tile and matrix-vector operand of the iteration comes from there.
 //   * Instruction footprint: a first version of this kernel was 118 KB of SASS (every shared-memory array address recomputed from
 //     the run-time horizon at each use, predictor and corrector code duplicated) and ran an interior-point iteration in 124 k cycles,
 //     no faster than qp_block_kernel.  The horizon is a template parameter now (NC; 0 = run-time fallback), predictor and corrector
@@ -66,11 +69,11 @@ template <int NX, int NU>
 __host__ __device__ inline size_t qp_mma_smem_doubles(int N) {
     using D = QpMma<NX, NU>;
     const size_t NE = (size_t)(N + 1) * D::NZ;
-    return mma_ev((size_t)N * NX * D::LDA) + mma_ev((size_t)N * NU * D::LDA) + mma_ev((size_t)N * NU * NU)      // Acl, K, L
-         + 11 * mma_ev(NE)                                                                                     // entry arrays
-         + 3 * mma_ev((size_t)N * NX) + mma_ev((size_t)(N + 1) * NX) + 2 * mma_ev((size_t)N * NU)              // rp, Sc, gv, wv, dff, tu
+    return mma_ev((size_t)N * NX * D::LDA) + mma_ev((size_t)N * NX * NU) + mma_ev((size_t)N * NU * D::LDA) + mma_ev((size_t)N * NU * NU)   // A, B, K, L
+         + 10 * mma_ev(NE)                                                                                     // entry arrays
+         + 3 * mma_ev((size_t)N * NX) + 2 * mma_ev((size_t)N * NU)                                             // rp, Sc, gv, dff, tu
          + mma_ev(D::SROWS * D::LDS) + mma_ev(D::WROWS * D::LDW) + mma_ev(D::MROWS * D::LDW)                   // S, W, M
-         + mma_ev(D::KP) + 3 * mma_ev(D::NZ) + mma_ev(NU) + 64;                                                // pv, rhs, dgn, xq, uc, red
+         + mma_ev(D::KP) + 2 * mma_ev(D::NZ) + mma_ev(D::NZ + NX) + mma_ev(NU) + mma_ev(NU * NU) + 64;         // pv, rhs, dgn, qdt, uc, R2, red
 }
 
 template <int NX, int NU, int NC>
@@ -79,7 +82,8 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
     constexpr int NZ = D::NZ, NI = 2 * NZ, NIF = 2 * NX, T = kMmaThreads, LDG = Slot<NX>::LD;
     constexpr int KP = D::KP, KS = D::KS, CB = D::CB, CRP = D::CRP, CP = D::CP, NT = D::NT, MTS = D::MTS, MTM = D::MTM;
     constexpr int LDS = D::LDS, LDW = D::LDW, LDA = D::LDA;
-    static_assert(NX <= 32 && NU <= 32, "one lane per vector entry in the sweeps");
+    static_assert(NZ <= 32, "one lane per state / input entry in the sweeps");
+    static_assert(LDA == LDG, "the resident copy of A_k has the layout of the engine's padded A");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
     if (b >= a.B) return;
@@ -95,16 +99,17 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
     double* sp = reinterpret_cast<double*>(smem_raw);
     auto take = [&](size_t n) { double* p = sp; sp += mma_ev(n); return p; };
     const int NE = (N + 1) * NZ;
-    double* Acl = take((size_t)N * NX * LDA); double* Kq = take((size_t)N * NU * LDA); double* Lq = take((size_t)N * NU * NU);
+    double* As = take((size_t)N * NX * LDA); double* Bs = take((size_t)N * NX * NU);
+    double* Kq = take((size_t)N * NU * LDA); double* Lq = take((size_t)N * NU * NU);
     double* e_su = take(NE); double* e_sl = take(NE); double* e_lu = take(NE); double* e_ll = take(NE);
     double* e_iu = take(NE); double* e_il = take(NE); double* e_z = take(NE); double* e_zn = take(NE);
-    double* e_da = take(NE); double* e_dc = take(NE); double* e_qd = take(NE);
+    double* e_da = take(NE); double* e_dc = take(NE);
     double* rp = take((size_t)N * NX); double* Sc = take((size_t)N * NX); double* gv = take((size_t)N * NX);
-    double* wv = take((size_t)(N + 1) * NX); double* dff = take((size_t)N * NU); double* tu = take((size_t)N * NU);
+    double* dff = take((size_t)N * NU); double* tu = take((size_t)N * NU);
     double* S = take(D::SROWS * LDS); double* W = take(D::WROWS * LDW); double* M = take(D::MROWS * LDW);
-    double* pv = take(KP); double* rhs = take(NZ); double* dgn = take(NZ); double* xq = take(NZ); double* uc = take(NU);
+    double* pv = take(KP); double* rhs = take(NZ); double* dgn = take(NZ); double* qdt = take(NZ + NX); double* uc = take(NU);
+    double* R2s = take(NU * NU);
     double* red = take(64);
-    (void)xq;
 
     const double* Ag = a.A + (size_t)b * N * NX * LDG;
     const double* Bg = a.Bm + (size_t)b * N * NX * NU;
@@ -141,13 +146,24 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
         if (prof_on) { const long long t = clock64(); pacc[slot] += t - t_last; t_last = t; }
     };
 
-    // ------------------------------------------------------------------ zero the padded tile buffers once
+    // ------------------------------------------------------------------ stage matrices -> shared memory (once per QP), padded buffers zeroed
+    {
+        const double2* A2 = reinterpret_cast<const double2*>(Ag);
+        double2* As2 = reinterpret_cast<double2*>(As);
+#pragma unroll 4
+        for (int e = rt; e < N * NX * LDA / 2; e += T) As2[e] = __ldg(A2 + e);
+#pragma unroll 4
+        for (int e = rt; e < N * NX * NU; e += T) Bs[e] = __ldg(Bg + e);
+    }
     for (int e = rt; e < D::SROWS * LDS; e += T) S[e] = 0.0;
     for (int e = rt; e < D::WROWS * LDW; e += T) W[e] = 0.0;
     for (int e = rt; e < D::MROWS * LDW; e += T) M[e] = 0.0;
-    for (int e = rt; e < N * NX * LDA; e += T) Acl[e] = 0.0;
     if (rt < KP) pv[rt] = 0.0;
+    if (rt < NU * NU) R2s[rt] = prm->R2[rt];
+    if (rt < NZ) qdt[rt] = 2.0 * (rt < NX ? prm->Q[rt * NX + rt] : prm->R[(rt - NX) * NU + (rt - NX)]);
+    else if (rt < NZ + NX) qdt[rt] = 2.0 * prm->Qf[(rt - NZ) * NX + (rt - NZ)];
     if (rt == 0) red[32] = 0.0;        // "a pivot of the factorisation was not positive" flag of the current iteration
+    auto qd_of = [&](const int k, const int i) -> double { return (k < N) ? qdt[i] : (i < NX ? qdt[NZ + i] : 0.0); };
 
     // ------------------------------------------------------------------ bounds, initial point, slacks (rnmpc_qp.cuh, cold start)
     const bool tight = a.tightened < 0 ? ((a.flags[b] & FLAG_TIGHT) != 0) : (a.tightened != 0);
@@ -157,12 +173,11 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
 #pragma unroll 1
         for (int idx = rt; idx < NE; idx += T) {
             const int k = idx / NZ, i = idx - k * NZ;
-            double h_ = 1e300, l_ = -1e300, z = 0.0, zn = 0.0, qd = 0.0;
+            double h_ = 1e300, l_ = -1e300, z = 0.0, zn = 0.0;
             bool box = false;
             if (i < NX) {
                 const double xn = Xn[k * NX + i];
                 zn = xn;
-                qd = 2.0 * ((k < N) ? prm->Q[i * NX + i] : prm->Qf[i * NX + i]);
                 if (k < N) {
                     const double bu = tight ? a.backoff[((size_t)b * N + k) * NI + i] : 0.0;
                     const double bl = tight ? a.backoff[((size_t)b * N + k) * NI + NZ + i] : 0.0;
@@ -183,7 +198,6 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
                 const int p = i - NX;
                 const double un = Un[k * NU + p];
                 zn = un;
-                qd = 2.0 * prm->R[p * NU + p];
                 const double bu = tight ? a.backoff[((size_t)b * N + k) * NI + i] : 0.0;
                 const double bl = tight ? a.backoff[((size_t)b * N + k) * NI + NZ + i] : 0.0;
                 h_ = (prm->uub[p] - un) - bu + eps;
@@ -204,7 +218,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
             }
             e_su[idx] = su; e_sl[idx] = sl;
             e_iu[idx] = (su < kBig) ? 1.0 / su : 0.0; e_il[idx] = (sl < kBig) ? 1.0 / sl : 0.0;
-            e_z[idx] = z; e_zn[idx] = zn; e_da[idx] = 0.0; e_dc[idx] = 0.0; e_qd[idx] = qd;
+            e_z[idx] = z; e_zn[idx] = zn; e_da[idx] = 0.0; e_dc[idx] = 0.0;
         }
     }
     block_reduce4(bad, dmy, n_box, s_sum);
@@ -225,14 +239,14 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
 #pragma unroll 1
     for (int e = rt; e < N * NX; e += T) {
         const int k = e / NX, r = e - k * NX;
-        const double* Ar = Ag + ((size_t)k * NX + r) * LDG;
-        const double* Br = Bg + ((size_t)k * NX + r) * NU;
+        const double* Ar = As + ((size_t)k * NX + r) * LDA;
+        const double* Br = Bs + ((size_t)k * NX + r) * NU;
         double acc = cg[e] - e_z[(k + 1) * NZ + r], acc2 = 0.0;
 #pragma unroll
-        for (int m = 0; m + 1 < NX; m += 2) { acc = fma(__ldg(Ar + m), e_z[k * NZ + m], acc); acc2 = fma(__ldg(Ar + m + 1), e_z[k * NZ + m + 1], acc2); }
-        if (NX & 1) acc = fma(__ldg(Ar + NX - 1), e_z[k * NZ + NX - 1], acc);
+        for (int m = 0; m + 1 < NX; m += 2) { acc = fma(Ar[m], e_z[k * NZ + m], acc); acc2 = fma(Ar[m + 1], e_z[k * NZ + m + 1], acc2); }
+        if (NX & 1) acc = fma(Ar[NX - 1], e_z[k * NZ + NX - 1], acc);
 #pragma unroll
-        for (int p = 0; p < NU; ++p) acc = fma(__ldg(Br + p), e_z[k * NZ + NX + p], acc);
+        for (int p = 0; p < NU; ++p) acc = fma(Br[p], e_z[k * NZ + NX + p], acc);
         acc += acc2;
         rp[e] = acc;
         rp_inf = fmax(rp_inf, fabs(acc));
@@ -252,8 +266,9 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
     auto sg_of = [&](int idx) -> double { return e_lu[idx] * e_iu[idx] + e_ll[idx] * e_il[idx]; };
     // right-hand side of one entry (rnmpc_qp.cuh rhs_eval): gradient (+ centring / second-order terms in the corrector pass)
     double sigma_mu = 0.0;
-    auto rhs_entry = [&](const int pass, const int idx) -> double {
-        double gq = e_qd[idx] * (e_z[idx] + e_zn[idx]);
+    auto rhs_entry = [&](const int pass, const int k, const int i) -> double {
+        const int idx = k * NZ + i;
+        double gq = qd_of(k, i) * (e_z[idx] + e_zn[idx]);
         if (pass == 1) {
             const double iu = e_iu[idx], il = e_il[idx], lu = e_lu[idx], ll = e_ll[idx], dza = e_da[idx];
             if (iu > 0.0) gq = fma(sigma_mu + dza * (lu * iu * dza - lu), iu, gq);
@@ -261,28 +276,8 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
         }
         return gq;
     };
-    // fragments of Z_k = [A_k | B_k | rp_k] (rows padded to KP with zeros): zf[s][n] = Z[4s + t][8n + g]
-    auto load_z = [&](const int k, double (&zf)[KS][NT]) {
-        const double* Ak = Ag + (size_t)k * NX * LDG;
-        const double* Bk = Bg + (size_t)k * NX * NU;
-#pragma unroll
-        for (int s = 0; s < KS; ++s) {
-            const int r = 4 * s + t4;
-#pragma unroll
-            for (int n = 0; n < NT; ++n) {
-                const int c = 8 * n + g;
-                double v = 0.0;
-                if (r < NX) {
-                    if (c < NX) v = __ldg(Ak + r * LDG + c);
-                    else if (c >= CB && c < CB + NU) v = __ldg(Bk + r * NU + (c - CB));
-                    else if (c == CRP) v = rp[k * NX + r];
-                }
-                zf[s][n] = v;
-            }
-        }
-    };
-
     mark(0);
+
     int stalled = 0, it = 0;
     bool done = status != 0;
 #pragma unroll 1
@@ -293,33 +288,50 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
         __syncthreads();
         // ================================================================ factorisation sweep + predictor backward recursion
 #pragma unroll 1
-        for (int e = rt; e < NX * NX; e += T) { const int i = e / NX, j = e - i * NX; S[i * LDS + j] = (i == j) ? (e_qd[N * NZ + i] + sg_of(N * NZ + i)) : 0.0; }
-        if (rt < NX) pv[rt] = rhs_entry(0, N * NZ + rt);
-        double zf[KS][NT];
-        load_z(N - 1, zf);
+        for (int e = rt; e < NX * NX; e += T) { const int i = e / NX, j = e - i * NX; S[i * LDS + j] = (i == j) ? (qdt[NZ + i] + sg_of(N * NZ + i)) : 0.0; }
+        if (rt < NX) pv[rt] = rhs_entry(0, N, rt);
         __syncthreads();
         mark(1);
 #pragma unroll 1
         for (int k = N - 1; k >= 0; --k) {
             double* Kk = Kq + (size_t)k * NU * LDA;
-            double zn_[KS][NT];
-            if (k > 0) load_z(k - 1, zn_);           // next stage's fragments: in flight during this stage
+            // fragments of Z_k = [A_k | B_k | rp_k] (rows padded to KP with zeros): zf[s][n] = Z[4s + t][8n + g]
+            double zf[KS][NT];
+            {
+                const double* Ak = As + (size_t)k * NX * LDA;
+                const double* Bk = Bs + (size_t)k * NX * NU;
+#pragma unroll
+                for (int s = 0; s < KS; ++s) {
+                    const int r = 4 * s + t4;
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) {
+                        const int c = 8 * n + g;
+                        double v = 0.0;
+                        if (r < NX) {
+                            if (c < NX) v = Ak[r * LDA + c];
+                            else if (c >= CB && c < CB + NU) v = Bk[r * NU + (c - CB)];
+                            else if (c == CRP) v = rp[k * NX + r];
+                        }
+                        zf[s][n] = v;
+                    }
+                }
+            }
             // ---- phase A: W = S [A B rp]  (one warp per row tile of S); the free warp prepares the stage scalars
             if (role < MTS) {
-                double sa[KS];
+                double sa[KS], c0[NT], c1[NT];
 #pragma unroll
                 for (int s = 0; s < KS; ++s) sa[s] = S[(8 * role + g) * LDS + 4 * s + t4];
 #pragma unroll
-                for (int n = 0; n < NT; ++n) {
-                    double c0 = 0.0, c1 = 0.0;
+                for (int n = 0; n < NT; ++n) { c0[n] = 0.0; c1[n] = 0.0; }
 #pragma unroll
-                    for (int s = 0; s < KS; ++s) dmma884(c0, c1, sa[s], zf[s][n]);
-                    *reinterpret_cast<double2*>(W + (8 * role + g) * LDW + 8 * n + 2 * t4) = make_double2(c0, c1);
-                }
+                for (int s = 0; s < KS; ++s)
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) dmma884(c0[n], c1[n], sa[s], zf[s][n]);       // NT independent accumulation chains
+#pragma unroll
+                for (int n = 0; n < NT; ++n) *reinterpret_cast<double2*>(W + (8 * role + g) * LDW + 8 * n + 2 * t4) = make_double2(c0[n], c1[n]);
             } else if (role == 3 && lane < NZ) {
-                const int idx = k * NZ + lane;
-                rhs[lane] = (lane < NX && k == 0) ? 0.0 : rhs_entry(0, idx);
-                dgn[lane] = (lane < NX ? e_qd[idx] : 0.0) + sg_of(idx);      // barrier weights (+ diagonal state cost); R2 is added to H below
+                rhs[lane] = (lane < NX && k == 0) ? 0.0 : rhs_entry(0, k, lane);
+                dgn[lane] = (lane < NX ? qdt[lane] : 0.0) + sg_of(k * NZ + lane);      // barrier weights (+ diagonal state cost); R2 is added to H below
             }
             __syncthreads();
             mark(2);
@@ -351,7 +363,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
 #pragma unroll
                     for (int q = 0; q < NU; ++q) {
                         const int lo = p < q ? p : q, hi = p < q ? q : p;
-                        L[p][q] = M[(CB + lo) * LDW + CB + hi] + prm->R2[p * NU + q] + (p == q ? dgn[NX + p] : 0.0);
+                        L[p][q] = M[(CB + lo) * LDW + CB + hi] + R2s[p * NU + q] + (p == q ? dgn[NX + p] : 0.0);
                     }
                 const bool ok = chol_inplace<NU>(L);
                 if (rt < NX) {
@@ -378,44 +390,29 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
             }
             __syncthreads();
             mark(4);
-            // ---- phase D: one more k-step per tile: S_k = A'SA + (A'SB) K + diag (upper triangle, mirrored: exactly symmetric) and
-            //      A + B K (kept for the three vector sweeps); p_k = rx + A'g + K't and S rp_k on the last threads
+            // ---- phase D: one more k-step per tile: S_k = A'SA + (A'SB) K + diag (upper triangle, mirrored: exactly symmetric);
+            //      p_k = rx + A'g + K't and S rp_k on the last threads
             {
-                const double* Ak = Ag + (size_t)k * NX * LDG;
-                const double* Bk = Bg + (size_t)k * NX * NU;
-                double* Ac = Acl + (size_t)k * NX * LDA;
-                double kf[MTS];                               // B operand: K[t][8n + g]
+                if (k > 0) {
+                    double kf[MTS];                               // B operand: K[t][8n + g]
 #pragma unroll
-                for (int n = 0; n < MTS; ++n) kf[n] = (t4 < NU && 8 * n + g < NX) ? Kk[t4 * LDA + 8 * n + g] : 0.0;
-                int ti = 0;
+                    for (int n = 0; n < MTS; ++n) kf[n] = (t4 < NU && 8 * n + g < NX) ? Kk[t4 * LDA + 8 * n + g] : 0.0;
+                    int ti = 0;
 #pragma unroll
-                for (int mt = 0; mt < MTS; ++mt) {
-                    const int r = 8 * mt + g;
+                    for (int mt = 0; mt < MTS; ++mt) {
+                        const int r = 8 * mt + g;
 #pragma unroll
-                    for (int n = 0; n < MTS; ++n) {
-                        const int c = 8 * n + 2 * t4;
-                        // closed loop tile (mt, n): accumulator = A tile, A operand = B_k[r][t]
-                        if ((ti & 3) == role) {
-                            double c0 = 0.0, c1 = 0.0;
-                            if (r < NX && c < NX) { c0 = __ldg(Ak + r * LDG + c); if (c + 1 < NX) c1 = __ldg(Ak + r * LDG + c + 1); }
-                            const double bf = (t4 < NU && r < NX) ? __ldg(Bk + r * NU + t4) : 0.0;
-                            dmma884(c0, c1, bf, kf[n]);
-                            if (r < NX && c < NX) { Ac[r * LDA + c] = c0; if (c + 1 < NX) Ac[r * LDA + c + 1] = c1; }
-                        }
-                        ++ti;
-                        // cost-to-go tile (mt <= n): accumulator = A'SA tile, A operand = (A'SB)[r][t]
-                        if (n >= mt) {
-                            if ((ti & 3) == role && k > 0) {
-                                const double2 mv = *reinterpret_cast<const double2*>(M + r * LDW + c);
-                                double c0 = mv.x, c1 = mv.y;
-                                const double gf = (t4 < NU) ? M[r * LDW + CB + t4] : 0.0;
-                                dmma884(c0, c1, gf, kf[n]);
-                                if (r < NX) {
-                                    if (c < NX && r <= c) { const double v = c0 + (r == c ? dgn[r] : 0.0); S[r * LDS + c] = v; S[c * LDS + r] = v; }
-                                    if (c + 1 < NX && r <= c + 1) { const double v = c1 + (r == c + 1 ? dgn[r] : 0.0); S[r * LDS + c + 1] = v; S[(c + 1) * LDS + r] = v; }
-                                }
+                        for (int n = mt; n < MTS; ++n, ++ti) {
+                            if ((ti & 3) != role) continue;
+                            const int c = 8 * n + 2 * t4;
+                            const double2 mv = *reinterpret_cast<const double2*>(M + r * LDW + c);
+                            double c0 = mv.x, c1 = mv.y;
+                            const double gf = (t4 < NU) ? M[r * LDW + CB + t4] : 0.0;      // A operand: (A'SB)[r][t]
+                            dmma884(c0, c1, gf, kf[n]);
+                            if (r < NX) {
+                                if (c < NX && r <= c) { const double v = c0 + (r == c ? dgn[r] : 0.0); S[r * LDS + c] = v; S[c * LDS + r] = v; }
+                                if (c + 1 < NX && r <= c + 1) { const double v = c1 + (r == c + 1 ? dgn[r] : 0.0); S[r * LDS + c + 1] = v; S[(c + 1) * LDS + r] = v; }
                             }
-                            ++ti;
                         }
                     }
                 }
@@ -432,10 +429,6 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
             }
             __syncthreads();
             mark(5);
-#pragma unroll
-            for (int s = 0; s < KS; ++s)
-#pragma unroll
-                for (int n = 0; n < NT; ++n) zf[s][n] = zn_[s][n];
         }
         chol_ok = red[32] == 0.0;
 
@@ -445,65 +438,67 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
         for (int pass = 0; pass < 2; ++pass) {
             double* e_dz = pass ? e_dc : e_da;
             if (pass == 1) {
-                // ---- corrector right-hand sides: r'_k = rx_k + K_k' ru_k (k >= 1), ru_k kept for the feed-forward; p_N = rx_N
+                // ---- corrector right-hand sides (e_dc doubles as scratch until the forward recursion overwrites it with the step)
 #pragma unroll 1
-                for (int idx = rt; idx < NE; idx += T) e_dc[idx] = rhs_entry(1, idx);      // e_dc doubles as scratch until the forward chain
-                __syncthreads();
-#pragma unroll 1
-                for (int e = rt; e < (N + 1) * NX; e += T) {
-                    const int k = e / NX, i = e - k * NX;
-                    double acc = e_dc[k * NZ + i];
-                    if (k < N) {
-#pragma unroll
-                        for (int p = 0; p < NU; ++p) acc = fma(Kq[((size_t)k * NU + p) * LDA + i], e_dc[k * NZ + NX + p], acc);
-                    }
-                    wv[e] = acc;
-                }
-#pragma unroll 1
-                for (int e = rt; e < N * NU; e += T) { const int k = e / NU, p = e - k * NU; tu[e] = e_dc[k * NZ + NX + p]; }
+                for (int idx = rt; idx < NE; idx += T) { const int k = idx / NZ; e_dc[idx] = rhs_entry(1, k, idx - k * NZ); }
                 __syncthreads();
                 mark(6);
                 if (role == 0) {
-                    // p_k = r'_k + (A_k + B_k K_k)' (p_{k+1} + rp_scale Sc_k) on one warp; g_k = p_{k+1} + rp_scale Sc_k is kept for every stage
+                    // backward recursion on one warp: g_k = p_{k+1} + rp_scale Sc_k ; lanes < NX: p_k = rx_k + A_k' g_k + K_k' t_k,
+                    // lanes NX .. NZ-1: t_k = ru_k + B_k' g_k (kept in tu for the feed-forward)
                     const int r = lane < NX ? lane : NX - 1;
-                    double pl = wv[N * NX + r];
+                    const int p = (lane >= NX && lane < NZ) ? lane - NX : 0;
+                    double pl = e_dc[N * NZ + r];
 #pragma unroll 1
                     for (int k = N - 1; k >= 0; --k) {
                         if (lane < NX) gv[k * NX + lane] = pl + rp_scale * Sc[k * NX + lane];
                         __syncwarp();
-                        if (k > 0) {
-                            const double* gk = gv + k * NX;
-                            const double* col = Acl + (size_t)k * NX * LDA + r;
-                            double a0 = wv[k * NX + r], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                        const double* gk = gv + k * NX;
+                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                        if (lane < NX) {
+                            if (k > 0) {
+                                const double* col = As + (size_t)k * NX * LDA + r;
+                                a0 = e_dc[k * NZ + r];
+#pragma unroll
+                                for (int m = 0; m + 3 < NX; m += 4) {
+                                    a0 = fma(col[m * LDA], gk[m], a0); a1 = fma(col[(m + 1) * LDA], gk[m + 1], a1);
+                                    a2 = fma(col[(m + 2) * LDA], gk[m + 2], a2); a3 = fma(col[(m + 3) * LDA], gk[m + 3], a3);
+                                }
+#pragma unroll
+                                for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(col[m * LDA], gk[m], a0);
+                            }
+                        } else if (lane < NZ) {
+                            const double* col = Bs + (size_t)k * NX * NU + p;
+                            a0 = e_dc[k * NZ + NX + p];
 #pragma unroll
                             for (int m = 0; m + 3 < NX; m += 4) {
-                                a0 = fma(col[m * LDA], gk[m], a0); a1 = fma(col[(m + 1) * LDA], gk[m + 1], a1);
-                                a2 = fma(col[(m + 2) * LDA], gk[m + 2], a2); a3 = fma(col[(m + 3) * LDA], gk[m + 3], a3);
+                                a0 = fma(col[m * NU], gk[m], a0); a1 = fma(col[(m + 1) * NU], gk[m + 1], a1);
+                                a2 = fma(col[(m + 2) * NU], gk[m + 2], a2); a3 = fma(col[(m + 3) * NU], gk[m + 3], a3);
                             }
 #pragma unroll
-                            for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(col[m * LDA], gk[m], a0);
-                            pl = (a0 + a1) + (a2 + a3);
+                            for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(col[m * NU], gk[m], a0);
+                            tu[k * NU + p] = (a0 + a1) + (a2 + a3);
+                        }
+                        __syncwarp();
+                        if (lane < NX && k > 0) {
+                            double acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+                            for (int q = 0; q < NU; ++q) acc = fma(Kq[((size_t)k * NU + q) * LDA + r], tu[k * NU + q], acc);
+                            pl = acc;
                         }
                     }
                 }
                 __syncthreads();
                 mark(7);
-                // ---- t_k = ru_k + B_k' g_k ; d_k = -H_k^{-1} t_k   (one thread per stage)
+                // ---- d_k = -H_k^{-1} t_k   (one thread per stage)
                 if (rt < N) {
                     const int k = rt;
-                    const double* Bk = Bg + (size_t)k * NX * NU;
                     double d[NU], L[NU][NU];
 #pragma unroll
                     for (int p = 0; p < NU; ++p) {
                         d[p] = tu[k * NU + p];
 #pragma unroll
                         for (int q = 0; q < NU; ++q) L[p][q] = Lq[k * NU * NU + p * NU + q];
-                    }
-#pragma unroll 1
-                    for (int i = 0; i < NX; ++i) {
-                        const double gi = gv[k * NX + i];
-#pragma unroll
-                        for (int p = 0; p < NU; ++p) d[p] = fma(__ldg(Bk + i * NU + p), gi, d[p]);
                     }
                     chol_solve<NU>(L, d);
 #pragma unroll
@@ -512,60 +507,64 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
                 __syncthreads();
                 mark(8);
             }
-            // ---- w_k = B_k d_k + rp_scale rp_k (right-hand side of the forward recursion)
-#pragma unroll 1
-            for (int e = rt; e < N * NX; e += T) {
-                const int k = e / NX;
-                const double* Br = Bg + (size_t)e * NU;
-                double acc = rp_scale * rp[e];
-#pragma unroll
-                for (int p = 0; p < NU; ++p) acc = fma(__ldg(Br + p), dff[k * NU + p], acc);
-                wv[e] = acc;
-            }
-            __syncthreads();
             mark(9);
-            // ---- forward recursion dx_{k+1} = (A_k + B_k K_k) dx_k + w_k, dx_0 = 0, on one warp (lane r owns row r); dx_k is left in
-            //      the x-entries of e_dz
+            // ---- forward recursion on one warp: lanes NX .. NZ-1: du_k = K_k dx_k + d_k ; lanes < NX: dx_{k+1} = A_k dx_k + B_k du_k +
+            //      rp_scale rp_k, dx_0 = 0.  The steps land in the entries of e_dz.
             if (role == 0) {
                 const int r = lane < NX ? lane : NX - 1;
-                if (lane < NX) { e_dz[lane] = 0.0; e_dz[NZ + lane] = wv[lane]; }      // dx_0 = 0, dx_1 = w_0
+                const int p = (lane >= NX && lane < NZ) ? lane - NX : 0;
+                if (lane < NX) e_dz[lane] = 0.0;
                 __syncwarp();
 #pragma unroll 1
-                for (int k = 1; k < N; ++k) {
+                for (int k = 0; k < N; ++k) {
                     const double* xk = e_dz + k * NZ;
-                    const double* row = Acl + ((size_t)k * NX + r) * LDA;
-                    double a0 = wv[k * NX + r], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                    if (lane < NX) {
+                        const double* row = As + ((size_t)k * NX + r) * LDA;
+                        a0 = rp_scale * rp[k * NX + r];
+                        if (k > 0) {
 #pragma unroll
-                    for (int m = 0; m + 3 < NX; m += 4) {
-                        const double2 r01 = *reinterpret_cast<const double2*>(row + m), r23 = *reinterpret_cast<const double2*>(row + m + 2);
-                        a0 = fma(r01.x, xk[m], a0); a1 = fma(r01.y, xk[m + 1], a1);
-                        a2 = fma(r23.x, xk[m + 2], a2); a3 = fma(r23.y, xk[m + 3], a3);
+                            for (int m = 0; m + 3 < NX; m += 4) {
+                                const double2 r01 = *reinterpret_cast<const double2*>(row + m), r23 = *reinterpret_cast<const double2*>(row + m + 2);
+                                a0 = fma(r01.x, xk[m], a0); a1 = fma(r01.y, xk[m + 1], a1);
+                                a2 = fma(r23.x, xk[m + 2], a2); a3 = fma(r23.y, xk[m + 3], a3);
+                            }
+#pragma unroll
+                            for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(row[m], xk[m], a0);
+                        }
+                    } else if (lane < NZ) {
+                        const double* row = Kq + ((size_t)k * NU + p) * LDA;
+                        a0 = dff[k * NU + p];
+                        if (k > 0) {
+#pragma unroll
+                            for (int m = 0; m + 3 < NX; m += 4) {
+                                const double2 r01 = *reinterpret_cast<const double2*>(row + m), r23 = *reinterpret_cast<const double2*>(row + m + 2);
+                                a0 = fma(r01.x, xk[m], a0); a1 = fma(r01.y, xk[m + 1], a1);
+                                a2 = fma(r23.x, xk[m + 2], a2); a3 = fma(r23.y, xk[m + 3], a3);
+                            }
+#pragma unroll
+                            for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(row[m], xk[m], a0);
+                        }
+                        e_dz[k * NZ + NX + p] = (a0 + a1) + (a2 + a3);
                     }
+                    __syncwarp();
+                    if (lane < NX) {
+                        double acc = (a0 + a1) + (a2 + a3);
+                        const double* Br = Bs + ((size_t)k * NX + r) * NU;
 #pragma unroll
-                    for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(row[m], xk[m], a0);
-                    if (lane < NX) e_dz[(k + 1) * NZ + lane] = (a0 + a1) + (a2 + a3);
+                        for (int q = 0; q < NU; ++q) acc = fma(Br[q], xk[NX + q], acc);
+                        e_dz[(k + 1) * NZ + lane] = acc;
+                    }
                     __syncwarp();
                 }
             }
             __syncthreads();
             mark(10);
-            // ---- du_k = K_k dx_k + d_k for the input entries, then the ratio test over all entries (rnmpc_qp.cuh ratio_entry)
+            // ---- ratio test over all entries (rnmpc_qp.cuh ratio_entry)
             double rpm = 0.0, rdm = 0.0, S3 = 0.0, S4 = 0.0;
 #pragma unroll 1
             for (int idx = rt; idx < NE; idx += T) {
-                const int k = idx / NZ, i = idx - k * NZ;
-                double dz;
-                if (i >= NX) {
-                    if (k == N) continue;
-                    const double* Kr = Kq + ((size_t)k * NU + (i - NX)) * LDA;
-                    const double* xk = e_dz + k * NZ;
-                    double u0 = dff[k * NU + i - NX], u1 = 0.0;
-#pragma unroll
-                    for (int m = 0; m + 1 < NX; m += 2) { u0 = fma(Kr[m], xk[m], u0); u1 = fma(Kr[m + 1], xk[m + 1], u1); }
-                    if (NX & 1) u0 = fma(Kr[NX - 1], xk[NX - 1], u0);
-                    dz = u0 + u1;
-                    e_dz[idx] = dz;
-                } else dz = e_dz[idx];
+                const double dz = e_dz[idx];
                 const double iu = e_iu[idx], il = e_il[idx], lu = e_lu[idx], ll = e_ll[idx];
                 const double dza = pass == 1 ? e_da[idx] : 0.0;
                 const double smu = pass == 1 ? sigma_mu : 0.0;
@@ -673,7 +672,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
             const int k = idx / NZ, i = idx - k * NZ;
             if (i >= NX && k == N) continue;
             const double z = e_z[idx];
-            acc = fma(z, 0.5 * e_qd[idx] * (z + 2.0 * e_zn[idx]), acc);
+            acc = fma(z, 0.5 * qd_of(k, i) * (z + 2.0 * e_zn[idx]), acc);
             if (i < NX) Xo[k * NX + i] = z; else Uo[k * NU + i - NX] = z;
             if (k < N) { mu[k * NI + i] = e_lu[idx]; mu[k * NI + NZ + i] = e_ll[idx]; }
             else { muf[i] = e_lu[idx]; muf[NX + i] = e_ll[idx]; }

@@ -27,6 +27,7 @@ struct SlsArgs {
     double* beta_f;        // [B][N+1][ni_f]
 };
 
+#ifndef RNMPC_EMU
 // Chain s of an instance covers column s (N-s steps) followed by column N-s (s steps): N Riccati steps and N
 // propagation steps for every chain, so all slots of a warp run the same trip counts.
 template <int NX, int NU>
@@ -301,6 +302,8 @@ __global__ void __launch_bounds__(160, 2) sls_kernel(const SlsArgs a, const Para
         }
     }
 }
+
+#endif  // RNMPC_EMU
 
 // backoff[k][i] = sum_{j<=k} sqrt(beta[k][j][i]),  backoff_f[i] = sum_{j<=N} sqrt(beta_f[j][i])
 // (solver/fast_SLS_jit.py:172-186); one thread per (instance, k, i).

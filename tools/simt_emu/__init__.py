@@ -79,3 +79,29 @@ def qp_mma(name, m, cfg, A, Bm, c, X, U, x0, backoff=None, backoff_f=None, max_i
     if rc != 0:
         raise RuntimeError(f"emu_qp_mma failed: {rc}")
     return out
+
+
+def sls_mma(name, m, cfg, A, Bm, eta=None, eta_f=None, mu=None, mu_f=None, beta_in=None, beta_f_in=None, want_S=True, want_phi=True, warps=3):
+    """sls_mma_kernel on the emulator (one instance batch axis optional: A [B,N,nx,nx] or [N,nx,nx])."""
+    lib = load()
+    conf, keep = _cfg(name, m, cfg)
+    f = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    A, Bm = f(A), f(Bm)
+    if A.ndim == 3:
+        A, Bm = A[None], Bm[None]
+        eta, eta_f, mu, mu_f, beta_in, beta_f_in = (None if t is None else np.asarray(t)[None] for t in (eta, eta_f, mu, mu_f, beta_in, beta_f_in))
+    Ap = pad_rows(A)
+    B, N, nx, nu = A.shape[0], int(cfg["N"]), m.nx, m.nu
+    ni, nif = 2 * (nx + nu), 2 * nx
+    eta, eta_f, mu, mu_f, beta_in, beta_f_in = (f(t) for t in (eta, eta_f, mu, mu_f, beta_in, beta_f_in))
+    out = dict(K=np.zeros((B, N, N + 1, nu, nx)), beta=np.zeros((B, N, N, ni)), beta_f=np.zeros((B, N + 1, nif)))
+    out["S"] = np.zeros((B, N + 1, N + 1, nx, nx)) if want_S else None
+    out["Phi_x"] = np.zeros((B, N + 1, N + 1, nx, nx)) if want_phi else None
+    out["Phi_u"] = np.zeros((B, N, N + 1, nu, nx)) if want_phi else None
+    lib.emu_sls_mma.restype = C.c_int
+    lib.emu_sls_mma.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 14
+    rc = lib.emu_sls_mma(C.byref(conf), B, int(warps), _p(Ap), _p(Bm), _p(eta), _p(eta_f), _p(mu), _p(mu_f), _p(beta_in), _p(beta_f_in),
+                         _p(out["K"]), _p(out["S"]), _p(out["Phi_x"]), _p(out["Phi_u"]), _p(out["beta"]), _p(out["beta_f"]))
+    if rc != 0:
+        raise RuntimeError(f"emu_sls_mma failed: {rc}")
+    return out

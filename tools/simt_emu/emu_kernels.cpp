@@ -6,6 +6,7 @@
 
 #include "../../include/rnmpc_b200.h"
 #include "../../robust-nonlinear-mpc_b200/csrc/rnmpc_qp_mma.cuh"
+#include "../../robust-nonlinear-mpc_b200/csrc/rnmpc_sls_mma.cuh"
 
 namespace rnmpc {
 alignas(128) unsigned char smem_raw[232448];
@@ -56,6 +57,38 @@ extern "C" int emu_qp_mma(const rnmpc_config* cfg, int B, int tightened, const d
         case RNMPC_PENDULUM: return run_qp_mma<4, 1>(cfg, a);
         case RNMPC_QUADROTOR: return run_qp_mma<13, 4>(cfg, a);
         case RNMPC_ROCKET: return run_qp_mma<17, 4>(cfg, a);
+    }
+    return -1;
+}
+
+template <int NX, int NU>
+static int run_sls_mma(const rnmpc_config* cfg, SlsArgs a, int warps) {
+    Params<NX, NU> hp;
+    fill_params<NX, NU>(cfg, hp);
+    int dense = 0;
+    for (int i = 0; i < NX; ++i)
+        for (int j = 0; j < NX; ++j)
+            if (i != j && hp.Qreg[i * NX + j] != 0.0) dense = 1;
+    const long long items = (long long)a.B * (a.N / 2 + 1);
+    const int grid = (int)((items + warps - 1) / warps);
+    if ((size_t)warps * SlsMma<NX, NU>::PER_WARP * sizeof(double) > sizeof(smem_raw)) return -4;
+    for (int blk = 0; blk < grid; ++blk)
+        simt::run_block(warps * 32, dim3(blk), dim3(grid), [&]() { sls_mma_kernel<NX, NU>(a, &hp, dense); });
+    return 0;
+}
+
+// fast-SLS pass with explicit weights (eta, eta_f) or from duals (mu, mu_f [+ beta_in, beta_f_in]); A padded [B][N][nx][ld]
+extern "C" int emu_sls_mma(const rnmpc_config* cfg, int B, int warps, const double* A_padded, const double* Bm, const double* eta,
+                           const double* eta_f, const double* mu, const double* mu_f, const double* beta_in, const double* beta_f_in,
+                           double* K, double* S, double* Phi_x, double* Phi_u, double* beta, double* beta_f) {
+    SlsArgs a{};
+    a.B = B; a.N = cfg->N; a.A = A_padded; a.Bm = Bm; a.eta = eta; a.eta_f = eta_f; a.mu = mu; a.mu_f = mu_f;
+    a.beta_in = beta_in; a.beta_f_in = beta_f_in;
+    a.K = K; a.S = S; a.Phi_x = Phi_x; a.Phi_u = Phi_u; a.beta = beta; a.beta_f = beta_f;
+    switch (cfg->model_id) {
+        case RNMPC_PENDULUM: return run_sls_mma<4, 1>(cfg, a, warps);
+        case RNMPC_QUADROTOR: return run_sls_mma<13, 4>(cfg, a, warps);
+        case RNMPC_ROCKET: return run_sls_mma<17, 4>(cfg, a, warps);
     }
     return -1;
 }
