@@ -158,6 +158,18 @@ __device__ __forceinline__ void chol_solve(const double (&L)[NU][NU], double (&f
     }
 }
 
+// 16-byte asynchronous global -> shared copies (LDGSTS) in a form the emulated build understands too (tools/simt_emu defers
+// the copy until the matching wait, so a read before the wait / barrier shows up as a wrong result on the CPU already).
+#ifndef RNMPC_EMU
+__device__ __forceinline__ void cpa16(double* dst_smem, const double* __restrict__ src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src));
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;"); }
+template <int PENDING>
+__device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+__device__ __forceinline__ void fence_block() { __threadfence_block(); }
+#endif
+
 #ifndef RNMPC_EMU      // the slot machinery below stages with cp.async: not emulated
 // Shared-memory working set of one slot (see SlotSmem below for the bank-conflict padding).
 template <int NX, int NU>

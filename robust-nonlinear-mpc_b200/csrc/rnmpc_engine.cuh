@@ -13,6 +13,7 @@
 #include "rnmpc_qp.cuh"
 #include "rnmpc_qp_block.cuh"
 #include "rnmpc_qp_mma.cuh"
+#include "rnmpc_qp_warp.cuh"
 #include "rnmpc_sls.cuh"
 #include "rnmpc_sls_mma.cuh"
 
@@ -205,10 +206,16 @@ struct Engine : IEngine {
     int *handoff_count = nullptr, *handoff_list = nullptr;
     double* handoff_state = nullptr;
     bool qp_block_ok = false;
-    // QP kernel selection ("qp_kernel"): 0 automatic = the tensor-pipe kernel (rnmpc_qp_mma.cuh, one CTA per instance) whenever it applies
-    // (diagonal cost, cold start, reference bounds, working set fits shared memory), at every batch size; 1 = instance-per-slot kernel
-    // (with its hand-off), 2 = the round-1 one-CTA-per-instance kernel (rnmpc_qp_block.cuh), 3 = as 0.  1 and 2 remain for comparison.
+    // QP kernel selection ("qp_kernel"): 0 automatic = a tensor-pipe kernel whenever one applies (diagonal cost, cold start, reference
+    // bounds, working set fits shared memory): the one-warp-per-instance throughput kernel (rnmpc_qp_warp.cuh) for batches of at least
+    // qp_warp_min instances, the one-CTA-per-instance latency kernel (rnmpc_qp_mma.cuh) below; 1 = instance-per-slot kernel (with its
+    // hand-off), 2 = the round-1 one-CTA-per-instance kernel (rnmpc_qp_block.cuh), 3 = rnmpc_qp_mma.cuh at every batch size,
+    // 4 = rnmpc_qp_warp.cuh at every batch size.  1 and 2 remain for comparison.
     int qp_kernel = 0;
+    int qp_warp_min = 600;         // "qp_warp_min": smallest batch the automatic selection gives to the one-warp-per-instance kernel
+    bool qp_warp_ok = false;
+    size_t qp_warp_smem = 0;
+    double* Kw = nullptr;          // [B][N][NU][LDA] Riccati gains of qp_warp_kernel (its own padded layout)
     int sls_kernel_sel = 0;        // "sls_kernel": 0 = tensor-pipe fast-SLS kernel (rnmpc_sls_mma.cuh, one warp per chain), 1 = round-1 slot kernel
     int sls_mma_warps = 7;         // warps (chains) per CTA of the tensor-pipe fast-SLS kernel ("sls_mma_warps")
     int dense_reg = 0;             // Q_reg has off-diagonal entries
@@ -321,6 +328,11 @@ struct Engine : IEngine {
         qp_mma_ok = qp_mma_smem <= 227 * 1024 &&
                     cudaFuncSetAttribute(qp_mma_kernel<NX, NU, kHorizonFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
                     cudaFuncSetAttribute(qp_mma_kernel<NX, NU, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+        cudaGetLastError();
+        qp_warp_smem = qp_warp_smem_doubles<NX, NU>(N) * sizeof(double);
+        qp_warp_ok = qp_warp_smem <= 227 * 1024 && alloc("Kw", Kw, B * N * NU * LDA) == 0 &&
+                     cudaFuncSetAttribute(qp_warp_kernel<NX, NU, kHorizonFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
+                     cudaFuncSetAttribute(qp_warp_kernel<NX, NU, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
         cudaGetLastError();
         RN_CUDA(cudaFuncSetAttribute(qp_ipm_kernel<NX, NU, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
         RN_CUDA(cudaFuncSetAttribute(qp_ipm_kernel<NX, NU, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
@@ -453,7 +465,12 @@ struct Engine : IEngine {
         cudaEvent_t te = region_begin(1, st);
         const bool may_warm = a.warm != 0;
         const bool plain = diag_cost && !may_warm && hi_in == nullptr && lo_in == nullptr && q_lin == nullptr;
-        if (plain && qp_mma_ok && (qp_kernel == 0 || qp_kernel == 3)) {
+        if (plain && qp_warp_ok && (qp_kernel == 4 || (qp_kernel == 0 && B >= qp_warp_min))) {
+            // one warp (one CTA of 32 threads) per instance: the throughput kernel for large batches (rnmpc_qp_warp.cuh)
+            a.Kq = Kw;
+            if (N == kHorizonFast) qp_warp_kernel<NX, NU, kHorizonFast><<<(unsigned)B, 32, qp_warp_smem, st>>>(a, d_prm);
+            else qp_warp_kernel<NX, NU, 0><<<(unsigned)B, 32, qp_warp_smem, st>>>(a, d_prm);
+        } else if (plain && qp_mma_ok && (qp_kernel == 0 || qp_kernel == 3 || qp_kernel == 4)) {
             // one CTA per instance, factorisation on the FP64 tensor pipe, iterate resident in shared memory (rnmpc_qp_mma.cuh)
             // (the horizon of all reference drivers is a compile-time constant of the fast instantiation; any other horizon runs the generic one)
             if (N == kHorizonFast) qp_mma_kernel<NX, NU, kHorizonFast><<<(unsigned)B, kMmaThreads, qp_mma_smem, st>>>(a, d_prm);
@@ -718,6 +735,7 @@ struct Engine : IEngine {
         else if (n == "qp_mu0") qp_mu0 = value;
         else if (n == "qp_block_max") qp_block_max = (int)value;
         else if (n == "qp_kernel") qp_kernel = (int)value;
+        else if (n == "qp_warp_min") qp_warp_min = (int)value;
         else if (n == "sls_kernel") sls_kernel_sel = (int)value;
         else if (n == "sls_mma_warps") sls_mma_warps = (int)value;
         else if (n == "qp_profile") {

@@ -26,14 +26,17 @@ def np_(t):
     return t.detach().cpu().numpy()
 
 
-QP_KERNELS = ["mma", "slot", "block"]
+QP_KERNELS = ["mma", "warp", "slot", "block"]
 
 
 def set_qp_kernel(s, which):
-    """mma: the tensor-pipe kernel (rnmpc_qp_mma.cuh, default at every batch size); slot: the instance-per-slot kernel
+    """mma: the one-CTA-per-instance tensor-pipe kernel (rnmpc_qp_mma.cuh, default for small batches); warp: the
+    one-warp-per-instance tensor-pipe kernel (rnmpc_qp_warp.cuh, default for large batches); slot: the instance-per-slot kernel
     (rnmpc_qp.cuh); block: the round-1 one-CTA-per-instance kernel (rnmpc_qp_block.cuh)."""
     if which == "mma":
-        s.set_option("qp_kernel", 0)
+        s.set_option("qp_kernel", 3)
+    elif which == "warp":
+        s.set_option("qp_kernel", 4)
     elif which == "slot":
         s.set_option("qp_kernel", 1)
         s.set_option("qp_block_max", 0)

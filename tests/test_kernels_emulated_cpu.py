@@ -23,9 +23,20 @@ def _linearize(m, X, U):
     return A, Bm, c
 
 
+QP_KERNELS = {"qp_mma_kernel": 0, "qp_warp_kernel": 1}
+
+
+@pytest.fixture(params=sorted(QP_KERNELS))
+def qp_kernel(request):
+    simt_emu.set_qp_kernel(QP_KERNELS[request.param])
+    yield request.param
+    simt_emu.set_qp_kernel(0)
+
+
 @pytest.mark.parametrize("name", MODELS)
-def test_qp_mma_kernel_source_vs_oracle_golden(name):
-    """qp_mma_kernel (rnmpc_qp_mma.cuh) on the emulator vs the oracle's exact QP solutions (same bounds as the GPU test)."""
+def test_qp_mma_kernel_source_vs_oracle_golden(name, qp_kernel):
+    """qp_mma_kernel (rnmpc_qp_mma.cuh) and qp_warp_kernel (rnmpc_qp_warp.cuh) on the emulator vs the oracle's exact QP solutions
+    (same bounds as the GPU test)."""
     g = load(f"qp_{name}.npz")
     m, cfg = om.CONFIGS[name]()
     A, Bm, c = _linearize(m, g["X"], g["U"])
@@ -45,7 +56,7 @@ def test_qp_mma_kernel_source_vs_oracle_golden(name):
             assert out["mu"][j].min() > -1e-12
 
 
-def test_qp_mma_kernel_source_is_schedule_independent():
+def test_qp_mma_kernel_source_is_schedule_independent(qp_kernel):
     """A missing barrier makes the result depend on the order in which the emulator runs the threads between barriers;
     ascending, descending and pseudo-random orders must agree bit for bit.  Also: the result must not depend on the block
     index (the kernel rotates its warps' roles with it)."""

@@ -1,0 +1,9 @@
+# first GPU run of the one-warp-per-instance QP kernel: parity tests, latency probe, phase profile, 29-step loop
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "qp_vs_oracle or closed_loop_vs_oracle or infeasible or seeded" > gpurun_out/r2b_pytest.log 2>&1; tail -4 gpurun_out/r2b_pytest.log
+{ echo "== latency, warp kernel (auto)"; timeout 300 python tools/latency_probe.py 296 1024 4096;
+  echo "== latency, mma kernel"; timeout 300 python tools/latency_probe.py 4096 qp_kernel=3; } > gpurun_out/r2b_latency.log 2>&1
+cat gpurun_out/r2b_latency.log
+{ timeout 300 python tools/qp_phase_profile.py 4096 qp_kernel=4; } > gpurun_out/r2b_phases.log 2>&1; cat gpurun_out/r2b_phases.log
+{ echo "== loop warp"; timeout 300 python tools/iter_stats.py 4096; } > gpurun_out/r2b_loop.log 2>&1
+grep -E "TOTAL|==|step  5|step 20" gpurun_out/r2b_loop.log

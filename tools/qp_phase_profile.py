@@ -9,6 +9,8 @@ from rnmpc_b200 import _lib
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 x0, W = rocket_scenarios(B, steps=8)
 m, cfg, s = make_solver("rocket", B)
+for a_ in sys.argv[2:]:
+    k_, v_ = a_.split("="); s.set_option(k_, float(v_))
 s.init_nominal(x0, 10)
 x = s.dev(x0).clone()
 names = ["init", "S_N + first fragments", "A: W = S Z", "B: M = Z'[W p]", "C: Cholesky, K, d", "D: S', A+BK, p", "corr: rhs, r'", "corr: backward chain",

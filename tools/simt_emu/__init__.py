@@ -35,6 +35,11 @@ def set_order(order):
     load().emu_set_order(int(order))
 
 
+def set_qp_kernel(k):
+    """Kernel run by qp_mma(): 0 = qp_mma_kernel (one CTA of four warps per instance), 1 = qp_warp_kernel (one warp per instance)."""
+    load().emu_set_qp_kernel(int(k))
+
+
 def _cfg(name, m, cfg):
     from rnmpc_b200._lib import Config
     keep = dict(Q=cfg["Q"], R=cfg["R"], Qf=cfg["Qf"], Q_reg=cfg["Q_reg"], R_reg=cfg["R_reg"], Q_reg_f=cfg["Q_reg_f"], E=m.E,

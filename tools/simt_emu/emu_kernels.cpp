@@ -6,6 +6,7 @@
 
 #include "../../include/rnmpc_b200.h"
 #include "../../robust-nonlinear-mpc_b200/csrc/rnmpc_qp_mma.cuh"
+#include "../../robust-nonlinear-mpc_b200/csrc/rnmpc_qp_warp.cuh"
 #include "../../robust-nonlinear-mpc_b200/csrc/rnmpc_sls_mma.cuh"
 
 namespace rnmpc {
@@ -31,10 +32,24 @@ static void fill_params(const rnmpc_config* cfg, Params<NX, NU>& hp) {
     hp.h = cfg->h;
 }
 
+static int g_qp_kernel = 0;    // 0: qp_mma_kernel (one CTA of 4 warps per instance), 1: qp_warp_kernel (one warp per instance)
+extern "C" void emu_set_qp_kernel(int k) { g_qp_kernel = k; }
+
 template <int NX, int NU>
 static int run_qp_mma(const rnmpc_config* cfg, QpArgs a) {
     Params<NX, NU> hp;
     fill_params<NX, NU>(cfg, hp);
+    if (g_qp_kernel == 1) {
+        if (qp_warp_smem_doubles<NX, NU>(a.N) * sizeof(double) > sizeof(smem_raw)) return -4;
+        std::vector<double> Kw((size_t)a.B * a.N * NU * QpWarp<NX, NU>::LDA, 0.0), Lw((size_t)a.B * a.N * NU * NU, 0.0);
+        a.Kq = Kw.data(); a.Lq = Lw.data();
+        for (int b = 0; b < a.B; ++b) {
+            simt::cpa_reset();
+            if (a.N == 15 && !g_generic) simt::run_block(32, dim3(b), dim3(a.B), [&]() { qp_warp_kernel<NX, NU, 15>(a, &hp); });
+            else simt::run_block(32, dim3(b), dim3(a.B), [&]() { qp_warp_kernel<NX, NU, 0>(a, &hp); });
+        }
+        return 0;
+    }
     if (qp_mma_smem_doubles<NX, NU>(a.N) * sizeof(double) > sizeof(smem_raw)) return -4;
     for (int b = 0; b < a.B; ++b) {
         if (a.N == 15 && !g_generic) simt::run_block(kMmaThreads, dim3(b), dim3(a.B), [&]() { qp_mma_kernel<NX, NU, 15>(a, &hp); });

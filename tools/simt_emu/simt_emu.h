@@ -2,7 +2,8 @@
 // one fiber (ucontext) per thread, so that the kernels of csrc/ can be checked against the oracle where no GPU exists (the
 // build container).  Supported: threadIdx / blockIdx / blockDim / gridDim, __syncthreads, __syncwarp, __shfl_xor_sync,
 // __shfl_sync, __ballot_sync, __all_sync, __any_sync, atomicAdd, extern __shared__ (one block at a time), the warp-collective
-// mma.sync.m8n8k4.f64 through the wrapper rnmpc::dmma884, the usual math functions.  Not supported: cp.async, static __shared__.
+// mma.sync.m8n8k4.f64 through the wrapper rnmpc::dmma884, cp.async through rnmpc::cpa16 / cpa_commit / cpa_wait (deferred until the wait), the
+// usual math functions.  Not supported: static __shared__.
 // Threads of a warp that call a collective block until every lane of the mask has arrived (two-phase exchange), so divergent
 // control flow around a collective is detected as a deadlock instead of being silently accepted.
 // The product never includes this file: csrc/*.cuh see it only under -DRNMPC_EMU (tools/simt_emu/Makefile).
@@ -109,6 +110,26 @@ static inline long long clock64() { return 0; }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 using std::fma; using std::fmax; using std::fmin; using std::fabs; using std::sqrt;
 
+// cp.async emulation: a copy is performed when its group is waited for (not when it is issued), per emulated thread
+namespace simt {
+struct CpaOp { double* d; const double* s; };
+inline std::vector<std::vector<CpaOp>> g_cpa_groups[1024];
+inline std::vector<CpaOp> g_cpa_open[1024];
+inline void cpa_reset() { for (int i = 0; i < 1024; ++i) { g_cpa_groups[i].clear(); g_cpa_open[i].clear(); } }
+}  // namespace simt
+namespace rnmpc {
+static inline void cpa16(double* dst, const double* src) { simt::g_cpa_open[simt::tid()].push_back({dst, src}); }
+static inline void cpa_commit() { const int t = simt::tid(); simt::g_cpa_groups[t].push_back(simt::g_cpa_open[t]); simt::g_cpa_open[t].clear(); }
+template <int PENDING>
+static inline void cpa_wait() {
+    auto& g = simt::g_cpa_groups[simt::tid()];
+    while ((int)g.size() > PENDING) {
+        for (auto& op : g.front()) { op.d[0] = op.s[0]; op.d[1] = op.s[1]; }
+        g.erase(g.begin());
+    }
+}
+static inline void fence_block() {}
+}  // namespace rnmpc
 namespace rnmpc {
 // D (8x8) += A (8x4) B (4x8) across the 32 lanes of the calling warp (fragment layout of mma.sync.m8n8k4.f64)
 static inline void dmma884(double& c0, double& c1, const double a, const double bb) {
