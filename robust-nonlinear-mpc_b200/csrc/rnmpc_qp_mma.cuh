@@ -64,6 +64,49 @@ struct QpMma {
 
 __host__ __device__ inline size_t mma_ev(size_t n) { return (n + 1) & ~(size_t)1; }
 
+// Operand fragments of Z_k = [A_k | B_k | rp_k] straight from memory: zf[s][n] = Z[4s + t][8n + g] (rows >= NX and unused columns
+// zero).  A column tile that lies inside A_k is a strided read-only load.  A tile that mixes the last columns of A_k, the pad, B_k and
+// the vector rp_k would make the lanes of a warp take three different branches per load (measured: 10 % of the stall samples of
+// qp_warp_kernel, "branch resolving" 0.8 warps per issue); instead every lane keeps ONE generic pointer per mixed tile (global A_k or
+// B_k, or the shared-memory vector) with its own stage and k-step strides, so a fragment is one predicated load on every lane.
+template <int NX, int NU, int NT, int KS, bool RP>
+struct ZFrag {
+    static constexpr int CB = (NX + 1) & ~1, CRP = CB + NU, LDG = (NX + 1) & ~1;
+    static constexpr int NPURE = (NX / 8) < NT ? (NX / 8) : NT;      // tiles 0 .. NPURE-1 hold columns of A_k only
+    static constexpr int NMIX = NT - NPURE > 0 ? NT - NPURE : 1;
+    const double* base[NMIX];     // element (row t, this lane's column) of stage 0
+    int ks[NMIX], ss[NMIX];       // doubles between stages / between k-steps (4 rows)
+    bool ok[NMIX];
+    int g, t4;
+    __device__ __forceinline__ void init(const double* Ag, const double* Bg, const double* rp, const int lane) {
+        g = lane >> 2; t4 = lane & 3;
+#pragma unroll
+        for (int j = 0; j < NMIX; ++j) {
+            const int c = 8 * (NPURE + j) + g;
+            base[j] = Ag; ks[j] = 0; ss[j] = 0; ok[j] = false;
+            if (NPURE + j < NT) {
+                if (c < NX) { base[j] = Ag + t4 * LDG + c; ks[j] = NX * LDG; ss[j] = 4 * LDG; ok[j] = true; }
+                else if (c >= CB && c < CB + NU) { base[j] = Bg + t4 * NU + (c - CB); ks[j] = NX * NU; ss[j] = 4 * NU; ok[j] = true; }
+                else if (RP && c == CRP) { base[j] = rp + t4; ks[j] = NX; ss[j] = 4; ok[j] = true; }
+            }
+        }
+    }
+    __device__ __forceinline__ void load(const int k, const double* Ag, double (&zf)[KS][NT]) const {
+        const double* Ak = Ag + (size_t)k * NX * LDG + t4 * LDG + g;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const bool row = 4 * s + t4 < NX;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                double v = 0.0;
+                if (n < NPURE) { if (row) v = __ldg(Ak + 4 * s * LDG + 8 * n); }
+                else { const int j = n - NPURE; if (row && ok[j]) v = base[j][(long long)k * ks[j] + s * ss[j]]; }
+                zf[s][n] = v;
+            }
+        }
+    }
+};
+
 // shared-memory footprint in doubles
 template <int NX, int NU>
 __host__ __device__ inline size_t qp_mma_smem_doubles(int N) {

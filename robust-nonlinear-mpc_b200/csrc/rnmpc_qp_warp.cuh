@@ -241,25 +241,9 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
     };
     // fragments of Z_k = [A_k | B_k | rp_k] (rows padded to KP with zeros): zf[s][n] = Z[4s + t][8n + g]; A_k, B_k from global
     // memory (L2), one stage ahead of their use
-    auto load_z = [&](const int k, double (&zf)[KS][NT]) {
-        const double* Ak = Ag + (size_t)k * NX * LDG;
-        const double* Bk = Bg + (size_t)k * NX * NU;
-#pragma unroll
-        for (int s = 0; s < KS; ++s) {
-            const int r = 4 * s + t4;
-#pragma unroll
-            for (int n = 0; n < NT; ++n) {
-                const int c = 8 * n + g;
-                double v = 0.0;
-                if (r < NX) {
-                    if (c < NX) v = __ldg(Ak + r * LDG + c);
-                    else if (c >= CB && c < CB + NU) v = __ldg(Bk + r * NU + (c - CB));
-                    else if (c == CRP) v = rp[k * NX + r];
-                }
-                zf[s][n] = v;
-            }
-        }
-    };
+    ZFrag<NX, NU, NT, KS, true> zsrc;
+    zsrc.init(Ag, Bg, rp, lane);
+    auto load_z = [&](const int k, double (&zf)[KS][NT]) { zsrc.load(k, Ag, zf); };
     // stage k of the sweep ring: A_k, B_k, K_k -> slot k % 3 (always commits one group, possibly empty: the waits count groups)
     auto ring_issue = [&](const int k) {
         if (k >= 0 && k < N) {

@@ -75,25 +75,10 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
         if (use_beta) be = fmax(a.beta_f_in[((size_t)b * (N + 1) + col) * NIF + i], kEpsBackoff);
         return m / (2.0 * sqrt(be));
     };
-    // fragments of Z_k = [A_k | B_k] (rows padded to KP with zeros): zf[s][n] = Z[4s + t][8n + g]
-    auto load_z = [&](const int k, double (&zf)[KS][NTZ]) {
-        const double* Ak = Ab + (size_t)k * NX * LDG;
-        const double* Bk = Bb + (size_t)k * NX * NU;
-#pragma unroll
-        for (int q = 0; q < KS; ++q) {
-            const int r = 4 * q + t4;
-#pragma unroll
-            for (int n = 0; n < NTZ; ++n) {
-                const int c = 8 * n + g;
-                double v = 0.0;
-                if (r < NX) {
-                    if (c < NX) v = __ldg(Ak + r * LDG + c);
-                    else if (c >= CB && c < CB + NU) v = __ldg(Bk + r * NU + (c - CB));
-                }
-                zf[q][n] = v;
-            }
-        }
-    };
+    // fragments of Z_k = [A_k | B_k] (rows padded to KP with zeros): zf[s][n] = Z[4s + t][8n + g]  (branch-free: ZFrag, rnmpc_qp_mma.cuh)
+    ZFrag<NX, NU, NTZ, KS, false> zsrc;
+    zsrc.init(Ab, Bb, nullptr, lane);
+    auto load_z = [&](const int k, double (&zf)[KS][NTZ]) { zsrc.load(k, Ab, zf); };
     auto zero_buf = [&](double* p, const int count) {
         for (int e = 2 * lane; e < count; e += 64) *reinterpret_cast<double2*>(p + e) = make_double2(0.0, 0.0);
     };

@@ -76,3 +76,24 @@ def test_qp_mma_kernel_source_is_schedule_independent(qp_kernel):
         for k in r:
             assert np.array_equal(r[k], res[0][k]), k
             assert all(np.array_equal(r[k][0], r[k][b]) for b in range(1, 4)), k
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_sls_mma_kernel_source_vs_reference_numba_golden(name):
+    """sls_mma_kernel (rnmpc_sls_mma.cuh) on the emulator vs the outputs of the reference's own Numba kernels
+    (tests/golden/sls_*.npz, solver/fast_SLS_jit.py:43-188), same assertions as the GPU test."""
+    from oracle.gen_golden import sls_inputs
+    g = load(f"sls_{name}.npz")
+    m, cfg, A, B, eta, eta_f = sls_inputs(name)
+    N = cfg["N"]
+    simt_emu.set_order(2)
+    out = {k: (None if v is None else v[0]) for k, v in simt_emu.sls_mma(name, m, cfg, A, B, eta=eta, eta_f=eta_f).items()}
+    simt_emu.set_order(0)
+    tol = 1e-9
+    assert relf(out["K"], g["K"], 0.0) < tol
+    assert relf(np.einsum("kjii->kji", out["S"]), g["S_diag"], 0.0) < tol
+    assert relf(out["Phi_x"][N], g["Phi_x_last"], 0.0) < tol
+    assert relf(out["Phi_u"].sum(axis=(2, 3)), g["Phi_u_sum"], 0.0) < tol
+    for key in ("beta", "beta_f"):
+        assert relf(out[key], g[key], 0.0) < tol, key
+    assert np.array_equal(out["S"], np.swapaxes(out["S"], 2, 3))    # symmetrised exactly
