@@ -12,7 +12,8 @@
 //   Here an instance therefore is one warp with ~36 KB of shared memory (6 instances per SM): the iterate (slacks, multipliers,
 //   primal, both steps) and the per-stage vectors stay on chip; A_k, B_k come from global memory (at most 6 x 148 instances are in
 //   flight: 38 MB of stage matrices, L2 resident) -- as operand fragments one stage ahead in the factorisation sweep, through a
-//   three-slot cp.async ring (the tile buffers, idle outside the factorisation) in the vector sweeps; K_k and the Cholesky factors
+//   three-slot ring of 1-D bulk copies (cp.async.bulk on the TMA unit, one lane issues a stage, completion on an mbarrier per slot;
+//   the ring lives in the tile buffers, idle outside the factorisation) in the vector sweeps; K_k and the Cholesky factors
 //   are written to a global (L2) workspace by the factorisation and come back through the same ring.  Reciprocal slacks are
 //   recomputed (hardware seed + 2 Newton steps) instead of stored.  One CTA per instance lets the hardware scheduler replace a
 //   finished instance at once (iteration counts spread from 8 to 25).
@@ -49,7 +50,7 @@ __host__ __device__ inline size_t qp_warp_smem_doubles(int N) {
     const size_t NE = (size_t)(N + 1) * D::NZ;
     return D::MAT + 7 * mma_ev(NE) + 2 * mma_ev((size_t)N * NX) + 2 * mma_ev((size_t)N * NU)      // tiles; iterate; rp, Sc; dff, tu
          + mma_ev(NX) + mma_ev(D::KP) + 2 * mma_ev(D::NZ) + mma_ev(NU) + mma_ev(NU * D::LDA)       // gv, pv, rhs, dgn, uc, kk
-         + mma_ev(D::NZ + NX) + mma_ev(NU * NU) + 16;                                             // qdt, R2, profile counters
+         + mma_ev(D::NZ + NX) + mma_ev(NU * NU) + 16 + 4;                                         // qdt, R2, profile counters, ring barriers
 }
 
 template <int NX, int NU, int NC>
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
     double* kk = take(NU * LDA);
     double* qdt = take(NZ + NX); double* R2s = take(NU * NU);
     long long* pacc = reinterpret_cast<long long*>(take(16));
+    unsigned long long* rbar = reinterpret_cast<unsigned long long*>(take(4));      // one mbarrier per ring slot
 
     const double* Ag = a.A + (size_t)b * N * NX * LDG;
     const double* Bg = a.Bm + (size_t)b * N * NX * NU;
@@ -114,6 +116,11 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
         if (prof_on) { const long long t = clock64(); pacc[slot] += t - t_last; t_last = t; }
     };
 
+    if (lane == 0) {
+        for (int i = 0; i < D::NSLOT; ++i) mbar_init(rbar + i, 1);
+        mbar_init_fence();
+    }
+    unsigned ring_par = 0;                     // bit i: parity of the next completion of slot i (the same in every lane)
     if (lane < KP) pv[lane] = 0.0;
     if (lane < NU * NU) R2s[lane] = prm->R2[lane];
     for (int e = lane; e < NZ + NX; e += 32)
@@ -244,19 +251,23 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
     ZFrag<NX, NU, NT, KS, true> zsrc;
     zsrc.init(Ag, Bg, rp, lane);
     auto load_z = [&](const int k, double (&zf)[KS][NT]) { zsrc.load(k, Ag, zf); };
-    // stage k of the sweep ring: A_k, B_k, K_k -> slot k % 3 (always commits one group, possibly empty: the waits count groups)
+    // stage k of the sweep ring: A_k, B_k, K_k -> slot k % 3 as three bulk copies (TMA unit) issued by one lane, completion on the
+    // slot's mbarrier.  The caller has made sure (__syncwarp) that no lane still reads the slot.
     auto ring_issue = [&](const int k) {
-        if (k >= 0 && k < N) {
-            double* sl = ring + (k % D::NSLOT) * D::SLOT;
-            const double* Ak = Ag + (size_t)k * NX * LDG;
-            const double* Bk = Bg + (size_t)k * NX * NU;
-            const double* Kk = Kg + (size_t)k * NU * LDA;
-#pragma unroll 2
-            for (int e = lane; e < NX * LDA / 2; e += 32) cpa16(sl + 2 * e, Ak + 2 * e);
-            for (int e = lane; e < NX * NU / 2; e += 32) cpa16(sl + D::OFFB + 2 * e, Bk + 2 * e);
-            for (int e = lane; e < NU * LDA / 2; e += 32) cpa16(sl + D::OFFK + 2 * e, Kk + 2 * e);
+        if (lane == 0 && k >= 0 && k < N) {
+            const int si = k % D::NSLOT;
+            double* sl = ring + si * D::SLOT;
+            mbar_expect_tx(rbar + si, (unsigned)(D::SLOT * sizeof(double)));
+            bulk_g2s(sl, Ag + (size_t)k * NX * LDG, (unsigned)(NX * LDA * sizeof(double)), rbar + si);
+            bulk_g2s(sl + D::OFFB, Bg + (size_t)k * NX * NU, (unsigned)(NX * NU * sizeof(double)), rbar + si);
+            bulk_g2s(sl + D::OFFK, Kg + (size_t)k * NU * LDA, (unsigned)(NU * LDA * sizeof(double)), rbar + si);
         }
-        cpa_commit();
+    };
+    auto ring_wait = [&](const int k) -> const double* {
+        const int si = k % D::NSLOT;
+        mbar_wait(rbar + si, (ring_par >> si) & 1u);
+        ring_par ^= 1u << si;
+        return ring + si * D::SLOT;
     };
     mark(0);
 
@@ -404,7 +415,9 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
                 mark(5);
             }
         }
-        fence_block();      // K_k, L_k written above come back through cp.async issued by other lanes
+        fence_block();          // L_k written above is read back by other lanes
+        fence_proxy_async();    // K_k (global) and the tile buffers (shared) written above are next touched by bulk copies
+        __syncwarp();
 
         // ================================================================ predictor (pass 0) and corrector (pass 1): one copy of the sweep code
         const double tau_c = mu_c > 1e-8 ? 0.995 : 0.9999;
@@ -414,7 +427,7 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
             if (pass == 1) {
                 ring_issue(N - 1); ring_issue(N - 2);
                 // ---- corrector right-hand sides (e_dc doubles as scratch until the forward recursion overwrites it with the step)
-#pragma unroll 1
+#pragma unroll 2
                 for (int idx = lane; idx < NE; idx += 32) { const int k = idx / NZ; e_dc[idx] = rhs_entry(1, k, idx - k * NZ); }
                 __syncwarp();
                 mark(6);
@@ -428,9 +441,8 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
                     for (int k = N - 1; k >= 0; --k) {
                         ring_issue(k - 2);                 // into the slot of stage k + 1 (finished: barrier at the end of the previous stage)
                         if (lane < NX) gv[lane] = pl + rp_scale * Sc[k * NX + lane];
-                        cpa_wait<2>();
+                        const double* sl = ring_wait(k);
                         __syncwarp();
-                        const double* sl = ring + (k % D::NSLOT) * D::SLOT;
                         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
                         if (lane < NX) {
                             if (k > 0) {
@@ -496,9 +508,8 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
 #pragma unroll 1
                 for (int k = 0; k < N; ++k) {
                     ring_issue(k + 2);                     // into the slot of stage k - 1
-                    cpa_wait<2>();
+                    const double* sl = ring_wait(k);
                     __syncwarp();
-                    const double* sl = ring + (k % D::NSLOT) * D::SLOT;
                     const double* xk = e_dz + k * NZ;
                     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
                     if (lane < NX) {
@@ -539,12 +550,11 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
                     }
                     __syncwarp();
                 }
-                cpa_wait<0>();
             }
             mark(10);
             // ---- ratio test over all entries (rnmpc_qp.cuh ratio_entry)
             double rpm = 0.0, rdm = 0.0, S3 = 0.0, S4 = 0.0;
-#pragma unroll 1
+#pragma unroll 2
             for (int idx = lane; idx < NE; idx += 32) {
                 const double dz = e_dz[idx];
                 const double su = e_su[idx], sl = e_sl[idx], lu = e_lu[idx], ll = e_ll[idx];
@@ -596,7 +606,7 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
             const bool upd = chol_ok;
             const double so = skip_corr ? 0.0 : 1.0;
             const double* e_dz = skip_corr ? e_da : e_dc;
-#pragma unroll 1
+#pragma unroll 2
             for (int idx = lane; idx < NE; idx += 32) {
                 double su = e_su[idx], sl = e_sl[idx], lu = e_lu[idx], ll = e_ll[idx];
                 if (upd) {

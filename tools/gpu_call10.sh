@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "qp_vs_oracle or closed_loop_vs_oracle or sls_vs_reference or sls_ragged or other_horizons" > gpurun_out/r2d_pytest.log 2>&1; tail -3 gpurun_out/r2d_pytest.log
-{ timeout 300 python tools/latency_probe.py 4096; } > gpurun_out/r2d_latency.log 2>&1; cat gpurun_out/r2d_latency.log
-{ timeout 300 python tools/qp_phase_profile.py 4096 qp_kernel=4; } > gpurun_out/r2d_phases.log 2>&1; cat gpurun_out/r2d_phases.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "qp_vs_oracle or closed_loop_vs_oracle or sls_vs_reference or sls_ragged or other_horizons" > gpurun_out/r2e_pytest.log 2>&1; tail -3 gpurun_out/r2e_pytest.log
+{ timeout 300 python tools/latency_probe.py 4096; } > gpurun_out/r2e_latency.log 2>&1; cat gpurun_out/r2e_latency.log
+{ timeout 300 python tools/qp_phase_profile.py 4096 qp_kernel=4; } > gpurun_out/r2e_phases.log 2>&1; cat gpurun_out/r2e_phases.log

@@ -129,6 +129,13 @@ static inline void cpa_wait() {
     }
 }
 static inline void fence_block() {}
+// bulk copies + mbarrier: the copy happens at issue, the wait is a no-op (the protocol's barriers are not checked by the emulator)
+static inline void mbar_init(unsigned long long* bar, int) { *bar = 0; }
+static inline void mbar_init_fence() {}
+static inline void mbar_expect_tx(unsigned long long*, unsigned) {}
+static inline void bulk_g2s(double* dst, const double* src, unsigned bytes, unsigned long long*) { std::memcpy(dst, src, bytes); }
+static inline void mbar_wait(unsigned long long*, unsigned) {}
+static inline void fence_proxy_async() {}
 }  // namespace rnmpc
 namespace rnmpc {
 // D (8x8) += A (8x4) B (4x8) across the 32 lanes of the calling warp (fragment layout of mma.sync.m8n8k4.f64)
