@@ -158,6 +158,13 @@ __device__ __forceinline__ void chol_solve(const double (&L)[NU][NU], double (&f
     }
 }
 
+// bit views of a double (TMEM moves 32-bit columns)
+#ifndef RNMPC_EMU
+__device__ __forceinline__ unsigned double_lo(const double v) { return (unsigned)__double2loint(v); }
+__device__ __forceinline__ unsigned double_hi(const double v) { return (unsigned)__double2hiint(v); }
+__device__ __forceinline__ double hilo2double(const unsigned hi, const unsigned lo) { return __hiloint2double((int)hi, (int)lo); }
+#endif
+
 // 16-byte asynchronous global -> shared copies (LDGSTS) in a form the emulated build understands too (tools/simt_emu defers
 // the copy until the matching wait, so a read before the wait / barrier shows up as a wrong result on the CPU already).
 #ifndef RNMPC_EMU
@@ -191,7 +198,68 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, const unsigne
 }
 // orders earlier generic-proxy accesses (st.global / st.shared of this thread) before later asynchronous-proxy accesses (bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Tensor memory (TMEM, 256 KB per SM) as lane-private, column-indexed storage for fp64 state: thread i of warp w of a CTA owns TMEM lane
+// 32 (w % 4) + i; a tcgen05.ld / st with the 32x32b shape moves N consecutive 32-bit columns of every thread's own lane (a double =
+// 2 columns), at a warp-uniform, run-time column address -- registers that can be indexed.  tools/tmem_probe.cu checks this on the
+// device (0 mismatches over 1184 CTAs, 40 cycles for a dependent store -> load round trip).  One warp of the CTA allocates and frees.
+__device__ __forceinline__ void tmem_alloc_256(unsigned* slot_smem) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"((unsigned)__cvta_generic_to_shared(slot_smem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_256(const unsigned base) { asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(base) : "memory"); }
+__device__ __forceinline__ void tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ unsigned tmem_warp_base(const unsigned base, const int warp_in_cta) { return base + ((unsigned)(32 * (warp_in_cta & 3)) << 16); }
+template <int NREG> __device__ __forceinline__ void tm_ld_raw(const unsigned taddr, unsigned (&r)[NREG]);      // load + wait::ld
+template <int NREG> __device__ __forceinline__ void tm_st_raw(const unsigned taddr, const unsigned (&r)[NREG]);
+template <> __device__ __forceinline__ void tm_ld_raw<2>(const unsigned taddr, unsigned (&r)[2]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+template <> __device__ __forceinline__ void tm_ld_raw<4>(const unsigned taddr, unsigned (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+template <> __device__ __forceinline__ void tm_ld_raw<8>(const unsigned taddr, unsigned (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+template <> __device__ __forceinline__ void tm_ld_raw<16>(const unsigned taddr, unsigned (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr) : "memory");
+}
+template <> __device__ __forceinline__ void tm_st_raw<2>(const unsigned taddr, const unsigned (&r)[2]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
+}
+template <> __device__ __forceinline__ void tm_st_raw<4>(const unsigned taddr, const unsigned (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+template <> __device__ __forceinline__ void tm_st_raw<8>(const unsigned taddr, const unsigned (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+template <> __device__ __forceinline__ void tm_st_raw<16>(const unsigned taddr, const unsigned (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tm_wait_st() { __syncwarp(); asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 #endif
+// ND doubles of this thread's TMEM lane from / to 2 ND consecutive columns (both builds: tools/simt_emu provides tm_*_raw too)
+// (the tcgen05 instructions are warp-collective and "aligned": the lanes re-converge first -- the compiler does not know that they must)
+template <int ND>
+__device__ __forceinline__ void tm_ld(const unsigned taddr, double (&v)[ND]) {
+    unsigned r[2 * ND];
+    __syncwarp();
+    tm_ld_raw<2 * ND>(taddr, r);
+#pragma unroll
+    for (int i = 0; i < ND; ++i) v[i] = hilo2double(r[2 * i + 1], r[2 * i]);
+}
+template <int ND>
+__device__ __forceinline__ void tm_st(const unsigned taddr, const double (&v)[ND]) {
+    unsigned r[2 * ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) { r[2 * i] = double_lo(v[i]); r[2 * i + 1] = double_hi(v[i]); }
+    __syncwarp();
+    tm_st_raw<2 * ND>(taddr, r);
+}
 
 #ifndef RNMPC_EMU      // the slot machinery below stages with cp.async: not emulated
 // Shared-memory working set of one slot (see SlotSmem below for the bank-conflict padding).

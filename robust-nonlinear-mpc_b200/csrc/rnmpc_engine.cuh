@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -14,6 +15,7 @@
 #include "rnmpc_qp_block.cuh"
 #include "rnmpc_qp_mma.cuh"
 #include "rnmpc_qp_warp.cuh"
+#include "rnmpc_qp_tmem.cuh"
 #include "rnmpc_sls.cuh"
 #include "rnmpc_sls_mma.cuh"
 
@@ -210,8 +212,13 @@ struct Engine : IEngine {
     // bounds, working set fits shared memory): the one-warp-per-instance throughput kernel (rnmpc_qp_warp.cuh) for batches of at least
     // qp_warp_min instances, the one-CTA-per-instance latency kernel (rnmpc_qp_mma.cuh) below; 1 = instance-per-slot kernel (with its
     // hand-off), 2 = the round-1 one-CTA-per-instance kernel (rnmpc_qp_block.cuh), 3 = rnmpc_qp_mma.cuh at every batch size,
-    // 4 = rnmpc_qp_warp.cuh at every batch size.  1 and 2 remain for comparison.
+    // 4 = rnmpc_qp_warp.cuh at every batch size, 5 = rnmpc_qp_tmem.cuh (one warp per instance, iterate in tensor memory; the
+    // automatic choice for large batches when the horizon fits its 16 stage columns, else rnmpc_qp_warp.cuh).  1 and 2 remain for comparison.
     int qp_kernel = 0;
+    bool qp_tm_ok = false;
+    size_t qp_tm_smem = 0;
+    int* qp_work = nullptr;        // [1] instance counter of qp_tm_kernel's persistent warps
+    int n_sm = 148;
     int qp_warp_min = 600;         // "qp_warp_min": smallest batch the automatic selection gives to the one-warp-per-instance kernel
     bool qp_warp_ok = false;
     size_t qp_warp_smem = 0;
@@ -328,6 +335,17 @@ struct Engine : IEngine {
         qp_mma_ok = qp_mma_smem <= 227 * 1024 &&
                     cudaFuncSetAttribute(qp_mma_kernel<NX, NU, kHorizonFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
                     cudaFuncSetAttribute(qp_mma_kernel<NX, NU, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+        cudaGetLastError();
+        {
+            cudaDeviceProp prop;
+            if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) n_sm = prop.multiProcessorCount;
+        }
+        qp_tm_smem = qp_tm_smem_bytes<NX, NU>(N);
+        qp_tm_ok = N + 1 <= kTmMaxStages && qp_tm_smem <= 227 * 1024 && alloc("qp_work", qp_work, 1) == 0 &&
+                   cudaFuncSetAttribute(qp_tm_kernel<NX, NU, kHorizonFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
+                   cudaFuncSetAttribute(qp_tm_kernel<NX, NU, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
+                   cudaFuncSetAttribute(qp_tm_kernel<NX, NU, kHorizonFast>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) == cudaSuccess &&
+                   cudaFuncSetAttribute(qp_tm_kernel<NX, NU, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) == cudaSuccess;
         cudaGetLastError();
         qp_warp_smem = qp_warp_smem_doubles<NX, NU>(N) * sizeof(double);
         qp_warp_ok = qp_warp_smem <= 227 * 1024 && alloc("Kw", Kw, B * N * NU * LDA) == 0 &&
@@ -465,7 +483,14 @@ struct Engine : IEngine {
         cudaEvent_t te = region_begin(1, st);
         const bool may_warm = a.warm != 0;
         const bool plain = diag_cost && !may_warm && hi_in == nullptr && lo_in == nullptr && q_lin == nullptr;
-        if (plain && qp_warp_ok && (qp_kernel == 4 || (qp_kernel == 0 && B >= qp_warp_min))) {
+        if (plain && qp_tm_ok && qp_warp_ok && (qp_kernel == 5 || (qp_kernel == 0 && B >= qp_warp_min))) {
+            // one warp per instance, iterate in tensor memory, persistent CTAs of four warps (rnmpc_qp_tmem.cuh)
+            a.Kq = Kw; a.work = qp_work;
+            cudaMemsetAsync(qp_work, 0, sizeof(int), st);
+            const unsigned gridt = (unsigned)std::min<long long>(2LL * n_sm, ((long long)B + kTmWarps - 1) / kTmWarps);
+            if (N == kHorizonFast) qp_tm_kernel<NX, NU, kHorizonFast><<<gridt, 32 * kTmWarps, qp_tm_smem, st>>>(a, d_prm);
+            else qp_tm_kernel<NX, NU, 0><<<gridt, 32 * kTmWarps, qp_tm_smem, st>>>(a, d_prm);
+        } else if (plain && qp_warp_ok && (qp_kernel == 4 || qp_kernel == 5 || (qp_kernel == 0 && B >= qp_warp_min))) {
             // one warp (one CTA of 32 threads) per instance: the throughput kernel for large batches (rnmpc_qp_warp.cuh)
             a.Kq = Kw;
             if (N == kHorizonFast) qp_warp_kernel<NX, NU, kHorizonFast><<<(unsigned)B, 32, qp_warp_smem, st>>>(a, d_prm);

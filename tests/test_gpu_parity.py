@@ -26,7 +26,7 @@ def np_(t):
     return t.detach().cpu().numpy()
 
 
-QP_KERNELS = ["mma", "warp", "slot", "block"]
+QP_KERNELS = ["mma", "warp", "tmem", "slot", "block"]
 
 
 def set_qp_kernel(s, which):
@@ -37,6 +37,8 @@ def set_qp_kernel(s, which):
         s.set_option("qp_kernel", 3)
     elif which == "warp":
         s.set_option("qp_kernel", 4)
+    elif which == "tmem":      # one warp per instance, iterate in tensor memory (rnmpc_qp_tmem.cuh, default for large batches)
+        s.set_option("qp_kernel", 5)
     elif which == "slot":
         s.set_option("qp_kernel", 1)
         s.set_option("qp_block_max", 0)

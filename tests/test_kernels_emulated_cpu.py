@@ -23,7 +23,7 @@ def _linearize(m, X, U):
     return A, Bm, c
 
 
-QP_KERNELS = {"qp_mma_kernel": 0, "qp_warp_kernel": 1}
+QP_KERNELS = {"qp_mma_kernel": 0, "qp_warp_kernel": 1, "qp_tm_kernel": 2}
 
 
 @pytest.fixture(params=sorted(QP_KERNELS))

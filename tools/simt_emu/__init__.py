@@ -36,7 +36,8 @@ def set_order(order):
 
 
 def set_qp_kernel(k):
-    """Kernel run by qp_mma(): 0 = qp_mma_kernel (one CTA of four warps per instance), 1 = qp_warp_kernel (one warp per instance)."""
+    """Kernel run by qp_mma(): 0 = qp_mma_kernel (one CTA of four warps per instance), 1 = qp_warp_kernel (one warp per instance),
+    2 = qp_tm_kernel (one warp per instance, iterate in tensor memory)."""
     load().emu_set_qp_kernel(int(k))
 
 

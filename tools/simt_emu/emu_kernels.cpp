@@ -7,6 +7,7 @@
 #include "../../include/rnmpc_b200.h"
 #include "../../robust-nonlinear-mpc_b200/csrc/rnmpc_qp_mma.cuh"
 #include "../../robust-nonlinear-mpc_b200/csrc/rnmpc_qp_warp.cuh"
+#include "../../robust-nonlinear-mpc_b200/csrc/rnmpc_qp_tmem.cuh"
 #include "../../robust-nonlinear-mpc_b200/csrc/rnmpc_sls_mma.cuh"
 
 namespace rnmpc {
@@ -32,13 +33,32 @@ static void fill_params(const rnmpc_config* cfg, Params<NX, NU>& hp) {
     hp.h = cfg->h;
 }
 
-static int g_qp_kernel = 0;    // 0: qp_mma_kernel (one CTA of 4 warps per instance), 1: qp_warp_kernel (one warp per instance)
+static int g_qp_kernel = 0;    // 0: qp_mma_kernel (one CTA of 4 warps per instance), 1: qp_warp_kernel (one warp per instance),
+                               // 2: qp_tm_kernel (one warp per instance, iterate in tensor memory, persistent CTAs of 4 warps)
 extern "C" void emu_set_qp_kernel(int k) { g_qp_kernel = k; }
 
 template <int NX, int NU>
 static int run_qp_mma(const rnmpc_config* cfg, QpArgs a) {
     Params<NX, NU> hp;
     fill_params<NX, NU>(cfg, hp);
+    if (g_qp_kernel == 2) {
+        if (qp_tm_smem_bytes<NX, NU>(a.N) > sizeof(smem_raw) || a.N + 1 > kTmMaxStages) return -4;
+        std::vector<double> Kw((size_t)a.B * a.N * NU * QpWarp<NX, NU>::LDA, 0.0), Lw((size_t)a.B * a.N * NU * NU, 0.0);
+        a.Kq = Kw.data(); a.Lq = Lw.data();
+        int work = 0;
+        a.work = &work;
+        const int grid = a.B >= 6 ? 2 : 1;          // two persistent CTAs: the warps of the second find the counter advanced by the first
+        for (int blk = 0; blk < grid; ++blk) {
+            simt::cpa_reset();
+            if (blk == 1) work = a.B / 2;            // (the emulator runs the blocks one after the other: hand the second CTA its share)
+            const int Bsave = a.B;
+            if (blk == 0 && grid == 2) a.B = Bsave / 2;
+            if (a.N == 15 && !g_generic) simt::run_block(32 * kTmWarps, dim3(blk), dim3(grid), [&]() { qp_tm_kernel<NX, NU, 15>(a, &hp); });
+            else simt::run_block(32 * kTmWarps, dim3(blk), dim3(grid), [&]() { qp_tm_kernel<NX, NU, 0>(a, &hp); });
+            a.B = Bsave;
+        }
+        return 0;
+    }
     if (g_qp_kernel == 1) {
         if (qp_warp_smem_doubles<NX, NU>(a.N) * sizeof(double) > sizeof(smem_raw)) return -4;
         std::vector<double> Kw((size_t)a.B * a.N * NU * QpWarp<NX, NU>::LDA, 0.0), Lw((size_t)a.B * a.N * NU * NU, 0.0);

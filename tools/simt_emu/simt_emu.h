@@ -136,6 +136,29 @@ static inline void mbar_expect_tx(unsigned long long*, unsigned) {}
 static inline void bulk_g2s(double* dst, const double* src, unsigned bytes, unsigned long long*) { std::memcpy(dst, src, bytes); }
 static inline void mbar_wait(unsigned long long*, unsigned) {}
 static inline void fence_proxy_async() {}
+// tensor memory: 128 lanes x 512 columns of 32 bits per (emulated) SM = per block; address = (lane << 16) | column
+}  // namespace rnmpc
+namespace simt { inline unsigned g_tmem[128][512]; }
+namespace rnmpc {
+static inline unsigned double_lo(const double v) { unsigned long long u; std::memcpy(&u, &v, 8); return (unsigned)(u & 0xffffffffu); }
+static inline unsigned double_hi(const double v) { unsigned long long u; std::memcpy(&u, &v, 8); return (unsigned)(u >> 32); }
+static inline double hilo2double(const unsigned hi, const unsigned lo) { unsigned long long u = ((unsigned long long)hi << 32) | lo; double v; std::memcpy(&v, &u, 8); return v; }
+static inline void tmem_alloc_256(unsigned* slot) { *slot = 0; }
+static inline void tmem_dealloc_256(unsigned) {}
+static inline void tmem_fence_before_sync() {}
+static inline void tmem_fence_after_sync() {}
+static inline unsigned tmem_warp_base(const unsigned base, const int warp_in_cta) { return base + ((unsigned)(32 * (warp_in_cta & 3)) << 16); }
+template <int NREG> static inline void tm_ld_raw(const unsigned taddr, unsigned (&r)[NREG]) {
+    const int lane = (int)(taddr >> 16) + (simt::tid() & 31), col = (int)(taddr & 0xffffu);
+    if (lane >= 128 || col + NREG > 512) { std::fprintf(stderr, "tmem load out of range\n"); std::abort(); }
+    for (int i = 0; i < NREG; ++i) r[i] = simt::g_tmem[lane][col + i];
+}
+template <int NREG> static inline void tm_st_raw(const unsigned taddr, const unsigned (&r)[NREG]) {
+    const int lane = (int)(taddr >> 16) + (simt::tid() & 31), col = (int)(taddr & 0xffffu);
+    if (lane >= 128 || col + NREG > 512) { std::fprintf(stderr, "tmem store out of range\n"); std::abort(); }
+    for (int i = 0; i < NREG; ++i) simt::g_tmem[lane][col + i] = r[i];
+}
+static inline void tm_wait_st() {}
 }  // namespace rnmpc
 namespace rnmpc {
 // D (8x8) += A (8x4) B (4x8) across the 32 lanes of the calling warp (fragment layout of mma.sync.m8n8k4.f64)
