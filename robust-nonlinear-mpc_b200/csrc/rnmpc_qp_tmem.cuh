@@ -277,9 +277,11 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
             tm_ld<4>(tcol(k, TM_SU), v);
             tm_ld<2>(tcol(k, TM_ZY), w);
             const double su = v[0], sl = v[1], lu = v[2], ll = v[3], dza = w[1];
+            // branch-free (a lane without a bound has reciprocal slack 0 and multiplier 0): the two reciprocals run side by side
+            const double iu = rc(su), il = rc(sl);
             double gq = qd_of(k) * w[0];
-            if (su < kBig) { const double iu = fast_rcp(su); gq = fma(sigma_mu + dza * (lu * iu * dza - lu), iu, gq); }
-            if (sl < kBig) { const double il = fast_rcp(sl); gq = fma(-(sigma_mu + dza * (ll * il * dza + ll)), il, gq); }
+            gq = fma(sigma_mu + dza * (lu * iu * dza - lu), iu, gq);
+            gq = fma(-(sigma_mu + dza * (ll * il * dza + ll)), il, gq);
             return gq;
         };
         mark(0);
@@ -368,20 +370,26 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                             }
                         const bool ok = chol_inplace<NU>(L);
                         chol_ok = chol_ok && ok;
+                        // one triangular solve per lane: lanes < NX a column of (A'SB)' -> column of K, lane NX the vector t -> d
+                        double f[NU];
                         if (lane < NX) {
-                            double f[NU];
 #pragma unroll
                             for (int p = 0; p < NU; ++p) f[p] = buf1[lane * LDW + CB + p];
-                            chol_solve<NU>(L, f);
+                        } else {
+#pragma unroll
+                            for (int p = 0; p < NU; ++p) f[p] = rhs[NX + p] + buf1[(CB + p) * LDW + CP] + rp_scale * buf1[(CB + p) * LDW + CRP];
+                            if (lane == NX) {
+#pragma unroll
+                                for (int p = 0; p < NU; ++p) uc[p] = f[p];
+                            }
+                        }
+                        chol_solve<NU>(L, f);
+                        if (lane < NX) {
 #pragma unroll
                             for (int p = 0; p < NU; ++p) { kk[p * LDA + lane] = -f[p]; Kg[((size_t)k * NU + p) * LDA + lane] = -f[p]; }
                         } else if (lane == NX) {
-                            double d[NU];
 #pragma unroll
-                            for (int p = 0; p < NU; ++p) { d[p] = rhs[NX + p] + buf1[(CB + p) * LDW + CP] + rp_scale * buf1[(CB + p) * LDW + CRP]; uc[p] = d[p]; }
-                            chol_solve<NU>(L, d);
-#pragma unroll
-                            for (int p = 0; p < NU; ++p) dff[k * NU + p] = -d[p];
+                            for (int p = 0; p < NU; ++p) dff[k * NU + p] = -f[p];
                         } else if (lane == NX + 1) {
 #pragma unroll
                             for (int p = 0; p < NU; ++p)
@@ -459,6 +467,8 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                         // lanes NX .. NZ-1: t_k = ru_k + B_k' g_k (kept in tu for the feed-forward); rx, ru from the TMEM columns of the stage
                         const int r = lane < NX ? lane : NX - 1;
                         const int p = (lane >= NX && lane < NZ) ? lane - NX : 0;
+                        const int bw_off = lane < NX ? lane : (lane < NZ ? D::OFFB + (lane - NX) : 0);
+                        const int bw_stride = lane < NX ? LDA : NU;
                         double pl = rhs_corr(N);
 #pragma unroll 1
                         for (int k = N - 1; k >= 0; --k) {
@@ -467,31 +477,19 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                             const double rk = rhs_corr(k);
                             const double* sl = ring_wait(k);
                             __syncwarp();
-                            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                            if (lane < NX) {
-                                if (k > 0) {
-                                    const double* col = sl + r;
-                                    a0 = rk;
-#pragma unroll
-                                    for (int m = 0; m + 3 < NX; m += 4) {
-                                        a0 = fma(col[m * LDA], gv[m], a0); a1 = fma(col[(m + 1) * LDA], gv[m + 1], a1);
-                                        a2 = fma(col[(m + 2) * LDA], gv[m + 2], a2); a3 = fma(col[(m + 3) * LDA], gv[m + 3], a3);
-                                    }
-#pragma unroll
-                                    for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(col[m * LDA], gv[m], a0);
-                                }
-                            } else if (lane < NZ) {
-                                const double* col = sl + D::OFFB + p;
-                                a0 = rk;
+                            // one code path for all lanes: column r of A_k (lanes < NX) or column p of B_k (lanes NX .. NZ-1), own stride
+                            double a0 = rk, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                            {
+                                const double* col = sl + bw_off;
 #pragma unroll
                                 for (int m = 0; m + 3 < NX; m += 4) {
-                                    a0 = fma(col[m * NU], gv[m], a0); a1 = fma(col[(m + 1) * NU], gv[m + 1], a1);
-                                    a2 = fma(col[(m + 2) * NU], gv[m + 2], a2); a3 = fma(col[(m + 3) * NU], gv[m + 3], a3);
+                                    a0 = fma(col[m * bw_stride], gv[m], a0); a1 = fma(col[(m + 1) * bw_stride], gv[m + 1], a1);
+                                    a2 = fma(col[(m + 2) * bw_stride], gv[m + 2], a2); a3 = fma(col[(m + 3) * bw_stride], gv[m + 3], a3);
                                 }
 #pragma unroll
-                                for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(col[m * NU], gv[m], a0);
-                                tu[k * NU + p] = (a0 + a1) + (a2 + a3);
+                                for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(col[m * bw_stride], gv[m], a0);
                             }
+                            if (lane >= NX && lane < NZ) tu[k * NU + p] = (a0 + a1) + (a2 + a3);
                             __syncwarp();
                             if (lane < NX && k > 0) {
                                 double acc = (a0 + a1) + (a2 + a3);
@@ -539,28 +537,25 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                     const double su = v[0], sl = v[1], lu = v[2], ll = v[3];
                     const double dza = w[0];
                     const double smu = pass == 1 ? sigma_mu : 0.0;
-                    if (su < kBig) {
-                        const double iu = fast_rcp(su);
-                        const double ru = lu * iu;
-                        const double tgt = pass == 1 ? smu + dza * (ru * dza - lu) : 0.0;
-                        const double dlu = tgt * iu - lu + ru * dz;
-                        rpm = fmax(rpm, dz * iu);
-                        if (dlu < 0.0) rdm = fmax(rdm, -dlu * fast_rcp(lu));
-                        if (pass == 0) { S3 = fma(-dz, lu, S3); S4 = fma(-dz, dlu, S4); }
-                    }
-                    if (sl < kBig) {
-                        const double il = fast_rcp(sl);
-                        const double rl = ll * il;
-                        const double tgt = pass == 1 ? smu + dza * (rl * dza + ll) : 0.0;
-                        const double dll = tgt * il - ll - rl * dz;
-                        rpm = fmax(rpm, -dz * il);
-                        if (dll < 0.0) rdm = fmax(rdm, -dll * fast_rcp(ll));
-                        if (pass == 0) { S3 = fma(dz, ll, S3); S4 = fma(dz, dll, S4); }
-                    }
+                    // branch-free: a lane without a bound has reciprocal slack 0 and multiplier 0 (every term vanishes); the four
+                    // reciprocals are independent and run side by side
+                    const double iu = rc(su), il = rc(sl);
+                    const double ilu = fast_rcp(lu), ill = fast_rcp(ll);          // inf for a zero multiplier: discarded by the selects below
+                    const double ru = lu * iu, rl = ll * il;
+                    const double tgu = pass == 1 ? smu + dza * (ru * dza - lu) : 0.0;
+                    const double tgl = pass == 1 ? smu + dza * (rl * dza + ll) : 0.0;
+                    const double dlu = tgu * iu - lu + ru * dz;
+                    const double dll = tgl * il - ll - rl * dz;
+                    rpm = fmax(rpm, fmax(dz * iu, -dz * il));
+                    rdm = fmax(rdm, fmax(dlu < 0.0 ? -dlu * ilu : 0.0, dll < 0.0 ? -dll * ill : 0.0));
+                    if (pass == 0) { S3 = fma(-dz, lu, S3); S4 = fma(-dz, dlu, S4); S3 = fma(dz, ll, S3); S4 = fma(dz, dll, S4); }
                 };
                 {
                     const int r = lane < NX ? lane : NX - 1;
-                    const int p = (lane >= NX && lane < NZ) ? lane - NX : 0;
+                    const int fw_off = lane < NX ? lane * LDA : (lane < NZ ? D::OFFK + (lane - NX) * LDA : 0);
+                    const double* fw_init = lane < NX ? rp + lane : (lane < NZ ? dff + (lane - NX) : rp);
+                    const int fw_istride = lane < NX ? NX : (lane < NZ ? NU : 0);
+                    const double fw_scale = lane < NX ? rp_scale : 1.0;
                     double dxk = 0.0;                          // lanes < NX: dx_k[lane]
                     if (lane < NX) xs0[lane] = 0.0;
 #pragma unroll 1
@@ -570,35 +565,20 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                         ring_issue(k + (T::NSLOT - 1));        // into the slot of stage k - 1
                         const double* sl = ring_wait(k);
                         __syncwarp();
-                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                        if (lane < NX) {
-                            const double* row = sl + r * LDA;
-                            a0 = rp_scale * rp[k * NX + r];
-                            if (k > 0) {
+                        // one code path for all lanes: row r of A_k from rp_scale rp_k (lanes < NX) or row p of K_k from d_k (lanes NX .. NZ-1)
+                        double a0 = fw_scale * fw_init[k * fw_istride], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                        if (k > 0) {
+                            const double* row = sl + fw_off;
 #pragma unroll
-                                for (int m = 0; m + 3 < NX; m += 4) {
-                                    const double2 r01 = *reinterpret_cast<const double2*>(row + m), r23 = *reinterpret_cast<const double2*>(row + m + 2);
-                                    a0 = fma(r01.x, xk[m], a0); a1 = fma(r01.y, xk[m + 1], a1);
-                                    a2 = fma(r23.x, xk[m + 2], a2); a3 = fma(r23.y, xk[m + 3], a3);
-                                }
-#pragma unroll
-                                for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(row[m], xk[m], a0);
+                            for (int m = 0; m + 3 < NX; m += 4) {
+                                const double2 r01 = *reinterpret_cast<const double2*>(row + m), r23 = *reinterpret_cast<const double2*>(row + m + 2);
+                                a0 = fma(r01.x, xk[m], a0); a1 = fma(r01.y, xk[m + 1], a1);
+                                a2 = fma(r23.x, xk[m + 2], a2); a3 = fma(r23.y, xk[m + 3], a3);
                             }
-                        } else if (lane < NZ) {
-                            const double* row = sl + D::OFFK + p * LDA;
-                            a0 = dff[k * NU + p];
-                            if (k > 0) {
 #pragma unroll
-                                for (int m = 0; m + 3 < NX; m += 4) {
-                                    const double2 r01 = *reinterpret_cast<const double2*>(row + m), r23 = *reinterpret_cast<const double2*>(row + m + 2);
-                                    a0 = fma(r01.x, xk[m], a0); a1 = fma(r01.y, xk[m + 1], a1);
-                                    a2 = fma(r23.x, xk[m + 2], a2); a3 = fma(r23.y, xk[m + 3], a3);
-                                }
-#pragma unroll
-                                for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(row[m], xk[m], a0);
-                            }
-                            xk[NX + p] = (a0 + a1) + (a2 + a3);
+                            for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(row[m], xk[m], a0);
                         }
+                        if (lane >= NX && lane < NZ) xk[lane] = (a0 + a1) + (a2 + a3);
                         __syncwarp();
                         double dz = dxk;                        // this lane's entry of stage k
                         if (lane < NX) {
@@ -649,18 +629,13 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                     double su = v[TM_SU], sl = v[TM_SL], lu = v[TM_LU], ll = v[TM_LL];
                     if (upd) {
                         const double dza = v[TM_DA], dz = skip_corr ? v[TM_DA] : v[TM_DC];
-                        if (su < kBig) {
-                            const double iu = fast_rcp(su);
-                            const double ru = lu * iu;
-                            const double dlu = so * (sigma_mu + dza * (ru * dza - lu)) * iu - lu + ru * dz;
-                            su -= ap * dz; lu += ad * dlu;
-                        }
-                        if (sl < kBig) {
-                            const double il = fast_rcp(sl);
-                            const double rl = ll * il;
-                            const double dll = so * (sigma_mu + dza * (rl * dza + ll)) * il - ll - rl * dz;
-                            sl += ap * dz; ll += ad * dll;
-                        }
+                        // branch-free (no bound: slack 1e300 stays, reciprocal 0, multiplier 0)
+                        const double iu = rc(su), il = rc(sl);
+                        const double ru = lu * iu, rl = ll * il;
+                        const double dlu = so * (sigma_mu + dza * (ru * dza - lu)) * iu - lu + ru * dz;
+                        const double dll = so * (sigma_mu + dza * (rl * dza + ll)) * il - ll - rl * dz;
+                        if (su < kBig) { su -= ap * dz; lu += ad * dlu; }
+                        if (sl < kBig) { sl += ap * dz; ll += ad * dll; }
                         const double w[4] = {su, sl, lu, ll};
                         tm_st<4>(tcol(k, 0), w);
                         const double zy[1] = {v[TM_ZY] + ap * dz};
