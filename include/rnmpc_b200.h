@@ -180,8 +180,10 @@ int rnmpc_closed_loop_host(rnmpc_handle* h, int B, int steps, const double* h_x0
  * Unknown names return -1. */
 int rnmpc_set_option(rnmpc_handle* h, const char* name, double value);
 
-/* Measured FP64 FMA peak of the device (TFLOP/s), for the roofline denominator. */
+/* Measured FP64 peaks of the device (TFLOP/s), for the roofline denominator: DFMA (16 independent chains per thread) and the FP64
+ * tensor pipe (mma.sync.m8n8k4.f64, 8 independent chains per warp) -- the QP and fast-SLS kernels run their products on the latter. */
 int rnmpc_fp64_peak(int device, double* tflops);
+int rnmpc_fp64_mma_peak(int device, double* tflops);
 
 /* Device times (ms) of the last rnmpc_solve when timing is enabled: out[0] linearisation (t_jac_ms), out[1] last QP
  * (t_qp_ms), out[2] last fast-SLS kernel (t_backward_ms); mirrors SCP_SLS_jit.py:339-341, qp_jit.py:392-395,

@@ -23,6 +23,7 @@ def load():
             build()
         _lib = C.CDLL(LIB)
         _lib.rnmpc_cpu_closed_loop.restype = C.c_longlong
+        _lib.rnmpc_cpu_closed_loop_resume.restype = C.c_longlong
     return _lib
 
 
@@ -46,3 +47,38 @@ def closed_loop(m, cfg, x0, W, steps, X0, U0, threads=0, return_ok=False):
     if return_ok:
         return states, inputs, int(nfail), ok
     return states, inputs, int(nfail)
+
+
+class ResumableLoops:
+    """B closed loops that can be advanced in several calls (bench.py: warm-up MPC steps in an untimed call, the timed steps in the
+    next one) with the GPU arm's Monte-Carlo rule: a scenario whose solve failed is frozen (freeze_failed) and costs nothing afterwards."""
+
+    def __init__(self, m, cfg, x0, X0, U0, freeze_failed=True, threads=0):
+        d = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+        self.m, self.cfg, self.threads, self.freeze = m, cfg, int(threads), bool(freeze_failed)
+        self.x = d(x0).reshape(-1, m.nx).copy()
+        self.B = self.x.shape[0]
+        self.X, self.U = d(X0).copy(), d(U0).copy()
+        self.prevX, self.prevU = np.zeros_like(self.X), np.zeros_like(self.U)
+        self.have_prev = np.zeros(self.B, dtype=np.int32)
+        self.alive = np.ones(self.B, dtype=np.int32)
+        self.started = False
+        self._keep = [d(cfg[k]) for k in ("Q", "R", "Qf", "Q_reg", "R_reg", "Q_reg_f")] + [d(m.E), d(m.x_ub), d(m.x_lb), d(m.u_ub), d(m.u_lb),
+                                                                                   d(m.x_ub), d(m.x_lb)]
+
+    def advance(self, W, steps):
+        """steps MPC steps of every live scenario with disturbances W [B,steps,nx] (None: noise free) -> (live solves, failed solves)."""
+        lib = load()
+        m, cfg = self.m, self.cfg
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        Wc = None if W is None else np.ascontiguousarray(np.asarray(W, dtype=np.float64)).reshape(self.B, steps, m.nx)
+        states = np.empty((self.B, steps + 1, m.nx))
+        live = C.c_longlong(0)
+        nfail = lib.rnmpc_cpu_closed_loop_resume(C.c_int(m.model_id), C.c_int(cfg["N"]), C.c_int(cfg["rti"]), C.c_int(cfg["fast_sls_rti_steps"]),
+                                                 *[p(a) for a in self._keep], C.c_double(0.05), C.c_int(self.B), C.c_int(steps), p(self.x), p(Wc),
+                                                 p(self.X), p(self.U), p(self.prevX), p(self.prevU), p(self.have_prev), p(self.alive),
+                                                 C.c_int(int(self.freeze)), C.c_int(int(self.started)), p(states), None, C.c_int(self.threads),
+                                                 C.byref(live))
+        self.x = np.ascontiguousarray(states[:, steps])
+        self.started = True
+        return int(live.value), int(nfail)

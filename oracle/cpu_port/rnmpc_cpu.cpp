@@ -349,25 +349,47 @@ bool solve(const Cfg& g, Work<M::NX, M::NU>& w, const double* x0) {
     return true;
 }
 
+// Resumable state of a scenario between two calls (bench.py runs the warm-up steps and the timed steps as two calls).
+struct Carry {
+    double* X;        // [B][N+1][NX] nominal trajectory in / out
+    double* U;        // [B][N][NU]
+    double* prevX;    // [B][N+1][NX] Q3 history in / out
+    double* prevU;    // [B][N][NU]
+    int* have_prev;   // [B]
+    int* alive;       // [B] 1 = still running; with freeze_failed a scenario whose solve failed stops (the GPU arm's sticky_fail)
+    int freeze_failed;
+    int shift_first;  // 1: this call continues a loop -> reset_warm_start also before its first step
+    long long* live;  // [1] out: solves attempted (= scenario steps of live scenarios)
+};
+
 template <class M>
 long long closed_loop(const Cfg& g, int B, int steps, const double* x0, const double* W, const double* X0, const double* U0,
-                      double* states, double* inputs, int threads, int* solve_ok) {
+                      double* states, double* inputs, int threads, int* solve_ok, const Carry* cy = nullptr) {
     constexpr int NX = M::NX, NU = M::NU;
     const int N = g.N;
-    std::atomic<long long> nfail{0};
+    std::atomic<long long> nfail{0}, nlive{0};
     std::atomic<int> next{0};
     auto worker = [&]() {
       for (;;) {
         const int b = next.fetch_add(1);
         if (b >= B) break;
         Work<NX, NU> w(N);
-        std::memcpy(w.X.data(), X0 + (size_t)b * (N + 1) * NX, sizeof(double) * (N + 1) * NX);
-        std::memcpy(w.U.data(), U0 + (size_t)b * N * NU, sizeof(double) * N * NU);
+        const size_t nxs = (size_t)(N + 1) * NX, nus = (size_t)N * NU;
+        std::memcpy(w.X.data(), (cy ? cy->X : X0) + b * nxs, sizeof(double) * nxs);
+        std::memcpy(w.U.data(), (cy ? cy->U : U0) + b * nus, sizeof(double) * nus);
+        bool alive = true;
+        if (cy) {
+            std::memcpy(w.prevX.data(), cy->prevX + b * nxs, sizeof(double) * nxs);
+            std::memcpy(w.prevU.data(), cy->prevU + b * nus, sizeof(double) * nus);
+            w.have_prev = cy->have_prev[b] != 0;
+            alive = cy->alive[b] != 0;
+        }
         double x[NX], xn[NX], u[NU];
         std::memcpy(x, x0 + (size_t)b * NX, sizeof(x));
         for (int i = 0; i < steps; ++i) {
             if (states) std::memcpy(states + ((size_t)b * (steps + 1) + i) * NX, x, sizeof(x));
-            if (i > 0) {   // reset_warm_start (SCP_SLS_jit.py:505-518)
+            if (!alive) { if (solve_ok) solve_ok[(size_t)b * steps + i] = 0; continue; }      // frozen: no work, not counted
+            if (i > 0 || (cy && cy->shift_first)) {   // reset_warm_start (SCP_SLS_jit.py:505-518)
                 double xN[NX], uN[NU], xo[NX];
                 std::memcpy(xN, &w.X[N * NX], sizeof(xN)); std::memcpy(uN, &w.U[(N - 1) * NU], sizeof(uN));
                 rk4_step<M, double>(xN, uN, g.h, xo);
@@ -375,15 +397,25 @@ long long closed_loop(const Cfg& g, int B, int steps, const double* x0, const do
                 std::memmove(&w.U[0], &w.U[NU], sizeof(double) * (N - 1) * NU);
                 std::memcpy(&w.X[N * NX], xo, sizeof(xo));
             }
+            nlive.fetch_add(1);
             const bool ok = solve<M>(g, w, x);
             if (!ok) nfail.fetch_add(1);
             if (solve_ok) solve_ok[(size_t)b * steps + i] = ok ? 1 : 0;      // per scenario and step (the loop goes on after a failure)
+            if (!ok && cy && cy->freeze_failed) { alive = false; continue; }
             std::memcpy(u, &w.U[0], sizeof(u));
             if (inputs) std::memcpy(inputs + ((size_t)b * steps + i) * NU, u, sizeof(u));
             rk4_step<M, double>(x, u, g.h, xn);
             for (int r = 0; r < NX; ++r) { double s = xn[r]; if (W) for (int j = 0; j < NX; ++j) s += g.E[r * NX + j] * W[((size_t)b * steps + i) * NX + j]; x[r] = s; }
         }
         if (states) std::memcpy(states + ((size_t)b * (steps + 1) + steps) * NX, x, sizeof(x));
+        if (cy) {
+            std::memcpy(cy->X + b * nxs, w.X.data(), sizeof(double) * nxs);
+            std::memcpy(cy->U + b * nus, w.U.data(), sizeof(double) * nus);
+            std::memcpy(cy->prevX + b * nxs, w.prevX.data(), sizeof(double) * nxs);
+            std::memcpy(cy->prevU + b * nus, w.prevU.data(), sizeof(double) * nus);
+            cy->have_prev[b] = w.have_prev ? 1 : 0;
+            cy->alive[b] = alive ? 1 : 0;
+        }
       }
     };
     const int T = std::max(1, std::min(threads > 0 ? threads : (int)std::thread::hardware_concurrency(), B));
@@ -391,6 +423,7 @@ long long closed_loop(const Cfg& g, int B, int steps, const double* x0, const do
     for (int t = 1; t < T; ++t) pool.emplace_back(worker);
     worker();
     for (auto& th : pool) th.join();
+    if (cy && cy->live) *cy->live = nlive.load();
     return nfail.load();
 }
 }  // namespace
@@ -405,6 +438,24 @@ extern "C" long long rnmpc_cpu_closed_loop(int model_id, int N, int rti, int sls
         case MODEL_PENDULUM: return closed_loop<PendulumModel>(g, B, steps, x0, W, X0, U0, states, inputs, threads, solve_ok);
         case MODEL_QUADROTOR: return closed_loop<QuadrotorModel>(g, B, steps, x0, W, X0, U0, states, inputs, threads, solve_ok);
         case MODEL_ROCKET: return closed_loop<RocketModel>(g, B, steps, x0, W, X0, U0, states, inputs, threads, solve_ok);
+    }
+    return -1;
+}
+
+// The same loops, resumable (see Carry): bench.py's CPU arm runs the warm-up MPC steps in one call and times the second call, on
+// the GPU arm's scenarios, with the GPU arm's freeze-on-failure rule.
+extern "C" long long rnmpc_cpu_closed_loop_resume(int model_id, int N, int rti, int sls_steps, const double* Q, const double* R, const double* Qf,
+                                                  const double* Qreg, const double* Rreg, const double* Qregf, const double* E, const double* xub,
+                                                  const double* xlb, const double* uub, const double* ulb, const double* xubf, const double* xlbf,
+                                                  double h, int B, int steps, const double* x0, const double* W, double* X, double* U,
+                                                  double* prevX, double* prevU, int* have_prev, int* alive, int freeze_failed, int shift_first,
+                                                  double* states, double* inputs, int threads, long long* live) {
+    Cfg g{N, rti, sls_steps, Q, R, Qf, Qreg, Rreg, Qregf, E, xub, xlb, uub, ulb, xubf, xlbf, h};
+    Carry cy{X, U, prevX, prevU, have_prev, alive, freeze_failed, shift_first, live};
+    switch (model_id) {
+        case MODEL_PENDULUM: return closed_loop<PendulumModel>(g, B, steps, x0, W, X, U, states, inputs, threads, nullptr, &cy);
+        case MODEL_QUADROTOR: return closed_loop<QuadrotorModel>(g, B, steps, x0, W, X, U, states, inputs, threads, nullptr, &cy);
+        case MODEL_ROCKET: return closed_loop<RocketModel>(g, B, steps, x0, W, X, U, states, inputs, threads, nullptr, &cy);
     }
     return -1;
 }

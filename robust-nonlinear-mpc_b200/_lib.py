@@ -55,6 +55,7 @@ SYMBOLS = {
     "rnmpc_solve_host": (_I, [_VP, _I] + [_VP] * 7),
     "rnmpc_closed_loop_host": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "rnmpc_fp64_peak": (_I, [_I, C.POINTER(_D)]),
+    "rnmpc_fp64_mma_peak": (_I, [_I, C.POINTER(_D)]),
     "rnmpc_set_option": (_I, [_VP, C.c_char_p, _D]),
     "rnmpc_enable_timing": (_I, [_VP, _I]),
     "rnmpc_get_timings": (_I, [_VP, C.POINTER(_D)]),

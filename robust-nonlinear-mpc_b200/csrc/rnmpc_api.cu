@@ -23,6 +23,20 @@ __global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
     for (int i = 0; i < 16; ++i) s += acc[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+// FP64 tensor-pipe probe: 8 independent mma.sync.m8n8k4.f64 accumulation chains per warp
+__global__ void fp64_mma_peak_kernel(double* out, int iters, double a, double b) {
+    double c0[8], c1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c0[i] = threadIdx.x + i; c1[i] = i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma884(c0[i], c1[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c0[i] + c1[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 }  // namespace rnmpc
 
 using namespace rnmpc;
@@ -314,6 +328,33 @@ int rnmpc_fp64_peak(int device, double* tflops) {
     cudaFree(out);
     RN_API_CUDA(cudaGetLastError());
     *tflops = 2.0 * 16 * iters * (double)blocks * thr / (best * 1e-3) * 1e-12;
+    return 0;
+}
+
+int rnmpc_fp64_mma_peak(int device, double* tflops) {
+    if (!tflops) return -1;
+    RN_API_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    RN_API_CUDA(cudaGetDeviceProperties(&p, device));
+    const int blocks = p.multiProcessorCount * 8, thr = 256, iters = 2048;
+    double* out;
+    RN_API_CUDA(cudaMalloc((void**)&out, sizeof(double) * blocks * thr));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 6; ++r) {
+        cudaEventRecord(e0);
+        fp64_mma_peak_kernel<<<blocks, thr>>>(out, iters, 1e-3, 1e-3);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    RN_API_CUDA(cudaGetLastError());
+    // one m8n8k4 = 8*8*4 multiply-adds per warp
+    *tflops = 2.0 * 256.0 * 8 * iters * (double)blocks * (thr / 32) / (best * 1e-3) * 1e-12;
     return 0;
 }
 

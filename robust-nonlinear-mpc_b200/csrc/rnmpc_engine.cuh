@@ -129,6 +129,14 @@ static __global__ void clear_flag_kernel(int B, int* flags, int bits) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) flags[b] &= ~bits;
 }
+// start of a solve: clears the per-solve flag bits and counts the instances that will actually be solved (not frozen by sticky_fail)
+static __global__ void begin_solve_kernel(int B, int* flags, int bits, unsigned long long* live_sum) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int live = 0;
+    if (b < B) { const int f = flags[b] & ~bits; flags[b] = f; live = (f & FLAG_FAIL) == 0; }
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    if ((threadIdx.x & 31) == 0 && m != 0) atomicAdd(live_sum, (unsigned long long)__popc(m));
+}
 static __global__ void set_tight_kernel(int B, int* flags, int skip_mask) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B && (flags[b] & skip_mask) == 0) flags[b] |= FLAG_TIGHT | FLAG_KVALID;
@@ -259,6 +267,7 @@ struct Engine : IEngine {
     double *wE, *wG, *rp, *Sc, *dff, *Kq, *Lq;
     int *flags, *status, *qp_iters, *iters_tmp, *status_tmp, *n_open, *ws_valid;
     unsigned long long* iters_sum;
+    unsigned long long* live_sum;      // instances solved (not frozen) summed over all rnmpc_solve calls since creation
     bool have_solution = false, shifted_since_solve = false;   // host-side warm-start bookkeeping
     int warm_enabled = 1;
     int qp_warps = 0, sls_warps = 0;   // warps per CTA of the slot kernels (0: automatic, see cta_warps)
@@ -320,7 +329,7 @@ struct Engine : IEngine {
         rc |= alloc("rp", rp, B * N * NX); rc |= alloc("Sc", Sc, B * N * NX); rc |= alloc("dff", dff, B * N * NU);
         rc |= alloc("Kq", Kq, B * N * NU * NX); rc |= alloc("Lq", Lq, B * N * NU * NU);
         rc |= alloc("flags", flags, B); rc |= alloc("status", status, B); rc |= alloc("qp_iters", qp_iters, B);
-        rc |= alloc("iters_tmp", iters_tmp, B); rc |= alloc("status_tmp", status_tmp, B); rc |= alloc("n_open", n_open, 1); rc |= alloc("iters_sum", iters_sum, 1);
+        rc |= alloc("iters_tmp", iters_tmp, B); rc |= alloc("status_tmp", status_tmp, B); rc |= alloc("n_open", n_open, 1); rc |= alloc("iters_sum", iters_sum, 1); rc |= alloc("live_sum", live_sum, 1);
         rc |= alloc("q3_margin", q3_margin, B); rc |= alloc("handoff_count", handoff_count, 1); rc |= alloc("handoff_list", handoff_list, B); rc |= alloc("handoff_state", handoff_state, B * 4); rc |= alloc("ws_valid", ws_valid, B);
         if (rc) return -2;
         const int smem_sls = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * kWarps;
@@ -615,7 +624,7 @@ struct Engine : IEngine {
     int solve(int B, const double* x0, cudaStream_t st) override {
         if (check_B(B)) return -1;
         // a new solve: failure flags of the previous solve are cleared, the Q3 history (FLAG_PREV) is kept
-        clear_flag_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags, (sticky_fail ? 0 : FLAG_FAIL) | FLAG_Q3 | FLAG_TIGHT);
+        begin_solve_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, flags, (sticky_fail ? 0 : FLAG_FAIL) | FLAG_Q3 | FLAG_TIGHT, live_sum);
         ++launches;
         if (!sticky_fail) RN_CUDA(cudaMemsetAsync(status, 0, (size_t)B * sizeof(int), st));   // frozen instances keep their failure status
         RN_CUDA(cudaMemsetAsync(qp_iters, 0, (size_t)B * sizeof(int), st));

@@ -247,6 +247,12 @@ class BatchSolver:
         _lib.check(self.lib.rnmpc_copy_buffer(self._h, b"iters_sum", C.c_void_p(v.ctypes.data), 8))
         return int(v[0])
 
+    def live_solves(self):
+        """Instances actually solved (not frozen by sticky_fail), summed over all solve() calls of this handle (device counter)."""
+        v = np.zeros(1, dtype=np.uint64)
+        _lib.check(self.lib.rnmpc_copy_buffer(self._h, b"live_sum", C.c_void_p(v.ctypes.data), 8))
+        return int(v[0])
+
     def launch_count(self):
         return int(self.lib.rnmpc_launch_count(self._h))
 
@@ -275,8 +281,10 @@ class BatchSolver:
         return dict(states=states, inputs=inputs, n_failed_solves=int(nfail.value))
 
 
-def fp64_peak_tflops(device=0):
+def fp64_peak_tflops(device=0, pipe="dfma"):
+    """Measured FP64 peak (TFLOP/s): pipe = "dfma" (scalar FMA) or "dmma" (FP64 tensor pipe, mma.sync.m8n8k4.f64)."""
     lib = _lib.load_library()
     v = C.c_double()
-    _lib.check(lib.rnmpc_fp64_peak(int(device), C.byref(v)))
+    fn = lib.rnmpc_fp64_mma_peak if pipe == "dmma" else lib.rnmpc_fp64_peak
+    _lib.check(fn(int(device), C.byref(v)))
     return float(v.value)

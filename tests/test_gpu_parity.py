@@ -277,14 +277,23 @@ def test_batch_properties_at_bench_size():
     # the one-CTA-per-instance QP kernels: deterministic per instance (the tensor-pipe kernel rotates its warps' roles with the
     # instance index: the results must not depend on it); against the slot kernel the same algorithm with different summation
     # orders -> equal to rounding, not bit for bit
-    _, _, s3 = make_solver("rocket", 7)
+    _, _, s3 = make_solver("rocket", 7)        # small batch: automatic choice = the one-CTA-per-instance tensor-pipe kernel
     s3.init_nominal(xs, 10)
     s3.solve(xs)
     Xb, Kb = s3.buffer("X"), s3.buffer("K")
     assert all(np.array_equal(Xb[0], Xb[i]) and np.array_equal(Kb[0], Kb[i]) for i in range(1, 7))
     assert rel(Xb[0], X7[0]) < 1e-9 and rel(Kb[0], K7[0]) < 1e-9
-    assert np.array_equal(Xb[0], s.buffer("X", 1)[0])                    # same kernel in the batch of 4096: bit for bit
-    s.close(); s2.close(); s3.close()
+    # the large batch ran the one-warp-per-instance kernel with the iterate in tensor memory (persistent warps drawing instances from
+    # a counter): forced on the small batch it gives the same bits, whichever warp of whichever CTA happened to solve the instance
+    _, _, s4 = make_solver("rocket", 7)
+    set_qp_kernel(s4, "tmem")
+    s4.init_nominal(xs, 10)
+    s4.solve(xs)
+    Xt, Kt = s4.buffer("X"), s4.buffer("K")
+    assert all(np.array_equal(Xt[0], Xt[i]) and np.array_equal(Kt[0], Kt[i]) for i in range(1, 7))
+    assert np.array_equal(Xt[0], s.buffer("X", 1)[0]) and np.array_equal(Kt[0], s.buffer("K", 1)[0])
+    assert rel(Xt[0], X7[0]) < 1e-9 and rel(Kt[0], K7[0]) < 1e-9
+    s.close(); s2.close(); s3.close(); s4.close()
 
 
 def test_host_entry_points_match_device_path():

@@ -172,11 +172,11 @@ def test_c_abi_exports_every_declared_symbol():
 
 
 def test_bench_gpu_arm_does_not_import_the_oracle():
-    """bench.py may touch oracle/ only in its CPU-baseline leg (cpu_baseline, cpu_single_latency); the measured arm imports the
+    """bench.py may touch oracle/ only in its CPU-baseline leg (cpu_loop, cpu_single_latency); the measured arm imports the
     product alone, and the product-side workload is the same as the oracle-side one the tests and the CPU arm use."""
     import ast
     tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
-    allowed = {"cpu_baseline", "cpu_single_latency"}
+    allowed = {"cpu_loop", "cpu_single_latency"}
     for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
         for node in ast.walk(fn):
             mod = node.module if isinstance(node, ast.ImportFrom) else None
