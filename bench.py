@@ -117,17 +117,26 @@ def cpu_single_latency(steps=29):
 
 def gpu_single_latency(m, cfg, device, steps=40):
     """Single-solve latency (BASELINE.json metric, second half): one rocket MPC instance, batch 1, driven from the host as a
-    controller would (measured state in from host memory, solve, nominal trajectory + back-offs out to host memory); wall
-    clock per rnmpc_solve_host call, percentiles over a disturbed closed loop."""
+    controller would (measured state in from host memory, solve, nominal trajectory + back-offs out to host memory); wall clock per
+    call over a disturbed closed loop, for the C-ABI entry point (rnmpc_solve_host) and for the drop-in call itself
+    (solver.SCP_SLS_jit.SCP_SLS.solve(x0), the call that replaces solver/SCP_SLS_jit.py:65-152)."""
     import torch
     from rnmpc_b200.engine import BatchSolver
+    from rnmpc_b200.solver.SCP_SLS_jit import SCP_SLS
     from rnmpc_b200.workloads import rocket_scenarios
     x_ub, x_lb, u_ub, u_lb, _, _ = m.box()
+    x0, W = rocket_scenarios(1, seed=777, steps=steps + 8)
+
+    def pct(lat):
+        lat = np.sort(np.array(lat))
+        return {"p50_ms": float(np.percentile(lat, 50)), "p90_ms": float(np.percentile(lat, 90)), "min_ms": float(lat[0]), "n": int(lat.size)}
+
+    # (a) C ABI: rnmpc_solve_host
     s = BatchSolver("rocket", cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], m.E, x_ub, x_lb,
                     u_ub, u_lb, rti=cfg["rti"], sls_steps=cfg["fast_sls_rti_steps"], capacity=1, device=device)
-    x0, W = rocket_scenarios(1, seed=777, steps=steps + 8)
     x = s.dev(x0).clone()
     s.init_nominal(x, 10)
+    X0, U0 = s.buffer("X", 1), s.buffer("U", 1)
     lat, fails = [], 0
     for i in range(steps + 8):
         if i > 0:
@@ -141,9 +150,29 @@ def gpu_single_latency(m, cfg, device, steps=40):
         if i >= 8:
             lat.append(1e3 * dt)
         s.plant_step(x, s.dev(W[:, i]))
-    lat = np.sort(np.array(lat))
-    return {"p50_ms": float(np.percentile(lat, 50)), "p90_ms": float(np.percentile(lat, 90)), "min_ms": float(lat[0]), "n": int(lat.size),
-            "failed": fails, "what": "rocket SCP_SLS.solve, batch 1, host buffers in/out (rnmpc_solve_host), wall clock"}
+    res = pct(lat)
+    res.update({"failed": fails, "what": "rocket SCP_SLS.solve, batch 1, host buffers in/out (rnmpc_solve_host: one CUDA graph per call), wall clock"})
+    s.close()
+    # (b) the drop-in class call
+    sc = SCP_SLS(cfg["N"], cfg["Q"], cfg["R"], m, cfg["Qf"], Q_reg=cfg["Q_reg"], R_reg=cfg["R_reg"], Q_reg_f=cfg["Q_reg_f"], rti=cfg["rti"],
+                 fast_sls_rti_steps=cfg["fast_sls_rti_steps"], verbose=False, save_it_data=False, timing=False, device=device)
+    sc.set_nominal_trajectory(X0[0].T, U0[0].T)
+    xk = x0[0].copy()
+    lat2, fails2 = [], 0
+    for i in range(steps + 8):
+        if i > 0:
+            sc.reset_warm_start()
+        t0 = time.perf_counter()
+        sol = sc.solve(xk)
+        dt = time.perf_counter() - t0
+        fails2 += 0 if sol["success"] else 1
+        if i >= 8:
+            lat2.append(1e3 * dt)
+        xk = np.array(m.ddyn(xk, sol["primal_u"][:, 0])).reshape(-1) + m.E @ W[0, i]
+    res["scp_sls_solve"] = dict(pct(lat2), failed=fails2,
+                                what="solver.SCP_SLS_jit.SCP_SLS.solve(x0) of this package (NumPy in, result dict out; keys beyond the "
+                                     "drivers' set are copied on first access), wall clock")
+    return res
 
 
 # ------------------------------------------------------------------------------------------------------------ main

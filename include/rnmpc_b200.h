@@ -114,6 +114,11 @@ int rnmpc_sls_duals(rnmpc_handle* h, int B, const double* d_A, const double* d_B
 
 /* ---- stateful solver on the handle's resident trajectories ----------------------------------------------- */
 
+/* Multipliers of the dynamics rows of the last nominal QP of the resident solve -- the first nx entries of every stage block of the
+ * reference's `dual_vec` (qp_jit.py:491-501; rows `A_k dx_k + B_k du_k - dx_{k+1} = -c_k`, qp_jit.py:194-273) -- recovered from the
+ * stationarity conditions of the solution (OSQP sign convention P x + q + A' y = 0).  d_lam [B][N][nx].  On demand: not on the solve path. */
+int rnmpc_costates(rnmpc_handle* h, int B, double* d_lam, void* stream);
+
 /* Load the nominal trajectories of B instances (replaces the IPOPT initial guess, SCP_SLS_jit.py:161-188, and is what
  * reset()/a fresh solver start from).  Clears the warm-start state incl. the Q3 history. */
 int rnmpc_set_nominal(rnmpc_handle* h, int B, const double* d_X, const double* d_U, void* stream);
@@ -155,7 +160,8 @@ int rnmpc_solve_host(rnmpc_handle* h, int B, const double* h_x0, double* h_X, do
 /* Whole closed loops (expe/main_rocket_compare_closed_loop.py:104-173 `_run_robust`) for B scenarios:
  * h_x0 [B][nx], h_W [B][steps][nx] (NULL = noise free), initial nominal h_X0/h_U0 ([B][N+1][nx], [B][N][nu]; NULL ->
  * rnmpc_init_nominal with init_iters).  Outputs (NULL to skip): h_states [B][steps+1][nx], h_inputs [B][steps][nu],
- * h_backoff_x0 [B][steps][nx] (first-stage... see INTEGRATION.md), h_nfail [1] number of failed solves.  Synchronous. */
+ * h_nfail [1] number of failed solves (= scenarios that died: a scenario whose solve failed is frozen for the rest of its loop and
+ * is not solved again).  Synchronous; the handle's "sticky_fail" option is restored to the caller's value on every path. */
 int rnmpc_closed_loop_host(rnmpc_handle* h, int B, int steps, const double* h_x0, const double* h_W, const double* h_X0,
                            const double* h_U0, int init_iters, double* h_states, double* h_inputs, long long* h_nfail);
 
@@ -175,6 +181,11 @@ int rnmpc_closed_loop_host(rnmpc_handle* h, int B, int steps, const double* h_x0
  * "qp_warps" / "sls_warps" (warps per
  * CTA of the QP / fast-SLS kernel, 1..5; default 0 = automatic, currently 1: the warps are independent chains and small CTAs
  * fill the SMs evenly; 3 and 4 measured 20 % slower at batch 4096 because the grid no longer fits one wave).
+ * "sls_steps" (fast-SLS iterations per SCP iteration at run time: SCP_SLS.set_fast_sls_rti_steps, SCP_SLS_jit.py:394-401, keeps the
+ * handle and with it the Q3 history and K; 0 = iterate until check_convergence_socp), "sls_max_iter" (fast_SLS.MAX_ITER, fast_SLS_jit.py:206:
+ * cap of that iteration, default 30), "qp_kernel" (0 automatic, 1 instance-per-slot, 2 round-1 block kernel, 3 one CTA per instance on
+ * the tensor pipe, 4 one warp per instance, 5 one warp per instance with the iterate in tensor memory), "qp_warp_min" (smallest batch
+ * the automatic choice gives to the one-warp-per-instance kernels, default 600), "sls_kernel" (0 tensor-pipe fast-SLS kernel, 1 slot kernel).
  * Diagnostics: "q3_eps" (threshold of the reference's check_convergence_socp, which hard-codes 1e-3, fast_SLS_jit.py:594), "q3_margin_reset" (resets the buffer
  * "q3_margin": per instance the closest the tested quantity came to that threshold since the reset).
  * Unknown names return -1. */

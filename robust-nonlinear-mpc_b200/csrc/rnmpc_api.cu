@@ -41,9 +41,22 @@ __global__ void fp64_mma_peak_kernel(double* out, int iters, double a, double b)
 
 using namespace rnmpc;
 
+// Host-buffer path of small batches (rnmpc_solve_host, the single-solve latency path): persistent device / pinned-host staging, and
+// the whole call -- input copy, every launch of the solve, output copies -- replayed as ONE CUDA graph on the handle's own stream.
+struct HostPath {
+    static constexpr int kMaxB = 64;
+    cudaStream_t hs = nullptr;
+    double* d_x0 = nullptr;
+    char* h_pin = nullptr;          // [x0 | X | U | backoff | backoff_f | flags | status] for kMaxB instances
+    size_t off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaGraphExec_t exec = nullptr;
+    int exec_B = 0;
+    long long exec_epoch = -1, exec_launches = 0;
+};
 struct rnmpc_handle {
     IEngine* e;
     int nx, nu, N, cap;
+    HostPath hp;
 };
 
 #define RN_API_CUDA(call)                                                                      \
@@ -98,6 +111,11 @@ int rnmpc_create(rnmpc_handle** out, const rnmpc_config* cfg, int capacity, int 
 
 int rnmpc_destroy(rnmpc_handle* h) {
     if (!h) return -1;
+    cudaSetDevice(h->e->device);
+    if (h->hp.exec) cudaGraphExecDestroy(h->hp.exec);
+    if (h->hp.hs) cudaStreamDestroy(h->hp.hs);
+    if (h->hp.d_x0) cudaFree(h->hp.d_x0);
+    if (h->hp.h_pin) cudaFreeHost(h->hp.h_pin);
     delete h->e;
     delete h;
     return 0;
@@ -142,6 +160,11 @@ int rnmpc_sls_duals(rnmpc_handle* h, int B, const double* A, const double* Bm, c
     if (!A || !Bm || !mu || !mu_f || !K || !beta || !beta_f || !backoff || !backoff_f) { set_error("null buffer"); return -1; }
     if ((beta_in == nullptr) != (beta_f_in == nullptr)) { set_error("beta_in and beta_f_in go together"); return -1; }
     return h->e->sls_duals(B, A, Bm, mu, mu_f, beta_in, beta_f_in, K, S, Phi_x, Phi_u, beta, beta_f, backoff, backoff_f, (cudaStream_t)stream);
+}
+int rnmpc_costates(rnmpc_handle* h, int B, double* lam, void* stream) {
+    RN_ENTER(h);
+    if (!lam) { set_error("null buffer"); return -1; }
+    return h->e->costates(B, lam, (cudaStream_t)stream);
 }
 int rnmpc_set_nominal(rnmpc_handle* h, int B, const double* X, const double* U, void* stream) {
     RN_ENTER(h);
@@ -209,11 +232,85 @@ static int copy_out(rnmpc_handle* h, const char* name, void* dst, size_t bytes, 
     return 0;
 }
 
+static int host_path_init(rnmpc_handle* h) {
+    HostPath& hp = h->hp;
+    if (hp.hs) return 0;
+    const int nx = h->nx, nu = h->nu, N = h->N, ni = 2 * (nx + nu), K = HostPath::kMaxB;
+    const size_t sz[7] = {(size_t)K * nx * 8, (size_t)K * (N + 1) * nx * 8, (size_t)K * N * nu * 8, (size_t)K * N * ni * 8,
+                          (size_t)K * 2 * nx * 8, (size_t)K * 4, (size_t)K * 4};
+    for (int i = 0; i < 7; ++i) hp.off[i + 1] = hp.off[i] + ((sz[i] + 15) & ~(size_t)15);
+    RN_API_CUDA(cudaStreamCreate(&hp.hs));        // a blocking stream: ordered with the caller's work on the default stream
+    RN_API_CUDA(cudaMalloc((void**)&hp.d_x0, sz[0]));
+    RN_API_CUDA(cudaMallocHost((void**)&hp.h_pin, hp.off[7]));
+    return 0;
+}
+
+// input copy + solve + output copies of B <= kMaxB instances, enqueued on the handle's stream (also the body of the captured graph)
+static int host_path_enqueue(rnmpc_handle* h, int B) {
+    HostPath& hp = h->hp;
+    const int nx = h->nx, nu = h->nu, N = h->N, ni = 2 * (nx + nu);
+    RN_API_CUDA(cudaMemcpyAsync(hp.d_x0, hp.h_pin + hp.off[0], (size_t)B * nx * 8, cudaMemcpyHostToDevice, hp.hs));
+    int rc = h->e->solve(B, hp.d_x0, hp.hs);
+    if (rc) return rc;
+    const char* names[6] = {"X", "U", "backoff", "backoff_f", "flags", "status"};
+    const size_t bytes[6] = {(size_t)B * (N + 1) * nx * 8, (size_t)B * N * nu * 8, (size_t)B * N * ni * 8, (size_t)B * 2 * nx * 8, (size_t)B * 4, (size_t)B * 4};
+    for (int i = 0; i < 6; ++i) {
+        void* p; long long n;
+        if (h->e->get_buffer(names[i], &p, &n)) return -1;
+        RN_API_CUDA(cudaMemcpyAsync(hp.h_pin + hp.off[i + 1], p, bytes[i], cudaMemcpyDeviceToHost, hp.hs));
+    }
+    return 0;
+}
+
 int rnmpc_solve_host(rnmpc_handle* h, int B, const double* h_x0, double* h_X, double* h_U, double* h_backoff, double* h_backoff_f,
                      int* h_flags, int* h_status) {
     RN_ENTER(h);
     if (!h_x0 || B <= 0 || B > h->cap) { set_error("bad arguments"); return -1; }
     const int nx = h->nx, nu = h->nu, N = h->N, ni = 2 * (nx + nu);
+    if (B <= HostPath::kMaxB) {
+        HostPath& hp = h->hp;
+        int rc = host_path_init(h);
+        if (rc) return rc;
+        memcpy(hp.h_pin + hp.off[0], h_x0, (size_t)B * nx * 8);
+        if (h->e->graphable()) {
+            if (hp.exec == nullptr || hp.exec_B != B || hp.exec_epoch != h->e->epoch) {
+                if (hp.exec) { cudaGraphExecDestroy(hp.exec); hp.exec = nullptr; }
+                const long long l0 = h->e->launches;
+                cudaGraph_t graph = nullptr;
+                RN_API_CUDA(cudaStreamBeginCapture(hp.hs, cudaStreamCaptureModeThreadLocal));
+                rc = host_path_enqueue(h, B);
+                cudaError_t ce = cudaStreamEndCapture(hp.hs, &graph);
+                hp.exec_launches = h->e->launches - l0;
+                h->e->launches = l0;
+                if (rc || ce != cudaSuccess || graph == nullptr) {
+                    if (graph) cudaGraphDestroy(graph);
+                    cudaGetLastError();
+                    if (rc) return rc;
+                    set_error(std::string("solve_host: graph capture failed: ") + cudaGetErrorString(ce));
+                    return -2;
+                }
+                ce = cudaGraphInstantiate(&hp.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) { hp.exec = nullptr; set_error(std::string("solve_host: cudaGraphInstantiate: ") + cudaGetErrorString(ce)); return -2; }
+                hp.exec_B = B; hp.exec_epoch = h->e->epoch;
+            }
+            RN_API_CUDA(cudaGraphLaunch(hp.exec, hp.hs));
+            h->e->launches += hp.exec_launches;
+        } else {
+            rc = host_path_enqueue(h, B);
+            if (rc) { cudaStreamSynchronize(hp.hs); return rc; }
+        }
+        cudaError_t e = cudaStreamSynchronize(hp.hs);
+        if (e != cudaSuccess) { set_error(std::string("solve: ") + cudaGetErrorString(e)); return -2; }
+        if (h_X) memcpy(h_X, hp.h_pin + hp.off[1], (size_t)B * (N + 1) * nx * 8);
+        if (h_U) memcpy(h_U, hp.h_pin + hp.off[2], (size_t)B * N * nu * 8);
+        if (h_backoff) memcpy(h_backoff, hp.h_pin + hp.off[3], (size_t)B * N * ni * 8);
+        if (h_backoff_f) memcpy(h_backoff_f, hp.h_pin + hp.off[4], (size_t)B * 2 * nx * 8);
+        if (h_flags) memcpy(h_flags, hp.h_pin + hp.off[5], (size_t)B * 4);
+        if (h_status) memcpy(h_status, hp.h_pin + hp.off[6], (size_t)B * 4);
+        return 0;
+    }
+    // large batches: direct copies (the staging would only add a host copy)
     double* d_x0;
     RN_API_CUDA(cudaMalloc((void**)&d_x0, (size_t)B * nx * sizeof(double)));
     RN_API_CUDA(cudaMemcpy(d_x0, h_x0, (size_t)B * nx * sizeof(double), cudaMemcpyHostToDevice));
@@ -235,74 +332,80 @@ int rnmpc_closed_loop_host(rnmpc_handle* h, int B, int steps, const double* h_x0
     RN_ENTER(h);
     if (!h_x0 || B <= 0 || B > h->cap || steps < 1) { set_error("bad arguments"); return -1; }
     const int nx = h->nx, nu = h->nu, N = h->N;
-    double *d_x = nullptr, *d_W = nullptr, *d_states = nullptr, *d_inputs = nullptr, *d_tmp = nullptr;
-    int rc = 0;
+    double *d_x = nullptr, *d_W = nullptr, *d_states = nullptr, *d_inputs = nullptr, *d_tmp = nullptr, *dX0 = nullptr, *dU0 = nullptr;
     cudaStream_t st = 0;
-    RN_API_CUDA(cudaMalloc((void**)&d_x, (size_t)B * nx * sizeof(double)));
-    RN_API_CUDA(cudaMalloc((void**)&d_states, (size_t)B * (steps + 1) * nx * sizeof(double)));
-    RN_API_CUDA(cudaMalloc((void**)&d_inputs, (size_t)B * steps * nu * sizeof(double)));
-    RN_API_CUDA(cudaMemcpyAsync(d_x, h_x0, (size_t)B * nx * sizeof(double), cudaMemcpyHostToDevice, st));
+    long long nfail = 0;
+    const double sticky_before = h->e->get_option("sticky_fail");
+    // one exit: every device buffer is freed and the caller's sticky_fail setting restored on success and on every error path
+    auto finish = [&](int rc) {
+        cudaStreamSynchronize(st);
+        for (double* p : {d_x, d_W, d_states, d_inputs, d_tmp, dX0, dU0}) if (p) cudaFree(p);
+        h->e->set_option("sticky_fail", sticky_before);
+        if (h_nfail) *h_nfail = nfail;
+        return rc;
+    };
+#define RN_LOOP_CUDA(call)                                                                             \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) { set_error(std::string(#call) + ": " + cudaGetErrorString(e_)); return finish(-2); } \
+    } while (0)
+    RN_LOOP_CUDA(cudaMalloc((void**)&d_x, (size_t)B * nx * sizeof(double)));
+    RN_LOOP_CUDA(cudaMalloc((void**)&d_states, (size_t)B * (steps + 1) * nx * sizeof(double)));
+    RN_LOOP_CUDA(cudaMalloc((void**)&d_inputs, (size_t)B * steps * nu * sizeof(double)));
+    RN_LOOP_CUDA(cudaMemcpyAsync(d_x, h_x0, (size_t)B * nx * sizeof(double), cudaMemcpyHostToDevice, st));
     if (h_W) {
         // [B][steps][nx] on the host -> step-major [steps][B][nx] slices are gathered with a strided 2-D copy per step
-        RN_API_CUDA(cudaMalloc((void**)&d_W, (size_t)B * steps * nx * sizeof(double)));
-        RN_API_CUDA(cudaMemcpyAsync(d_W, h_W, (size_t)B * steps * nx * sizeof(double), cudaMemcpyHostToDevice, st));
-        RN_API_CUDA(cudaMalloc((void**)&d_tmp, (size_t)B * nx * sizeof(double)));
+        RN_LOOP_CUDA(cudaMalloc((void**)&d_W, (size_t)B * steps * nx * sizeof(double)));
+        RN_LOOP_CUDA(cudaMemcpyAsync(d_W, h_W, (size_t)B * steps * nx * sizeof(double), cudaMemcpyHostToDevice, st));
+        RN_LOOP_CUDA(cudaMalloc((void**)&d_tmp, (size_t)B * nx * sizeof(double)));
     }
+    int rc = 0;
     if (h_X0 && h_U0) {
-        double *dX0, *dU0;
-        RN_API_CUDA(cudaMalloc((void**)&dX0, (size_t)B * (N + 1) * nx * sizeof(double)));
-        RN_API_CUDA(cudaMalloc((void**)&dU0, (size_t)B * N * nu * sizeof(double)));
-        RN_API_CUDA(cudaMemcpyAsync(dX0, h_X0, (size_t)B * (N + 1) * nx * sizeof(double), cudaMemcpyHostToDevice, st));
-        RN_API_CUDA(cudaMemcpyAsync(dU0, h_U0, (size_t)B * N * nu * sizeof(double), cudaMemcpyHostToDevice, st));
+        RN_LOOP_CUDA(cudaMalloc((void**)&dX0, (size_t)B * (N + 1) * nx * sizeof(double)));
+        RN_LOOP_CUDA(cudaMalloc((void**)&dU0, (size_t)B * N * nu * sizeof(double)));
+        RN_LOOP_CUDA(cudaMemcpyAsync(dX0, h_X0, (size_t)B * (N + 1) * nx * sizeof(double), cudaMemcpyHostToDevice, st));
+        RN_LOOP_CUDA(cudaMemcpyAsync(dU0, h_U0, (size_t)B * N * nu * sizeof(double), cudaMemcpyHostToDevice, st));
         rc = h->e->set_nominal(B, dX0, dU0, st);
-        cudaStreamSynchronize(st);
-        cudaFree(dX0); cudaFree(dU0);
     } else {
         rc = h->e->init_nominal(B, d_x, init_iters > 0 ? init_iters : 10, st);
     }
-    long long nfail = 0;
-    std::vector<int> fl(B);
+    if (rc) return finish(rc);
+    std::vector<int> fl(B), dead(B, 0);
     h->e->set_option("sticky_fail", 1.0);      // Monte-Carlo semantics: a scenario whose solve failed is dead (the reference's driver would stop)
     void* d_flags; long long nb;
     h->e->get_buffer("flags", &d_flags, &nb);
     const size_t srow = (size_t)(steps + 1) * nx * sizeof(double);
-    for (int i = 0; i < steps && !rc; ++i) {
-        RN_API_CUDA(cudaMemcpy2DAsync(d_states + (size_t)i * nx, srow, d_x, nx * sizeof(double), nx * sizeof(double), B,
-                                      cudaMemcpyDeviceToDevice, st));
-        if (i > 0) rc = h->e->reset_warm_start(B, st);
-        if (!rc) rc = h->e->solve(B, d_x, st);
+    for (int i = 0; i < steps; ++i) {
+        RN_LOOP_CUDA(cudaMemcpy2DAsync(d_states + (size_t)i * nx, srow, d_x, nx * sizeof(double), nx * sizeof(double), B,
+                                       cudaMemcpyDeviceToDevice, st));
+        if (i > 0 && (rc = h->e->reset_warm_start(B, st)) != 0) return finish(rc);
+        if ((rc = h->e->solve(B, d_x, st)) != 0) return finish(rc);
         const double* w = nullptr;
-        if (h_W && !rc) {
-            RN_API_CUDA(cudaMemcpy2DAsync(d_tmp, nx * sizeof(double), d_W + (size_t)i * nx, (size_t)steps * nx * sizeof(double),
-                                          nx * sizeof(double), B, cudaMemcpyDeviceToDevice, st));
+        if (h_W) {
+            RN_LOOP_CUDA(cudaMemcpy2DAsync(d_tmp, nx * sizeof(double), d_W + (size_t)i * nx, (size_t)steps * nx * sizeof(double),
+                                           nx * sizeof(double), B, cudaMemcpyDeviceToDevice, st));
             w = d_tmp;
         }
-        if (!rc) rc = h->e->plant_step(B, d_x, w, nullptr, st);
-        if (!rc) {
-            void* dU; h->e->get_buffer("U", &dU, &nb);
-            RN_API_CUDA(cudaMemcpy2DAsync(d_inputs + (size_t)i * nu, (size_t)steps * nu * sizeof(double), dU,
-                                          (size_t)N * nu * sizeof(double), nu * sizeof(double), B, cudaMemcpyDeviceToDevice, st));
-        }
-        if (h_nfail && !rc) {
-            RN_API_CUDA(cudaMemcpyAsync(fl.data(), d_flags, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
-            RN_API_CUDA(cudaStreamSynchronize(st));
-            for (int b = 0; b < B; ++b) nfail += (fl[b] & 1);
+        if ((rc = h->e->plant_step(B, d_x, w, nullptr, st)) != 0) return finish(rc);
+        void* dU; h->e->get_buffer("U", &dU, &nb);
+        RN_LOOP_CUDA(cudaMemcpy2DAsync(d_inputs + (size_t)i * nu, (size_t)steps * nu * sizeof(double), dU,
+                                       (size_t)N * nu * sizeof(double), nu * sizeof(double), B, cudaMemcpyDeviceToDevice, st));
+        if (h_nfail) {
+            // failed solves = scenarios that died at THIS step (a dead scenario is not solved again)
+            RN_LOOP_CUDA(cudaMemcpyAsync(fl.data(), d_flags, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+            RN_LOOP_CUDA(cudaStreamSynchronize(st));
+            for (int b = 0; b < B; ++b)
+                if ((fl[b] & 1) && !dead[b]) { dead[b] = 1; ++nfail; }
         }
     }
-    if (!rc) {
-        RN_API_CUDA(cudaMemcpy2DAsync(d_states + (size_t)steps * nx, srow, d_x, nx * sizeof(double), nx * sizeof(double), B,
-                                      cudaMemcpyDeviceToDevice, st));
-        if (h_states) RN_API_CUDA(cudaMemcpyAsync(h_states, d_states, (size_t)B * srow, cudaMemcpyDeviceToHost, st));
-        if (h_inputs) RN_API_CUDA(cudaMemcpyAsync(h_inputs, d_inputs, (size_t)B * steps * nu * sizeof(double), cudaMemcpyDeviceToHost, st));
-    }
-    h->e->set_option("sticky_fail", 0.0);
+    RN_LOOP_CUDA(cudaMemcpy2DAsync(d_states + (size_t)steps * nx, srow, d_x, nx * sizeof(double), nx * sizeof(double), B,
+                                   cudaMemcpyDeviceToDevice, st));
+    if (h_states) RN_LOOP_CUDA(cudaMemcpyAsync(h_states, d_states, (size_t)B * srow, cudaMemcpyDeviceToHost, st));
+    if (h_inputs) RN_LOOP_CUDA(cudaMemcpyAsync(h_inputs, d_inputs, (size_t)B * steps * nu * sizeof(double), cudaMemcpyDeviceToHost, st));
     cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(d_x); cudaFree(d_states); cudaFree(d_inputs);
-    if (d_W) cudaFree(d_W);
-    if (d_tmp) cudaFree(d_tmp);
-    if (h_nfail) *h_nfail = nfail;
-    if (e != cudaSuccess) { set_error(std::string("closed_loop: ") + cudaGetErrorString(e)); return -2; }
-    return rc;
+    if (e != cudaSuccess) { set_error(std::string("closed_loop: ") + cudaGetErrorString(e)); return finish(-2); }
+#undef RN_LOOP_CUDA
+    return finish(0);
 }
 
 int rnmpc_fp64_peak(int device, double* tflops) {

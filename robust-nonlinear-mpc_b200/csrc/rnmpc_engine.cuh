@@ -52,6 +52,7 @@ struct IEngine {
     virtual int sls_duals(int B, const double* A, const double* Bm, const double* mu, const double* mu_f, const double* beta_in,
                           const double* beta_f_in, double* K, double* S, double* Phi_x, double* Phi_u, double* beta, double* beta_f,
                           double* backoff, double* backoff_f, cudaStream_t st) = 0;
+    virtual int costates(int B, double* lam, cudaStream_t st) = 0;
     virtual int set_nominal(int B, const double* X, const double* U, cudaStream_t st) = 0;
     virtual int init_nominal(int B, const double* x0, int iters, cudaStream_t st) = 0;
     virtual int solve(int B, const double* x0, cudaStream_t st) = 0;
@@ -60,8 +61,11 @@ struct IEngine {
     virtual int get_buffer(const char* name, void** ptr, long long* bytes) = 0;
     virtual int enable_phi(int enable) = 0;
     virtual int set_option(const char* name, double value) = 0;
+    virtual double get_option(const char* name) = 0;
     virtual int dims(int* nx, int* nu, int* N, int* cap) = 0;
+    virtual bool graphable() = 0;          // one solve is a fixed sequence of launches (no host decision inside): it can be captured in a CUDA graph
     long long launches = 0;
+    long long epoch = 0;                   // bumped by every option / timing change: captured graphs of older epochs are stale
     int device = 0;
 };
 
@@ -170,6 +174,41 @@ static __global__ void interp_nominal_kernel(int B, int N, int nx, int nu, const
         for (int i = 0; i < nx; ++i) X[((size_t)b * (N + 1) + k) * nx + i] = x0[(size_t)b * nx + i] * (1.0 - (double)k / (double)N);
     for (int k = 0; k < N; ++k)
         for (int p = 0; p < nu; ++p) U[((size_t)b * N + k) * nu + p] = 0.0;
+}
+
+// Multipliers of the dynamics rows of the last nominal QP (the rows `A_k dx_k + B_k du_k - dx_{k+1} = -c_k` of qp_jit.py:194-273, whose
+// duals the reference returns inside `dual_vec`, qp_jit.py:491-501), recovered from the stationarity conditions of the solution the
+// solve left behind: with y = x_nom + dx (the updated nominal), 2 H y + G' mu + A' lam = 0 gives
+//   lam_{N-1} = 2 Qf y_N + mu_f,up - mu_f,lo ,   lam_{k-1} = 2 Q y_k + (mu_k,up - mu_k,lo)_x + A_k' lam_k   (k = N-1 .. 1).
+// One thread per instance (an on-demand diagnostic output: never on the solve path).
+template <int NX, int NU>
+__global__ void costate_kernel(int B, int N, int lda, const double* __restrict__ A, const double* __restrict__ X,
+                               const double* __restrict__ mu, const double* __restrict__ mu_f, const Params<NX, NU>* __restrict__ prm,
+                               double* __restrict__ lam) {
+    constexpr int NZ = NX + NU, NI = 2 * NZ;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double* Xb = X + (size_t)b * (N + 1) * NX;
+    double y[NX], yn[NX];
+    for (int i = 0; i < NX; ++i) {
+        double g = mu_f[(size_t)b * 2 * NX + i] - mu_f[(size_t)b * 2 * NX + NX + i];
+        for (int j = 0; j < NX; ++j) g = fma(2.0 * prm->Qf[i * NX + j], Xb[N * NX + j], g);
+        y[i] = g;
+    }
+    for (int k = N - 1; k >= 0; --k) {
+        double* out = lam + ((size_t)b * N + k) * NX;
+        for (int i = 0; i < NX; ++i) out[i] = y[i];
+        if (k == 0) break;
+        const double* Ak = A + ((size_t)b * N + k) * NX * lda;
+        const double* mk = mu + ((size_t)b * N + k) * NI;
+        for (int i = 0; i < NX; ++i) {
+            double g = mk[i] - mk[NZ + i];
+            for (int j = 0; j < NX; ++j) g = fma(2.0 * prm->Q[i * NX + j], Xb[k * NX + j], g);
+            for (int j = 0; j < NX; ++j) g = fma(Ak[j * lda + i], y[j], g);
+            yn[i] = g;
+        }
+        for (int i = 0; i < NX; ++i) y[i] = yn[i];
+    }
 }
 
 template <class M>
@@ -579,6 +618,13 @@ struct Engine : IEngine {
         if (rc) return rc;
         return launch_backoff(B, beta_, beta_f_, nullptr, 0, backoff_, backoff_f_, st);
     }
+    int costates(int B, double* lam, cudaStream_t st) override {
+        if (check_B(B)) return -1;
+        costate_kernel<NX, NU><<<(B + 63) / 64, 64, 0, st>>>(B, N, LDA, A, X, mu, mu_f, d_prm, lam);
+        ++launches;
+        RN_CUDA(cudaGetLastError());
+        return 0;
+    }
     int set_nominal(int B, const double* X_, const double* U_, cudaStream_t st) override {
         if (check_B(B)) return -1;
         RN_CUDA(cudaMemcpyAsync(X, X_, (size_t)B * (N + 1) * NX * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -721,6 +767,7 @@ struct Engine : IEngine {
             for (auto& e : ev) RN_CUDA(cudaEventCreate(&e));
         timing = enable != 0;
         timing_mode = enable;
+        ++epoch;
         return 0;
     }
     int kernel_time(const char* kernel, double* total_ms, long long* count) override {
@@ -758,8 +805,11 @@ struct Engine : IEngine {
         if (bytes) *bytes = (long long)it->second.second;
         return 0;
     }
+    // (not while phase timing is on: events recorded by the nodes of a replayed graph give no elapsed times -- measured: -1)
+    bool graphable() override { return sls_steps > 0 && !timing && timing_mode == 0 && warm_mask == 0; }
     int set_option(const char* name, double value) override {
         const std::string n(name);
+        ++epoch;
         if (n == "qp_warps") { qp_warps = (int)value; return 0; }
         if (n == "sls_warps") { sls_warps = (int)value; return 0; }
         if (n == "warm_mask") warm_mask = (int)value;            // bit0: first QP of a solve from the previous solve, bit1: later QPs of a solve
@@ -768,6 +818,8 @@ struct Engine : IEngine {
         else if (n == "qp_tol_mu") qp_tol_mu = value;
         else if (n == "qp_mu0") qp_mu0 = value;
         else if (n == "qp_block_max") qp_block_max = (int)value;
+        else if (n == "sls_max_iter") { if (value < 1) { set_error("sls_max_iter must be >= 1"); return -1; } sls_max_iter = (int)value; }
+        else if (n == "sls_steps") { if (value < 0) { set_error("sls_steps must be >= 0"); return -1; } sls_steps = (int)value; }
         else if (n == "qp_kernel") qp_kernel = (int)value;
         else if (n == "qp_warp_min") qp_warp_min = (int)value;
         else if (n == "sls_kernel") sls_kernel_sel = (int)value;
@@ -782,6 +834,14 @@ struct Engine : IEngine {
         else if (n == "qp_handoff_iter") qp_handoff_iter = (int)value;
         else { set_error("unknown option " + n); return -1; }
         return 0;
+    }
+    double get_option(const char* name) override {
+        const std::string n(name);
+        if (n == "sticky_fail") return sticky_fail ? 1.0 : 0.0;
+        if (n == "sls_steps") return sls_steps;
+        if (n == "sls_max_iter") return sls_max_iter;
+        if (n == "qp_kernel") return qp_kernel;
+        return 0.0;
     }
     int enable_phi(int enable) override {
         if (enable && Phi_x == nullptr) {

@@ -198,6 +198,13 @@ class BatchSolver:
         return out
 
     # -- stateful solver ---------------------------------------------------------------------------------------------
+    def costates(self, B=None):
+        """Multipliers of the dynamics rows of the last nominal QP of the resident solve, [B, N, nx] (rnmpc_costates)."""
+        B = self.capacity if B is None else int(B)
+        lam = self.empty(B, self.N, self.nx)
+        _lib.check(self.lib.rnmpc_costates(self._h, B, _ptr(lam), self._stream()))
+        return lam
+
     def set_nominal(self, X, U):
         X, U = self.dev(X), self.dev(U)
         _lib.check(self.lib.rnmpc_set_nominal(self._h, X.shape[0], _ptr(X), _ptr(U), self._stream()))

@@ -17,8 +17,9 @@ _FAIL, _Q3, _TIGHT, _KVALID = 1, 2, 4, 16
 
 
 class _FastSLSView:
-    """Attribute bag standing in for ``SCP_SLS.fast_SLS_solver`` (drivers poke ``verbose``, ``CONV_EPS``, ...;
-    expe/main_rocket_robust_closed_loop.py:86-93)."""
+    """Stands in for ``SCP_SLS.fast_SLS_solver`` (drivers poke ``verbose``, ``CONV_EPS``, ``MAX_ITER``, ...;
+    expe/main_rocket_robust_closed_loop.py:86-93).  Settings that change the computation are forwarded to the engine or refused;
+    none is silently ignored."""
 
     class _QPView:
         verbose = False
@@ -28,13 +29,95 @@ class _FastSLSView:
         self._owner = owner
         self.verbose = False
         self.save_it_data = False
+        # the reference stores CONV_EPS but check_convergence_socp tests against a hard-coded 1e-3 (fast_SLS_jit.py:594): kept, unused
         self.CONV_EPS = 1e-6
-        self.MAX_ITER = 30
-        self.epsilon_backoff = 1e-10
+        self._max_iter = 30
         self.solver_forward = self._QPView()
+
+    @property
+    def MAX_ITER(self):
+        """fast_SLS.MAX_ITER (fast_SLS_jit.py:206): cap of the iterate-to-convergence mode; forwarded to the engine."""
+        return self._max_iter
+
+    @MAX_ITER.setter
+    def MAX_ITER(self, value):
+        value = int(value)
+        if value < 1:
+            raise ValueError("MAX_ITER must be >= 1")
+        self._max_iter = value
+        if self._owner._engine is not None:
+            self._owner._engine.set_option("sls_max_iter", value)
+
+    @property
+    def epsilon_backoff(self):
+        return 1e-10
+
+    @epsilon_backoff.setter
+    def epsilon_backoff(self, value):
+        # a compile-time constant of the kernels (rnmpc_common.cuh: kEpsBackoff = fast_SLS_jit.py:205)
+        if float(value) != 1e-10:
+            raise NotImplementedError("epsilon_backoff is fixed at the reference's 1e-10 in the CUDA kernels")
 
     def set_rti_steps(self, steps):
         self._owner.set_fast_sls_rti_steps(steps)
+
+
+class LazySolution(dict):
+    """Result dict of ``SCP_SLS.solve``: the keys every driver reads (trajectories, back-offs, success, timings) are plain
+    entries; the rest of the reference's key set (duals, eta, K, beta, the linearisation lists, ...) is copied from the GPU on first
+    access.  ``materialize()`` evaluates everything.  Once the solver has advanced (next ``solve`` / ``reset_warm_start``) keys that
+    were never read are gone: they describe device buffers that have been overwritten."""
+
+    def __init__(self, eager, thunks):
+        super().__init__(eager)
+        self._thunks = dict(thunks)
+        self._expired = False
+
+    def __missing__(self, key):
+        th = self._thunks.pop(key, None)
+        if th is None:
+            raise KeyError(key)
+        if self._expired:
+            raise KeyError(f"result key {key!r} was not read before the solver advanced; read it right after solve() or call materialize()")
+        for k, v in th().items():
+            dict.__setitem__(self, k, v)
+            self._thunks.pop(k, None)
+        return dict.__getitem__(self, key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._thunks
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def keys(self):
+        return list(dict.keys(self)) + [k for k in self._thunks if not dict.__contains__(self, k)]
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return len(self.keys())
+
+    def materialize(self):
+        for k in list(self._thunks):
+            if k in self._thunks:
+                self[k]
+        return self
+
+    def items(self):
+        self.materialize()
+        return dict.items(self)
+
+    def values(self):
+        self.materialize()
+        return dict.values(self)
+
+    def copy(self):
+        return dict(self.items())
+
+    def _expire(self):
+        self._expired = True
 
 
 class SCP_SLS(OCP):
@@ -55,6 +138,11 @@ class SCP_SLS(OCP):
         self.batch = int(kwargs.get("batch", 1))
         self.device = int(kwargs.get("device", 0))
         self.nominal_init_iters = int(kwargs.get("nominal_init_iters", 10))
+        self.lazy_results = bool(kwargs.get("lazy_results", True))      # False: every key is copied at solve time, as in the reference
+        # phase timers behind the reference's t_jac_ms / t_qp_ms / t_backward_ms keys; False: the keys are NaN and a solve of a small
+        # batch is replayed as one CUDA graph (rnmpc_solve_host)
+        self.timing = bool(kwargs.get("timing", True))
+        self._last_solution = None
         self.MAX_ITER_SCP = 100
         self.fast_SLS_solver = _FastSLSView(self)
         self._engine = None
@@ -77,7 +165,8 @@ class SCP_SLS(OCP):
         self._engine = BatchSolver(m.model_name, self.N, self.Q, self.R, self.Qf, self.Q_reg, self.R_reg, self.Q_reg_f,
                                    np.asarray(m.E, float), x_ub, x_lb, u_ub, u_lb, xf_ub, xf_lb, rti=rti,
                                    sls_steps=sls_steps, capacity=self.batch, device=self.device)
-        self._engine.enable_timing(True)
+        self._engine.enable_timing(self.timing)
+        self._engine.set_option("sls_max_iter", self.fast_SLS_solver.MAX_ITER)
         self._has_nominal = False
 
     @property
@@ -85,15 +174,10 @@ class SCP_SLS(OCP):
         return self._engine
 
     def set_fast_sls_rti_steps(self, steps):
-        """solver/SCP_SLS_jit.py:394-401."""
+        """solver/SCP_SLS_jit.py:394-401 -> fast_SLS.set_rti_steps: changes the step count only; the nominal trajectory, the Q3 history
+        and the gains stay (engine option "sls_steps", no new handle)."""
         self.fast_sls_rti_steps = steps
-        X = U = None
-        if self._has_nominal:
-            X, U = self._engine.buffer("X", self.batch), self._engine.buffer("U", self.batch)
-        self._build_engine()
-        if X is not None:
-            self._engine.set_nominal(X, U)
-            self._has_nominal = True
+        self._engine.set_option("sls_steps", int(steps) if (steps is not None and steps > 0) else 0)
 
     # ------------------------------------------------------------------------------------------------- nominal
     def _b(self, a, shape):
@@ -125,16 +209,23 @@ class SCP_SLS(OCP):
         return a[0] if self.batch == 1 else a
 
     # ---------------------------------------------------------------------------------------------------- solve
+    def _advance(self):
+        if self._last_solution is not None:
+            self._last_solution._expire()
+            self._last_solution = None
+
     def solve(self, x0):
         """solver/SCP_SLS_jit.py:65-152."""
         nx, nu, N, B = self.m.nx, self.m.nu, self.N, self.batch
-        x0b = self._b(x0, (nx,))
+        x0b = np.ascontiguousarray(self._b(x0, (nx,)))
         if not self._has_nominal:
             if not self.solve_nominal_trajectory(x0b):
                 return {'success': False}
+        self._advance()
         eng = self._engine
         if self.rti is not None and self.rti > 0:
-            eng.solve(x0b)
+            # one call: x0 in, the solve, trajectories / back-offs / flags out (rnmpc_solve_host: one CUDA graph for small batches)
+            res = eng.solve_host(x0b)
             iterations = int(self.rti) - 1
             converged = None
         else:
@@ -142,98 +233,126 @@ class SCP_SLS(OCP):
             converged, iterations = False, 0
             for ii in range(int(self.MAX_ITER_SCP)):
                 iterations = ii
-                eng.solve(x0b)
-                if (eng.buffer("flags", B) & _FAIL).any():
+                res = eng.solve_host(x0b)
+                if (res["flags"] & _FAIL).any():
                     break
                 delta = max(np.abs(eng.buffer("dX", B)).max(), np.abs(eng.buffer("dU", B)).max())
                 if delta < self.epsilon_convergence:
                     converged = True
                     break
-        flags = eng.buffer("flags", B)
+        flags = res["flags"]
         ok = (flags & _FAIL) == 0
         tight = (flags & _TIGHT) != 0
         kvalid = (flags & _KVALID) != 0
         ni = self.m.ni
-        X, U = eng.buffer("X", B), eng.buffer("U", B)
-        dX, dU = eng.buffer("dX", B), eng.buffer("dU", B)
-        mu, mu_f = eng.buffer("mu", B), eng.buffer("mu_f", B)
-        backoff, backoff_f = eng.buffer("backoff", B), eng.buffer("backoff_f", B)
-        beta, beta_f, K = eng.buffer("beta", B), eng.buffer("beta_f", B), eng.buffer("K", B)
+        X, U, backoff, backoff_f = res["X"], res["U"], res["backoff"], res["backoff_f"]
         eps = self.fast_SLS_solver.epsilon_backoff
         # instances whose last fast-SLS solve took the Q3 early return hold the initial back-offs
         # (fast_SLS_jit.py:444-454): beta = eps, backoff = N*sqrt(eps), backoff_x = backoff_u = 0
         nt = ~tight
         if nt.any():
-            beta[nt], beta_f[nt] = eps, eps
             backoff[nt], backoff_f[nt] = N * np.sqrt(eps), (N + 1) * np.sqrt(eps)
         backoff_x = np.concatenate([backoff[:, :, :nx], backoff_f[:, None, :nx]], axis=1)      # (B, N+1, nx)  Q7
         backoff_u = backoff[:, :, nx:nx + nu].copy()
         backoff_x[nt], backoff_u[nt] = 0.0, 0.0
         primal_x, primal_u = np.swapaxes(X, 1, 2), np.swapaxes(U, 1, 2)
-        delta_x, delta_u = np.swapaxes(dX, 1, 2), np.swapaxes(dU, 1, 2)
         pack = lambda Xb, Ub: np.stack([self.pack_primal_nominal(Xb[b], Ub[b]) for b in range(B)])
-        eta = np.zeros((B, N, N, ni))
-        sq = 2.0 * np.sqrt(np.maximum(beta, eps))
-        for k in range(N):
-            eta[:, k, :k + 1, :] = mu[:, k, None, :] / sq[:, k, :k + 1, :]
-        eta_f = mu_f[:, None, :] / (2.0 * np.sqrt(np.maximum(beta_f, eps)))
-        cost_qp = eng.buffer("cost", B)
-        Qs = np.einsum("bik,ij,bjk->b", primal_x[:, :, :N], self.Q, primal_x[:, :, :N]) \
-            + np.einsum("bik,ij,bjk->b", primal_u, self.R, primal_u) \
-            + np.einsum("bi,ij,bj->b", primal_x[:, :, N], self.Qf, primal_x[:, :, N])
-        tm = eng.timings()
-        sol = self.current_iteration_scp
+        tm = eng.timings() if self.timing else dict(t_jac_ms=float('nan'), t_qp_ms=float('nan'), t_backward_ms=float('nan'))
         o = self._out
-        sol.update({
-            'primal_x': o(primal_x), 'primal_u': o(primal_u), 'primal_vec': o(pack(primal_x, primal_u)),
-            'delta_vec': o(pack(delta_x, delta_u)),
-            'dual_mu': o(np.swapaxes(mu, 1, 2)), 'dual_mu_f': o(mu_f),
-            'dual_vec': o(self._dual_vec(mu, mu_f)),
-            'dual_eta': o(eta), 'dual_eta_f': o(eta_f),
+        if converged is None:
+            success = ok
+        else:
+            success = ok & bool(converged)
+        eager = {
+            'primal_x': o(primal_x), 'primal_u': o(primal_u),
             'backoff': o(backoff), 'backoff_f': o(backoff_f), 'backoff_x': o(backoff_x), 'backoff_u': o(backoff_u),
-            'beta': o(beta), 'beta_f': o(beta_f),
-            'cost_QP': o(cost_qp), 'cost': o(cost_qp + Qs),
             'SOCP_steps': o(np.where(tight, int(self.fast_sls_rti_steps or 0), 0)),
             'iterations': iterations,
             't_jac_ms': float(tm['t_jac_ms']), 't_qp_ms': float(tm['t_qp_ms']),
             't_backward_ms': float(tm['t_backward_ms']) if tight.all() else float('nan'),
             'E_list': [np.asarray(self.m.E, float) for _ in range(N + 1)],
-            'status': o(eng.buffer("status", B)), 'qp_iterations': o(eng.buffer("qp_iters", B)),
-        })
-        # K / Phi are None when no tube was computed since the last reset (fast_SLS_jit.py:629-632 after the Q3 early
-        # return); a stale K of an earlier SCP iteration of the same solve is returned as in the reference
-        if B == 1:
-            sol['K'] = K[0] if kvalid[0] else None
-        else:
-            sol['K'] = K
-            sol['tube_updated'] = tight
-        if eng._views.get("phi"):
-            Px, Pu = eng.buffer("Phi_x", B), eng.buffer("Phi_u", B)
-            sol['Phi_x'] = (Px[0] if kvalid[0] else None) if B == 1 else Px
-            sol['Phi_u'] = (Pu[0] if kvalid[0] else None) if B == 1 else Pu
-        else:
-            sol['Phi_x'] = sol['Phi_u'] = None
-        if converged is None:
-            success = ok
-        else:
-            success = ok & bool(converged)
-        sol['success'] = bool(success[0]) if B == 1 else success
+            'status': o(res["status"]),
+            'success': bool(success[0]) if B == 1 else success,
+        }
+        if B > 1:
+            eager['tube_updated'] = tight
+
+        # ---- the rest of the reference's key set, copied from the device on first access
+        def t_primal_vec():
+            return {'primal_vec': o(pack(primal_x, primal_u))}
+
+        def t_delta():
+            dX, dU = eng.buffer("dX", B), eng.buffer("dU", B)
+            return {'delta_vec': o(pack(np.swapaxes(dX, 1, 2), np.swapaxes(dU, 1, 2)))}
+
+        def t_duals():
+            mu, mu_f = eng.buffer("mu", B), eng.buffer("mu_f", B)
+            beta, beta_f = eng.buffer("beta", B), eng.buffer("beta_f", B)
+            if nt.any():
+                beta[nt], beta_f[nt] = eps, eps
+            eta = np.zeros((B, N, N, ni))
+            sq = 2.0 * np.sqrt(np.maximum(beta, eps))
+            for k in range(N):
+                eta[:, k, :k + 1, :] = mu[:, k, None, :] / sq[:, k, :k + 1, :]
+            eta_f = mu_f[:, None, :] / (2.0 * np.sqrt(np.maximum(beta_f, eps)))
+            lam = eng.costates(B).cpu().numpy()
+            return {'dual_mu': o(np.swapaxes(mu, 1, 2)), 'dual_mu_f': o(mu_f), 'dual_vec': o(self._dual_vec(mu, mu_f, lam)),
+                    'dual_eta': o(eta), 'dual_eta_f': o(eta_f), 'beta': o(beta), 'beta_f': o(beta_f)}
+
+        def t_cost():
+            cost_qp = eng.buffer("cost", B)
+            Qs = np.einsum("bik,ij,bjk->b", primal_x[:, :, :N], self.Q, primal_x[:, :, :N]) \
+                + np.einsum("bik,ij,bjk->b", primal_u, self.R, primal_u) \
+                + np.einsum("bi,ij,bj->b", primal_x[:, :, N], self.Qf, primal_x[:, :, N])
+            return {'cost_QP': o(cost_qp), 'cost': o(cost_qp + Qs), 'qp_iterations': o(eng.buffer("qp_iters", B))}
+
+        def t_gains():
+            # K / Phi are None when no tube was computed since the last reset (fast_SLS_jit.py:629-632 after the Q3 early
+            # return); a stale K of an earlier SCP iteration of the same solve is returned as in the reference
+            K = eng.buffer("K", B)
+            out = {'K': (K[0] if kvalid[0] else None) if B == 1 else K}
+            if eng._views.get("phi"):
+                Px, Pu = eng.buffer("Phi_x", B), eng.buffer("Phi_u", B)
+                out['Phi_x'] = (Px[0] if kvalid[0] else None) if B == 1 else Px
+                out['Phi_u'] = (Pu[0] if kvalid[0] else None) if B == 1 else Pu
+            else:
+                out['Phi_x'] = out['Phi_u'] = None
+            return out
+
+        def t_lin():
+            # what the trailing update_jacobian (SCP_SLS_jit.py:139) and the diagnostics (:451-455) leave in the reference's dict:
+            # the linearisation of the UPDATED nominal trajectory and the signed maximum of its dynamics defect
+            lin = self.linearization()
+            c = lin['c_offset_list']
+            cmax = np.max(np.stack([ck.reshape(-1) for ck in c])) if B == 1 else np.asarray(c).reshape(B, -1).max(axis=1)
+            lin['primal_infeasibility'] = float(cmax) if B == 1 else cmax
+            return lin
+
+        groups = [(('primal_vec',), t_primal_vec), (('delta_vec',), t_delta),
+                  (('dual_mu', 'dual_mu_f', 'dual_vec', 'dual_eta', 'dual_eta_f', 'beta', 'beta_f'), t_duals),
+                  (('cost_QP', 'cost', 'qp_iterations'), t_cost), (('K', 'Phi_x', 'Phi_u'), t_gains),
+                  (('A_list', 'B_list', 'c_offset_list', 'g_list', 'primal_infeasibility'), t_lin)]
+        thunks = {k: th for keys, th in groups for k in keys}
+        sol = LazySolution(eager, thunks)
         if self.save_it_data:
             self.it_data[iterations] = {k: sol[k] for k in ('primal_x', 'primal_u', 'backoff_x', 'backoff_u', 'cost')}
-        out = dict(sol)
-        out.update(self.convergence_data_scp)
-        out['it_data'] = self.it_data.copy()
-        if B == 1 and not out['success'] and not self._keep_failed:
-            return {'success': False} if 'primal_x' not in out else out
-        return out
+        sol.update(self.convergence_data_scp)
+        dict.__setitem__(sol, 'it_data', self.it_data.copy())
+        if not self.lazy_results:
+            sol.materialize()
+        else:
+            self._last_solution = sol
+        self.current_iteration_scp = sol
+        return sol
 
     _keep_failed = True
 
-    def _dual_vec(self, mu, mu_f):
-        """Inequality part of ``dual_vec`` in the reference's row order (qp_jit.py:493-501); the multipliers of the
-        dynamics rows are not formed by the Riccati solver and are reported as NaN."""
+    def _dual_vec(self, mu, mu_f, lam_dyn):
+        """``dual_vec`` in the reference's row order (qp_jit.py:493-501): per stage the nx multipliers of the dynamics rows
+        (rnmpc_costates) and the ni inequality multipliers, then the terminal ones (the x0 rows are dropped as in the reference)."""
         B, N, nx, ni = mu.shape[0], self.N, self.m.nx, self.m.ni
-        lam = np.full((B, N, nx + ni), np.nan)
+        lam = np.empty((B, N, nx + ni))
+        lam[:, :, :nx] = lam_dyn
         lam[:, :, nx:] = mu
         return np.concatenate([lam.reshape(B, -1), mu_f], axis=1)
 
@@ -262,6 +381,7 @@ class SCP_SLS(OCP):
         """solver/SCP_SLS_jit.py:500-551."""
         if not self._has_nominal:
             return
+        self._advance()
         self._engine.reset_warm_start(self.batch)
         self.current_iteration_scp = {}
         self.convergence_data_scp = {}

@@ -366,6 +366,56 @@ def test_reference_api_drop_in():
         assert np.abs(x - g["states"][i + 1]).max() < TOL_STATE
     lin = solver.linearization()
     assert len(lin['A_list']) == 15 and lin['A_list'][0].shape == (17, 17) and len(lin['g_list']) == 16
+    # the full key set of the reference's result dict (SCP_SLS_jit.py:343-346, 414-465) against the oracle on one step: all 919 duals
+    # incl. the multipliers of the dynamics rows (qp_jit.py:491-501), primal_infeasibility, the linearisation lists
+    ref = oscp.SCPSLS(N, cfg["Q"], cfg["R"], mo, cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], rti=1, fast_sls_rti_steps=1)
+    ref.set_nominal(g["X0"].T, g["U0"].T)
+    rsol = ref.solve(g["x0"])
+    s2 = SCP_SLS(N, cfg["Q"], cfg["R"], m, cfg["Qf"], Q_reg=1e4 * np.eye(m.nx), R_reg=1e4 * np.eye(m.nu),
+                 Q_reg_f=1e4 * np.eye(m.nx), rti=1, fast_sls_rti_steps=1, verbose=False)
+    s2.set_nominal_trajectory(g["X0"].T, g["U0"].T)
+    sol = s2.solve(g["x0"])
+    for key in ('primal_vec', 'dual_vec', 'dual_mu', 'dual_mu_f', 'dual_eta', 'dual_eta_f', 'cost', 'cost_QP', 'SOCP_steps', 'backoff', 'Phi_x',
+                'Phi_u', 'delta_vec', 'primal_infeasibility', 'A_list', 'B_list', 'c_offset_list', 'E_list', 'g_list', 'iterations', 'it_data'):
+        assert key in sol, key
+    assert sol['dual_vec'].shape == (919,) and np.isfinite(sol['dual_vec']).all()
+    scale = max(1.0, np.abs(rsol['dual_vec']).max())
+    assert np.abs(sol['dual_vec'] - rsol['dual_vec']).max() < 1e-6 * scale
+    lam_dyn = sol['dual_vec'][:-34].reshape(15, 17 + 42)[:, :17]
+    assert np.abs(lam_dyn).max() > 1e-3                                   # the dynamics rows carry multipliers (not a vacuous comparison)
+    assert abs(sol['primal_infeasibility'] - rsol['primal_infeasibility']) < 1e-9
+    assert rel(sol['delta_vec'], rsol['delta_vec']) < TOL_TRAJ and rel(sol['cost'], rsol['cost']) < TOL_TRAJ
+    # A_list / B_list / c_offset_list / g_list: linearisation of the updated nominal (the trailing update_jacobian, SCP_SLS_jit.py:139)
+    A2, B2, c2, g2 = ref.linearize(rsol['primal_x'], rsol['primal_u'])
+    assert all(np.abs(a - b).max() < 1e-8 for a, b in zip(sol['A_list'], A2)) and all(np.abs(a - b).max() < 1e-8 for a, b in zip(sol['B_list'], B2))
+    assert all(np.abs(np.asarray(a).reshape(-1) - np.asarray(b).reshape(-1)).max() < 1e-8 for a, b in zip(sol['c_offset_list'], c2))
+    assert all(np.abs(a - b).max() < 1e-7 for a, b in zip(sol['g_list'], g2))
+    # a result key that was not read before the solver advanced is refused, not silently stale
+    s2.reset_warm_start()
+    sol_b = s2.solve(np.array(m.ddyn(g["x0"], sol['primal_u'][:, 0])).reshape(-1))
+    s2.reset_warm_start()
+    with pytest.raises(KeyError):
+        sol_b['dual_vec']
+    # settings of fast_SLS_solver are forwarded or refused, never swallowed
+    s2.fast_SLS_solver.MAX_ITER = 12
+    assert s2.engine.lib.rnmpc_launch_count(s2.engine._h) >= 0
+    with pytest.raises(NotImplementedError):
+        s2.fast_SLS_solver.epsilon_backoff = 1e-8
+    s2.fast_SLS_solver.epsilon_backoff = 1e-10
+    with pytest.raises(ValueError):
+        s2.fast_SLS_solver.MAX_ITER = 0
+    # set_fast_sls_rti_steps keeps the handle (Q3 history, nominal trajectory): the next solve continues the loop
+    h_before = s2.engine._h.value
+    s2.set_fast_sls_rti_steps(2)
+    assert s2.engine._h.value == h_before
+    assert s2.solve(np.array(m.ddyn(g["x0"], sol['primal_u'][:, 0])).reshape(-1))['success']
+    # eager mode: every key copied at solve time, as the reference does
+    s3 = SCP_SLS(N, cfg["Q"], cfg["R"], m, cfg["Qf"], Q_reg=1e4 * np.eye(m.nx), R_reg=1e4 * np.eye(m.nu),
+                 Q_reg_f=1e4 * np.eye(m.nx), rti=1, fast_sls_rti_steps=1, verbose=False, lazy_results=False)
+    s3.set_nominal_trajectory(g["X0"].T, g["U0"].T)
+    sol3 = s3.solve(g["x0"])
+    s3.reset_warm_start()
+    assert np.array_equal(sol3['dual_vec'], sol['dual_vec']) and np.array_equal(sol3['primal_x'], sol['primal_x'])
     # batch mode of the same class
     sb = SCP_SLS(N, cfg["Q"], cfg["R"], m, cfg["Qf"], Q_reg=1e4 * np.eye(m.nx), R_reg=1e4 * np.eye(m.nu),
                  Q_reg_f=1e4 * np.eye(m.nx), rti=1, fast_sls_rti_steps=1, batch=3, verbose=False)
