@@ -582,9 +582,12 @@ def test_dense_cost_matrices_vs_oracle(name):
     s.close()
 
 
-@pytest.mark.parametrize("name,B,seed,warm_mask", [("rocket", 2048, 2025, 0), ("rocket", 2048, 2025, 2), ("rocket", 1024, 99, 0),
-                                                   ("quadrotor", 512, 5, 0), ("quadrotor", 2048, 5, 0), ("pendulum", 256, 5, 0)])
-def test_monte_carlo_population_vs_cpu_port(name, B, seed, warm_mask):
+@pytest.mark.parametrize("name,B,seed,warm_mask,x0_scale", [
+    ("rocket", 2048, 2025, 0, 0.0), ("rocket", 2048, 2025, 2, 0.0), ("rocket", 1024, 99, 0, 0.0),
+    ("rocket", 4096, 2025, 0, 0.0),           # BASELINE configs[3] at the bench's batch size (the tensor-memory QP kernel)
+    ("rocket", 8192, 2025, 0, 0.05),          # BASELINE configs[4] distribution: x0 perturbed by 5 % of the half range, one GPU's share of 65,536
+    ("quadrotor", 512, 5, 0, 0.0), ("quadrotor", 2048, 5, 0, 0.0), ("pendulum", 256, 5, 0, 0.0)])
+def test_monte_carlo_population_vs_cpu_port(name, B, seed, warm_mask, x0_scale):
     """Disturbed closed loops of a whole population (lengths of the reference drivers' loops; default solver options = every QP
     cold, and once with the optional warm start of the tightened QP, `warm_mask` = 2, so that this path stays covered)
     against the C++ CPU port of the same path on identical scenarios and nominal trajectory (batches of 2048 run the
@@ -601,12 +604,21 @@ def test_monte_carlo_population_vs_cpu_port(name, B, seed, warm_mask):
     steps = {"rocket": 29, "pendulum": 60, "quadrotor": 30}[name]
     s.set_option("sticky_fail", 1)
     s.set_option("warm_mask", warm_mask)
-    if name == "rocket":
+    init_ok = np.ones(B, dtype=bool)
+    if name == "rocket" and x0_scale == 0.0:
         x0, W = rocket_scenarios(B, seed=seed, steps=steps)
         X0, U0, ok = oscp.nominal_sqp(m, cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"], x0[0], iters=10)
         assert ok
         X0b, U0b = np.repeat(X0.T[None], B, 0), np.repeat(U0.T[None], B, 0)
         s.set_nominal(X0b, U0b)
+    elif name == "rocket":
+        # perturbed initial states (configs[4]): every scenario has its own nominal trajectory; the GPU's initialiser result is
+        # handed to the CPU port, scenarios it could not initialise are left out on both sides
+        x0, W = rocket_scenarios(B, seed=seed, steps=steps, x0_scale=x0_scale)
+        s.init_nominal(x0, 10)
+        init_ok = (s.buffer("flags", B) & 1) == 0
+        X0b, U0b = s.buffer("X", B).copy(), s.buffer("U", B).copy()
+        assert init_ok.mean() > 0.9
     else:       # the nominal initialiser is not the subject here: the GPU's is handed to the CPU port
         x0 = np.repeat(om.PENDULUM_X0[None], B, 0) if name == "pendulum" else np.stack([om.quadrotor_x0(seed + b) for b in range(B)])
         W = np.random.default_rng(seed).uniform(-1, 1, size=(B, steps, m.nx))
@@ -626,11 +638,21 @@ def test_monte_carlo_population_vs_cpu_port(name, B, seed, warm_mask):
         s.plant_step(x, W[:, i])
     st_g[:, steps] = x.cpu().numpy()
     s.close()
+    if not init_ok.all():
+        keep = np.where(init_ok)[0]
+        first_c, first_g, st_c, st_g, B = first_c[keep], first_g[keep], st_c[keep], st_g[keep], len(keep)
     if name != "pendulum":
         assert (first_c < steps).sum() >= 5, "the population should exercise the failure path"
-    assert np.array_equal(first_c, first_g), "scenarios failing / first failure step differ: %s" % np.where(first_c != first_g)[0][:10]
     scale = np.maximum(1.0, np.abs(st_c).max(axis=(0, 1)))
-    err = np.array([float((np.abs(st_c[b, :first_c[b] + 1] - st_g[b, :first_c[b] + 1]) / scale).max()) for b in range(B)])
+    both = np.minimum(first_c, first_g)
+    err = np.array([float((np.abs(st_c[b, :both[b] + 1] - st_g[b, :both[b] + 1]) / scale).max()) for b in range(B)])
+    print("population %s B=%d x0_scale=%g: %d failing scenarios (CPU) / %d (GPU), %d with a different failure step, state error max %.2e, "
+          "q99.9 %.2e, scenarios above 1e-6: %d" % (name, B, x0_scale, (first_c < steps).sum(), (first_g < steps).sum(),
+                                                     (first_c != first_g).sum(), err.max(), np.quantile(err, 0.999), (err > 1e-6).sum()))
+    # (measured on B200 for the configs[4] distribution, 7900 initialised scenarios of 8192: 2265 scenarios fail, every one at the same
+    # step on both sides, states agree to 8.4e-8, no scenario above 1e-6 -- the perturbed initial states near the bounds do not
+    # produce the degenerate-multiplier outliers seen on random quadrotor states)
+    assert np.array_equal(first_c, first_g), "scenarios failing / first failure step differ: %s" % np.where(first_c != first_g)[0][:10]
     if name == "quadrotor" and B > 1000:
         # Random initial states: about one scenario in a thousand is so sensitive that ANY two arithmetic orders of the same
         # algorithm disagree at 1e-5 ... 4e-4 from the first solve on (the two CUDA QP kernels among themselves as much as
