@@ -119,6 +119,16 @@ int rnmpc_sls_duals(rnmpc_handle* h, int B, const double* d_A, const double* d_B
  * stationarity conditions of the solution (OSQP sign convention P x + q + A' y = 0).  d_lam [B][N][nx].  On demand: not on the solve path. */
 int rnmpc_costates(rnmpc_handle* h, int B, double* d_lam, void* stream);
 
+/* Soft-constrained NMPC comparator (solver/nlp_soft_constraints.py:175-276 `NLPSoftConstraints`, handed to IPOPT by the reference;
+ * expe/main_rocket_compare_closed_loop.py:176-222 `_run_soft`):  min sum x'Qx + u'Ru + x_N'Qf x_N + rho (|gamma|^2 + |gamma_f|^2) + rho1 sum(gamma)
+ * s.t. x_{k+1} = ddyn(x_k, u_k), x_0 = x0, G [x_k; u_k] - g <= gamma_k, Gf x_N - gf <= gamma_f, gamma >= 0, by full-step SQP from the
+ * trajectory guess in d_X [B][N+1][nx] / d_U [B][N][nu] (in / out) until max |step| < tol per instance, at most max_iter iterations
+ * (status 4 = not converged; a QP failure gives its status).  Every iteration = the linearisation kernel + the interior-point QP kernel
+ * with the slack variables eliminated entry-wise (rnmpc_qp_warp.cuh, SOFT).  Outputs: d_gamma [B][N][ni], d_gamma_f [B][ni_f] (both NULL to
+ * skip), d_sqp_iters [B], d_status [B].  Uses the handle's workspace (not its resident robust trajectories).  Synchronises once per iteration. */
+int rnmpc_soft_nmpc(rnmpc_handle* h, int B, const double* d_x0, double* d_X, double* d_U, double rho, double rho1, int max_iter, double tol,
+                    double* d_gamma, double* d_gamma_f, int* d_sqp_iters, int* d_status, void* stream);
+
 /* Load the nominal trajectories of B instances (replaces the IPOPT initial guess, SCP_SLS_jit.py:161-188, and is what
  * reset()/a fresh solver start from).  Clears the warm-start state incl. the Q3 history. */
 int rnmpc_set_nominal(rnmpc_handle* h, int B, const double* d_X, const double* d_U, void* stream);

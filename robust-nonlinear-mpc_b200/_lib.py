@@ -45,6 +45,7 @@ SYMBOLS = {
     "rnmpc_qp_general": (_I, [_VP, _I] + [_VP] * 15),
     "rnmpc_sls_duals": (_I, [_VP, _I] + [_VP] * 15),
     "rnmpc_costates": (_I, [_VP, _I, _VP, _VP]),
+    "rnmpc_soft_nmpc": (_I, [_VP, _I, _VP, _VP, _VP, _D, _D, _I, _D, _VP, _VP, _VP, _VP, _VP]),
     "rnmpc_set_nominal": (_I, [_VP, _I, _VP, _VP, _VP]),
     "rnmpc_init_nominal": (_I, [_VP, _I, _VP, _I, _VP]),
     "rnmpc_solve": (_I, [_VP, _I, _VP, _VP]),

@@ -166,6 +166,14 @@ int rnmpc_costates(rnmpc_handle* h, int B, double* lam, void* stream) {
     if (!lam) { set_error("null buffer"); return -1; }
     return h->e->costates(B, lam, (cudaStream_t)stream);
 }
+int rnmpc_soft_nmpc(rnmpc_handle* h, int B, const double* x0, double* X, double* U, double rho, double rho1, int max_iter, double tol,
+                    double* gamma, double* gamma_f, int* sqp_iters, int* status, void* stream) {
+    RN_ENTER(h);
+    if (!x0 || !X || !U || !sqp_iters || !status) { set_error("null buffer"); return -1; }
+    if (!(rho > 0.0) || rho1 < 0.0 || max_iter < 1 || !(tol > 0.0)) { set_error("soft_nmpc: rho > 0, rho1 >= 0, max_iter >= 1, tol > 0"); return -1; }
+    if ((gamma == nullptr) != (gamma_f == nullptr)) { set_error("gamma and gamma_f go together"); return -1; }
+    return h->e->soft_nmpc(B, x0, X, U, rho, rho1, max_iter, tol, gamma, gamma_f, sqp_iters, status, (cudaStream_t)stream);
+}
 int rnmpc_set_nominal(rnmpc_handle* h, int B, const double* X, const double* U, void* stream) {
     RN_ENTER(h);
     return h->e->set_nominal(B, X, U, (cudaStream_t)stream);

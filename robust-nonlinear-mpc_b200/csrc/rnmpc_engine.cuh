@@ -53,6 +53,8 @@ struct IEngine {
                           const double* beta_f_in, double* K, double* S, double* Phi_x, double* Phi_u, double* beta, double* beta_f,
                           double* backoff, double* backoff_f, cudaStream_t st) = 0;
     virtual int costates(int B, double* lam, cudaStream_t st) = 0;
+    virtual int soft_nmpc(int B, const double* x0, double* Xs, double* Us, double rho, double rho1, int max_iter, double tol, double* gamma,
+                          double* gamma_f, int* sqp_iters, int* status, cudaStream_t st) = 0;
     virtual int set_nominal(int B, const double* X, const double* U, cudaStream_t st) = 0;
     virtual int init_nominal(int B, const double* x0, int iters, cudaStream_t st) = 0;
     virtual int solve(int B, const double* x0, cudaStream_t st) = 0;
@@ -208,6 +210,32 @@ __global__ void costate_kernel(int B, int N, int lda, const double* __restrict__
             yn[i] = g;
         }
         for (int i = 0; i < NX; ++i) y[i] = yn[i];
+    }
+}
+
+// One SQP iteration of the soft-constrained comparator is done: full step X += dX, U += dU of every open instance, convergence test
+// max |delta| < tol (-> FLAG_SLSDONE), failed QP -> FLAG_FAIL.  One warp per instance.
+static __global__ void soft_step_kernel(int B, int nxs, int nus, const double* __restrict__ dX, const double* __restrict__ dU,
+                                        double* __restrict__ X, double* __restrict__ U, const int* __restrict__ qp_status, double tol,
+                                        int* __restrict__ flags, int* __restrict__ sqp_iters, int* __restrict__ status, int* n_open) {
+    const int b = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const int f = flags[b];
+    if (f & (FLAG_FAIL | FLAG_SLSDONE)) return;
+    if (qp_status[b] != 0) {
+        if (lane == 0) { flags[b] = f | FLAG_FAIL; status[b] = qp_status[b]; }
+        return;
+    }
+    double m = 0.0;
+    for (int i = lane; i < nxs; i += 32) { const double v = dX[(size_t)b * nxs + i]; m = fmax(m, fabs(v)); X[(size_t)b * nxs + i] += v; }
+    for (int i = lane; i < nus; i += 32) { const double v = dU[(size_t)b * nus + i]; m = fmax(m, fabs(v)); U[(size_t)b * nus + i] += v; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) {
+        sqp_iters[b] += 1;
+        if (m < tol) flags[b] = f | FLAG_SLSDONE;
+        else atomicAdd(n_open, 1);
     }
 }
 
@@ -621,6 +649,51 @@ struct Engine : IEngine {
     int costates(int B, double* lam, cudaStream_t st) override {
         if (check_B(B)) return -1;
         costate_kernel<NX, NU><<<(B + 63) / 64, 64, 0, st>>>(B, N, LDA, A, X, mu, mu_f, d_prm, lam);
+        ++launches;
+        RN_CUDA(cudaGetLastError());
+        return 0;
+    }
+    // Soft-constrained NMPC comparator (solver/nlp_soft_constraints.py:175-276, expe/main_rocket_compare_closed_loop.py:176-222): the NLP with
+    // every inequality row softened, solved by full-step SQP from the caller's trajectory guess (Xs, Us; in / out): linearise, soft QP
+    // (qp_warp_kernel<.., SOFT>), step, until max |delta| < tol per instance (one 4-byte device -> host read per iteration).
+    int* soft_flags = nullptr;
+    size_t soft_smem = 0;
+    int soft_nmpc(int B, const double* x0, double* Xs, double* Us, double rho, double rho1, int max_iter, double tol, double* gamma,
+                  double* gamma_f, int* sqp_iters, int* status_, cudaStream_t st) override {
+        if (check_B(B)) return -1;
+        if (!diag_cost) { set_error("soft_nmpc: diagonal cost matrices only"); return -1; }
+        if (soft_flags == nullptr) {
+            if (alloc("soft_flags", soft_flags, cap)) return -2;
+            soft_smem = (qp_warp_smem_doubles<NX, NU>(N) + qp_warp_soft_extra_doubles<NX, NU>(N)) * sizeof(double);
+            if (soft_smem > 227 * 1024 ||
+                cudaFuncSetAttribute(qp_warp_kernel<NX, NU, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+                set_error("soft_nmpc: the working set does not fit shared memory for this horizon"); return -1;
+            }
+        }
+        RN_CUDA(cudaMemsetAsync(soft_flags, 0, (size_t)B * sizeof(int), st));
+        RN_CUDA(cudaMemsetAsync(sqp_iters, 0, (size_t)B * sizeof(int), st));
+        RN_CUDA(cudaMemsetAsync(status_, 0, (size_t)B * sizeof(int), st));
+        for (int it = 0; it < max_iter; ++it) {
+            int rc = linearize_ld(B, Xs, Us, A, LDA, Bm, c, st);
+            if (rc) return rc;
+            QpArgs a{};
+            a.B = B; a.N = N; a.tightened = 0; a.max_iter = qp_max_iter + 20; a.tol_mu = 1e-16; a.tol_res = qp_tol_res; a.mu0 = qp_mu0;      // (terminal slacks sit at sqrt(mu / 2 rho) on the central path)
+            a.A = A; a.Bm = Bm; a.c = c; a.Xnom = Xs; a.Unom = Us; a.x0 = x0;
+            a.flags = soft_flags; a.skip_mask = FLAG_FAIL | FLAG_SLSDONE;
+            a.dX = dX; a.dU = dU; a.mu = mu; a.mu_f = mu_f; a.cost = cost; a.iters = iters_tmp; a.status = status_tmp;
+            a.diag_cost = 1; a.Kq = Kw; a.Lq = Lq; a.rho = rho; a.rho1 = rho1; a.gamma = gamma; a.gamma_f = gamma_f;
+            qp_warp_kernel<NX, NU, 0, true><<<(unsigned)B, 32, soft_smem, st>>>(a, d_prm);
+            ++launches;
+            RN_CUDA(cudaMemsetAsync(n_open, 0, sizeof(int), st));
+            soft_step_kernel<<<(B + 3) / 4, 128, 0, st>>>(B, (N + 1) * NX, N * NU, dX, dU, Xs, Us, status_tmp, tol, soft_flags, sqp_iters, status_, n_open);
+            ++launches;
+            int open_host = 0;
+            RN_CUDA(cudaMemcpyAsync(&open_host, n_open, sizeof(int), cudaMemcpyDeviceToHost, st));
+            RN_CUDA(cudaStreamSynchronize(st));
+            if (open_host == 0) break;
+        }
+        // instances still open after max_iter: not converged
+        fail_open_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, soft_flags, status_);
         ++launches;
         RN_CUDA(cudaGetLastError());
         return 0;

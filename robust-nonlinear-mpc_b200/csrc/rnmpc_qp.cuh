@@ -79,6 +79,11 @@ struct QpArgs {
     int* handoff_list;      // [B] their indices
     double* handoff_state;  // [B][4] rp_scale, mu, rp_inf, n_box
     int resume;             // qp_block_kernel only: 1 = finish the instances of handoff_list
+    // soft-constrained comparator (qp_warp_kernel<.., SOFT = true>): every bound row softened, cost rho gam^2 + rho1 gam per row
+    // (terminal rows: rho only), solver/nlp_soft_constraints.py:222-232
+    double rho, rho1;
+    double* gamma;          // [B][N][ni] slack variables (output, may be nullptr)
+    double* gamma_f;        // [B][ni_f]
     int* work;              // qp_tm_kernel only: [1] next instance of the batch (zeroed by the caller): its warps draw instances from it
     long long* prof;        // qp_mma_kernel only, diagnostic ("qp_profile"): [16] cycles of instance 0 per phase, summed over the launches
 };

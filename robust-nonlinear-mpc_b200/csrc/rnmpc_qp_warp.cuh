@@ -43,7 +43,34 @@ struct QpWarp {
     static_assert(NX + 2 <= 32 && NZ <= 32, "one lane per state / input entry");
 };
 
+// One softened bound row of the soft-constrained comparator (solver/nlp_soft_constraints.py:175-232): row slack s >= 0 (multiplier lam)
+// of `+-z - bound <= gam`, slack variable gam >= 0 (multiplier nu), cost rho gam^2 + rho1 gam.  The slack variable only couples to its
+// own row, so it is eliminated from the Newton system entry by entry: with ru = lam / s, rg = nu / gam, D = 2 rho + ru + rg
+//   d gam = (ru (+-dz) + b) / D,  b = tgt / s + tg / gam - 2 rho gam - rho1      (tgt, tg: complementarity targets of the two pairs)
+//   the row enters the Riccati system with weight ru (2 rho + rg) / D  (-> ru as rho -> inf: the hard constraint)
+//   and right-hand side  tgt / s - ru b / D.
+// The Riccati factorisation and the vector sweeps are those of the hard-constrained QP.
+struct SoftSide {
+    double s, lam, gam, nu, rho2, rho1;
+    double is, ig, ru, rg, iD;
+    __device__ __forceinline__ void prep() {
+        is = fast_rcp(s); ig = fast_rcp(gam); ru = lam * is; rg = nu * ig; iD = fast_rcp(rho2 + ru + rg);
+    }
+    __device__ __forceinline__ double weight() const { return ru * (rho2 + rg) * iD; }
+    __device__ __forceinline__ double bgam(const double tgt, const double tg) const { return tgt * is + tg * ig - rho2 * gam - rho1; }
+    __device__ __forceinline__ double rhs(const double tgt, const double tg) const { return tgt * is - ru * bgam(tgt, tg) * iD; }
+    // steps of the four quantities for a step sdz = +dz (upper bound) / -dz (lower bound) of the primal entry
+    __device__ __forceinline__ void steps(const double sdz, const double tgt, const double tg, double& ds, double& dl, double& dg, double& dn) const {
+        dg = (ru * sdz + bgam(tgt, tg)) * iD;
+        ds = dg - sdz;
+        dl = tgt * is - lam - ru * ds;
+        dn = tg * ig - nu - rg * dg;
+    }
+};
+
 // shared-memory footprint in doubles
+template <int NX, int NU>
+__host__ __device__ inline size_t qp_warp_soft_extra_doubles(int N) { return 4 * mma_ev((size_t)(N + 1) * (NX + NU)); }
 template <int NX, int NU>
 __host__ __device__ inline size_t qp_warp_smem_doubles(int N) {
     using D = QpWarp<NX, NU>;
@@ -53,8 +80,10 @@ __host__ __device__ inline size_t qp_warp_smem_doubles(int N) {
          + mma_ev(D::NZ + NX) + mma_ev(NU * NU) + 16 + 4;                                         // qdt, R2, profile counters, ring barriers
 }
 
-template <int NX, int NU, int NC>
-__global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Params<NX, NU>* __restrict__ prm) {
+// SOFT: the soft-constrained comparator's QP (every bound row softened, QpArgs::rho / rho1; slack variables and their multipliers in
+// four more entry arrays).  The hard-constrained instantiation compiles none of it.
+template <int NX, int NU, int NC, bool SOFT = false>
+__global__ void __launch_bounds__(32, SOFT ? 4 : 6) qp_warp_kernel(const QpArgs a, const Params<NX, NU>* __restrict__ prm) {
     using D = QpWarp<NX, NU>;
     constexpr int NZ = D::NZ, NI = 2 * NZ, NIF = 2 * NX, LDG = Slot<NX>::LD;
     constexpr int KP = D::KP, KS = D::KS, CB = D::CB, CRP = D::CRP, CP = D::CP, NT = D::NT, MTS = D::MTS, MTM = D::MTM;
@@ -76,6 +105,8 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
     double* e_su = take(NE); double* e_sl = take(NE); double* e_lu = take(NE); double* e_ll = take(NE);
     double* e_zy = take(NE);                                         // z + z_nom (the gradient needs the sum, the outputs the difference)
     double* e_da = take(NE); double* e_dc = take(NE);
+    double* e_gu = SOFT ? take(NE) : nullptr; double* e_gl = SOFT ? take(NE) : nullptr;      // slack variables of the upper / lower rows
+    double* e_nu = SOFT ? take(NE) : nullptr; double* e_nl = SOFT ? take(NE) : nullptr;      // their multipliers
     double* rp = take((size_t)N * NX); double* Sc = take((size_t)N * NX);
     double* dff = take((size_t)N * NU); double* tu = take((size_t)N * NU);
     double* gv = take(NX); double* pv = take(KP); double* rhs = take(NZ); double* dgn = take(NZ); double* uc = take(NU);
@@ -129,10 +160,10 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
     auto qd_of = [&](const int k, const int i) -> double { return (k < N) ? qdt[i] : (i < NX ? qdt[NZ + i] : 0.0); };
 
     // ------------------------------------------------------------------ bounds, initial point, slacks (rnmpc_qp_mma.cuh, cold start)
-    const bool tight = a.tightened < 0 ? ((a.flags[b] & FLAG_TIGHT) != 0) : (a.tightened != 0);
+    const bool tight = SOFT ? false : (a.tightened < 0 ? ((a.flags[b] & FLAG_TIGHT) != 0) : (a.tightened != 0));
     double bad = 0.0, n_box = 0.0, s_sum = 0.0, dmy = 0.0;
     {
-        const double eps = tight ? 0.0 : kEpsQP;
+        const double eps = (tight || SOFT) ? 0.0 : kEpsQP;
 #pragma unroll 1
         for (int idx = lane; idx < NE; idx += 32) {
             const int k = idx / NZ, i = idx - k * NZ;
@@ -154,7 +185,7 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
                 }
                 if (k == 0) {
                     z = a.x0[(size_t)b * NX + i] - xn;                                  // x(0) is pinned to the measurement
-                    if (z > h_ + kX0Tol || z < l_ - kX0Tol) bad = 1.0;
+                    if (!SOFT && (z > h_ + kX0Tol || z < l_ - kX0Tol)) bad = 1.0;      // (softened: its slack absorbs the violation, a constant)
                 } else box = true;
             } else if (k < N) {
                 const int p = i - NX;
@@ -166,7 +197,13 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
                 box = true;
             }
             double su = 1e300, sl = 1e300;
-            if (box) {
+            if (SOFT) {
+                // start on the nominal trajectory (z = 0); e_su / e_sl carry the row violations v = +-z - bound until the second pass
+                if (box) {
+                    if (h_ < kBig) { su = z - h_; n_box += 2.0; s_sum += fmax(-su, 0.0); }
+                    if (l_ > -kBig) { sl = l_ - z; n_box += 2.0; s_sum += fmax(-sl, 0.0); }
+                }
+            } else if (box) {
                 const bool hu = h_ < kBig, hl = l_ > -kBig;
                 if (hu && hl) {
                     const double m = 0.01 * (h_ - l_);
@@ -185,9 +222,22 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
     warp_reduce4(bad, dmy, n_box, s_sum);
     int status = bad > 0.0 ? 2 : 0;
     {   // centred cold start: multipliers mu_bar / slack (QpArgs::mu0)
-        const double mu_bar = a.mu0 < 0.0 ? (n_box > 0.0 ? -a.mu0 * s_sum / n_box : 1.0) : a.mu0;
+        const double mu_bar = a.mu0 < 0.0 ? (n_box > 0.0 ? -a.mu0 * s_sum / n_box * (SOFT ? 2.0 : 1.0) : 1.0) : a.mu0;
 #pragma unroll 1
         for (int idx = lane; idx < NE; idx += 32) {
+            if (SOFT) {
+                // slack variables start as far from their bound as the row slacks do on average (the primal steps of the first
+                // iterations are of that size: a start near the boundary, however well centred, blocks them): gam = max(v, 0) + g0,
+                // row slack s = gam - v, multipliers mu_bar / s and mu_bar / gam
+                const double g0 = n_box > 0.0 ? 2.0 * s_sum / n_box : 1.0;
+                const double vu = e_su[idx], vl = e_sl[idx];
+                double su = 1e300, sl = 1e300, lu = 0.0, ll = 0.0, gu = 1.0, gl = 1.0, nu_ = 0.0, nl_ = 0.0;
+                if (vu < kBig) { gu = fmax(vu, 0.0) + g0; su = gu - vu; lu = mu_bar / su; nu_ = mu_bar / gu; }
+                if (vl < kBig) { gl = fmax(vl, 0.0) + g0; sl = gl - vl; ll = mu_bar / sl; nl_ = mu_bar / gl; }
+                e_su[idx] = su; e_sl[idx] = sl; e_lu[idx] = lu; e_ll[idx] = ll;
+                e_gu[idx] = gu; e_gl[idx] = gl; e_nu[idx] = nu_; e_nl[idx] = nl_;
+                continue;
+            }
             const double su = e_su[idx], sl = e_sl[idx];
             double lu, ll;
             if (a.mu0 != 0.0) { lu = su < kBig ? mu_bar / su : 0.0; ll = sl < kBig ? mu_bar / sl : 0.0; }
@@ -220,8 +270,8 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
 #pragma unroll 1
     for (int idx = lane; idx < NE; idx += 32) {
         const int k = idx / NZ, i = idx - k * NZ;
-        if (e_su[idx] < kBig) mu_acc = fma(e_su[idx], e_lu[idx], mu_acc);
-        if (e_sl[idx] < kBig) mu_acc = fma(e_sl[idx], e_ll[idx], mu_acc);
+        if (e_su[idx] < kBig) { mu_acc = fma(e_su[idx], e_lu[idx], mu_acc); if (SOFT) mu_acc = fma(e_gu[idx], e_nu[idx], mu_acc); }
+        if (e_sl[idx] < kBig) { mu_acc = fma(e_sl[idx], e_ll[idx], mu_acc); if (SOFT) mu_acc = fma(e_gl[idx], e_nl[idx], mu_acc); }
         if (i < NX) e_zy[idx] += Xn[k * NX + i];                                       // from here on: z + z_nom
         else if (k < N) e_zy[idx] += Un[k * NU + i - NX];
     }
@@ -233,12 +283,50 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
     double rp_scale = 1.0;
     __syncwarp();
 
-    auto sg_of = [&](const int idx) -> double { return e_lu[idx] * rc(e_su[idx]) + e_ll[idx] * rc(e_sl[idx]); };
-    // right-hand side of one entry (rnmpc_qp.cuh rhs_eval): gradient (+ centring / second-order terms in the corrector pass)
     double sigma_mu = 0.0;
+    // the two softened rows of an entry (SOFT): state + derived coefficients
+    auto soft_side = [&](const int idx, const bool upper, SoftSide& sd) -> bool {
+        sd.s = upper ? e_su[idx] : e_sl[idx];
+        if (!(sd.s < kBig)) return false;
+        sd.lam = upper ? e_lu[idx] : e_ll[idx];
+        sd.gam = upper ? e_gu[idx] : e_gl[idx];
+        sd.nu = upper ? e_nu[idx] : e_nl[idx];
+        sd.rho2 = 2.0 * a.rho;
+        sd.rho1 = idx < N * NZ ? a.rho1 : 0.0;
+        sd.prep();
+        return true;
+    };
+    // complementarity targets of the corrector for one side: sigma mu - (affine step products), from the affine primal step dza
+    auto soft_targets = [&](const SoftSide& sd, const double sdza, double& tgt, double& tg) {
+        double ds, dl, dg, dn;
+        sd.steps(sdza, 0.0, 0.0, ds, dl, dg, dn);
+        tgt = sigma_mu - ds * dl;
+        tg = sigma_mu - dg * dn;
+    };
+    auto sg_of = [&](const int idx) -> double {
+        if (SOFT) {
+            SoftSide sd;
+            double w = 0.0;
+            if (soft_side(idx, true, sd)) w += sd.weight();
+            if (soft_side(idx, false, sd)) w += sd.weight();
+            return w;
+        }
+        return e_lu[idx] * rc(e_su[idx]) + e_ll[idx] * rc(e_sl[idx]);
+    };
+    // right-hand side of one entry (rnmpc_qp.cuh rhs_eval): gradient (+ centring / second-order terms in the corrector pass)
     auto rhs_entry = [&](const int pass, const int k, const int i) -> double {
         const int idx = k * NZ + i;
         double gq = qd_of(k, i) * e_zy[idx];
+        if (SOFT) {
+            // the softened rows contribute in the predictor too: lam + d lam = w dz + (tgt / s - ru b / D)
+            const double dza = e_da[idx];
+            SoftSide sd;
+            double tgt = 0.0, tg = 0.0;
+            if (soft_side(idx, true, sd)) { if (pass == 1) soft_targets(sd, dza, tgt, tg); gq += sd.rhs(tgt, tg); }
+            tgt = 0.0; tg = 0.0;
+            if (soft_side(idx, false, sd)) { if (pass == 1) soft_targets(sd, -dza, tgt, tg); gq -= sd.rhs(tgt, tg); }
+            return gq;
+        }
         if (pass == 1) {
             const double su = e_su[idx], sl = e_sl[idx], lu = e_lu[idx], ll = e_ll[idx], dza = e_da[idx];
             if (su < kBig) { const double iu = fast_rcp(su); gq = fma(sigma_mu + dza * (lu * iu * dza - lu), iu, gq); }
@@ -560,6 +648,21 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
                 const double su = e_su[idx], sl = e_sl[idx], lu = e_lu[idx], ll = e_ll[idx];
                 const double dza = pass == 1 ? e_da[idx] : 0.0;
                 const double smu = pass == 1 ? sigma_mu : 0.0;
+                if (SOFT) {
+#pragma unroll
+                    for (int side = 0; side < 2; ++side) {
+                        SoftSide sd;
+                        if (!soft_side(idx, side == 0, sd)) continue;
+                        const double sg = side == 0 ? 1.0 : -1.0;
+                        double tgt = 0.0, tg = 0.0, ds, dl, dg, dn;
+                        if (pass == 1) soft_targets(sd, sg * e_da[idx], tgt, tg);
+                        sd.steps(sg * dz, tgt, tg, ds, dl, dg, dn);
+                        rpm = fmax(rpm, fmax(-ds * sd.is, -dg * sd.ig));
+                        rdm = fmax(rdm, fmax(dl < 0.0 ? -dl * fast_rcp(sd.lam) : 0.0, dn < 0.0 ? -dn * fast_rcp(sd.nu) : 0.0));
+                        if (pass == 0) { S3 = fma(ds, sd.lam, S3); S3 = fma(dg, sd.nu, S3); S4 = fma(ds, dl, S4); S4 = fma(dg, dn, S4); }
+                    }
+                    continue;
+                }
                 if (su < kBig) {
                     const double iu = fast_rcp(su);
                     const double ru = lu * iu;
@@ -609,6 +712,26 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
 #pragma unroll 2
             for (int idx = lane; idx < NE; idx += 32) {
                 double su = e_su[idx], sl = e_sl[idx], lu = e_lu[idx], ll = e_ll[idx];
+                if (SOFT) {
+                    const double dza = e_da[idx], dz = e_dz[idx];
+#pragma unroll
+                    for (int side = 0; side < 2; ++side) {
+                        SoftSide sd;
+                        if (!soft_side(idx, side == 0, sd)) continue;
+                        if (upd) {
+                            const double sg = side == 0 ? 1.0 : -1.0;
+                            double tgt = 0.0, tg = 0.0, ds, dl, dg, dn;
+                            if (!skip_corr) soft_targets(sd, sg * dza, tgt, tg);
+                            sd.steps(sg * dz, tgt, tg, ds, dl, dg, dn);
+                            sd.s += ap * ds; sd.gam += ap * dg; sd.lam += ad * dl; sd.nu += ad * dn;
+                            if (side == 0) { e_su[idx] = sd.s; e_lu[idx] = sd.lam; e_gu[idx] = sd.gam; e_nu[idx] = sd.nu; }
+                            else { e_sl[idx] = sd.s; e_ll[idx] = sd.lam; e_gl[idx] = sd.gam; e_nl[idx] = sd.nu; }
+                        }
+                        acc = fma(sd.s, sd.lam, acc); acc = fma(sd.gam, sd.nu, acc);
+                    }
+                    if (upd) e_zy[idx] += ap * dz;
+                    continue;
+                }
                 if (upd) {
                     const double dza = e_da[idx], dz = e_dz[idx];
                     if (su < kBig) {
@@ -637,6 +760,9 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
         }
         mark(12);
         const double mu_new = n_box > 0.0 ? acc / n_box : 0.0;
+#ifdef RNMPC_EMU_DEBUG
+        if (lane == 0) std::printf("it %d mu %.3e -> %.3e ap %.3e ad %.3e sigma_mu %.3e rp %.3e skip %d chol %d\n", it, mu_c, mu_new, ap, ad, sigma_mu, rp_inf * rp_scale, (int)skip_corr, (int)chol_ok);
+#endif
         if (!chol_ok) {
             if (mu_c > 1e-9) status = 3;           // a non-positive pivot at mu ~ 1e-14 means converged to working precision
             done = true;
@@ -666,6 +792,18 @@ __global__ void __launch_bounds__(32, 6) qp_warp_kernel(const QpArgs a, const Pa
             const double zn = i < NX ? Xn[k * NX + i] : Un[k * NU + i - NX];
             const double z = e_zy[idx] - zn;
             acc = fma(z, 0.5 * qd_of(k, i) * (z + 2.0 * zn), acc);
+            if (SOFT) {
+                // slack variables in the reference's row order [x_ub, u_ub, x_lb, u_lb] (+ their cost); the rows of the pinned x(0) carry
+                // their violation
+                double gu = e_su[idx] < kBig ? e_gu[idx] : 0.0, gl = e_sl[idx] < kBig ? e_gl[idx] : 0.0;
+                if (k == 0 && i < NX) { gu = fmax(0.0, (z + zn) - prm->xub[i]); gl = fmax(0.0, prm->xlb[i] - (z + zn)); }
+                const double r1 = k < N ? a.rho1 : 0.0;
+                acc += a.rho * (gu * gu + gl * gl) + r1 * (gu + gl);
+                if (a.gamma != nullptr) {
+                    if (k < N) { a.gamma[((size_t)b * N + k) * NI + i] = gu; a.gamma[((size_t)b * N + k) * NI + NZ + i] = gl; }
+                    else { a.gamma_f[(size_t)b * NIF + i] = gu; a.gamma_f[(size_t)b * NIF + NX + i] = gl; }
+                }
+            }
             if (i < NX) Xo[k * NX + i] = z; else Uo[k * NU + i - NX] = z;
             if (k < N) { mu[k * NI + i] = e_lu[idx]; mu[k * NI + NZ + i] = e_ll[idx]; }
             else { muf[i] = e_lu[idx]; muf[NX + i] = e_ll[idx]; }

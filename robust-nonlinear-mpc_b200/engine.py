@@ -205,6 +205,18 @@ class BatchSolver:
         _lib.check(self.lib.rnmpc_costates(self._h, B, _ptr(lam), self._stream()))
         return lam
 
+    def soft_nmpc(self, x0, X, U, rho=1e6, rho1=1e6, max_iter=60, tol=1e-9):
+        """Soft-constrained NMPC comparator (rnmpc_soft_nmpc): SQP from the guess X [B,N+1,nx], U [B,N,nu] -> dict(X, U, gamma, gamma_f,
+        sqp_iters, status) of device tensors."""
+        x0 = self.dev(x0).reshape(-1, self.nx)
+        B = x0.shape[0]
+        X, U = self.dev(X).reshape(B, self.N + 1, self.nx).clone(), self.dev(U).reshape(B, self.N, self.nu).clone()
+        out = dict(X=X, U=U, gamma=self.zeros(B, self.N, self.ni), gamma_f=self.zeros(B, self.ni_f),
+                   sqp_iters=self.zeros(B, dtype=torch.int32), status=self.zeros(B, dtype=torch.int32))
+        _lib.check(self.lib.rnmpc_soft_nmpc(self._h, B, _ptr(x0), _ptr(X), _ptr(U), float(rho), float(rho1), int(max_iter), float(tol),
+                                            _ptr(out["gamma"]), _ptr(out["gamma_f"]), _ptr(out["sqp_iters"]), _ptr(out["status"]), self._stream()))
+        return out
+
     def set_nominal(self, X, U):
         X, U = self.dev(X), self.dev(U)
         _lib.check(self.lib.rnmpc_set_nominal(self._h, X.shape[0], _ptr(X), _ptr(U), self._stream()))

@@ -4,6 +4,8 @@
 plus size-independent properties at the benchmark batch sizes.  Tolerances: linearisation / fast-SLS are pure
 floating-point restatements (<= 1e-9 relative); QP-dependent quantities follow BASELINE.json's north star
 (nominal trajectory, feedback gains, back-offs <= 1e-6 relative; closed-loop states <= 1e-5)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -765,3 +767,54 @@ def test_rocket_compare_driver_robust_arm(tmp_path):
     X, U = d["r_state_trajectory"][0], d["r_input_trajectory"][0]
     J = sum(X[:, t] @ cfg["Q"] @ X[:, t] + U[:, t] @ cfg["R"] @ U[:, t] for t in range(T - 1)) + X[:, -1] @ cfg["Qf"] @ X[:, -1]
     assert abs(d["Jr_total"][0] - J) < 1e-9 * abs(J)
+    # soft-constrained arm of the same driver (:176-222): the reference's s_* / Js_* keys for the scenarios it ran (default: the first)
+    assert {"s_state_trajectory", "s_input_trajectory", "s_nominal_trajectory_x", "s_nominal_trajectory_u", "s_backoff_trajectory_x",
+            "s_backoff_trajectory_u", "Js_stage", "Js_terminal", "Js_total"} <= set(d.files)
+    assert d["s_state_trajectory"].shape == (1, nx, T) and d["s_input_trajectory"].shape == (1, nu, T - 1) and d["s_success"][0]
+    assert not d["s_backoff_trajectory_x"].any()
+    Xs, Us = d["s_state_trajectory"][0], d["s_input_trajectory"][0]
+    Js = sum(Xs[:, t] @ cfg["Q"] @ Xs[:, t] + Us[:, t] @ cfg["R"] @ Us[:, t] for t in range(T - 1)) + Xs[:, -1] @ cfg["Qf"] @ Xs[:, -1]
+    assert abs(d["Js_total"][0] - Js) < 1e-9 * abs(Js)
+    # the comparison the driver exists for (:248-253): the soft controller is cheaper and leaves the state box, the robust one does not
+    ub, lb = m.x_ub[:, None], m.x_lb[:, None]
+    viol_r = max((d["r_state_trajectory"][0] - ub).max(), (lb - d["r_state_trajectory"][0]).max())
+    viol_s = max((Xs - ub).max(), (lb - Xs).max())
+    print("closed-loop cost robust %.3f soft %.3f; worst state-bound violation robust %.3e soft %.3e" % (d["Jr_total"][0], d["Js_total"][0], viol_r, viol_s))
+    assert viol_r <= 1e-9
+    if os.path.exists(os.path.join(os.path.dirname(__file__), "golden", "soft_rocket.npz")):
+        gs = load("soft_rocket.npz")
+        k = gs["states"].shape[0]
+        assert rel(Xs[:, :k].T, gs["states"]) < TOL_STATE
+
+
+@pytest.mark.parametrize("name", ["pendulum", "rocket"])
+def test_soft_constrained_nmpc_vs_oracle_golden(name):
+    """``solver.nlp_soft_constraints.NLPSoftConstraints`` (the reference's soft-constrained comparator, solver/nlp_soft_constraints.py:8-276:
+    same class name, constructor and solve() keys) against the fixtures of the CPU restatement (oracle/soft.py): closed loops with
+    rho = rho_l1 = 1e6; the pendulum fixture starts outside its box (active slacks), the rocket one is the compare driver's scenario."""
+    path = os.path.join(os.path.dirname(__file__), "golden", f"soft_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    from rnmpc_b200.solver.nlp_soft_constraints import NLPSoftConstraints
+    import rnmpc_b200.dyn.pendulum as dp, rnmpc_b200.dyn.rocket as dr
+    g = load(f"soft_{name}.npz")
+    mo, cfg = om.CONFIGS[name]()
+    m = dp.Pendulum() if name == "pendulum" else dr.Rocket()
+    m.E = mo.E
+    solver = NLPSoftConstraints(cfg["N"], cfg["Q"], cfg["R"], m, cfg["Qf"], rho_soft=1e6, rho_soft_l1=1e6)
+    x = g["x0"].copy()
+    for i in range(g["Xn"].shape[0]):
+        sol = solver.solve(x, x_guess=g["X0"].T, u_guess=g["U0"].T) if i == 0 else solver.solve(x)
+        assert sol["success"], sol
+        assert sol["primal_x"].shape == (mo.nx, cfg["N"] + 1) and sol["primal_gamma"].shape == (mo.ni * cfg["N"] + mo.ni_f,)
+        assert rel(sol["primal_x"], g["Xn"][i].T) < TOL_TRAJ and relf(sol["primal_u"], g["Un"][i].T) < TOL_TRAJ
+        assert np.abs(sol["primal_gamma"] - g["gamma"][i]).max() < 1e-6 * max(1.0, g["gamma"][i].max())
+        assert abs(sol["cost"] / g["cost"][i] - 1) < 1e-8
+        x = np.array(m.ddyn(x, sol["primal_u"][:, 0])).reshape(-1) + mo.E @ g["W"][i]
+        assert np.abs(x - g["states"][i + 1]).max() < TOL_STATE
+    if name == "pendulum":
+        assert g["gamma"][0].max() > 0.5            # the slacks carry a real violation in this fixture
+    # batch mode: the same instance three times
+    sb = NLPSoftConstraints(cfg["N"], cfg["Q"], cfg["R"], m, cfg["Qf"], rho_soft=1e6, rho_soft_l1=1e6, batch=3)
+    solb = sb.solve(np.stack([g["x0"]] * 3), x_guess=np.stack([g["X0"].T] * 3), u_guess=np.stack([g["U0"].T] * 3))
+    assert solb["success"].all() and rel(solb["primal_x"][2], g["Xn"][0].T) < TOL_TRAJ

@@ -97,3 +97,29 @@ def test_sls_mma_kernel_source_vs_reference_numba_golden(name):
     for key in ("beta", "beta_f"):
         assert relf(out[key], g[key], 0.0) < tol, key
     assert np.array_equal(out["S"], np.swapaxes(out["S"], 2, 3))    # symmetrised exactly
+
+
+def test_soft_qp_kernel_source_vs_dense_oracle():
+    """The soft-constrained comparator's QP (qp_warp_kernel, SOFT: slack variables eliminated entry by entry inside the interior
+    point) on the emulator vs the dense QP in (delta, gamma) of oracle/soft.py, for a state inside the box (all slacks zero: the
+    hard-constrained solution) and one outside (active slacks)."""
+    from oracle import scp as oscp, soft as osoft
+    name = "pendulum"
+    m, cfg = om.CONFIGS[name]()
+    N, Q, R, Qf = cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"]
+    X0, U0, ok = oscp.nominal_sqp(m, N, Q, R, Qf, om.PENDULUM_X0, iters=10)
+    assert ok
+    A, Bm, c = _linearize(m, X0.T[None], U0.T[None])
+    sq = osoft.SoftQP(m, N, Q, R, Qf, 1e6, 1e6)
+    x_out = om.PENDULUM_X0.copy()
+    x_out[0] = 1.05 * m.x_ub[0]
+    simt_emu.set_order(2)
+    for xs, active in ((om.PENDULUM_X0, False), (x_out, True)):
+        ref = sq.solve(X0, U0, xs)
+        assert max(ref["kkt"].values()) < 1e-7
+        out = simt_emu.qp_soft(name, m, cfg, A, Bm, c, X0.T[None], U0.T[None], np.asarray(xs)[None])
+        assert out["status"][0] == 0 and out["iters"][0] <= 60
+        assert np.abs(out["dX"][0].T - ref["dX"]).max() < 1e-9 and np.abs(out["dU"][0].T - ref["dU"]).max() < 1e-9
+        assert np.abs(out["gamma"][0] - ref["gamma"]).max() < 1e-9 and np.abs(out["gamma_f"][0] - ref["gamma_f"]).max() < 1e-9
+        assert (ref["gamma"].max() > 0.1) == active
+    simt_emu.set_order(0)

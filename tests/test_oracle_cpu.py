@@ -246,3 +246,26 @@ def test_driver_modules_import_and_mirror_the_reference_command_line(capsys, mon
         sys.modules.pop(f"rnmpc_b200.expe.main_{name}_closed_loop", None)        # run it as a script, not as the imported module
         runpy.run_module(f"rnmpc_b200.expe.main_{name}_closed_loop", run_name="__main__")
         assert "plot" in capsys.readouterr().out
+
+
+def test_soft_nmpc_oracle_satisfies_the_nlp_optimality_conditions():
+    """oracle/soft.py (restatement of solver/nlp_soft_constraints.py:175-276 solved by SQP): its fixed point satisfies the first-order
+    conditions of the NLP evaluated from scratch (dynamics defect, stationarity with the returned multipliers, slack stationarity,
+    complementarity), with inactive and with active slacks; and it reproduces the committed fixture (tests/golden/soft_pendulum.npz)."""
+    from oracle import soft as osoft
+    m, cfg = om.pendulum_config()
+    N, Q, R, Qf = cfg["N"], cfg["Q"], cfg["R"], cfg["Qf"]
+    g = load("soft_pendulum.npz")
+    X0, U0 = g["X0"].T, g["U0"].T
+    x_out = g["x0"]
+    assert x_out[0] > m.x_ub[0]                                     # the fixture starts outside the box
+    for xs in (om.PENDULUM_X0, x_out):
+        sol = osoft.soft_nlp_solve(m, N, Q, R, Qf, xs, X0, U0)
+        assert sol["success"] and sol["last_step"] < 1e-9
+        k = osoft.kkt_nlp(m, N, Q, R, Qf, xs, sol)
+        assert k["defect"] < 1e-10 and k["stationarity"] < 1e-6 and k["sign"] < 1e-8 and k["complementarity"] < 1e-6, k
+        # the optimal slacks are the violations of the trajectory, the cost the reference's objective
+        gam, gam_f = osoft.slacks_of(m, sol["primal_x"], sol["primal_u"])
+        assert np.abs(gam - sol["gamma"]).max() < 1e-9 and np.abs(gam_f - sol["gamma_f"]).max() < 1e-9
+    assert rel(sol["primal_x"], g["Xn"][0].T) < 1e-9 and abs(sol["cost"] / g["cost"][0] - 1) < 1e-9
+    assert g["gamma"][0].max() > 0.5                                 # active slacks in the fixture

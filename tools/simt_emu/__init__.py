@@ -111,3 +111,24 @@ def sls_mma(name, m, cfg, A, Bm, eta=None, eta_f=None, mu=None, mu_f=None, beta_
     if rc != 0:
         raise RuntimeError(f"emu_sls_mma failed: {rc}")
     return out
+
+
+def qp_soft(name, m, cfg, A, Bm, c, X, U, x0, rho=1e6, rho1=1e6, max_iter=60, tol_mu=1e-16):
+    """The soft-constrained comparator's QP (qp_warp_kernel, SOFT) on the emulator; shapes as qp_mma()."""
+    lib = load()
+    conf, keep = _cfg(name, m, cfg)
+    f = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    Ap, Bm, c, X, U, x0 = pad_rows(f(A)), f(Bm), f(c), f(X), f(U), f(x0)
+    B, N, nx, nu = X.shape[0], int(cfg["N"]), m.nx, m.nu
+    ni, nif = 2 * (nx + nu), 2 * nx
+    out = dict(dX=np.zeros((B, N + 1, nx)), dU=np.zeros((B, N, nu)), mu=np.zeros((B, N, ni)), mu_f=np.zeros((B, nif)),
+               gamma=np.zeros((B, N, ni)), gamma_f=np.zeros((B, nif)), cost=np.zeros(B), iters=np.zeros(B, dtype=np.int32),
+               status=np.zeros(B, dtype=np.int32))
+    lib.emu_qp_soft.restype = C.c_int
+    lib.emu_qp_soft.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_double, C.c_double, C.c_int, C.c_double] + [C.c_void_p] * 9
+    rc = lib.emu_qp_soft(C.byref(conf), B, _p(Ap), _p(Bm), _p(c), _p(X), _p(U), _p(x0), float(rho), float(rho1), int(max_iter), float(tol_mu),
+                         _p(out["dX"]), _p(out["dU"]), _p(out["mu"]), _p(out["mu_f"]), _p(out["gamma"]), _p(out["gamma_f"]), _p(out["cost"]),
+                         _p(out["iters"]), _p(out["status"]))
+    if rc != 0:
+        raise RuntimeError(f"emu_qp_soft failed: {rc}")
+    return out

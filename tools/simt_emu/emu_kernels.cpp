@@ -112,6 +112,36 @@ static int run_sls_mma(const rnmpc_config* cfg, SlsArgs a, int warps) {
     return 0;
 }
 
+// soft-constrained comparator QP (qp_warp_kernel<.., SOFT = true>) on given linearisation data
+template <int NX, int NU>
+static int run_qp_soft(const rnmpc_config* cfg, QpArgs a) {
+    Params<NX, NU> hp;
+    fill_params<NX, NU>(cfg, hp);
+    if ((qp_warp_smem_doubles<NX, NU>(a.N) + qp_warp_soft_extra_doubles<NX, NU>(a.N)) * sizeof(double) > sizeof(smem_raw)) return -4;
+    std::vector<double> Kw((size_t)a.B * a.N * NU * QpWarp<NX, NU>::LDA, 0.0), Lw((size_t)a.B * a.N * NU * NU, 0.0);
+    a.Kq = Kw.data(); a.Lq = Lw.data();
+    for (int b = 0; b < a.B; ++b) {
+        simt::cpa_reset();
+        simt::run_block(32, dim3(b), dim3(a.B), [&]() { qp_warp_kernel<NX, NU, 0, true>(a, &hp); });
+    }
+    return 0;
+}
+extern "C" int emu_qp_soft(const rnmpc_config* cfg, int B, const double* A_padded, const double* Bm, const double* c, const double* X,
+                           const double* U, const double* x0, double rho, double rho1, int max_iter, double tol_mu, double* dX, double* dU,
+                           double* mu, double* mu_f, double* gamma, double* gamma_f, double* cost, int* iters, int* status) {
+    QpArgs a{};
+    a.B = B; a.N = cfg->N; a.tightened = 0; a.max_iter = max_iter; a.tol_mu = tol_mu; a.tol_res = 1e-9; a.mu0 = -0.3;
+    a.A = A_padded; a.Bm = Bm; a.c = c; a.Xnom = X; a.Unom = U; a.x0 = x0;
+    a.dX = dX; a.dU = dU; a.mu = mu; a.mu_f = mu_f; a.cost = cost; a.iters = iters; a.status = status;
+    a.diag_cost = 1; a.rho = rho; a.rho1 = rho1; a.gamma = gamma; a.gamma_f = gamma_f;
+    switch (cfg->model_id) {
+        case RNMPC_PENDULUM: return run_qp_soft<4, 1>(cfg, a);
+        case RNMPC_QUADROTOR: return run_qp_soft<13, 4>(cfg, a);
+        case RNMPC_ROCKET: return run_qp_soft<17, 4>(cfg, a);
+    }
+    return -1;
+}
+
 // fast-SLS pass with explicit weights (eta, eta_f) or from duals (mu, mu_f [+ beta_in, beta_f_in]); A padded [B][N][nx][ld]
 extern "C" int emu_sls_mma(const rnmpc_config* cfg, int B, int warps, const double* A_padded, const double* Bm, const double* eta,
                            const double* eta_f, const double* mu, const double* mu_f, const double* beta_in, const double* beta_f_in,
