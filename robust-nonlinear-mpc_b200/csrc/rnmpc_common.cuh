@@ -244,20 +244,21 @@ __device__ __forceinline__ void tm_wait_st() { __syncwarp(); asm volatile("tcgen
 #endif
 // ND doubles of this thread's TMEM lane from / to 2 ND consecutive columns (both builds: tools/simt_emu provides tm_*_raw too)
 // (the tcgen05 instructions are warp-collective and "aligned": the lanes re-converge first -- the compiler does not know that they must)
-template <int ND>
+// SYNC = false: the caller knows the warp is converged (directly behind a __syncwarp)
+template <int ND, bool SYNC = true>
 __device__ __forceinline__ void tm_ld(const unsigned taddr, double (&v)[ND]) {
     unsigned r[2 * ND];
-    __syncwarp();
+    if (SYNC) __syncwarp();
     tm_ld_raw<2 * ND>(taddr, r);
 #pragma unroll
     for (int i = 0; i < ND; ++i) v[i] = hilo2double(r[2 * i + 1], r[2 * i]);
 }
-template <int ND>
+template <int ND, bool SYNC = true>
 __device__ __forceinline__ void tm_st(const unsigned taddr, const double (&v)[ND]) {
     unsigned r[2 * ND];
 #pragma unroll
     for (int i = 0; i < ND; ++i) { r[2 * i] = double_lo(v[i]); r[2 * i + 1] = double_hi(v[i]); }
-    __syncwarp();
+    if (SYNC) __syncwarp();
     tm_st_raw<2 * ND>(taddr, r);
 }
 

@@ -82,8 +82,13 @@ struct QpArgs {
     // soft-constrained comparator (qp_warp_kernel<.., SOFT = true>): every bound row softened, cost rho gam^2 + rho1 gam per row
     // (terminal rows: rho only), solver/nlp_soft_constraints.py:222-232
     double rho, rho1;
+    const double* prox;     // [B] or nullptr: proximal weight sigma_b of the SQP driver, cost + sigma/2 |dz|^2 (a damped Gauss-Newton step;
+                            // vanishes at the fixed point, so the limit is unchanged)
     double* gamma;          // [B][N][ni] slack variables (output, may be nullptr)
     double* gamma_f;        // [B][ni_f]
+    const int* order;       // qp_tm_kernel only: [B] instance index of the i-th work item (nullptr: identity); the engine sorts the instances
+                            // by the interior-point iterations of their previous solve, longest first, so that the last instances a
+                            // launch hands out are short ones (a launch ends with its slowest warp)
     int* work;              // qp_tm_kernel only: [1] next instance of the batch (zeroed by the caller): its warps draw instances from it
     long long* prof;        // qp_mma_kernel only, diagnostic ("qp_profile"): [16] cycles of instance 0 per phase, summed over the launches
 };

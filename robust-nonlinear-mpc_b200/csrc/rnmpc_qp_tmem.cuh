@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
         if (lane == 0) b = atomicAdd(a.work, 1);
         b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= a.B) break;
+        if (a.order != nullptr) b = a.order[b];
         if (a.flags != nullptr && (a.flags[b] & a.skip_mask) != 0) continue;
 
         const double* Ag = a.A + (size_t)b * N * NX * LDG;
@@ -527,15 +528,20 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                 //      rp_scale rp_k, dx_0 = 0.  Lane i keeps its own entry of the step (dx_k[i] or du_k[i - NX]), stores it into the stage's
                 //      TMEM column and runs the ratio test of that entry (rnmpc_qp.cuh ratio_entry) while the next ring slot is in flight.
                 double rpm = 0.0, rdm = 0.0, S3 = 0.0, S4 = 0.0;
-                auto ratio_entry = [&](const int k, const double dz) {
-                    double v[4], w[1];
-                    tm_ld<4>(tcol(k, TM_SU), v);
-                    w[0] = 0.0;
-                    if (pass == 1) tm_ld<1>(tcol(k, TM_DA), w);
+                // The ratio test of stage k - 1 is software-pipelined into stage k: its TMEM loads are issued at the head of the stage and its
+                // arithmetic (four reciprocals) sits in the same basic block as the stage's matrix-vector product, so the two independent
+                // dependency chains interleave instead of following each other.
+                double rt_v[4], rt_w[1];
+                auto ratio_load = [&](const int k, const double dz) {        // the warp is converged here (directly behind a __syncwarp)
+                    tm_ld<4, false>(tcol(k, TM_SU), rt_v);
+                    rt_w[0] = 0.0;
+                    if (pass == 1) tm_ld<1, false>(tcol(k, TM_DA), rt_w);
                     const double dzs[1] = {dz};
-                    tm_st<1>(tcol(k, arr_dz), dzs);
-                    const double su = v[0], sl = v[1], lu = v[2], ll = v[3];
-                    const double dza = w[0];
+                    tm_st<1, false>(tcol(k, arr_dz), dzs);
+                };
+                auto ratio_math = [&](const double dz) {
+                    const double su = rt_v[0], sl = rt_v[1], lu = rt_v[2], ll = rt_v[3];
+                    const double dza = rt_w[0];
                     const double smu = pass == 1 ? sigma_mu : 0.0;
                     // branch-free: a lane without a bound has reciprocal slack 0 and multiplier 0 (every term vanishes); the four
                     // reciprocals are independent and run side by side
@@ -557,7 +563,8 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                     const int fw_istride = lane < NX ? NX : (lane < NZ ? NU : 0);
                     const double fw_scale = lane < NX ? rp_scale : 1.0;
                     double dxk = 0.0;                          // lanes < NX: dx_k[lane]
-                    if (lane < NX) xs0[lane] = 0.0;
+                    double dz_prev = 0.0;                      // this lane's entry of the step of stage k - 1
+                    if (lane < NZ) { xs0[lane] = 0.0; xs1[lane] = 0.0; }
 #pragma unroll 1
                     for (int k = 0; k < N; ++k) {
                         double* xk = (k & 1) ? xs1 : xs0;      // [dx_k ; du_k]
@@ -565,9 +572,11 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                         ring_issue(k + (T::NSLOT - 1));        // into the slot of stage k - 1
                         const double* sl = ring_wait(k);
                         __syncwarp();
-                        // one code path for all lanes: row r of A_k from rp_scale rp_k (lanes < NX) or row p of K_k from d_k (lanes NX .. NZ-1)
+                        if (k > 0) ratio_load(k - 1, dz_prev);
+                        // one code path for all lanes: row r of A_k from rp_scale rp_k (lanes < NX) or row p of K_k from d_k (lanes NX .. NZ-1);
+                        // dx_0 = 0, so stage 0 needs no special case
                         double a0 = fw_scale * fw_init[k * fw_istride], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                        if (k > 0) {
+                        {
                             const double* row = sl + fw_off;
 #pragma unroll
                             for (int m = 0; m + 3 < NX; m += 4) {
@@ -578,6 +587,7 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
 #pragma unroll
                             for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(row[m], xk[m], a0);
                         }
+                        if (k > 0) ratio_math(dz_prev);
                         if (lane >= NX && lane < NZ) xk[lane] = (a0 + a1) + (a2 + a3);
                         __syncwarp();
                         double dz = dxk;                        // this lane's entry of stage k
@@ -589,10 +599,13 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                             xn[lane] = acc;
                             dxk = acc;
                         } else dz = (a0 + a1) + (a2 + a3);
+                        dz_prev = lane < NZ ? dz : 0.0;
                         __syncwarp();                           // dx_{k+1} visible; every lane is done with the slot of stage k
-                        ratio_entry(k, lane < NZ ? dz : 0.0);
                     }
-                    ratio_entry(N, lane < NX ? dxk : 0.0);
+                    if (N > 0) { ratio_load(N - 1, dz_prev); ratio_math(dz_prev); }
+                    __syncwarp();
+                    dz_prev = lane < NX ? dxk : 0.0;
+                    ratio_load(N, dz_prev); ratio_math(dz_prev);
                     tm_wait_st();
                 }
                 mark(10);

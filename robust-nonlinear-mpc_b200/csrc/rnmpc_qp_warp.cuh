@@ -284,6 +284,8 @@ __global__ void __launch_bounds__(32, SOFT ? 4 : 6) qp_warp_kernel(const QpArgs 
     __syncwarp();
 
     double sigma_mu = 0.0;
+    const double prox = (SOFT && a.prox != nullptr) ? a.prox[b] : 0.0;
+    auto zn_of = [&](const int k, const int i) -> double { return i < NX ? Xn[k * NX + i] : Un[k * NU + i - NX]; };
     // the two softened rows of an entry (SOFT): state + derived coefficients
     auto soft_side = [&](const int idx, const bool upper, SoftSide& sd) -> bool {
         sd.s = upper ? e_su[idx] : e_sl[idx];
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(32, SOFT ? 4 : 6) qp_warp_kernel(const QpArgs 
     auto sg_of = [&](const int idx) -> double {
         if (SOFT) {
             SoftSide sd;
-            double w = 0.0;
+            double w = prox;
             if (soft_side(idx, true, sd)) w += sd.weight();
             if (soft_side(idx, false, sd)) w += sd.weight();
             return w;
@@ -320,6 +322,7 @@ __global__ void __launch_bounds__(32, SOFT ? 4 : 6) qp_warp_kernel(const QpArgs 
         if (SOFT) {
             // the softened rows contribute in the predictor too: lam + d lam = w dz + (tgt / s - ru b / D)
             const double dza = e_da[idx];
+            if (prox != 0.0 && (i < NX || k < N)) gq = fma(prox, e_zy[idx] - zn_of(k, i), gq);
             SoftSide sd;
             double tgt = 0.0, tg = 0.0;
             if (soft_side(idx, true, sd)) { if (pass == 1) soft_targets(sd, dza, tgt, tg); gq += sd.rhs(tgt, tg); }

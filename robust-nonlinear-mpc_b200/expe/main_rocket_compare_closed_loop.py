@@ -77,12 +77,14 @@ def run_soft(x0, W, device=0):
     X = np.zeros((B, nx, steps + 1)); U = np.zeros((B, nu, steps))
     Xn = np.zeros((B, nx, N + 1, steps)); Un = np.zeros((B, nu, N, steps))
     ok = np.ones(B, dtype=bool)
+    done = np.zeros(B, dtype=int)              # MPC steps completed per scenario
     X[:, :, 0] = x
     eng = solver._engine
     for i in range(steps):
         sol = solver.solve(x if B > 1 else x[0])
         succ = np.atleast_1d(sol['success'])
         ok &= succ
+        done += ok
         if not ok.any():
             break
         px = sol['primal_x'] if B > 1 else sol['primal_x'][None]
@@ -95,7 +97,7 @@ def run_soft(x0, W, device=0):
     eng.close()
     return dict(state_trajectory=X, input_trajectory=U, nominal_trajectory_x=Xn, nominal_trajectory_u=Un,
                 backoff_trajectory_x=np.zeros((B, nx, N + 1, steps)), backoff_trajectory_u=np.zeros((B, nu, N, steps)), success=ok,
-                g=m.g, nx=nx, nu=nu, dt=m.dt, N=N)
+                steps_completed=done, g=m.g, nx=nx, nu=nu, dt=m.dt, N=N)
 
 
 def generate(batch=4096, keep=1, out_dir=None, device=0, soft=1):
@@ -112,8 +114,10 @@ def generate(batch=4096, keep=1, out_dir=None, device=0, soft=1):
         sres = run_soft(ROCKET_X0, W[:soft], device)
         sJs, sJT, sJ = closed_loop_cost(sres["state_trajectory"], sres["input_trajectory"], cfg["Q"], cfg["R"], cfg["Qf"])
         soft_keys = {"s_" + k: sres[k] for k in ("state_trajectory", "input_trajectory", "nominal_trajectory_x", "nominal_trajectory_u",
-                                                 "backoff_trajectory_x", "backoff_trajectory_u", "success")}
+                                                 "backoff_trajectory_x", "backoff_trajectory_u", "success", "steps_completed")}
         soft_keys.update(Js_stage=sJs, Js_terminal=sJT, Js_total=sJ)
+        for b in np.where(~sres["success"])[0][:4]:
+            print(f"scenario {b}: the soft-constrained arm stopped after {sres['steps_completed'][b]} of {T - 1} MPC steps (its NLP solve failed)")
         # the reference's cost table (:248-253, 403-406) for the scenarios both arms ran
         both = ok[:soft] & sres["success"]
         for b in np.where(both)[0][:4]:
