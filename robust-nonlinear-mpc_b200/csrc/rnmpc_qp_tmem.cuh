@@ -141,6 +141,8 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
             if (prof_on) { const long long t = clock64(); pacc[slot] += t - t_last; t_last = t; }
         };
         if (lane < KP) pv[lane] = 0.0;
+        zero_buf(buf1, D::MAT + T::EXTRA);          // tile buffers + ring: finite contents from here on (see phase D)
+        __syncwarp();
 
         // ------------------------------------------------------------------ bounds, initial point, slacks (rnmpc_qp_mma.cuh, cold start)
         // lane i handles component i of every stage; lanes without an entry hold "no bound" slacks and zero multipliers
@@ -310,21 +312,26 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
             {
                 double zf[KS][NT];
                 load_z(N - 1, zf);
+                double rhs_n = 0.0, dgn_n = 0.0;
+                auto stage_scalars = [&](const int k, double& r_out, double& d_out) {
+                    double v[4], w[1];
+                    tm_ld<4>(tcol(k, TM_SU), v);
+                    tm_ld<1>(tcol(k, TM_ZY), w);
+                    r_out = (lane < NX && k == 0) ? 0.0 : (lane < NZ ? qdt[lane] * w[0] : 0.0);
+                    d_out = (lane < NX ? qdt[lane] : 0.0) + (v[2] * rc(v[0]) + v[3] * rc(v[1]));   // R2 is added to H below
+                };
+                stage_scalars(N - 1, rhs_n, dgn_n);
                 __syncwarp();
                 mark(1);
 #pragma unroll 1
                 for (int k = N - 1; k >= 0; --k) {
                     double zn_[KS][NT];
                     if (k > 0) load_z(k - 1, zn_);
-                    {   // gradient and barrier weight of this lane's entry (lanes >= NZ hold a neutral entry)
-                        double v[4], w[1];
-                        tm_ld<4>(tcol(k, TM_SU), v);
-                        tm_ld<1>(tcol(k, TM_ZY), w);
-                        if (lane < NZ) {
-                            rhs[lane] = (lane < NX && k == 0) ? 0.0 : qdt[lane] * w[0];
-                            dgn[lane] = (lane < NX ? qdt[lane] : 0.0) + (v[2] * rc(v[0]) + v[3] * rc(v[1]));   // R2 is added to H below
-                        }
-                    }
+                    // gradient and barrier weight of this lane's entry (lanes >= NZ hold a neutral entry): the values of THIS stage were
+                    // computed during the previous one (two TMEM loads and two reciprocals off the critical path); phase C is the first
+                    // reader, behind the barrier that follows phase A
+                    if (lane < NZ) { rhs[lane] = rhs_n; dgn[lane] = dgn_n; }
+                    if (k > 0) stage_scalars(k - 1, rhs_n, dgn_n);
                     // ---- phase A: W = S [A B rp]
 #pragma unroll
                     for (int mt = 0; mt < MTS; ++mt) {
@@ -422,8 +429,8 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                                 mc0[ti] = mv.x; mc1[ti] = mv.y;
                             }
                         }
-                        __syncwarp();
-                        zero_buf(buf1, 8 * MTS * LDS);
+                        // (no zeroing: the pads of the S layout may hold finite leftovers of the M tiles -- they only ever multiply the zero
+                        // rows of Z_k; the buffers are cleared once per instance, so nothing non-finite can be left in them)
                         __syncwarp();
                         ti = 0;
 #pragma unroll

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(32, SOFT ? 4 : 6) qp_warp_kernel(const QpArgs 
     }
     unsigned ring_par = 0;                     // bit i: parity of the next completion of slot i (the same in every lane)
     if (lane < KP) pv[lane] = 0.0;
+    zero_buf(buf1, D::MAT);                        // tile buffers: finite contents from here on (see phase D)
     if (lane < NU * NU) R2s[lane] = prm->R2[lane];
     for (int e = lane; e < NZ + NX; e += 32)
         qdt[e] = 2.0 * (e < NX ? prm->Q[e * NX + e] : e < NZ ? prm->R[(e - NX) * NU + (e - NX)] : prm->Qf[(e - NZ) * NX + (e - NZ)]);
@@ -478,8 +479,8 @@ __global__ void __launch_bounds__(32, SOFT ? 4 : 6) qp_warp_kernel(const QpArgs 
                             mc0[ti] = mv.x; mc1[ti] = mv.y;
                         }
                     }
-                    __syncwarp();
-                    zero_buf(buf1, 8 * MTS * LDS);
+                    // (no zeroing: the pads of the S layout may hold finite leftovers of the M tiles -- they only ever multiply the zero
+                    // rows of Z_k; the buffers are cleared once per instance, so nothing non-finite can be left in them)
                     __syncwarp();
                     ti = 0;
 #pragma unroll

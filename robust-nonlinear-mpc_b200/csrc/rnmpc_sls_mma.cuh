@@ -117,8 +117,16 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
             // next stage of this chain (same column: k - 1; first stage of the second column: N - 1): fragments in flight during this stage
             double zn_[KS][NTZ];
             if (t + 1 < n_steps) load_z((t + 1 == n_first) ? (N - 1) : (k - 1), zn_);
-            // C_kj = G' diag(eta[k, col]) G : diagonal additions to Q_reg / R_reg
-            if (lane < NZ) dg[lane] = weight(k, col, lane) + weight(k, col, lane + NZ);
+            // C_kj = G' diag(eta[k, col]) G : diagonal additions to Q_reg / R_reg.  The weight of the NEXT stage (two global loads, a
+            // square root and a division per bound) is started here and lands in dg at the end of this stage: off the critical path.
+            if (t == 0 && lane < NZ) dg[lane] = weight(k, col, lane) + weight(k, col, lane + NZ);
+            double dg_next = 0.0;
+            if (t + 1 < n_steps && lane < NZ) {
+                const bool first_n = t + 1 < n_first;
+                const int col_n = first_n ? s : N - s;
+                const int k_n = first_n ? (N - 2 - t) : (N - 1 - (t + 1 - n_first));
+                dg_next = weight(k_n, col_n, lane) + weight(k_n, col_n, lane + NZ);
+            }
             // ---- W = S [A B]
 #pragma unroll
             for (int mt = 0; mt < MTS; ++mt) {
@@ -187,8 +195,8 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
                         mc0[ti] = mv.x; mc1[ti] = mv.y;
                     }
                 }
-                __syncwarp();
-                zero_buf(buf1, 8 * MTS * LDS);
+                // (no zeroing: the pads of the S layout may hold finite leftovers of the M tiles -- they only multiply the zero rows of
+                // Z_k; the buffer was cleared when the column started)
                 __syncwarp();
                 ti = 0;
 #pragma unroll
@@ -223,6 +231,7 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
             for (int q = 0; q < KS; ++q)
 #pragma unroll
                 for (int n = 0; n < NTZ; ++n) zf[q][n] = zn_[q][n];
+            if (lane < NZ) dg[lane] = dg_next;          // every lane is past its last read of dg (barrier above)
         }
     }
     __syncwarp();
