@@ -320,6 +320,7 @@ struct Engine : IEngine {
     int* qp_work = nullptr;        // [1] instance counter of qp_tm_kernel's persistent warps
     int* qp_order = nullptr;       // [cap] work order of qp_tm_kernel (order_by_key_kernel), valid for the resident solve
     bool qp_order_valid = false;
+    int qp_tm_ctas = 2;            // "qp_tm_ctas": persistent CTAs of qp_tm_kernel per SM (2 = all the tensor memory; 1 for occupancy experiments)
     int qp_lpt = 0;                // "qp_lpt": 1 = resident solves hand the instances to qp_tm_kernel longest first (previous solve's iterations).
                                    // Off: measured 285.0 ms with it against 278.7 ms without on the 29-step rocket loop at batch 4096 -- the previous
                                    // solve's count predicts little and the scattered instance order costs locality
@@ -594,7 +595,7 @@ struct Engine : IEngine {
             a.Kq = Kw; a.work = qp_work;
             a.order = (qp_order_valid && fl == flags) ? qp_order : nullptr;      // only the resident solve has a history
             cudaMemsetAsync(qp_work, 0, sizeof(int), st);
-            const unsigned gridt = (unsigned)std::min<long long>(2LL * n_sm, ((long long)B + kTmWarps - 1) / kTmWarps);
+            const unsigned gridt = (unsigned)std::min<long long>((long long)qp_tm_ctas * n_sm, ((long long)B + kTmWarps - 1) / kTmWarps);
             if (N == kHorizonFast) qp_tm_kernel<NX, NU, kHorizonFast><<<gridt, 32 * kTmWarps, qp_tm_smem, st>>>(a, d_prm);
             else qp_tm_kernel<NX, NU, 0><<<gridt, 32 * kTmWarps, qp_tm_smem, st>>>(a, d_prm);
         } else if (plain && qp_warp_ok && (qp_kernel == 4 || qp_kernel == 5 || (qp_kernel == 0 && B >= qp_warp_min))) {
@@ -935,6 +936,7 @@ struct Engine : IEngine {
         else if (n == "qp_kernel") qp_kernel = (int)value;
         else if (n == "qp_warp_min") qp_warp_min = (int)value;
         else if (n == "qp_lpt") qp_lpt = (int)value;
+        else if (n == "qp_tm_ctas") qp_tm_ctas = value >= 2 ? 2 : 1;
         else if (n == "sls_kernel") sls_kernel_sel = (int)value;
         else if (n == "sls_mma_warps") sls_mma_warps = (int)value;
         else if (n == "qp_profile") {

@@ -66,14 +66,14 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
         const double m = a.mu[((size_t)b * N + k) * NI + i];
         double be = kEpsBackoff;
         if (use_beta) be = fmax(a.beta_in[(((size_t)b * N + k) * N + col) * NI + i], kEpsBackoff);
-        return m / (2.0 * sqrt(be));
-    };
+        return 0.5 * m * rsqrt(be);        // mu / (2 sqrt(beta)): one reciprocal square root instead of an IEEE square root and division
+    };                                     // (the two were 20 % of this kernel's instructions, profiles/r2_notes.md)
     auto weight_f = [&](int col, int i) -> double {        // eta_f[col][i]
         if (a.eta_f != nullptr) return a.eta_f[((size_t)b * (N + 1) + col) * NIF + i];
         const double m = a.mu_f[(size_t)b * NIF + i];
         double be = kEpsBackoff;
         if (use_beta) be = fmax(a.beta_f_in[((size_t)b * (N + 1) + col) * NIF + i], kEpsBackoff);
-        return m / (2.0 * sqrt(be));
+        return 0.5 * m * rsqrt(be);
     };
     // fragments of Z_k = [A_k | B_k] (rows padded to KP with zeros): zf[s][n] = Z[4s + t][8n + g]  (branch-free: ZFrag, rnmpc_qp_mma.cuh)
     ZFrag<NX, NU, NTZ, KS, false> zsrc;
@@ -102,11 +102,12 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
                 __syncwarp();
                 zero_buf(buf1, 8 * MTS * LDS);
                 __syncwarp();
-                for (int e = lane; e < NX * NX; e += 32) {
-                    const int i = e / NX, j = e - i * NX;
-                    double v = prm->Qregf[e];
-                    if (i == j) v += weight_f(col, i) + weight_f(col, i + NX);
-                    buf1[i * LDS + j] = v;
+                {
+                    // the terminal weights go on the diagonal: one pair per lane, started before the copy of Q_reg_f
+                    const double wd = lane < NX ? weight_f(col, lane) + weight_f(col, lane + NX) : 0.0;
+                    for (int e = lane; e < NX * NX; e += 32) { const int i = e / NX, j = e - i * NX; buf1[i * LDS + j] = prm->Qregf[e]; }
+                    __syncwarp();
+                    if (lane < NX) buf1[lane * LDS + lane] += wd;
                 }
                 __syncwarp();
                 if (a.S != nullptr) {
