@@ -498,7 +498,7 @@ struct Engine : IEngine {
     }
     int linearize_ld(int B, const double* X_, const double* U_, double* A_, int lda, double* B_, double* c_, cudaStream_t st) {
         if (B <= 0) return -1;
-        const long long n = (long long)B * N * NZ;
+        const long long n = (long long)B * N * (NZ - M::NPAS);      // one thread per differentiated column (rnmpc_lin.cuh)
         cudaEvent_t te = region_begin(0, st);
         linearize_kernel<M><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(B, N, X_, U_, h, A_, lda, B_, c_);
         region_end(te, st);
