@@ -49,7 +49,7 @@ template <int NX, int NU>
 __host__ __device__ inline size_t qp_tm_smem_bytes(int N) { return (kTmWarps * qp_tm_warp_doubles<NX, NU>(N) + 2) * sizeof(double); }
 
 // TMEM columns of a stage: 8 doubles
-enum { TM_SU = 0, TM_SL = 1, TM_LU = 2, TM_LL = 3, TM_ZY = 4, TM_DA = 5, TM_DC = 6 };
+enum { TM_SU = 0, TM_SL = 1, TM_LU = 2, TM_LL = 3, TM_ZY = 4, TM_DA = 5, TM_DC = 6, TM_ZN = 7 };    // ZN: nominal entry (constant)
 
 template <int NX, int NU, int NC>
 __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a, const Params<NX, NU>* __restrict__ prm) {
@@ -95,8 +95,15 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
             v2 += __shfl_xor_sync(0xffffffffu, v2, o); v3 += __shfl_xor_sync(0xffffffffu, v3, o);
         }
     };
+    // Loops in front of the warp-collective tcgen05 loads / stores have WARP-UNIFORM trip counts and predicated bodies: with a
+    // lane-dependent trip count here ptxas moved the loop's reconvergence point behind the first TMEM stores of an instance and
+    // turned the bar.warp.sync in front of them into NOPs -- the lanes then ran the stores in two groups and the first group's were
+    // lost (pendulum instantiation, found on the device; the CPU emulator cannot see it).
     auto zero_buf = [&](double* p, const int count) {
-        for (int e = 2 * lane; e < count; e += 64) *reinterpret_cast<double2*>(p + e) = make_double2(0.0, 0.0);
+        for (int e0 = 0; e0 < count; e0 += 64) {
+            const int e = e0 + 2 * lane;
+            if (e < count) *reinterpret_cast<double2*>(p + e) = make_double2(0.0, 0.0);
+        }
     };
     auto rc = [&](const double s) -> double { return s < kBig ? fast_rcp(s) : 0.0; };
 
@@ -106,8 +113,10 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
     }
     unsigned ring_par = 0;                     // bit i: parity of the next completion of slot i (the same in every lane)
     if (lane < NU * NU) R2s[lane] = prm->R2[lane];
-    for (int e = lane; e < NZ + NX; e += 32)
-        qdt[e] = 2.0 * (e < NX ? prm->Q[e * NX + e] : e < NZ ? prm->R[(e - NX) * NU + (e - NX)] : prm->Qf[(e - NZ) * NX + (e - NZ)]);
+    for (int e0 = 0; e0 < NZ + NX; e0 += 32) {
+        const int e = e0 + lane;
+        if (e < NZ + NX) qdt[e] = 2.0 * (e < NX ? prm->Q[e * NX + e] : e < NZ ? prm->R[(e - NX) * NU + (e - NX)] : prm->Qf[(e - NZ) * NX + (e - NZ)]);
+    }
     __syncwarp();
     // 2 H_ii of entry (k, lane); 0 for lanes that hold no entry
     auto qd_of = [&](const int k) -> double { return lane < NX ? (k < N ? qdt[lane] : qdt[NZ + lane]) : (lane < NZ && k < N ? qdt[lane] : 0.0); };
@@ -149,80 +158,129 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
         const bool tight = a.tightened < 0 ? ((a.flags[b] & FLAG_TIGHT) != 0) : (a.tightened != 0);
         double bad = 0.0, n_box = 0.0, s_sum = 0.0, dmy = 0.0;
         double* ztmp = buf1;                       // z of the initial point, [N+1][NZ], for the residual below (tile buffers are idle)
+        unsigned nzmask = 0;                       // bit k: the initial point has a nonzero entry in stage k (the same in every lane)
         {
             const double eps = tight ? 0.0 : kEpsQP;
+            const int i = lane;
+            const bool isx = i < NX, isu = !isx && i < NZ;
+            // The inputs of this pass are cold (first touch of the instance): everything that does not depend on the stage is loaded once,
+            // the nominal entry and the back-offs of EIGHT stages are requested before the first of them is used (the TMEM stores are
+            // volatile asm, so the compiler cannot overlap the misses of consecutive stages by itself: 84 k -> ~20 k cycles per QP).
+            double ub = 1e300, lb = -1e300, ubf = 1e300, lbf = -1e300, x0i = 0.0, bfu = 0.0, bfl = 0.0;
+            if (isx) {
+                ub = prm->xub[i]; lb = prm->xlb[i]; ubf = prm->xubf[i]; lbf = prm->xlbf[i];
+                x0i = a.x0[(size_t)b * NX + i];
+                if (tight) { bfu = a.backoff_f[(size_t)b * NIF + i]; bfl = a.backoff_f[(size_t)b * NIF + NX + i]; }
+            } else if (isu) { ub = prm->uub[i - NX]; lb = prm->ulb[i - NX]; }
+            const double* znp = isx ? Xn + i : Un + (isu ? i - NX : 0);
+            const int zn_stride = isx ? NX : NU;
+            const double* bop = a.backoff + (size_t)b * N * NI + (i < NZ ? i : 0);
+#ifndef RNMPC_TM_CH
+#define RNMPC_TM_CH 8
+#endif
+            constexpr int CH = RNMPC_TM_CH;
 #pragma unroll 1
-            for (int k = 0; k <= N; ++k) {
-                const int i = lane;
-                double h_ = 1e300, l_ = -1e300, z = 0.0;
-                bool box = false;
-                if (i < NX) {
-                    const double xn = Xn[k * NX + i];
-                    if (k < N) {
-                        const double bu = tight ? a.backoff[((size_t)b * N + k) * NI + i] : 0.0;
-                        const double bl = tight ? a.backoff[((size_t)b * N + k) * NI + NZ + i] : 0.0;
-                        h_ = (prm->xub[i] - xn) - bu + eps;
-                        l_ = -((xn - prm->xlb[i]) - bl + eps);
-                    } else if (tight) {
-                        h_ = prm->xubf[i] - a.backoff_f[(size_t)b * NIF + i];              // Q4: terminal bound not shifted by x_N
-                        l_ = -(-prm->xlbf[i] - a.backoff_f[(size_t)b * NIF + NX + i]);
-                    } else {
-                        h_ = (prm->xubf[i] - xn) + eps;
-                        l_ = -((xn - prm->xlbf[i]) + eps);
+            for (int k0 = 0; k0 <= N; k0 += CH) {
+                double zn_[CH], bu_[CH], bl_[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int k = k0 + j;
+                    const bool has = isx ? (k <= N) : (isu && k < N);
+                    const bool hb = tight && i < NZ && k < N;
+                    zn_[j] = has ? znp[k * zn_stride] : 0.0;
+                    bu_[j] = hb ? bop[(size_t)k * NI] : 0.0;
+                    bl_[j] = hb ? bop[(size_t)k * NI + NZ] : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int k = k0 + j;
+                    if (k > N) break;                      // warp-uniform
+                    const double zn = zn_[j];
+                    double h_ = 1e300, l_ = -1e300, z = 0.0;
+                    bool box = false;
+                    if (isx) {
+                        if (k < N) {
+                            h_ = (ub - zn) - bu_[j] + eps;
+                            l_ = -((zn - lb) - bl_[j] + eps);
+                        } else if (tight) {
+                            h_ = ubf - bfu;                                                     // Q4: terminal bound not shifted by x_N
+                            l_ = -(-lbf - bfl);
+                        } else {
+                            h_ = (ubf - zn) + eps;
+                            l_ = -((zn - lbf) + eps);
+                        }
+                        if (k == 0) {
+                            z = x0i - zn;                                                       // x(0) is pinned to the measurement
+                            if (z > h_ + kX0Tol || z < l_ - kX0Tol) bad = 1.0;
+                        } else box = true;
+                    } else if (isu && k < N) {
+                        h_ = (ub - zn) - bu_[j] + eps;
+                        l_ = -((zn - lb) - bl_[j] + eps);
+                        box = true;
                     }
-                    if (k == 0) {
-                        z = a.x0[(size_t)b * NX + i] - xn;                                  // x(0) is pinned to the measurement
-                        if (z > h_ + kX0Tol || z < l_ - kX0Tol) bad = 1.0;
-                    } else box = true;
-                } else if (i < NZ && k < N) {
-                    const int p = i - NX;
-                    const double un = Un[k * NU + p];
-                    const double bu = tight ? a.backoff[((size_t)b * N + k) * NI + i] : 0.0;
-                    const double bl = tight ? a.backoff[((size_t)b * N + k) * NI + NZ + i] : 0.0;
-                    h_ = (prm->uub[p] - un) - bu + eps;
-                    l_ = -((un - prm->ulb[p]) - bl + eps);
-                    box = true;
+                    double su = 1e300, sl = 1e300;
+                    if (box) {
+                        const bool hu = h_ < kBig, hl = l_ > -kBig;
+                        if (hu && hl) {
+                            const double m = 0.01 * (h_ - l_);
+                            if (!(h_ - l_ > 1e-12)) bad = 1.0;
+                            z = fmin(fmax(0.0, l_ + m), h_ - m);
+                        } else if (hu) z = fmin(0.0, h_ - 1.0);
+                        else if (hl) z = fmax(0.0, l_ + 1.0);
+                        if (hu) { su = h_ - z; n_box += 1.0; s_sum += su; }
+                        if (hl) { sl = z - l_; n_box += 1.0; s_sum += sl; }
+                    }
+                    if (i < NZ) ztmp[k * NZ + i] = z;
+                    if (i < NZ && z != 0.0) nzmask |= 1u << k;                   // this lane's entries; combined over the warp below
+                    const double v[8] = {su, sl, 0.0, 0.0, z, 0.0, 0.0, zn};      // the nominal entry rides in the spare column
+                    tm_st<8>(tcol(k, 0), v);
+#ifdef RNMPC_DBG_TM
+                    if (prof_on && k == 1) { a.prof[0] = __double_as_longlong(su); a.prof[10] = __double_as_longlong(h_); a.prof[11] = __double_as_longlong(l_); a.prof[12] = __double_as_longlong(zn); }
+#endif
                 }
-                double su = 1e300, sl = 1e300;
-                if (box) {
-                    const bool hu = h_ < kBig, hl = l_ > -kBig;
-                    if (hu && hl) {
-                        const double m = 0.01 * (h_ - l_);
-                        if (!(h_ - l_ > 1e-12)) bad = 1.0;
-                        z = fmin(fmax(0.0, l_ + m), h_ - m);
-                    } else if (hu) z = fmin(0.0, h_ - 1.0);
-                    else if (hl) z = fmax(0.0, l_ + 1.0);
-                    if (hu) { su = h_ - z; n_box += 1.0; s_sum += su; }
-                    if (hl) { sl = z - l_; n_box += 1.0; s_sum += sl; }
-                }
-                if (i < NZ) ztmp[k * NZ + i] = z;
-                const double v[8] = {su, sl, 0.0, 0.0, z, 0.0, 0.0, 0.0};
-                tm_st<8>(tcol(k, 0), v);
             }
         }
         tm_wait_st();
         warp_reduce4(bad, dmy, n_box, s_sum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nzmask |= __shfl_xor_sync(0xffffffffu, nzmask, o);
         int status = bad > 0.0 ? 2 : 0;
         __syncwarp();
-        // dynamics residual at the initial point: rp_k = A x_k + B u_k + c_k - x_{k+1}
+        // dynamics residual at the initial point: rp_k = A x_k + B u_k + c_k - x_{k+1}.  The initial point is zero wherever zero lies inside
+        // the bounds: only the stages with a nonzero entry (stage 0, clipped entries) read their A_k and B_k here.
         double rp_inf = 0.0, mu_acc = 0.0;
-#pragma unroll 1
-        for (int e = lane; e < N * NX; e += 32) {
-            const int k = e / NX, r = e - k * NX;
-            const double* Ar = Ag + ((size_t)k * NX + r) * LDG;
-            const double* Br = Bg + ((size_t)k * NX + r) * NU;
-            double acc = cg[e] - ztmp[(k + 1) * NZ + r], acc2 = 0.0;
-#pragma unroll
-            for (int m = 0; m + 1 < NX; m += 2) {
-                const double2 av = __ldg(reinterpret_cast<const double2*>(Ar + m));
-                acc = fma(av.x, ztmp[k * NZ + m], acc); acc2 = fma(av.y, ztmp[k * NZ + m + 1], acc2);
+#pragma unroll 4
+        for (int e0 = 0; e0 < N * NX; e0 += 32) {
+            const int e = e0 + lane;
+            if (e < N * NX) {
+                const int k = e / NX, r = e - k * NX;
+                rp[e] = cg[e] - ztmp[(k + 1) * NZ + r];
             }
-            if (NX & 1) acc = fma(__ldg(Ar + NX - 1), ztmp[k * NZ + NX - 1], acc);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+            if (!((nzmask >> k) & 1u)) continue;           // warp-uniform
+            if (lane < NX) {
+                const int r = lane;
+                const double* Ar = Ag + ((size_t)k * NX + r) * LDG;
+                const double* Br = Bg + ((size_t)k * NX + r) * NU;
+                double acc = rp[k * NX + r], acc2 = 0.0;
 #pragma unroll
-            for (int p = 0; p < NU; ++p) acc = fma(__ldg(Br + p), ztmp[k * NZ + NX + p], acc);
-            acc += acc2;
-            rp[e] = acc;
-            rp_inf = fmax(rp_inf, fabs(acc));
+                for (int m = 0; m + 1 < NX; m += 2) {
+                    const double2 av = __ldg(reinterpret_cast<const double2*>(Ar + m));
+                    acc = fma(av.x, ztmp[k * NZ + m], acc); acc2 = fma(av.y, ztmp[k * NZ + m + 1], acc2);
+                }
+                if (NX & 1) acc = fma(__ldg(Ar + NX - 1), ztmp[k * NZ + NX - 1], acc);
+#pragma unroll
+                for (int p = 0; p < NU; ++p) acc = fma(__ldg(Br + p), ztmp[k * NZ + NX + p], acc);
+                rp[k * NX + r] = acc + acc2;
+            }
+        }
+        __syncwarp();
+        for (int e0 = 0; e0 < N * NX; e0 += 32) {
+            const int e = e0 + lane;
+            if (e < N * NX) rp_inf = fmax(rp_inf, fabs(rp[e]));
         }
         {   // centred cold start: multipliers mu_bar / slack (QpArgs::mu0); the primal entry becomes z + z_nom
             const double mu_bar = a.mu0 < 0.0 ? (n_box > 0.0 ? -a.mu0 * s_sum / n_box : 1.0) : a.mu0;
@@ -231,15 +289,16 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                 double v[8];
                 tm_ld<8>(tcol(k, 0), v);
                 const double su = v[TM_SU], sl = v[TM_SL];
+#ifdef RNMPC_DBG_TM
+                if (prof_on && k == 1) { a.prof[1] = __double_as_longlong(su); a.prof[2] = __double_as_longlong(v[TM_ZY]); a.prof[3] = __double_as_longlong(v[TM_ZN]);
+                    a.prof[4] = __double_as_longlong(mu_bar); a.prof[5] = __double_as_longlong(n_box); a.prof[6] = __double_as_longlong(s_sum); a.prof[7] = nzmask; a.prof[9] = __double_as_longlong(rp_inf); }
+#endif
                 double lu, ll;
                 if (a.mu0 != 0.0) { lu = su < kBig ? mu_bar / su : 0.0; ll = sl < kBig ? mu_bar / sl : 0.0; }
                 else { lu = su < kBig ? 1.0 : 0.0; ll = sl < kBig ? 1.0 : 0.0; }
                 if (su < kBig) mu_acc = fma(su, lu, mu_acc);
                 if (sl < kBig) mu_acc = fma(sl, ll, mu_acc);
-                double zn = 0.0;
-                if (lane < NX) zn = Xn[k * NX + lane];
-                else if (lane < NZ && k < N) zn = Un[k * NU + lane - NX];
-                const double w[4] = {lu, ll, v[TM_ZY] + zn, 0.0};
+                const double w[4] = {lu, ll, v[TM_ZY] + v[TM_ZN], 0.0};
                 tm_st<4>(tcol(k, TM_LU), w);
             }
             tm_wait_st();
@@ -512,7 +571,9 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
 #pragma unroll
                     for (int j = 0; j < T::NSLOT - 1; ++j) ring_issue(j);      // the forward recursion's first stages are in flight during the small solves
                     // ---- d_k = -H_k^{-1} t_k   (one lane per stage)
-                    for (int k = lane; k < N; k += 32) {
+                    for (int k0 = 0; k0 < N; k0 += 32) {
+                        const int k = k0 + lane;
+                        if (k >= N) continue;
                         double d[NU], L[NU][NU];
 #pragma unroll
                         for (int p = 0; p < NU; ++p) {
@@ -697,11 +758,12 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
             double acc = 0.0;
 #pragma unroll 1
             for (int k = 0; k <= N; ++k) {
-                double v[4];
+                double v[4], zq[1];
                 tm_ld<4>(tcol(k, TM_LU), v);           // lu, ll, zy, (da)
+                tm_ld<1>(tcol(k, TM_ZN), zq);
                 const int i = lane;
                 if (i < NX || (i < NZ && k < N)) {
-                    const double zn = i < NX ? Xn[k * NX + i] : Un[k * NU + i - NX];
+                    const double zn = zq[0];
                     const double z = v[2] - zn;
                     acc = fma(z, 0.5 * qd_of(k) * (z + 2.0 * zn), acc);
                     if (i < NX) Xo[k * NX + i] = z; else Uo[k * NU + i - NX] = z;
@@ -712,7 +774,9 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
             double d0 = 0.0, d1 = 0.0, d3 = 0.0;
             warp_reduce4(d0, d1, acc, d3);
             mark(13);
+#ifndef RNMPC_DBG_TM
             if (prof_on) { for (int i = 0; i < 16; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + i, (unsigned long long)pacc[i]); }
+#endif
             if (lane == 0) {
                 a.cost[b] = acc;
                 a.iters[b] = it;
