@@ -189,6 +189,21 @@ __device__ __forceinline__ void bulk_g2s(double* dst_smem, const double* __restr
                  "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
                  : "memory");
 }
+// Arm the barrier and issue the copy from ONE elected lane without a branch: both instructions are predicated on elect.sync's result.
+// Called by all lanes with warp-uniform operands (see uniform_u32): the operands then sit in uniform registers and the copy is a
+// handful of instructions.  (An `if (lane == 0)` around bulk_g2s with operands the compiler cannot prove uniform becomes a loop
+// over the active lanes with four R2UR.BROADCAST per copy: ~200 cycles per call on the issuing warp, measured in qp_tm_kernel.)
+__device__ __forceinline__ void bulk_g2s_elect(double* dst_smem, const double* __restrict__ src, const unsigned bytes, unsigned long long* bar) {
+    asm volatile(
+        "{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\n"
+        "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n"
+        "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n}"
+        ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+        : "memory");
+}
+// A value that is the same in every lane, in a form the compiler knows to be warp-uniform (a vote result lives in a uniform register):
+// lane i contributes bit i.
+__device__ __forceinline__ unsigned uniform_u32(const unsigned v) { return __ballot_sync(0xffffffffu, (v >> (threadIdx.x & 31)) & 1u); }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, const unsigned parity) {
     const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
     unsigned ok = 0;

@@ -329,6 +329,7 @@ struct Engine : IEngine {
     bool qp_warp_ok = false;
     size_t qp_warp_smem = 0;
     double* Kw = nullptr;          // [B][N][NU][LDA] Riccati gains of qp_warp_kernel (its own padded layout)
+    double* Wimg = nullptr;        // [B][N][SLOT] sweep images of qp_tm_kernel: A_k | B_k | K_k per stage, one bulk copy per ring slot
     int sls_kernel_sel = 0;        // "sls_kernel": 0 = tensor-pipe fast-SLS kernel (rnmpc_sls_mma.cuh, one warp per chain), 1 = round-1 slot kernel
     int sls_mma_warps = 7;         // warps (chains) per CTA of the tensor-pipe fast-SLS kernel ("sls_mma_warps")
     int dense_reg = 0;             // Q_reg has off-diagonal entries
@@ -449,6 +450,7 @@ struct Engine : IEngine {
         }
         qp_tm_smem = qp_tm_smem_bytes<NX, NU>(N);
         qp_tm_ok = N + 1 <= kTmMaxStages && qp_tm_smem <= 227 * 1024 && alloc("qp_work", qp_work, 1) == 0 && alloc("qp_order", qp_order, B) == 0 &&
+                   alloc("Wimg", Wimg, (size_t)B * N * QpWarp<NX, NU>::SLOT) == 0 &&
                    cudaFuncSetAttribute(qp_tm_kernel<NX, NU, kHorizonFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
                    cudaFuncSetAttribute(qp_tm_kernel<NX, NU, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
                    cudaFuncSetAttribute(qp_tm_kernel<NX, NU, kHorizonFast>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) == cudaSuccess &&
@@ -592,7 +594,7 @@ struct Engine : IEngine {
         const bool plain = diag_cost && !may_warm && hi_in == nullptr && lo_in == nullptr && q_lin == nullptr;
         if (plain && qp_tm_ok && qp_warp_ok && (qp_kernel == 5 || (qp_kernel == 0 && B >= qp_warp_min))) {
             // one warp per instance, iterate in tensor memory, persistent CTAs of four warps (rnmpc_qp_tmem.cuh)
-            a.Kq = Kw; a.work = qp_work;
+            a.Kq = Wimg; a.work = qp_work;
             a.order = (qp_order_valid && fl == flags) ? qp_order : nullptr;      // only the resident solve has a history
             cudaMemsetAsync(qp_work, 0, sizeof(int), st);
             const unsigned gridt = (unsigned)std::min<long long>((long long)qp_tm_ctas * n_sm, ((long long)B + kTmWarps - 1) / kTmWarps);

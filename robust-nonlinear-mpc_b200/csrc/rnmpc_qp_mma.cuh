@@ -69,9 +69,12 @@ __host__ __device__ inline size_t mma_ev(size_t n) { return (n + 1) & ~(size_t)1
 // the vector rp_k would make the lanes of a warp take three different branches per load (measured: 10 % of the stall samples of
 // qp_warp_kernel, "branch resolving" 0.8 warps per issue); instead every lane keeps ONE generic pointer per mixed tile (global A_k or
 // B_k, or the shared-memory vector) with its own stage and k-step strides, so a fragment is one predicated load on every lane.
-template <int NX, int NU, int NT, int KS, bool RP>
+// STAGE > 0: A_k and B_k are parts of one image per stage with that stride (qp_tm_kernel's sweep image, written by the kernel itself:
+// coherent loads); STAGE = 0: the engine's separate arrays (read-only path).
+template <int NX, int NU, int NT, int KS, bool RP, int STAGE = 0>
 struct ZFrag {
     static constexpr int CB = (NX + 1) & ~1, CRP = CB + NU, LDG = (NX + 1) & ~1;
+    static constexpr int STA = STAGE > 0 ? STAGE : NX * LDG, STB = STAGE > 0 ? STAGE : NX * NU;
     static constexpr int NPURE = (NX / 8) < NT ? (NX / 8) : NT;      // tiles 0 .. NPURE-1 hold columns of A_k only
     static constexpr int NMIX = NT - NPURE > 0 ? NT - NPURE : 1;
     const double* base[NMIX];     // element (row t, this lane's column) of stage 0
@@ -85,21 +88,21 @@ struct ZFrag {
             const int c = 8 * (NPURE + j) + g;
             base[j] = Ag; ks[j] = 0; ss[j] = 0; ok[j] = false;
             if (NPURE + j < NT) {
-                if (c < NX) { base[j] = Ag + t4 * LDG + c; ks[j] = NX * LDG; ss[j] = 4 * LDG; ok[j] = true; }
-                else if (c >= CB && c < CB + NU) { base[j] = Bg + t4 * NU + (c - CB); ks[j] = NX * NU; ss[j] = 4 * NU; ok[j] = true; }
+                if (c < NX) { base[j] = Ag + t4 * LDG + c; ks[j] = STA; ss[j] = 4 * LDG; ok[j] = true; }
+                else if (c >= CB && c < CB + NU) { base[j] = Bg + t4 * NU + (c - CB); ks[j] = STB; ss[j] = 4 * NU; ok[j] = true; }
                 else if (RP && c == CRP) { base[j] = rp + t4; ks[j] = NX; ss[j] = 4; ok[j] = true; }
             }
         }
     }
     __device__ __forceinline__ void load(const int k, const double* Ag, double (&zf)[KS][NT]) const {
-        const double* Ak = Ag + (size_t)k * NX * LDG + t4 * LDG + g;
+        const double* Ak = Ag + (size_t)k * STA + t4 * LDG + g;
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
             const bool row = 4 * s + t4 < NX;
 #pragma unroll
             for (int n = 0; n < NT; ++n) {
                 double v = 0.0;
-                if (n < NPURE) { if (row) v = __ldg(Ak + 4 * s * LDG + 8 * n); }
+                if (n < NPURE) { if (row) v = STAGE > 0 ? Ak[4 * s * LDG + 8 * n] : __ldg(Ak + 4 * s * LDG + 8 * n); }
                 else { const int j = n - NPURE; if (row && ok[j]) v = base[j][(long long)k * ks[j] + s * ss[j]]; }
                 zf[s][n] = v;
             }

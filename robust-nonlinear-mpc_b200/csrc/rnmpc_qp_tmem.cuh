@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
     constexpr int LDS = D::LDS, LDW = D::LDW, LDA = D::LDA;
     static_assert(LDA == LDG, "the ring copies the engine's padded A_k as it is");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = (int)uniform_u32(threadIdx.x >> 5);      // warp index as a uniform value: shared-memory bases below are uniform
     const int g = lane >> 2, t4 = lane & 3;
     const int N = NC > 0 ? NC : a.N;
 
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
         // ---- next instance of the batch
         int b = 0;
         if (lane == 0) b = atomicAdd(a.work, 1);
-        b = __shfl_sync(0xffffffffu, b, 0);
+        b = (int)uniform_u32((unsigned)__shfl_sync(0xffffffffu, b, 0));      // uniform for the compiler too: global bases of the instance are uniform
         if (b >= a.B) break;
         if (a.order != nullptr) b = a.order[b];
         if (a.flags != nullptr && (a.flags[b] & a.skip_mask) != 0) continue;
@@ -136,7 +136,11 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
         const double* cg = a.c + (size_t)b * N * NX;
         const double* Xn = a.Xnom + (size_t)b * (N + 1) * NX;
         const double* Un = a.Unom + (size_t)b * N * NU;
-        double* Kg = a.Kq + (size_t)b * N * NU * LDA;                // layout [N][NU][LDA]
+        // sweep image of the instance in the workspace: [N][A_k (NX x LDA) | B_k (NX x NU) | K_k (NU x LDA)], one contiguous block per stage,
+        // so that a ring slot is ONE bulk copy (three copies -- A_k, B_k, K_k from their own arrays -- cost the issuing lane ~300 cycles
+        // per stage on the critical path of the sweeps: profiles/r2_notes.md).  A_k, B_k are copied in once per solve, K_k is written
+        // by the factorisation.
+        double* Wg = a.Kq + (size_t)b * N * D::SLOT;
         double* Lg = a.Lq + (size_t)b * N * NU * NU;
 
         // diagnostic phase timer (option "qp_profile"): cycles of lane 0 of instance 0 between consecutive marks
@@ -175,10 +179,7 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
             const double* znp = isx ? Xn + i : Un + (isu ? i - NX : 0);
             const int zn_stride = isx ? NX : NU;
             const double* bop = a.backoff + (size_t)b * N * NI + (i < NZ ? i : 0);
-#ifndef RNMPC_TM_CH
-#define RNMPC_TM_CH 8
-#endif
-            constexpr int CH = RNMPC_TM_CH;
+            constexpr int CH = 8;
 #pragma unroll 1
             for (int k0 = 0; k0 <= N; k0 += CH) {
                 double zn_[CH], bu_[CH], bl_[CH];
@@ -234,9 +235,6 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                     if (i < NZ && z != 0.0) nzmask |= 1u << k;                   // this lane's entries; combined over the warp below
                     const double v[8] = {su, sl, 0.0, 0.0, z, 0.0, 0.0, zn};      // the nominal entry rides in the spare column
                     tm_st<8>(tcol(k, 0), v);
-#ifdef RNMPC_DBG_TM
-                    if (prof_on && k == 1) { a.prof[0] = __double_as_longlong(su); a.prof[10] = __double_as_longlong(h_); a.prof[11] = __double_as_longlong(l_); a.prof[12] = __double_as_longlong(zn); }
-#endif
                 }
             }
         }
@@ -282,6 +280,24 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
             const int e = e0 + lane;
             if (e < N * NX) rp_inf = fmax(rp_inf, fabs(rp[e]));
         }
+        {   // A_k, B_k -> sweep image (16-byte copies, five stages in flight; the bulk copies that read it are behind the first factorisation
+            // and its fence.proxy.async)
+            constexpr int CA = NX * LDA / 2, CB2 = NX * NU / 2, CT = CA + CB2;      // double2 per stage: A part, B part
+            static_assert((D::OFFB % 2) == 0 && (D::SLOT % 2) == 0, "16-byte aligned image parts");
+#pragma unroll 5
+            for (int k = 0; k < N; ++k) {
+                const double2* As = reinterpret_cast<const double2*>(Ag + (size_t)k * NX * LDG);
+                const double2* Bs = reinterpret_cast<const double2*>(Bg + (size_t)k * NX * NU);
+                double2* Wd = reinterpret_cast<double2*>(Wg + (size_t)k * D::SLOT);
+#pragma unroll
+                for (int c0 = 0; c0 < CT; c0 += 32) {
+                    const int c = c0 + lane;
+                    if (c < CT) Wd[c] = c < CA ? __ldg(As + c) : __ldg(Bs + (c - CA));      // B part follows the A part (OFFB = NX * LDA)
+                }
+            }
+            fence_block();          // the image is read back by other lanes (operand fragments) and by the bulk copies
+            __syncwarp();
+        }
         {   // centred cold start: multipliers mu_bar / slack (QpArgs::mu0); the primal entry becomes z + z_nom
             const double mu_bar = a.mu0 < 0.0 ? (n_box > 0.0 ? -a.mu0 * s_sum / n_box : 1.0) : a.mu0;
 #pragma unroll 1
@@ -289,10 +305,6 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                 double v[8];
                 tm_ld<8>(tcol(k, 0), v);
                 const double su = v[TM_SU], sl = v[TM_SL];
-#ifdef RNMPC_DBG_TM
-                if (prof_on && k == 1) { a.prof[1] = __double_as_longlong(su); a.prof[2] = __double_as_longlong(v[TM_ZY]); a.prof[3] = __double_as_longlong(v[TM_ZN]);
-                    a.prof[4] = __double_as_longlong(mu_bar); a.prof[5] = __double_as_longlong(n_box); a.prof[6] = __double_as_longlong(s_sum); a.prof[7] = nzmask; a.prof[9] = __double_as_longlong(rp_inf); }
-#endif
                 double lu, ll;
                 if (a.mu0 != 0.0) { lu = su < kBig ? mu_bar / su : 0.0; ll = sl < kBig ? mu_bar / sl : 0.0; }
                 else { lu = su < kBig ? 1.0 : 0.0; ll = sl < kBig ? 1.0 : 0.0; }
@@ -311,23 +323,22 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
         double rp_scale = 1.0;
         __syncwarp();
 
-        ZFrag<NX, NU, NT, KS, true> zsrc;
-        zsrc.init(Ag, Bg, rp, lane);
-        auto load_z = [&](const int k, double (&zf)[KS][NT]) { zsrc.load(k, Ag, zf); };
-        // sweep ring: stage k -> slot k % NSLOT as three bulk copies issued by one lane (rnmpc_qp_warp.cuh)
+        // operand fragments come from the sweep image too: the instance's hot set in L2 is the image alone (with A_k, B_k read from their
+        // own arrays next to it, the resident instances' 114 MB no longer fit and phase A waited on HBM: +30 %)
+        ZFrag<NX, NU, NT, KS, true, D::SLOT> zsrc;
+        zsrc.init(Wg, Wg + D::OFFB, rp, lane);
+        auto load_z = [&](const int k, double (&zf)[KS][NT]) { zsrc.load(k, Wg, zf); };
+        // sweep ring: stage k -> slot k % NSLOT, one bulk copy of the stage image issued by one lane
         auto slot_ptr = [&](const int si) -> double* { return si < 3 ? ring_lo + si * D::SLOT : ring_hi + (si - 3) * D::SLOT; };
-        auto ring_issue = [&](const int k) {
-            if (lane == 0 && k >= 0 && k < N) {
-                const int si = k % T::NSLOT;
-                double* sl = slot_ptr(si);
-                mbar_expect_tx(rbar + si, (unsigned)(D::SLOT * sizeof(double)));
-                bulk_g2s(sl, Ag + (size_t)k * NX * LDG, (unsigned)(NX * LDA * sizeof(double)), rbar + si);
-                bulk_g2s(sl + D::OFFB, Bg + (size_t)k * NX * NU, (unsigned)(NX * NU * sizeof(double)), rbar + si);
-                bulk_g2s(sl + D::OFFK, Kg + (size_t)k * NU * LDA, (unsigned)(NU * LDA * sizeof(double)), rbar + si);
+        auto slot_of = [&](const int k) -> int { return T::NSLOT == 5 ? k - 5 * ((k * 13) >> 6) : k % T::NSLOT; };      // k < 64
+        auto ring_issue = [&](const int k) {        // all lanes, uniform operands; one elected lane issues (bulk_g2s_elect)
+            if (k >= 0 && k < N) {
+                const int si = slot_of(k);
+                bulk_g2s_elect(slot_ptr(si), Wg + (size_t)k * D::SLOT, (unsigned)(D::SLOT * sizeof(double)), rbar + si);
             }
         };
         auto ring_wait = [&](const int k) -> const double* {
-            const int si = k % T::NSLOT;
+            const int si = slot_of(k);
             mbar_wait(rbar + si, (ring_par >> si) & 1u);
             ring_par ^= 1u << si;
             return slot_ptr(si);
@@ -453,7 +464,7 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                         chol_solve<NU>(L, f);
                         if (lane < NX) {
 #pragma unroll
-                            for (int p = 0; p < NU; ++p) { kk[p * LDA + lane] = -f[p]; Kg[((size_t)k * NU + p) * LDA + lane] = -f[p]; }
+                            for (int p = 0; p < NU; ++p) { kk[p * LDA + lane] = -f[p]; Wg[(size_t)k * D::SLOT + D::OFFK + p * LDA + lane] = -f[p]; }
                         } else if (lane == NX) {
 #pragma unroll
                             for (int p = 0; p < NU; ++p) dff[k * NU + p] = -f[p];
@@ -774,9 +785,7 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
             double d0 = 0.0, d1 = 0.0, d3 = 0.0;
             warp_reduce4(d0, d1, acc, d3);
             mark(13);
-#ifndef RNMPC_DBG_TM
             if (prof_on) { for (int i = 0; i < 16; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + i, (unsigned long long)pacc[i]); }
-#endif
             if (lane == 0) {
                 a.cost[b] = acc;
                 a.iters[b] = it;

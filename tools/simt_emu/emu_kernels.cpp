@@ -43,7 +43,7 @@ static int run_qp_mma(const rnmpc_config* cfg, QpArgs a) {
     fill_params<NX, NU>(cfg, hp);
     if (g_qp_kernel == 2) {
         if (qp_tm_smem_bytes<NX, NU>(a.N) > sizeof(smem_raw) || a.N + 1 > kTmMaxStages) return -4;
-        std::vector<double> Kw((size_t)a.B * a.N * NU * QpWarp<NX, NU>::LDA, 0.0), Lw((size_t)a.B * a.N * NU * NU, 0.0);
+        std::vector<double> Kw((size_t)a.B * a.N * QpWarp<NX, NU>::SLOT, 0.0), Lw((size_t)a.B * a.N * NU * NU, 0.0);      // sweep images
         a.Kq = Kw.data(); a.Lq = Lw.data();
         int work = 0;
         a.work = &work;

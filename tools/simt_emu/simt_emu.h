@@ -135,6 +135,8 @@ static inline void mbar_init_fence() {}
 static inline void mbar_expect_tx(unsigned long long*, unsigned) {}
 static inline void bulk_g2s(double* dst, const double* src, unsigned bytes, unsigned long long*) { std::memcpy(dst, src, bytes); }
 static inline void mbar_wait(unsigned long long*, unsigned) {}
+static inline void bulk_g2s_elect(double* dst, const double* src, unsigned bytes, unsigned long long*) { if ((threadIdx.x & 31) == 0) std::memcpy(dst, src, bytes); }
+static inline unsigned uniform_u32(const unsigned v) { return v; }
 static inline void fence_proxy_async() {}
 // tensor memory: 128 lanes x 512 columns of 32 bits per (emulated) SM = per block; address = (lane << 16) | column
 }  // namespace rnmpc
