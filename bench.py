@@ -358,29 +358,26 @@ def main():
 
     # ---- e2e: same steps through host buffers (pinned host memory in, results out, copies inside the timed region)
     xh = torch.empty((B, m.nx), dtype=torch.float64, pin_memory=True)
-    wh = torch.empty((B, m.nx), dtype=torch.float64, pin_memory=True)
-    oh = torch.empty((B, m.nx + m.nu), dtype=torch.float64, pin_memory=True)
+    uh = torch.empty((B, m.nu), dtype=torch.float64, pin_memory=True)
     fh = torch.empty((B,), dtype=torch.int32, pin_memory=True)
     Wpin = torch.as_tensor(np.ascontiguousarray(np.swapaxes(W, 0, 1))).pin_memory()
     xds, wds = [torch.empty_like(x) for x in xs], [torch.empty_like(x) for x in xs]
 
     def e2e_step():
         i = step_idx[0]
-        wh.copy_(Wpin[i])                                   # this step's disturbance draw arrives from the host
         for (lo, hi), s, st, xd, wd in zip(bounds, solvers, streams, xds, wds):
             with torch.cuda.stream(st):
-                xd.copy_(xh[lo:hi], non_blocking=True)
-                wd.copy_(wh[lo:hi], non_blocking=True)
+                xd.copy_(xh[lo:hi], non_blocking=True)              # measured state: pinned host -> device
+                wd.copy_(Wpin[i, lo:hi], non_blocking=True)         # this step's disturbance draw arrives from the host (pinned)
                 if i > 0:
                     s.reset_warm_start(hi - lo)
                 s.solve(xd)
                 s.plant_step(xd, wd)
                 Uv = torch.as_tensor(s.buffer_view("U", hi - lo))
-                oh[lo:hi, :m.nx].copy_(xd, non_blocking=True)
-                oh[lo:hi, m.nx:].copy_(Uv[:, 0], non_blocking=True)
+                xh[lo:hi].copy_(xd, non_blocking=True)              # next state, applied input and flags: device -> pinned host
+                uh[lo:hi].copy_(Uv[:, 0], non_blocking=True)
                 fh[lo:hi].copy_(torch.as_tensor(s.buffer_view("flags", hi - lo)), non_blocking=True)
         torch.cuda.synchronize(dev)
-        xh.copy_(oh[:, :m.nx])
         step_idx[0] += 1
 
     # the SAME scenarios and the SAME MPC steps as the device-resident measurement: state and nominal trajectory are
