@@ -34,7 +34,9 @@ template <int NX, int NU>
 struct QpTm {
     using W = QpWarp<NX, NU>;
     static constexpr int NSLOT = 5;
-    static constexpr int EXTRA = (NSLOT - 3) * W::SLOT;        // ring slots 3, 4 (slots 0..2 live in the tile buffers)
+    static constexpr int SLOTS = (W::MAT / 3) & ~1;            // slot stride: slots 0..2 fill the tile buffers, 3.. follow them contiguously
+    static_assert(SLOTS >= W::SLOT, "three slots fit the tile buffers");
+    static constexpr int EXTRA = (NSLOT - 3) * SLOTS + (W::MAT - 3 * SLOTS);        // ring slots 3, 4 (slots 0..2 live in the tile buffers)
 };
 
 // shared-memory footprint of one warp in doubles
@@ -329,16 +331,17 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
         zsrc.init(Wg, Wg + D::OFFB, rp, lane);
         auto load_z = [&](const int k, double (&zf)[KS][NT]) { zsrc.load(k, Wg, zf); };
         // sweep ring: stage k -> slot k % NSLOT, one bulk copy of the stage image issued by one lane
-        auto slot_ptr = [&](const int si) -> double* { return si < 3 ? ring_lo + si * D::SLOT : ring_hi + (si - 3) * D::SLOT; };
+        // (the slots are contiguous with one stride and the sweeps carry the slot index along instead of computing k % NSLOT: the
+        // uniform-datapath address chain of the issue was a visible part of a stage)
+        auto slot_ptr = [&](const int si) -> double* { return ring_lo + si * T::SLOTS; };
         auto slot_of = [&](const int k) -> int { return T::NSLOT == 5 ? k - 5 * ((k * 13) >> 6) : k % T::NSLOT; };      // k < 64
-        auto ring_issue = [&](const int k) {        // all lanes, uniform operands; one elected lane issues (bulk_g2s_elect)
-            if (k >= 0 && k < N) {
-                const int si = slot_of(k);
+        auto slot_inc = [&](const int si) -> int { return si + 1 == T::NSLOT ? 0 : si + 1; };
+        auto slot_dec = [&](const int si) -> int { return si == 0 ? T::NSLOT - 1 : si - 1; };
+        auto ring_issue = [&](const int k, const int si) {        // all lanes, uniform operands; one elected lane issues (bulk_g2s_elect)
+            if (k >= 0 && k < N)
                 bulk_g2s_elect(slot_ptr(si), Wg + (size_t)k * D::SLOT, (unsigned)(D::SLOT * sizeof(double)), rbar + si);
-            }
         };
-        auto ring_wait = [&](const int k) -> const double* {
-            const int si = slot_of(k);
+        auto ring_wait = [&](const int si) -> const double* {
             mbar_wait(rbar + si, (ring_par >> si) & 1u);
             ring_par ^= 1u << si;
             return slot_ptr(si);
@@ -538,7 +541,7 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                 const int arr_dz = pass ? TM_DC : TM_DA;
                 if (pass == 1) {
 #pragma unroll
-                    for (int j = 1; j < T::NSLOT; ++j) ring_issue(N - j);
+                    for (int j = 1; j < T::NSLOT; ++j) ring_issue(N - j, slot_of(N - j));
                     mark(6);
                     {
                         // backward recursion: g_k = p_{k+1} + rp_scale Sc_k ; lanes < NX: p_k = rx_k + A_k' g_k + K_k' t_k,
@@ -548,12 +551,14 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                         const int bw_off = lane < NX ? lane : (lane < NZ ? D::OFFB + (lane - NX) : 0);
                         const int bw_stride = lane < NX ? LDA : NU;
                         double pl = rhs_corr(N);
+                        int si = slot_of(N - 1);
 #pragma unroll 1
                         for (int k = N - 1; k >= 0; --k) {
-                            ring_issue(k - (T::NSLOT - 1));    // into the slot of stage k + 1 (finished: barrier at the end of the previous stage)
+                            ring_issue(k - (T::NSLOT - 1), slot_inc(si));    // into the slot of stage k + 1 (finished: barrier at the end of the previous stage)
                             if (lane < NX) gv[lane] = pl + rp_scale * Sc[k * NX + lane];
                             const double rk = rhs_corr(k);
-                            const double* sl = ring_wait(k);
+                            const double* sl = ring_wait(si);
+                            si = slot_dec(si);
                             __syncwarp();
                             // one code path for all lanes: column r of A_k (lanes < NX) or column p of B_k (lanes NX .. NZ-1), own stride
                             double a0 = rk, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -580,7 +585,7 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                     }
                     mark(7);
 #pragma unroll
-                    for (int j = 0; j < T::NSLOT - 1; ++j) ring_issue(j);      // the forward recursion's first stages are in flight during the small solves
+                    for (int j = 0; j < T::NSLOT - 1; ++j) ring_issue(j, j);   // the forward recursion's first stages are in flight during the small solves
                     // ---- d_k = -H_k^{-1} t_k   (one lane per stage)
                     for (int k0 = 0; k0 < N; k0 += 32) {
                         const int k = k0 + lane;
@@ -600,7 +605,7 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                     mark(8);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < T::NSLOT - 1; ++j) ring_issue(j);
+                    for (int j = 0; j < T::NSLOT - 1; ++j) ring_issue(j, j);
                 }
                 mark(9);
                 // ---- forward recursion: lanes NX .. NZ-1: du_k = K_k dx_k + d_k ; lanes < NX: dx_{k+1} = A_k dx_k + B_k du_k +
@@ -644,12 +649,14 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                     double dxk = 0.0;                          // lanes < NX: dx_k[lane]
                     double dz_prev = 0.0;                      // this lane's entry of the step of stage k - 1
                     if (lane < NZ) { xs0[lane] = 0.0; xs1[lane] = 0.0; }
+                    int si = 0;
 #pragma unroll 1
                     for (int k = 0; k < N; ++k) {
                         double* xk = (k & 1) ? xs1 : xs0;      // [dx_k ; du_k]
                         double* xn = (k & 1) ? xs0 : xs1;
-                        ring_issue(k + (T::NSLOT - 1));        // into the slot of stage k - 1
-                        const double* sl = ring_wait(k);
+                        ring_issue(k + (T::NSLOT - 1), slot_dec(si));        // into the slot of stage k - 1
+                        const double* sl = ring_wait(si);
+                        si = slot_inc(si);
                         __syncwarp();
                         if (k > 0) ratio_load(k - 1, dz_prev);
                         // one code path for all lanes: row r of A_k from rp_scale rp_k (lanes < NX) or row p of K_k from d_k (lanes NX .. NZ-1);
