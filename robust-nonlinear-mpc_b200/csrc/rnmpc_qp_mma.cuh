@@ -71,7 +71,9 @@ __host__ __device__ inline size_t mma_ev(size_t n) { return (n + 1) & ~(size_t)1
 // B_k, or the shared-memory vector) with its own stage and k-step strides, so a fragment is one predicated load on every lane.
 // STAGE > 0: A_k and B_k are parts of one image per stage with that stride (qp_tm_kernel's sweep image, written by the kernel itself:
 // coherent loads); STAGE = 0: the engine's separate arrays (read-only path).
-template <int NX, int NU, int NT, int KS, bool RP, int STAGE = 0>
+// PLAIN: ordinary (coherent, any address space) loads instead of the read-only path -- sources the kernel wrote itself or keeps in
+// shared memory (qp_mma_kernel's resident copies of A_k, B_k).
+template <int NX, int NU, int NT, int KS, bool RP, int STAGE = 0, bool PLAIN = (STAGE > 0)>
 struct ZFrag {
     static constexpr int CB = (NX + 1) & ~1, CRP = CB + NU, LDG = (NX + 1) & ~1;
     static constexpr int STA = STAGE > 0 ? STAGE : NX * LDG, STB = STAGE > 0 ? STAGE : NX * NU;
@@ -102,7 +104,7 @@ struct ZFrag {
 #pragma unroll
             for (int n = 0; n < NT; ++n) {
                 double v = 0.0;
-                if (n < NPURE) { if (row) v = STAGE > 0 ? Ak[4 * s * LDG + 8 * n] : __ldg(Ak + 4 * s * LDG + 8 * n); }
+                if (n < NPURE) { if (row) v = PLAIN ? Ak[4 * s * LDG + 8 * n] : __ldg(Ak + 4 * s * LDG + 8 * n); }
                 else { const int j = n - NPURE; if (row && ok[j]) v = base[j][(long long)k * ks[j] + s * ss[j]]; }
                 zf[s][n] = v;
             }
@@ -338,30 +340,16 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
         if (rt < NX) pv[rt] = rhs_entry(0, N, rt);
         __syncthreads();
         mark(1);
+        ZFrag<NX, NU, NT, KS, true, 0, true> zsrc;
+        zsrc.init(As, Bs, rp, lane);
 #pragma unroll 1
         for (int k = N - 1; k >= 0; --k) {
             double* Kk = Kq + (size_t)k * NU * LDA;
             // fragments of Z_k = [A_k | B_k | rp_k] (rows padded to KP with zeros): zf[s][n] = Z[4s + t][8n + g]
+            // (branch-free: one pointer per lane and mixed column tile, see ZFrag -- the three-way branch per element had made this
+            // load the largest part of phase A)
             double zf[KS][NT];
-            {
-                const double* Ak = As + (size_t)k * NX * LDA;
-                const double* Bk = Bs + (size_t)k * NX * NU;
-#pragma unroll
-                for (int s = 0; s < KS; ++s) {
-                    const int r = 4 * s + t4;
-#pragma unroll
-                    for (int n = 0; n < NT; ++n) {
-                        const int c = 8 * n + g;
-                        double v = 0.0;
-                        if (r < NX) {
-                            if (c < NX) v = Ak[r * LDA + c];
-                            else if (c >= CB && c < CB + NU) v = Bk[r * NU + (c - CB)];
-                            else if (c == CRP) v = rp[k * NX + r];
-                        }
-                        zf[s][n] = v;
-                    }
-                }
-            }
+            zsrc.load(k, As, zf);
             // ---- phase A: W = S [A B rp]  (one warp per row tile of S); the free warp prepares the stage scalars
             if (role < MTS) {
                 double sa[KS], c0[NT], c1[NT];
