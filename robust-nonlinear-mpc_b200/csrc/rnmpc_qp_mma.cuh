@@ -400,20 +400,22 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
                         L[p][q] = M[(CB + lo) * LDW + CB + hi] + R2s[p * NU + q] + (p == q ? dgn[NX + p] : 0.0);
                     }
                 const bool ok = chol_inplace<NU>(L);
-                if (rt < NX) {
-                    double f[NU];
+                // one triangular solve per thread on one code path: threads < NX a column of (A'SB)' -> column of K, thread NX the vector t -> d
+                // (thread NX + 1 solves a copy of t and stores the factor instead)
+                double f[NU];
 #pragma unroll
-                    for (int p = 0; p < NU; ++p) f[p] = M[rt * LDW + CB + p];
-                    chol_solve<NU>(L, f);
+                for (int p = 0; p < NU; ++p)
+                    f[p] = rt < NX ? M[rt * LDW + CB + p] : rhs[NX + p] + M[(CB + p) * LDW + CP] + rp_scale * M[(CB + p) * LDW + CRP];
+                if (rt == NX) {
 #pragma unroll
-                    for (int p = 0; p < NU; ++p) Kk[p * LDA + rt] = -f[p];
-                } else if (rt == NX) {
-                    double d[NU];
+                    for (int p = 0; p < NU; ++p) uc[p] = f[p];
+                }
+                chol_solve<NU>(L, f);
+                double* fo = rt < NX ? Kk + rt : dff + k * NU;          // K_k[p][rt] (stride LDA) or d_k[p] (stride 1)
+                const int fs = rt < NX ? LDA : 1;
+                if (rt <= NX) {
 #pragma unroll
-                    for (int p = 0; p < NU; ++p) { d[p] = rhs[NX + p] + M[(CB + p) * LDW + CP] + rp_scale * M[(CB + p) * LDW + CRP]; uc[p] = d[p]; }
-                    chol_solve<NU>(L, d);
-#pragma unroll
-                    for (int p = 0; p < NU; ++p) dff[k * NU + p] = -d[p];
+                    for (int p = 0; p < NU; ++p) fo[p * fs] = -f[p];
                 } else {
 #pragma unroll
                     for (int p = 0; p < NU; ++p)
@@ -482,37 +484,28 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
                     // lanes NX .. NZ-1: t_k = ru_k + B_k' g_k (kept in tu for the feed-forward)
                     const int r = lane < NX ? lane : NX - 1;
                     const int p = (lane >= NX && lane < NZ) ? lane - NX : 0;
+                    const double* bw_base = lane < NX ? As + r : Bs + p;                  // lanes >= NZ read A too; their result is not used
+                    const int bw_kstride = lane < NX || lane >= NZ ? NX * LDA : NX * NU;
+                    const int bw_stride = lane < NX || lane >= NZ ? LDA : NU;
                     double pl = e_dc[N * NZ + r];
 #pragma unroll 1
                     for (int k = N - 1; k >= 0; --k) {
                         if (lane < NX) gv[k * NX + lane] = pl + rp_scale * Sc[k * NX + lane];
                         __syncwarp();
                         const double* gk = gv + k * NX;
-                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                        if (lane < NX) {
-                            if (k > 0) {
-                                const double* col = As + (size_t)k * NX * LDA + r;
-                                a0 = e_dc[k * NZ + r];
-#pragma unroll
-                                for (int m = 0; m + 3 < NX; m += 4) {
-                                    a0 = fma(col[m * LDA], gk[m], a0); a1 = fma(col[(m + 1) * LDA], gk[m + 1], a1);
-                                    a2 = fma(col[(m + 2) * LDA], gk[m + 2], a2); a3 = fma(col[(m + 3) * LDA], gk[m + 3], a3);
-                                }
-#pragma unroll
-                                for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(col[m * LDA], gk[m], a0);
-                            }
-                        } else if (lane < NZ) {
-                            const double* col = Bs + (size_t)k * NX * NU + p;
-                            a0 = e_dc[k * NZ + NX + p];
+                        // one code path for all lanes: column r of A_k (lanes < NX) or column p of B_k (lanes NX .. NZ-1), own base and strides
+                        double a0 = lane < NZ ? e_dc[k * NZ + lane] : 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                        {
+                            const double* col = bw_base + (size_t)k * bw_kstride;
 #pragma unroll
                             for (int m = 0; m + 3 < NX; m += 4) {
-                                a0 = fma(col[m * NU], gk[m], a0); a1 = fma(col[(m + 1) * NU], gk[m + 1], a1);
-                                a2 = fma(col[(m + 2) * NU], gk[m + 2], a2); a3 = fma(col[(m + 3) * NU], gk[m + 3], a3);
+                                a0 = fma(col[m * bw_stride], gk[m], a0); a1 = fma(col[(m + 1) * bw_stride], gk[m + 1], a1);
+                                a2 = fma(col[(m + 2) * bw_stride], gk[m + 2], a2); a3 = fma(col[(m + 3) * bw_stride], gk[m + 3], a3);
                             }
 #pragma unroll
-                            for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(col[m * NU], gk[m], a0);
-                            tu[k * NU + p] = (a0 + a1) + (a2 + a3);
+                            for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(col[m * bw_stride], gk[m], a0);
                         }
+                        if (lane >= NX && lane < NZ) tu[k * NU + p] = (a0 + a1) + (a2 + a3);
                         __syncwarp();
                         if (lane < NX && k > 0) {
                             double acc = (a0 + a1) + (a2 + a3);
@@ -547,40 +540,31 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
             if (role == 0) {
                 const int r = lane < NX ? lane : NX - 1;
                 const int p = (lane >= NX && lane < NZ) ? lane - NX : 0;
+                const double* fw_base = lane < NX || lane >= NZ ? As + (size_t)r * LDA : Kq + (size_t)p * LDA;      // lanes >= NZ: unused result
+                const int fw_kstride = lane < NX || lane >= NZ ? NX * LDA : NU * LDA;
+                const double* fw_init = lane < NX || lane >= NZ ? rp + r : dff + p;
+                const int fw_istride = lane < NX || lane >= NZ ? NX : NU;
+                const double fw_scale = lane < NX || lane >= NZ ? rp_scale : 1.0;
                 if (lane < NX) e_dz[lane] = 0.0;
                 __syncwarp();
 #pragma unroll 1
                 for (int k = 0; k < N; ++k) {
                     const double* xk = e_dz + k * NZ;
-                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                    if (lane < NX) {
-                        const double* row = As + ((size_t)k * NX + r) * LDA;
-                        a0 = rp_scale * rp[k * NX + r];
-                        if (k > 0) {
+                    // one code path for all lanes: row r of A_k from rp_scale rp_k (lanes < NX) or row p of K_k from d_k (lanes NX .. NZ-1);
+                    // dx_0 = 0, so stage 0 needs no special case
+                    double a0 = fw_scale * fw_init[k * fw_istride], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                    {
+                        const double* row = fw_base + (size_t)k * fw_kstride;
 #pragma unroll
-                            for (int m = 0; m + 3 < NX; m += 4) {
-                                const double2 r01 = *reinterpret_cast<const double2*>(row + m), r23 = *reinterpret_cast<const double2*>(row + m + 2);
-                                a0 = fma(r01.x, xk[m], a0); a1 = fma(r01.y, xk[m + 1], a1);
-                                a2 = fma(r23.x, xk[m + 2], a2); a3 = fma(r23.y, xk[m + 3], a3);
-                            }
-#pragma unroll
-                            for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(row[m], xk[m], a0);
+                        for (int m = 0; m + 3 < NX; m += 4) {
+                            const double2 r01 = *reinterpret_cast<const double2*>(row + m), r23 = *reinterpret_cast<const double2*>(row + m + 2);
+                            a0 = fma(r01.x, xk[m], a0); a1 = fma(r01.y, xk[m + 1], a1);
+                            a2 = fma(r23.x, xk[m + 2], a2); a3 = fma(r23.y, xk[m + 3], a3);
                         }
-                    } else if (lane < NZ) {
-                        const double* row = Kq + ((size_t)k * NU + p) * LDA;
-                        a0 = dff[k * NU + p];
-                        if (k > 0) {
 #pragma unroll
-                            for (int m = 0; m + 3 < NX; m += 4) {
-                                const double2 r01 = *reinterpret_cast<const double2*>(row + m), r23 = *reinterpret_cast<const double2*>(row + m + 2);
-                                a0 = fma(r01.x, xk[m], a0); a1 = fma(r01.y, xk[m + 1], a1);
-                                a2 = fma(r23.x, xk[m + 2], a2); a3 = fma(r23.y, xk[m + 3], a3);
-                            }
-#pragma unroll
-                            for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(row[m], xk[m], a0);
-                        }
-                        e_dz[k * NZ + NX + p] = (a0 + a1) + (a2 + a3);
+                        for (int m = NX / 4 * 4; m < NX; ++m) a0 = fma(row[m], xk[m], a0);
                     }
+                    if (lane >= NX && lane < NZ) e_dz[k * NZ + NX + p] = (a0 + a1) + (a2 + a3);
                     __syncwarp();
                     if (lane < NX) {
                         double acc = (a0 + a1) + (a2 + a3);
