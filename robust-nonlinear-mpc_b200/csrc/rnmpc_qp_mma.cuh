@@ -369,14 +369,23 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
             }
             __syncthreads();
             mark(2);
-            // ---- phase B: M = [A B]^T [W p]  (upper triangle of tiles, round robin over the warps)
+            // ---- phase B: M = [A B]^T [W p]  (upper triangle of tiles, round robin over the warps).  When H = B'SB + .. lies inside ONE tile
+            //      (rocket, pendulum), that tile goes to warp 3 alone, which then factorises H while the other warps finish their tiles:
+            //      the Cholesky chain (four dependent rsqrt, ~450 cycles) leaves the critical path of the stage.
+            constexpr bool HT = (CB / 8 == (CB + NU - 1) / 8) && (CB / 8 < MTM);
+            constexpr int TH = CB / 8;
+            double L[NU][NU];
+            bool chol_stage_ok = true;
             {
-                int ti = 0;
+                int ti = 0, tj = 0;
 #pragma unroll
                 for (int mt = 0; mt < MTM; ++mt) {
 #pragma unroll
                     for (int n = mt; n < NT; ++n, ++ti) {
-                        if ((ti & 3) != role) continue;
+                        const bool htile = HT && mt == TH && n == TH;
+                        const int owner = HT ? (htile ? 3 : tj % 3) : (ti & 3);
+                        if (!htile) ++tj;
+                        if (owner != role) continue;
                         double c0 = 0.0, c1 = 0.0;
 #pragma unroll
                         for (int s = 0; s < KS; ++s) {
@@ -387,11 +396,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
                     }
                 }
             }
-            __syncthreads();
-            mark(3);
-            // ---- phase C: H = R2 + diag + B'SB -> Cholesky; K = -H^{-1} (A'SB)' column by column; t = ru + B'(p + rp_scale S rp), d = -H^{-1} t
-            if (rt < NX + 2) {
-                double L[NU][NU];
+            auto factor_h = [&]() {
 #pragma unroll
                 for (int p = 0; p < NU; ++p)
 #pragma unroll
@@ -399,7 +404,20 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
                         const int lo = p < q ? p : q, hi = p < q ? q : p;
                         L[p][q] = M[(CB + lo) * LDW + CB + hi] + R2s[p * NU + q] + (p == q ? dgn[NX + p] : 0.0);
                     }
-                const bool ok = chol_inplace<NU>(L);
+                chol_stage_ok = chol_inplace<NU>(L);
+            };
+            if (HT && role == 3) {          // H's tile and dgn were written by this warp: a warp barrier makes them visible
+                __syncwarp();
+                factor_h();
+            }
+            __syncthreads();
+            mark(3);
+            // ---- phase C: H = R2 + diag + B'SB -> Cholesky (above when HT); K = -H^{-1} (A'SB)' column by column; t = ru + B'(p + rp_scale S rp),
+            //      d = -H^{-1} t   (warp 3, one thread per column)
+            if (role == 3 && lane < NX + 2) {
+                if (!HT) factor_h();
+                const bool ok = chol_stage_ok;
+                const int rt = lane;             // (shadows the logical thread index: this phase is laid out on warp 3's lanes)
                 // one triangular solve per thread on one code path: threads < NX a column of (A'SB)' -> column of K, thread NX the vector t -> d
                 // (thread NX + 1 solves a copy of t and stores the factor instead)
                 double f[NU];
