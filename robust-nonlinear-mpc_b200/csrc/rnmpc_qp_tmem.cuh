@@ -405,9 +405,27 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                     // reader, behind the barrier that follows phase A
                     if (lane < NZ) { rhs[lane] = rhs_n; dgn[lane] = dgn_n; }
                     if (k > 0) stage_scalars(k - 1, rhs_n, dgn_n);
-                    // ---- phase A: W = S [A B rp]
+                    // ---- phase A: W = S [A B rp].  When the last row tile of S holds ONE row (NX = 8 j + 1: the rocket's 17), that row of W is
+                    //      15 DFMA on the operand fragments already in registers plus two shuffle steps instead of 15 DMMA that are 1/8
+                    //      useful: the tensor pipe is what phases A and B wait on (two warps per scheduler share it).
+                    constexpr bool ROW1 = (NX - 8 * (MTS - 1)) == 1;
+                    if (ROW1) {
+                        constexpr int R = 8 * (MTS - 1);
+                        double sr[KS];
 #pragma unroll
-                    for (int mt = 0; mt < MTS; ++mt) {
+                        for (int s = 0; s < KS; ++s) sr[s] = buf1[R * LDS + 4 * s + t4];          // S[R][4s + t]
+#pragma unroll
+                        for (int n = 0; n < NT; ++n) {
+                            double acc = 0.0;
+#pragma unroll
+                            for (int s = 0; s < KS; ++s) acc = fma(sr[s], zf[s][n], acc);           // rows 4s + t of column 8n + g
+                            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                            if (t4 == 0) buf2[R * LDW + 8 * n + g] = acc;
+                        }
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < (ROW1 ? MTS - 1 : MTS); ++mt) {
                         double sa[KS];
 #pragma unroll
                         for (int s = 0; s < KS; ++s) sa[s] = buf1[(8 * mt + g) * LDS + 4 * s + t4];
