@@ -51,6 +51,12 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
     const int s = (int)(item - (long long)b * n_chain);
     if (a.flags != nullptr && (a.flags[b] & a.skip_mask) != 0) return;
 
+    // When the last row tile of an NX-row matrix holds ONE row (NX = 8 j + 1: the rocket's 17), that row of a product is 15 DFMA on
+    // the operand fragments already in registers plus two shuffle steps instead of 15 DMMA that are 1/8 useful -- this kernel waits
+    // on the tensor pipe (50 % busy, the top stall reason): 150 -> 117 DMMA per (Riccati, propagation) pair.
+    constexpr bool ROW1 = (NX - 8 * (MTS - 1)) == 1;
+    constexpr int RL = 8 * (MTS - 1);              // the single row
+    constexpr int MTD = ROW1 ? MTS - 1 : MTS;       // row tiles that go to the tensor pipe
     double* buf1 = reinterpret_cast<double*>(smem_raw) + (size_t)warp_in_cta * D::PER_WARP;
     double* buf2 = buf1 + D::BUF1;
     double* kk = buf2 + D::BUF2;
@@ -90,6 +96,10 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
 
     // ---------------- backward: Riccati recursion (solver/fast_SLS_jit.py:65-84) ----------------
     {
+        if (ROW1) {            // rows RL + 1 .. of W are no longer written by a tile product: they only meet zero operand rows, but must be finite
+            zero_buf(buf2, D::BUF2);
+            __syncwarp();
+        }
         double zf[KS][NTZ];
         if (n_steps > 0) load_z(N - 1, zf);
 #pragma unroll 1
@@ -129,8 +139,22 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
                 dg_next = weight(k_n, col_n, lane) + weight(k_n, col_n, lane + NZ);
             }
             // ---- W = S [A B]
+            if (ROW1) {
+                double sr[KS];
 #pragma unroll
-            for (int mt = 0; mt < MTS; ++mt) {
+                for (int q = 0; q < KS; ++q) sr[q] = buf1[RL * LDS + 4 * q + t4];             // S[RL][4q + t]
+#pragma unroll
+                for (int n = 0; n < NTZ; ++n) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int q = 0; q < KS; ++q) acc = fma(sr[q], zf[q][n], acc);              // rows 4q + t of column 8n + g
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                    if (t4 == 0) buf2[RL * LDW + 8 * n + g] = acc;
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < MTD; ++mt) {
                 double sa[KS];
 #pragma unroll
                 for (int q = 0; q < KS; ++q) sa[q] = buf1[(8 * mt + g) * LDS + 4 * q + t4];
@@ -275,8 +299,14 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
         for (int n = 0; n < MTS; ++n) kf[n] = (t4 < NU && 8 * n + g < NX) ? Kin[t4 * NX + 8 * n + g] : 0.0;      // B operand K[t][8n + g]
 #pragma unroll
         for (int q = 0; q < KS; ++q) ka[q] = (g < NU && 4 * q + t4 < NX) ? Kin[g * NX + 4 * q + t4] : 0.0;       // A operand K[g][4q + t]
+        if (ROW1 && lane < NX) {          // row RL of A + B K: NU DFMA per column
+            double acc = __ldg(Ak + RL * LDG + lane);
 #pragma unroll
-        for (int mt = 0; mt < MTS; ++mt) {
+            for (int p = 0; p < NU; ++p) acc = fma(__ldg(Bk + RL * NU + p), Kin[p * NX + lane], acc);
+            buf1[RL * LDS + lane] = acc;
+        }
+#pragma unroll
+        for (int mt = 0; mt < MTD; ++mt) {
             const int r = 8 * mt + g;
             const double bf = (t4 < NU && r < NX) ? __ldg(Bk + r * NU + t4) : 0.0;
 #pragma unroll
@@ -312,9 +342,28 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
             bu += __shfl_xor_sync(0xffffffffu, bu, 2);
         }
         // ---- Phi+ = (A + B K) Phi, row norms of the result from the accumulator fragments
-        double nc0[MTS][MTS], nc1[MTS][MTS], nx_new[MTS];
+        double nc0[MTS][MTS], nc1[MTS][MTS], nx_new[MTS], rowl[MTS];
+        if (ROW1) {                          // row RL of Phi+: lanes with t4 == 0 end up with columns g, 8 + g, 16 + g
+            double sr[KS], nn = 0.0;
 #pragma unroll
-        for (int mt = 0; mt < MTS; ++mt) {
+            for (int q = 0; q < KS; ++q) sr[q] = buf1[RL * LDS + 4 * q + t4];
+#pragma unroll
+            for (int n = 0; n < MTS; ++n) {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < KS; ++q) acc = fma(sr[q], pf[q][n], acc);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                rowl[n] = acc;
+                nn = fma(acc, acc, nn);
+            }
+            nn += __shfl_xor_sync(0xffffffffu, nn, 4);
+            nn += __shfl_xor_sync(0xffffffffu, nn, 8);
+            nn += __shfl_xor_sync(0xffffffffu, nn, 16);
+            nx_new[MTS - 1] = nn;            // squared norm of the row (pad columns of Phi are zero); every lane has it
+        }
+#pragma unroll
+        for (int mt = 0; mt < MTD; ++mt) {
             double af[KS];
 #pragma unroll
             for (int q = 0; q < KS; ++q) af[q] = buf1[(8 * mt + g) * LDS + 4 * q + t4];
@@ -353,7 +402,7 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
         {
             double* Po = a.Phi_x != nullptr ? a.Phi_x + ((((size_t)b * (N + 1) + k + 1) * (N + 1)) + col) * NX * NX : nullptr;
 #pragma unroll
-            for (int mt = 0; mt < MTS; ++mt) {
+            for (int mt = 0; mt < MTD; ++mt) {
                 const int r = 8 * mt + g;
 #pragma unroll
                 for (int n = 0; n < MTS; ++n) {
@@ -362,6 +411,17 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
                     if (Po != nullptr && r < NX) { if (c < NX) Po[r * NX + c] = nc0[mt][n]; if (c + 1 < NX) Po[r * NX + c + 1] = nc1[mt][n]; }
                 }
                 nx_cur[mt] = nx_new[mt];
+            }
+            if (ROW1) {
+                if (t4 == 0) {
+#pragma unroll
+                    for (int n = 0; n < MTS; ++n) {
+                        const int c = 8 * n + g;
+                        buf2[RL * LDF + c] = rowl[n];
+                        if (Po != nullptr && c < NX) Po[RL * NX + c] = rowl[n];
+                    }
+                }
+                nx_cur[MTS - 1] = nx_new[MTS - 1];
             }
         }
         __syncwarp();
