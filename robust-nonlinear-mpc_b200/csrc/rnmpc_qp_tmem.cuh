@@ -398,8 +398,6 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                 mark(1);
 #pragma unroll 1
                 for (int k = N - 1; k >= 0; --k) {
-                    double zn_[KS][NT];
-                    if (k > 0) load_z(k - 1, zn_);
                     // gradient and barrier weight of this lane's entry (lanes >= NZ hold a neutral entry): the values of THIS stage were
                     // computed during the previous one (two TMEM loads and two reciprocals off the critical path); phase C is the first
                     // reader, behind the barrier that follows phase A
@@ -456,6 +454,9 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                     }
                     __syncwarp();
                     mark(3);
+                    // operand fragments of the NEXT stage straight into zf (its last use in this stage was the product above): the L2 round
+                    // trip is covered by the Cholesky phase and the S update, no second fragment buffer and no copy
+                    if (k > 0) load_z(k - 1, zf);
                     // ---- phase C: H = R2 + diag + B'SB -> Cholesky (every lane its own copy); K = -H^{-1} (A'SB)' column by column;
                     //      t = ru + B'(p + rp_scale S rp), d = -H^{-1} t
                     {
@@ -539,10 +540,6 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                             }
                         }
                         if (lane < NX) pv[lane] = pk;          // p_k: the p column of the next stage's second product
-#pragma unroll
-                        for (int s = 0; s < KS; ++s)
-#pragma unroll
-                            for (int n = 0; n < NT; ++n) zf[s][n] = zn_[s][n];
                     }
                     __syncwarp();
                     mark(5);
