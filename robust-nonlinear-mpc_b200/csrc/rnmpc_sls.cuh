@@ -318,13 +318,28 @@ static __global__ void backoff_reduce_kernel(int B, int N, int ni, int ni_f, con
     const int e = (int)(gid - (long long)b * per);
     if (e < N * ni) {
         const int k = e / ni, i = e - k * ni;
+        // eight loads in flight, summed in the reference's order (j ascending)
+        const double* bp = beta + (((size_t)b * N + k) * N) * ni + i;
         double acc = 0.0;
-        for (int j = 0; j <= k; ++j) acc += sqrt(beta[(((size_t)b * N + k) * N + j) * ni + i]);
+        for (int j0 = 0; j0 <= k; j0 += 8) {
+            double v[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) v[jj] = (j0 + jj <= k) ? bp[(size_t)(j0 + jj) * ni] : 0.0;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) if (j0 + jj <= k) acc += sqrt(v[jj]);
+        }
         backoff[((size_t)b * N + k) * ni + i] = acc;
     } else {
         const int i = e - N * ni;
+        const double* bp = beta_f + ((size_t)b * (N + 1)) * ni_f + i;
         double acc = 0.0;
-        for (int j = 0; j <= N; ++j) acc += sqrt(beta_f[((size_t)b * (N + 1) + j) * ni_f + i]);
+        for (int j0 = 0; j0 <= N; j0 += 8) {
+            double v[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) v[jj] = (j0 + jj <= N) ? bp[(size_t)(j0 + jj) * ni_f] : 0.0;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) if (j0 + jj <= N) acc += sqrt(v[jj]);
+        }
         backoff_f[(size_t)b * ni_f + i] = acc;
     }
 }
