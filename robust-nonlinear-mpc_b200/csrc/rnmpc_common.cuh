@@ -115,6 +115,18 @@ __device__ __forceinline__ double fast_rcp(const double x) {
 }
 #endif
 
+// Reciprocal for quantities that only steer the iteration (ratio tests, the predictor's complementarity estimate): seed + NEWTON
+// Newton steps (0: 20+ bits, 1: 40+ bits).
+#ifndef RNMPC_EMU
+template <int NEWTON>
+__device__ __forceinline__ double rough_rcp(const double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    if (NEWTON >= 1) { const double e = fma(-x, r, 1.0); r = fma(r, e, r); }
+    return r;
+}
+#endif
+
 // Cholesky factor of an SPD NU x NU matrix held in registers (lower triangle, in place; the diagonal is stored
 // as its reciprocal).  Returns false if a pivot is not positive.
 template <int NU>

@@ -179,4 +179,5 @@ static inline void dmma884(double& c0, double& c1, const double a, const double 
     c0 = r0; c1 = r1;
 }
 static inline double fast_rcp(const double x) { return 1.0 / x; }
+template <int NEWTON> static inline double rough_rcp(const double x) { return 1.0 / x; }
 }  // namespace rnmpc
