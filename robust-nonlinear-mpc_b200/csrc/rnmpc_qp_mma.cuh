@@ -342,14 +342,15 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
         mark(1);
         ZFrag<NX, NU, NT, KS, true, 0, true> zsrc;
         zsrc.init(As, Bs, rp, lane);
+        double zf[KS][NT];
+        zsrc.load(N - 1, As, zf);
 #pragma unroll 1
         for (int k = N - 1; k >= 0; --k) {
             double* Kk = Kq + (size_t)k * NU * LDA;
             // fragments of Z_k = [A_k | B_k | rp_k] (rows padded to KP with zeros): zf[s][n] = Z[4s + t][8n + g]
             // (branch-free: one pointer per lane and mixed column tile, see ZFrag -- the three-way branch per element had made this
             // load the largest part of phase A)
-            double zf[KS][NT];
-            zsrc.load(k, As, zf);
+            // (loaded behind the second product of the previous stage: off the critical path of phase A)
             // ---- phase A: W = S [A B rp]  (one warp per row tile of S); the free warp prepares the stage scalars
             if (role < MTS) {
                 double sa[KS], c0[NT], c1[NT];
@@ -410,6 +411,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
                 __syncwarp();
                 factor_h();
             }
+            if (k > 0) zsrc.load(k - 1, As, zf);      // next stage's operand fragments (rp, A, B do not change during the factorisation)
             __syncthreads();
             mark(3);
             // ---- phase C: H = R2 + diag + B'SB -> Cholesky (above when HT); K = -H^{-1} (A'SB)' column by column; t = ru + B'(p + rp_scale S rp),
