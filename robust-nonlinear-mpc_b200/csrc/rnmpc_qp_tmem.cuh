@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
         auto slot_of = [&](const int k) -> int { return T::NSLOT == 5 ? k - 5 * ((k * 13) >> 6) : k % T::NSLOT; };      // k < 64
         auto slot_inc = [&](const int si) -> int { return si + 1 == T::NSLOT ? 0 : si + 1; };
         auto slot_dec = [&](const int si) -> int { return si == 0 ? T::NSLOT - 1 : si - 1; };
+#ifdef RNMPC_RING_BULK       // one bulk copy per slot issued by an elected lane, completion on an mbarrier (measured: 1.7 % slower, below)
         auto ring_issue = [&](const int k, const int si) {        // all lanes, uniform operands; one elected lane issues (bulk_g2s_elect)
             if (k >= 0 && k < N)
                 bulk_g2s_elect(slot_ptr(si), Wg + (size_t)k * D::SLOT, (unsigned)(D::SLOT * sizeof(double)), rbar + si);
@@ -346,6 +347,28 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
             ring_par ^= 1u << si;
             return slot_ptr(si);
         };
+#else
+        // default: the stage image as 16-byte cp.async of all lanes (7 per lane for the rocket), one commit group per stage (empty when
+        // out of range, so the group count of the wait is a constant), completion by cp.async.wait_group.  Against the bulk copy +
+        // mbarrier version: QP launch 2.670 -> 2.624 ms -- with one copy per slot the TMA issue was no longer the cost, the mbarrier round
+        // trip of every wait (~125 cycles per stage) was.
+        auto ring_issue = [&](const int k, const int si) {
+            if (k >= 0 && k < N) {
+                const double* src = Wg + (size_t)k * D::SLOT;
+                double* dst = slot_ptr(si);
+#pragma unroll
+                for (int c0 = 0; c0 < D::SLOT / 2; c0 += 32) {
+                    const int c = c0 + lane;
+                    if (c < D::SLOT / 2) cpa16(dst + 2 * c, src + 2 * c);
+                }
+            }
+            cpa_commit();
+        };
+        auto ring_wait = [&](const int si) -> const double* {
+            cpa_wait<T::NSLOT - 1>();
+            return slot_ptr(si);
+        };
+#endif
         double sigma_mu = 0.0;
         // corrector right-hand side of this lane's entry of a stage from its TMEM columns (rnmpc_qp.cuh rhs_eval, pass 1)
         auto rhs_corr = [&](const int k) -> double {
