@@ -196,6 +196,9 @@ int rnmpc_closed_loop_host(rnmpc_handle* h, int B, int steps, const double* h_x0
  * cap of that iteration, default 30), "qp_kernel" (0 automatic, 1 instance-per-slot, 2 round-1 block kernel, 3 one CTA per instance on
  * the tensor pipe, 4 one warp per instance, 5 one warp per instance with the iterate in tensor memory), "qp_warp_min" (smallest batch
  * the automatic choice gives to the one-warp-per-instance kernels, default 600), "sls_kernel" (0 tensor-pipe fast-SLS kernel, 1 slot kernel).
+ * "sls_mma_warps" (warps = chains per CTA of the tensor-pipe fast-SLS kernel, 1..7, default 7), "qp_tm_ctas" (persistent CTAs of the
+ * tensor-memory QP kernel per SM: 2 = all of the tensor memory, 1 for occupancy experiments: 4 instead of 8 resident instances per SM
+ * measured 1.47 x slower), "qp_lpt" (1 = resident solves hand the instances to the tensor-memory kernel longest first; measured: no gain, off).
  * Diagnostics: "q3_eps" (threshold of the reference's check_convergence_socp, which hard-codes 1e-3, fast_SLS_jit.py:594), "q3_margin_reset" (resets the buffer
  * "q3_margin": per instance the closest the tested quantity came to that threshold since the reset).
  * Unknown names return -1. */
