@@ -568,8 +568,11 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                     mark(5);
                 }
             }
+#ifdef RNMPC_RING_BULK
             fence_block();          // L_k written above is read back by other lanes
             fence_proxy_async();    // K_k (global) and the tile buffers (shared) written above are next touched by bulk copies
+#endif
+            // (cp.async ring: the readers of K_k, L_k are lanes of this warp behind the warp barrier below, which orders memory among them)
             __syncwarp();
 
             // ================================================================ predictor (pass 0) and corrector (pass 1): one copy of the sweep code
