@@ -461,7 +461,9 @@ struct Engine : IEngine {
         qp_mma_smem = qp_mma_smem_doubles<NX, NU>(N) * sizeof(double);
         qp_mma_ok = qp_mma_smem <= 227 * 1024 &&
                     cudaFuncSetAttribute(qp_mma_kernel<NX, NU, kHorizonFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
-                    cudaFuncSetAttribute(qp_mma_kernel<NX, NU, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+                    cudaFuncSetAttribute(qp_mma_kernel<NX, NU, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
+                    cudaFuncSetAttribute(qp_mma_kernel<NX, NU, kHorizonFast, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
+                    cudaFuncSetAttribute(qp_mma_kernel<NX, NU, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
         cudaGetLastError();
         {
             cudaDeviceProp prop;
@@ -473,7 +475,11 @@ struct Engine : IEngine {
                    cudaFuncSetAttribute(qp_tm_kernel<NX, NU, kHorizonFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
                    cudaFuncSetAttribute(qp_tm_kernel<NX, NU, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
                    cudaFuncSetAttribute(qp_tm_kernel<NX, NU, kHorizonFast>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) == cudaSuccess &&
-                   cudaFuncSetAttribute(qp_tm_kernel<NX, NU, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) == cudaSuccess;
+                   cudaFuncSetAttribute(qp_tm_kernel<NX, NU, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) == cudaSuccess &&
+                   cudaFuncSetAttribute(qp_tm_kernel<NX, NU, kHorizonFast, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
+                   cudaFuncSetAttribute(qp_tm_kernel<NX, NU, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
+                   cudaFuncSetAttribute(qp_tm_kernel<NX, NU, kHorizonFast, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) == cudaSuccess &&
+                   cudaFuncSetAttribute(qp_tm_kernel<NX, NU, 0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) == cudaSuccess;
         cudaGetLastError();
         qp_warp_smem = qp_warp_smem_doubles<NX, NU>(N) * sizeof(double);
         qp_warp_ok = qp_warp_smem <= 227 * 1024 && alloc("Kw", Kw, B * N * NU * LDA) == 0 &&
@@ -617,7 +623,10 @@ struct Engine : IEngine {
             a.order = (qp_order_valid && fl == flags) ? qp_order : nullptr;      // only the resident solve has a history
             cudaMemsetAsync(qp_work, 0, sizeof(int), st);
             const unsigned gridt = (unsigned)std::min<long long>((long long)qp_tm_ctas * n_sm, ((long long)B + kTmWarps - 1) / kTmWarps);
-            if (N == kHorizonFast) qp_tm_kernel<NX, NU, kHorizonFast><<<gridt, 32 * kTmWarps, qp_tm_smem, st>>>(a, d_prm);
+            if (a.prof != nullptr) {          // phase-timer instantiation (option "qp_profile")
+                if (N == kHorizonFast) qp_tm_kernel<NX, NU, kHorizonFast, true><<<gridt, 32 * kTmWarps, qp_tm_smem, st>>>(a, d_prm);
+                else qp_tm_kernel<NX, NU, 0, true><<<gridt, 32 * kTmWarps, qp_tm_smem, st>>>(a, d_prm);
+            } else if (N == kHorizonFast) qp_tm_kernel<NX, NU, kHorizonFast><<<gridt, 32 * kTmWarps, qp_tm_smem, st>>>(a, d_prm);
             else qp_tm_kernel<NX, NU, 0><<<gridt, 32 * kTmWarps, qp_tm_smem, st>>>(a, d_prm);
         } else if (plain && qp_warp_ok && (qp_kernel == 4 || qp_kernel == 5 || (qp_kernel == 0 && B >= qp_warp_min))) {
             // one warp (one CTA of 32 threads) per instance: the throughput kernel for large batches (rnmpc_qp_warp.cuh)
@@ -627,7 +636,10 @@ struct Engine : IEngine {
         } else if (plain && qp_mma_ok && (qp_kernel == 0 || qp_kernel == 3 || qp_kernel == 4)) {
             // one CTA per instance, factorisation on the FP64 tensor pipe, iterate resident in shared memory (rnmpc_qp_mma.cuh)
             // (the horizon of all reference drivers is a compile-time constant of the fast instantiation; any other horizon runs the generic one)
-            if (N == kHorizonFast) qp_mma_kernel<NX, NU, kHorizonFast><<<(unsigned)B, kMmaThreads, qp_mma_smem, st>>>(a, d_prm);
+            if (a.prof != nullptr) {          // phase-timer instantiation (option "qp_profile")
+                if (N == kHorizonFast) qp_mma_kernel<NX, NU, kHorizonFast, true><<<(unsigned)B, kMmaThreads, qp_mma_smem, st>>>(a, d_prm);
+                else qp_mma_kernel<NX, NU, 0, true><<<(unsigned)B, kMmaThreads, qp_mma_smem, st>>>(a, d_prm);
+            } else if (N == kHorizonFast) qp_mma_kernel<NX, NU, kHorizonFast><<<(unsigned)B, kMmaThreads, qp_mma_smem, st>>>(a, d_prm);
             else qp_mma_kernel<NX, NU, 0><<<(unsigned)B, kMmaThreads, qp_mma_smem, st>>>(a, d_prm);
         } else if (qp_block_ok && (B <= qp_block_max || qp_kernel == 2) && qp_kernel != 1 && diag_cost && !may_warm && hi_in == nullptr && lo_in == nullptr && q_lin == nullptr) {
             // small batch: one CTA per instance, working set in shared memory (rnmpc_qp_block.cuh)

@@ -124,7 +124,7 @@ __host__ __device__ inline size_t qp_mma_smem_doubles(int N) {
          + mma_ev(D::KP) + 2 * mma_ev(D::NZ) + mma_ev(D::NZ + NX) + mma_ev(NU) + mma_ev(NU * NU) + 64;         // pv, rhs, dgn, qdt, uc, R2, red
 }
 
-template <int NX, int NU, int NC>
+template <int NX, int NU, int NC, bool PROF = false>          // PROF: phase timer (option "qp_profile") as its own instantiation
 __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, const Params<NX, NU>* __restrict__ prm) {
     using D = QpMma<NX, NU>;
     constexpr int NZ = D::NZ, NI = 2 * NZ, NIF = 2 * NX, T = kMmaThreads, LDG = Slot<NX>::LD;
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
     };
 
     // diagnostic phase timer (option "qp_profile"): cycles of the logical thread 0 of instance 0 between consecutive marks
-    const bool prof_on = a.prof != nullptr && b == 0 && rt == 0;
+    const bool prof_on = PROF && a.prof != nullptr && b == 0 && rt == 0;
     long long* pacc = reinterpret_cast<long long*>(red + 40);
     long long t_last = 0;
     if (prof_on) {
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) qp_mma_kernel(const QpArgs a, 
         t_last = clock64();
     }
     auto mark = [&](const int slot) {
-        if (prof_on) { const long long t = clock64(); pacc[slot] += t - t_last; t_last = t; }
+        if (PROF && prof_on) { const long long t = clock64(); pacc[slot] += t - t_last; t_last = t; }
     };
 
     // ------------------------------------------------------------------ stage matrices -> shared memory (once per QP), padded buffers zeroed

@@ -53,7 +53,9 @@ __host__ __device__ inline size_t qp_tm_smem_bytes(int N) { return (kTmWarps * q
 // TMEM columns of a stage: 8 doubles
 enum { TM_SU = 0, TM_SL = 1, TM_LU = 2, TM_LL = 3, TM_ZY = 4, TM_DA = 5, TM_DC = 6, TM_ZN = 7 };    // ZN: nominal entry (constant)
 
-template <int NX, int NU, int NC>
+// PROF: the phase timer (option "qp_profile") is its own instantiation -- its predicated clock reads between the phases cost the
+// production kernel 1.2 % when they were merely switched off at run time.
+template <int NX, int NU, int NC, bool PROF = false>
 __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a, const Params<NX, NU>* __restrict__ prm) {
     using D = QpWarp<NX, NU>;
     using T = QpTm<NX, NU>;
@@ -146,14 +148,14 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
         double* Lg = a.Lq + (size_t)b * N * NU * NU;
 
         // diagnostic phase timer (option "qp_profile"): cycles of lane 0 of instance 0 between consecutive marks
-        const bool prof_on = a.prof != nullptr && b == 0 && lane == 0;
+        const bool prof_on = PROF && a.prof != nullptr && b == 0 && lane == 0;
         long long t_last = 0;
         if (prof_on) {
             for (int i = 0; i < 16; ++i) pacc[i] = 0;
             t_last = clock64();
         }
         auto mark = [&](const int slot) {
-            if (prof_on) { const long long t = clock64(); pacc[slot] += t - t_last; t_last = t; }
+            if (PROF && prof_on) { const long long t = clock64(); pacc[slot] += t - t_last; t_last = t; }
         };
         if (lane < KP) pv[lane] = 0.0;
         zero_buf(buf1, D::MAT + T::EXTRA);          // tile buffers + ring: finite contents from here on (see phase D)
