@@ -20,6 +20,7 @@
 // from a global counter until the batch is exhausted, so a warp that finishes early (8 to 25 iterations) starts the next instance.
 // Requires N + 1 <= 16 (16 columns per stage, 256 columns per CTA, two CTAs per SM share the 512 columns).
 #pragma once
+#include <type_traits>
 #include "rnmpc_common.cuh"
 #include "rnmpc_qp.cuh"
 #include "rnmpc_qp_mma.cuh"
@@ -658,18 +659,23 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                 // The ratio test of stage k - 1 is software-pipelined into stage k: its TMEM loads are issued at the head of the stage and its
                 // arithmetic (four reciprocals) sits in the same basic block as the stage's matrix-vector product, so the two independent
                 // dependency chains interleave instead of following each other.
+                // (the forward recursion is instantiated per pass: the predictor carries no corrector terms, the corrector no predictor sums --
+                //  with the pass as a run-time value both sets of instructions were issued in both)
+                auto forward = [&](auto PASSC) {
+                constexpr int PS = decltype(PASSC)::value;
+                const int arr_dz = PS ? TM_DC : TM_DA;
                 double rt_v[4], rt_w[1];
                 auto ratio_load = [&](const int k, const double dz) {        // the warp is converged here (directly behind a __syncwarp)
                     tm_ld<4, false>(tcol(k, TM_SU), rt_v);
                     rt_w[0] = 0.0;
-                    if (pass == 1) tm_ld<1, false>(tcol(k, TM_DA), rt_w);
+                    if (PS == 1) tm_ld<1, false>(tcol(k, TM_DA), rt_w);
                     const double dzs[1] = {dz};
                     tm_st<1, false>(tcol(k, arr_dz), dzs);
                 };
                 auto ratio_math = [&](const double dz) {
                     const double su = rt_v[0], sl = rt_v[1], lu = rt_v[2], ll = rt_v[3];
                     const double dza = rt_w[0];
-                    const double smu = pass == 1 ? sigma_mu : 0.0;
+                    const double smu = PS == 1 ? sigma_mu : 0.0;
                     // branch-free: a lane without a bound has reciprocal slack 0 and multiplier 0 (every term vanishes); the four
                     // reciprocals are independent and run side by side
                     // (these reciprocals only steer the iteration -- step lengths with a 0.5 % safety factor, the complementarity estimate of
@@ -677,13 +683,13 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                     const double iu = su < kBig ? rough_rcp<1>(su) : 0.0, il = sl < kBig ? rough_rcp<1>(sl) : 0.0;
                     const double ilu = rough_rcp<0>(lu), ill = rough_rcp<0>(ll);  // inf for a zero multiplier: discarded by the selects below
                     const double ru = lu * iu, rl = ll * il;
-                    const double tgu = pass == 1 ? smu + dza * (ru * dza - lu) : 0.0;
-                    const double tgl = pass == 1 ? smu + dza * (rl * dza + ll) : 0.0;
+                    const double tgu = PS == 1 ? smu + dza * (ru * dza - lu) : 0.0;
+                    const double tgl = PS == 1 ? smu + dza * (rl * dza + ll) : 0.0;
                     const double dlu = tgu * iu - lu + ru * dz;
                     const double dll = tgl * il - ll - rl * dz;
                     rpm = fmax(rpm, fmax(dz * iu, -dz * il));
                     rdm = fmax(rdm, fmax(dlu < 0.0 ? -dlu * ilu : 0.0, dll < 0.0 ? -dll * ill : 0.0));
-                    if (pass == 0) { S3 = fma(-dz, lu, S3); S4 = fma(-dz, dlu, S4); S3 = fma(dz, ll, S3); S4 = fma(dz, dll, S4); }
+                    if (PS == 0) { S3 = fma(-dz, lu, S3); S4 = fma(-dz, dlu, S4); S3 = fma(dz, ll, S3); S4 = fma(dz, dll, S4); }
                 };
                 {
                     const int r = lane < NX ? lane : NX - 1;
@@ -739,6 +745,8 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                     ratio_load(N, dz_prev); ratio_math(dz_prev);
                     tm_wait_st();
                 }
+                };
+                if (pass == 0) forward(std::integral_constant<int, 0>{}); else forward(std::integral_constant<int, 1>{});
                 mark(10);
                 warp_reduce4(rpm, rdm, S3, S4);
                 mark(11);
