@@ -453,6 +453,7 @@ struct Engine : IEngine {
         const int smem_sls = (int)sizeof(SlotSmem<NX, NU>) * Slot<NX>::SPW * kWarps;
         RN_CUDA(cudaFuncSetAttribute(sls_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sls));
         RN_CUDA(cudaFuncSetAttribute(sls_mma_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * SlsMma<NX, NU>::PER_WARP * (int)sizeof(double)));
+        RN_CUDA(cudaFuncSetAttribute(sls_mma_kernel<NX, NU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * SlsMma<NX, NU>::PER_WARP * (int)sizeof(double)));
         qp_block_smem = qp_block_smem_doubles<NX, NU>(N) * sizeof(double);
         // the attribute belongs to the kernel, not to this handle (handles with different horizons share it): always the maximum
         qp_block_ok = qp_block_smem <= 227 * 1024 &&
@@ -554,7 +555,9 @@ struct Engine : IEngine {
             // one warp per chain, every product of a stage on the FP64 tensor pipe (rnmpc_sls_mma.cuh)
             const int wpc = sls_mma_warps < 1 ? 1 : (sls_mma_warps > 7 ? 7 : sls_mma_warps);
             const unsigned gridm = (unsigned)((items + wpc - 1) / wpc);
-            sls_mma_kernel<NX, NU><<<gridm, wpc * 32, wpc * SlsMma<NX, NU>::PER_WARP * sizeof(double), st>>>(a, d_prm, dense_reg);
+            const bool lean = a.S == nullptr && a.Phi_x == nullptr && a.Phi_u == nullptr && a.eta == nullptr && a.eta_f == nullptr && !dense_reg;
+            if (lean) sls_mma_kernel<NX, NU, true><<<gridm, wpc * 32, wpc * SlsMma<NX, NU>::PER_WARP * sizeof(double), st>>>(a, d_prm, dense_reg);
+            else sls_mma_kernel<NX, NU><<<gridm, wpc * 32, wpc * SlsMma<NX, NU>::PER_WARP * sizeof(double), st>>>(a, d_prm, dense_reg);
         } else sls_kernel<NX, NU><<<grid, w * 32, smem, st>>>(a, d_prm);
         region_end(te, st);
         ++launches;

@@ -34,8 +34,16 @@ struct SlsMma {
     static_assert(NU <= 4, "rank-NU updates are one k-step");
 };
 
-template <int NX, int NU>
+// LEAN: the resident solve's configuration (no S / Phi outputs, diagonal regularisation, weights from mu and beta) as its own
+// instantiation: those run-time switches sit inside the stage loops (predicated stores per tile, selects per element).
+template <int NX, int NU, bool LEAN = false>
 __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const Params<NX, NU>* __restrict__ prm, const int dense_reg) {
+    double* const aS = LEAN ? nullptr : a.S;
+    double* const aPhi_x = LEAN ? nullptr : a.Phi_x;
+    double* const aPhi_u = LEAN ? nullptr : a.Phi_u;
+    const double* const aeta = LEAN ? nullptr : a.eta;
+    const double* const aeta_f = LEAN ? nullptr : a.eta_f;
+    const int dreg = LEAN ? 0 : dense_reg;
     using D = SlsMma<NX, NU>;
     constexpr int NZ = NX + NU, NI = 2 * NZ, NIF = 2 * NX, LDG = Slot<NX>::LD;
     constexpr int KP = D::KP, KS = D::KS, CB = D::CB, MTS = D::MTS, NTZ = D::NTZ, LDS = D::LDS, LDW = D::LDW, LDF = D::LDF, LDA = D::LDA;
@@ -68,14 +76,14 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
     const size_t kstride = (size_t)NU * NX;
 
     auto weight = [&](int k, int col, int i) -> double {   // eta[k][col][i]
-        if (a.eta != nullptr) return a.eta[(((size_t)b * N + k) * N + col) * NI + i];
+        if (aeta != nullptr) return aeta[(((size_t)b * N + k) * N + col) * NI + i];
         const double m = a.mu[((size_t)b * N + k) * NI + i];
         double be = kEpsBackoff;
         if (use_beta) be = fmax(a.beta_in[(((size_t)b * N + k) * N + col) * NI + i], kEpsBackoff);
         return 0.5 * m * rsqrt(be);        // mu / (2 sqrt(beta)): one reciprocal square root instead of an IEEE square root and division
     };                                     // (the two were 20 % of this kernel's instructions, profiles/r2_notes.md)
     auto weight_f = [&](int col, int i) -> double {        // eta_f[col][i]
-        if (a.eta_f != nullptr) return a.eta_f[((size_t)b * (N + 1) + col) * NIF + i];
+        if (aeta_f != nullptr) return aeta_f[((size_t)b * (N + 1) + col) * NIF + i];
         const double m = a.mu_f[(size_t)b * NIF + i];
         double be = kEpsBackoff;
         if (use_beta) be = fmax(a.beta_f_in[((size_t)b * (N + 1) + col) * NIF + i], kEpsBackoff);
@@ -120,8 +128,8 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
                     if (lane < NX) buf1[lane * LDS + lane] += wd;
                 }
                 __syncwarp();
-                if (a.S != nullptr) {
-                    double* So = a.S + ((((size_t)b * (N + 1) + N) * (N + 1)) + col) * NX * NX;
+                if (aS != nullptr) {
+                    double* So = aS + ((((size_t)b * (N + 1) + N) * (N + 1)) + col) * NX * NX;
                     for (int e = lane; e < NX * NX; e += 32) { const int i = e / NX, j = e - i * NX; So[e] = buf1[i * LDS + j]; }
                 }
             }
@@ -235,12 +243,12 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
                         if (r < NX) {
                             if (c < NX && r <= c) {
                                 double v = c0 + (r == c ? dg[r] : 0.0);
-                                v += dense_reg ? 0.5 * (prm->Qreg[r * NX + c] + prm->Qreg[c * NX + r]) : (r == c ? prm->Qreg[r * NX + r] : 0.0);
+                                v += dreg ? 0.5 * (prm->Qreg[r * NX + c] + prm->Qreg[c * NX + r]) : (r == c ? prm->Qreg[r * NX + r] : 0.0);
                                 buf1[r * LDS + c] = v; buf1[c * LDS + r] = v;
                             }
                             if (c + 1 < NX && r <= c + 1) {
                                 double v = c1 + (r == c + 1 ? dg[r] : 0.0);
-                                v += dense_reg ? 0.5 * (prm->Qreg[r * NX + c + 1] + prm->Qreg[(c + 1) * NX + r]) : (r == c + 1 ? prm->Qreg[r * NX + r] : 0.0);
+                                v += dreg ? 0.5 * (prm->Qreg[r * NX + c + 1] + prm->Qreg[(c + 1) * NX + r]) : (r == c + 1 ? prm->Qreg[r * NX + r] : 0.0);
                                 buf1[r * LDS + c + 1] = v; buf1[(c + 1) * LDS + r] = v;
                             }
                         }
@@ -248,8 +256,8 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
                 }
             }
             __syncwarp();
-            if (a.S != nullptr) {
-                double* So = a.S + ((((size_t)b * (N + 1) + k) * (N + 1)) + col) * NX * NX;
+            if (aS != nullptr) {
+                double* So = aS + ((((size_t)b * (N + 1) + k) * (N + 1)) + col) * NX * NX;
                 for (int e = lane; e < NX * NX; e += 32) { const int i = e / NX, j = e - i * NX; So[e] = buf1[i * LDS + j]; }
             }
 #pragma unroll
@@ -285,8 +293,8 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
             for (int e = lane; e < NX * NX; e += 32) { const int i = e / NX, j = e - i * NX; buf2[i * LDF + j] = prm->E[e]; }
 #pragma unroll
             for (int mt = 0; mt < MTS; ++mt) nx_cur[mt] = __shfl_sync(0xffffffffu, e_norm, (8 * mt + g) & 31);
-            if (a.Phi_x != nullptr) {
-                double* Po = a.Phi_x + ((((size_t)b * (N + 1) + col) * (N + 1)) + col) * NX * NX;
+            if (aPhi_x != nullptr) {
+                double* Po = aPhi_x + ((((size_t)b * (N + 1) + col) * (N + 1)) + col) * NX * NX;
                 for (int e = lane; e < NX * NX; e += 32) Po[e] = prm->E[e];
             }
         }
@@ -328,7 +336,7 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
         // ---- Phi_u = K Phi (rows g < NU), its row norms
         double bu = 0.0;
         {
-            double* Po = a.Phi_u != nullptr ? a.Phi_u + (((size_t)b * N + k) * (N + 1) + col) * kstride : nullptr;
+            double* Po = aPhi_u != nullptr ? aPhi_u + (((size_t)b * N + k) * (N + 1) + col) * kstride : nullptr;
 #pragma unroll
             for (int n = 0; n < MTS; ++n) {
                 double c0 = 0.0, c1 = 0.0;
@@ -400,7 +408,7 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
         }
         // ---- Phi+ over Phi (every lane has its fragments of the old one in registers)
         {
-            double* Po = a.Phi_x != nullptr ? a.Phi_x + ((((size_t)b * (N + 1) + k + 1) * (N + 1)) + col) * NX * NX : nullptr;
+            double* Po = aPhi_x != nullptr ? aPhi_x + ((((size_t)b * (N + 1) + k + 1) * (N + 1)) + col) * NX * NX : nullptr;
 #pragma unroll
             for (int mt = 0; mt < MTD; ++mt) {
                 const int r = 8 * mt + g;
@@ -433,13 +441,13 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
             double* bf = a.beta_f + ((size_t)b * (N + 1) + N) * NIF;
             bf[lane] = v; bf[lane + NX] = v;
         }
-        if (a.Phi_x != nullptr) {
-            double* Po = a.Phi_x + ((((size_t)b * (N + 1) + N) * (N + 1)) + N) * NX * NX;
+        if (aPhi_x != nullptr) {
+            double* Po = aPhi_x + ((((size_t)b * (N + 1) + N) * (N + 1)) + N) * NX * NX;
             for (int e = lane; e < NX * NX; e += 32) Po[e] = prm->E[e];
         }
-        if (a.S != nullptr) {
+        if (aS != nullptr) {
             // S[N, N] = Gf' diag(eta_f[N]) Gf + Q_reg_f (set by the reference although column N has no Riccati step)
-            double* So = a.S + ((((size_t)b * (N + 1) + N) * (N + 1)) + N) * NX * NX;
+            double* So = aS + ((((size_t)b * (N + 1) + N) * (N + 1)) + N) * NX * NX;
             for (int e = lane; e < NX * NX; e += 32) {
                 const int i = e / NX, j = e - i * NX;
                 So[e] = prm->Qregf[e] + (i == j ? weight_f(N, i) + weight_f(N, i + NX) : 0.0);
