@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
     }
     __syncwarp();
     // 2 H_ii of entry (k, lane); 0 for lanes that hold no entry
-    auto qd_of = [&](const int k) -> double { return lane < NX ? (k < N ? qdt[lane] : qdt[NZ + lane]) : (lane < NZ && k < N ? qdt[lane] : 0.0); };
+    const double qd_s = lane < NZ ? qdt[lane] : 0.0, qd_t = lane < NX ? qdt[NZ + lane] : 0.0;      // this lane's entry: stage / terminal value
+    auto qd_of = [&](const int k) -> double { return k < N ? qd_s : qd_t; };
 
 #pragma unroll 1
     for (;;) {
@@ -404,8 +405,8 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                 tm_ld<4>(tcol(N, TM_SU), v);
                 tm_ld<1>(tcol(N, TM_ZY), w);
                 if (lane < NX) {
-                    buf1[lane * LDS + lane] = qdt[NZ + lane] + (v[2] * rc(v[0]) + v[3] * rc(v[1]));
-                    pv[lane] = qdt[NZ + lane] * w[0];
+                    buf1[lane * LDS + lane] = qd_t + (v[2] * rc(v[0]) + v[3] * rc(v[1]));
+                    pv[lane] = qd_t * w[0];
                 }
             }
             {
@@ -416,8 +417,8 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                     double v[4], w[1];
                     tm_ld<4>(tcol(k, TM_SU), v);
                     tm_ld<1>(tcol(k, TM_ZY), w);
-                    r_out = (lane < NX && k == 0) ? 0.0 : (lane < NZ ? qdt[lane] * w[0] : 0.0);
-                    d_out = (lane < NX ? qdt[lane] : 0.0) + (v[2] * rc(v[0]) + v[3] * rc(v[1]));   // R2 is added to H below
+                    r_out = (lane < NX && k == 0) ? 0.0 : qd_s * w[0];
+                    d_out = (lane < NX ? qd_s : 0.0) + (v[2] * rc(v[0]) + v[3] * rc(v[1]));   // R2 is added to H below
                 };
                 stage_scalars(N - 1, rhs_n, dgn_n);
                 __syncwarp();
