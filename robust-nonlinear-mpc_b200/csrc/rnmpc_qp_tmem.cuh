@@ -535,15 +535,25 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
 #pragma unroll
                             for (int p = 0; p < NU; ++p) pk = fma(kk[p * LDA + lane], uc[p], pk);
                         }
+                        // ROW1: the last column tile of S holds ONE column -- its NX entries S_k[r][R] are NU DFMA each on lane r instead of MTS
+                        // tile updates on the tensor pipe with their predicated, mirrored stores
+                        constexpr int MTE = ROW1 ? MTS - 1 : MTS;
+                        double scol = 0.0;
+                        if (ROW1 && lane < NX) {
+                            constexpr int R = 8 * (MTS - 1);
+                            scol = buf1[lane * LDW + R] + (lane == R ? dgn[R] : 0.0);          // M[r][R] (upper triangle: r <= R)
+#pragma unroll
+                            for (int p = 0; p < NU; ++p) scol = fma(buf1[lane * LDW + CB + p], kk[p * LDA + R], scol);
+                        }
                         double kf[MTS], mc0[MTS * (MTS + 1) / 2], mc1[MTS * (MTS + 1) / 2], gf[MTS];
 #pragma unroll
-                        for (int n = 0; n < MTS; ++n) kf[n] = (t4 < NU && 8 * n + g < NX) ? kk[t4 * LDA + 8 * n + g] : 0.0;      // B operand K[t][8n + g]
+                        for (int n = 0; n < MTE; ++n) kf[n] = (t4 < NU && 8 * n + g < NX) ? kk[t4 * LDA + 8 * n + g] : 0.0;      // B operand K[t][8n + g]
                         int ti = 0;
 #pragma unroll
-                        for (int mt = 0; mt < MTS; ++mt) {
+                        for (int mt = 0; mt < MTE; ++mt) {
                             gf[mt] = (t4 < NU) ? buf1[(8 * mt + g) * LDW + CB + t4] : 0.0;                                        // A operand (A'SB)[r][t]
 #pragma unroll
-                            for (int n = mt; n < MTS; ++n, ++ti) {
+                            for (int n = mt; n < MTE; ++n, ++ti) {
                                 const double2 mv = *reinterpret_cast<const double2*>(buf1 + (8 * mt + g) * LDW + 8 * n + 2 * t4);
                                 mc0[ti] = mv.x; mc1[ti] = mv.y;
                             }
@@ -551,12 +561,16 @@ __global__ void __launch_bounds__(32 * kTmWarps, 2) qp_tm_kernel(const QpArgs a,
                         // (no zeroing: the pads of the S layout may hold finite leftovers of the M tiles -- they only ever multiply the zero
                         // rows of Z_k; the buffers are cleared once per instance, so nothing non-finite can be left in them)
                         __syncwarp();
+                        if (ROW1 && lane < NX) {
+                            constexpr int R = 8 * (MTS - 1);
+                            buf1[lane * LDS + R] = scol; buf1[R * LDS + lane] = scol;
+                        }
                         ti = 0;
 #pragma unroll
-                        for (int mt = 0; mt < MTS; ++mt) {
+                        for (int mt = 0; mt < MTE; ++mt) {
                             const int r = 8 * mt + g;
 #pragma unroll
-                            for (int n = mt; n < MTS; ++n, ++ti) {
+                            for (int n = mt; n < MTE; ++n, ++ti) {
                                 const int c = 8 * n + 2 * t4;
                                 double c0 = mc0[ti], c1 = mc1[ti];
                                 dmma884(c0, c1, gf[mt], kf[n]);
