@@ -215,15 +215,23 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
             // ---- S_k = Cx + A'SA + (A'SB) K : one k-step per upper tile on top of the A'SA tile; operands to registers first, the
             //      buffer then changes from the M layout back to the (zero padded) S layout
             {
+                // ROW1: the single column of the last tile as NU DFMA per lane (as in qp_tm_kernel's phase D)
+                double scol = 0.0;
+                if (ROW1 && lane < NX) {
+                    scol = buf1[lane * LDW + RL] + (lane == RL ? dg[RL] : 0.0);
+                    scol += dreg ? 0.5 * (prm->Qreg[lane * NX + RL] + prm->Qreg[RL * NX + lane]) : (lane == RL ? prm->Qreg[RL * NX + RL] : 0.0);
+#pragma unroll
+                    for (int p = 0; p < NU; ++p) scol = fma(buf1[lane * LDW + CB + p], kk[p * LDA + RL], scol);
+                }
                 double kf[MTS], mc0[MTS * (MTS + 1) / 2], mc1[MTS * (MTS + 1) / 2], gf[MTS];
 #pragma unroll
-                for (int n = 0; n < MTS; ++n) kf[n] = (t4 < NU && 8 * n + g < NX) ? kk[t4 * LDA + 8 * n + g] : 0.0;
+                for (int n = 0; n < MTD; ++n) kf[n] = (t4 < NU && 8 * n + g < NX) ? kk[t4 * LDA + 8 * n + g] : 0.0;
                 int ti = 0;
 #pragma unroll
-                for (int mt = 0; mt < MTS; ++mt) {
+                for (int mt = 0; mt < MTD; ++mt) {
                     gf[mt] = (t4 < NU) ? buf1[(8 * mt + g) * LDW + CB + t4] : 0.0;
 #pragma unroll
-                    for (int n = mt; n < MTS; ++n, ++ti) {
+                    for (int n = mt; n < MTD; ++n, ++ti) {
                         const double2 mv = *reinterpret_cast<const double2*>(buf1 + (8 * mt + g) * LDW + 8 * n + 2 * t4);
                         mc0[ti] = mv.x; mc1[ti] = mv.y;
                     }
@@ -231,12 +239,13 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
                 // (no zeroing: the pads of the S layout may hold finite leftovers of the M tiles -- they only multiply the zero rows of
                 // Z_k; the buffer was cleared when the column started)
                 __syncwarp();
+                if (ROW1 && lane < NX) { buf1[lane * LDS + RL] = scol; buf1[RL * LDS + lane] = scol; }
                 ti = 0;
 #pragma unroll
-                for (int mt = 0; mt < MTS; ++mt) {
+                for (int mt = 0; mt < MTD; ++mt) {
                     const int r = 8 * mt + g;
 #pragma unroll
-                    for (int n = mt; n < MTS; ++n, ++ti) {
+                    for (int n = mt; n < MTD; ++n, ++ti) {
                         const int c = 8 * n + 2 * t4;
                         double c0 = mc0[ti], c1 = mc1[ti];
                         dmma884(c0, c1, gf[mt], kf[n]);
