@@ -117,6 +117,33 @@ def test_sls_ragged_batch_and_zero_duals(name):
     s.close()
 
 
+@pytest.mark.parametrize("kernel", ["mma", "tmem"])
+def test_qp_phase_timer_instantiation_is_bit_identical(kernel):
+    """The phase timer of the tensor-pipe QP kernels (option qp_profile) is a template instantiation of its own (PROF): same results
+    bit for bit as the production instantiation, and its counters move."""
+    import ctypes as C
+    from rnmpc_b200 import _lib
+    g = load("qp_rocket.npz")
+    m, cfg, s = make_solver("rocket", 8)
+    set_qp_kernel(s, kernel)
+    A, B, c = s.linearize(g["X"], g["U"])
+    idx = np.where(g["tight"] == False)[0]          # noqa: E712
+    ti = torch.as_tensor(idx, device=A.device)
+    outs = []
+    for prof in (0, 1):
+        s.set_option("qp_profile", prof)
+        out = s.qp(A[ti], B[ti], c[ti], g["X"][idx], g["U"][idx], g["x0"][idx], None, None)
+        outs.append({k: np_(v).copy() for k, v in out.items()})
+        if prof:
+            v = np.zeros(16, dtype=np.int64)
+            _lib.check(s.lib.rnmpc_copy_buffer(s._h, b"qp_prof", C.c_void_p(v.ctypes.data), 128))
+            assert v.sum() > 0
+    s.set_option("qp_profile", 0)
+    for k in ("dX", "dU", "mu", "mu_f", "iters", "status"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    s.close()
+
+
 @pytest.mark.parametrize("kernel", QP_KERNELS)
 @pytest.mark.parametrize("name", MODELS)
 def test_qp_vs_oracle_golden(name, kernel):
