@@ -82,6 +82,16 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
         if (use_beta) be = fmax(a.beta_in[(((size_t)b * N + k) * N + col) * NI + i], kEpsBackoff);
         return 0.5 * m * rsqrt(be);        // mu / (2 sqrt(beta)): one reciprocal square root instead of an IEEE square root and division
     };                                     // (the two were 20 % of this kernel's instructions, profiles/r2_notes.md)
+    // eta[k][col][i] + eta[k][col][i + NZ], the diagonal addition of entry i.  LEAN: beta comes from this kernel's own previous launch,
+    // which stores the same value for the two sides of a box row -- one load and ONE rsqrt for both (the weights were 7 % of the
+    // instructions).
+    auto weight2 = [&](int k, int col, int i) -> double {
+        if (!LEAN) return weight(k, col, i) + weight(k, col, i + NZ);
+        const double* mp = a.mu + ((size_t)b * N + k) * NI + i;
+        double be = kEpsBackoff;
+        if (use_beta) be = fmax(a.beta_in[(((size_t)b * N + k) * N + col) * NI + i], kEpsBackoff);
+        return 0.5 * (mp[0] + mp[NZ]) * rsqrt(be);
+    };
     auto weight_f = [&](int col, int i) -> double {        // eta_f[col][i]
         if (aeta_f != nullptr) return aeta_f[((size_t)b * (N + 1) + col) * NIF + i];
         const double m = a.mu_f[(size_t)b * NIF + i];
@@ -138,13 +148,13 @@ __global__ void __launch_bounds__(224, 2) sls_mma_kernel(const SlsArgs a, const 
             if (t + 1 < n_steps) load_z((t + 1 == n_first) ? (N - 1) : (k - 1), zn_);
             // C_kj = G' diag(eta[k, col]) G : diagonal additions to Q_reg / R_reg.  The weight of the NEXT stage (two global loads, a
             // square root and a division per bound) is started here and lands in dg at the end of this stage: off the critical path.
-            if (t == 0 && lane < NZ) dg[lane] = weight(k, col, lane) + weight(k, col, lane + NZ);
+            if (t == 0 && lane < NZ) dg[lane] = weight2(k, col, lane);
             double dg_next = 0.0;
             if (t + 1 < n_steps && lane < NZ) {
                 const bool first_n = t + 1 < n_first;
                 const int col_n = first_n ? s : N - s;
                 const int k_n = first_n ? (N - 2 - t) : (N - 1 - (t + 1 - n_first));
-                dg_next = weight(k_n, col_n, lane) + weight(k_n, col_n, lane + NZ);
+                dg_next = weight2(k_n, col_n, lane);
             }
             // ---- W = S [A B]
             if (ROW1) {
