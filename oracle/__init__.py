@@ -16,7 +16,9 @@ Parity pinning:
   * Dynamics/Jacobians are pinned against closed-form SymPy differentiation of the same ODE and against
     finite differences (the reference evaluates them through CasADi 3.7.1, absent here).
   * The nominal QP is solved in the reference by OSQP 1.0.4 (absent here, un-vendored) with default
-    tolerances plus polish: PARITY UNPINNED at that boundary.  The QP is strictly convex, so its primal
+    tolerances plus polish: PARITY UNPINNED against the library at that boundary; ``oracle/osqp_restated.py``
+    restates its published algorithm, and its polished answer coincides with this oracle's on every QP fixture
+    (tests/test_oracle_cpu.py::test_restated_osqp_*).  The QP is strictly convex, so its primal
     solution is unique; the oracle solves it to KKT residual <= 1e-9 with an independent dense primal-dual
     interior-point method plus exact active-set refinement.  The MULTIPLIERS, which the algorithm also consumes
     (eta = mu / (2 sqrt(beta))), are unique only where the active-constraint gradients are linearly independent:

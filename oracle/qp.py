@@ -7,7 +7,8 @@ Follows (reference file:line):
   * ``solver/qp_jit.py:487-513``          unpacking of primal / dual vectors (``dual_mu`` is (ni, N))
   * ``solver/qp_jit.py:578-610``          update_ubg / offset_constraints bound bookkeeping
 The reference solves this QP with OSQP 1.0.4 (``requirements.txt:31``; un-vendored C library, absent here), default
-tolerances + polish (quirk Q1).  PARITY UNPINNED at that boundary: no OSQP output exists to compare with.  The QP
+tolerances + polish (quirk Q1).  PARITY UNPINNED at that boundary: no OSQP output exists to compare with (the
+published algorithm is restated in ``oracle/osqp_restated.py`` and lands on this file's solution).  The QP
 is strictly convex (P = 2*diag(Q,R,..) > 0), its primal solution is unique, and OSQP's polished answer is that
 solution.  This file therefore solves the same QP to high accuracy with an independent algorithm: a dense
 Mehrotra primal-dual interior-point method followed by an exact active-set refinement; ``kkt_residuals`` lets the

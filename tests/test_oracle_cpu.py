@@ -269,3 +269,35 @@ def test_soft_nmpc_oracle_satisfies_the_nlp_optimality_conditions():
         assert np.abs(gam - sol["gamma"]).max() < 1e-9 and np.abs(gam_f - sol["gamma_f"]).max() < 1e-9
     assert rel(sol["primal_x"], g["Xn"][0].T) < 1e-9 and abs(sol["cost"] / g["cost"][0] - 1) < 1e-9
     assert g["gamma"][0].max() > 0.5                                 # active slacks in the fixture
+
+
+@pytest.mark.parametrize("name", ["pendulum", "quadrotor", "rocket"])
+def test_restated_osqp_polish_lands_on_the_exact_oracle_solution(name):
+    """The QP boundary against a restatement of OSQP's published algorithm (oracle/osqp_restated.py; the library itself
+    is absent): on every QP fixture, with the bounds exactly as the reference hands them to OSQP (solver/qp_jit.py:370-386),
+    ADMM + polish returns the fixtures' exact solution (what the CUDA interior point is tested against at 1e-6) to
+    <= 1e-6 relative in the primal and <= 1e-6 in the inequality multipliers as soon as eps is small enough for the
+    ADMM iterate to identify the active set -- the default 1e-3 on most fixtures, 1e-4 / 1e-5 on the others
+    (profiles/r3f_osqp_restated_gap.txt) -- while the un-polished ADMM point stays within a few eps of it."""
+    from oracle import osqp_restated as osr
+    from tools.osqp_gap import fixture_qps, gaps
+    n_default = n = 0
+    for i, tight, qp, P, q, A, l, u, y, mu in fixture_qps(name):
+        if name == "rocket" and i in (0, 2):
+            continue            # these two need 3000+ ADMM iterations: covered by the committed table, not by every CI run
+        for eps in (1e-3, 1e-4, 1e-5):
+            x, lam, info = osr.solve(P, q, A, l, u, eps_abs=eps, eps_rel=eps)
+            assert info["status"] == "solved"
+            dx, dmu = gaps(qp, x, lam, y, mu)
+            Ax = A @ x
+            wrong = np.sum((lam > 1e-9) & (u - Ax > 1e-7)) + np.sum((lam < -1e-9) & (Ax - l > 1e-7))
+            dxa, _ = gaps(qp, info["x_admm"], info["y_admm"], y, mu)
+            assert dxa < 0.1                       # the ADMM point itself: eps-accurate only (rocket: 8e-2 at eps 1e-3)
+            if info["polished"] and wrong == 0:
+                assert dx < 1e-6 and dmu < 1e-6, (name, i, eps, dx, dmu)
+                n_default += eps == 1e-3
+                n += 1
+                break
+        else:
+            raise AssertionError(f"{name} fixture {i}: the polish never identified the active set")
+    assert n >= 2 and n_default >= 1
