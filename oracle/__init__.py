@@ -14,7 +14,9 @@ Parity pinning:
     kernels (``solver/fast_SLS_jit.py:43-188``), imported in the build container under import stubs by
     ``oracle/gen_golden.py``; their outputs are committed as ``tests/golden/sls_*.npz``.
   * Dynamics/Jacobians are pinned against closed-form SymPy differentiation of the same ODE and against
-    finite differences (the reference evaluates them through CasADi 3.7.1, absent here).
+    finite differences (the reference evaluates them through CasADi 3.7.1, absent here).  The ODEs themselves
+    are pinned against the reference's own ``dyn/*.py`` executed with a numeric CasADi stand-in
+    (``oracle/ref_models.py`` -> ``tests/golden/refdyn_*.npz``).
   * The nominal QP is solved in the reference by OSQP 1.0.4 (absent here, un-vendored) with default
     tolerances plus polish: PARITY UNPINNED against the library at that boundary; ``oracle/osqp_restated.py``
     restates its published algorithm, and its polished answer coincides with this oracle's on every QP fixture

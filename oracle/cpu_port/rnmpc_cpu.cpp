@@ -459,3 +459,23 @@ extern "C" long long rnmpc_cpu_closed_loop_resume(int model_id, int N, int rti, 
     }
     return -1;
 }
+
+// The product's model header evaluated on the host: ode (what = 0) or one RK4 step (what = 1) for n points.  Lets the CPU tests
+// hold csrc/rnmpc_models.cuh against the outputs of the reference's own dyn/*.py (tests/golden/refdyn_*.npz).
+template <class M>
+static int model_eval(int what, int n, const double* x, const double* u, double h, double* out) {
+    for (int i = 0; i < n; ++i) {
+        if (what == 0) M::template ode<double>(x + i * M::NX, u + i * M::NU, out + i * M::NX);
+        else rk4_step<M, double>(x + i * M::NX, u + i * M::NU, h, out + i * M::NX);
+    }
+    return 0;
+}
+
+extern "C" int rnmpc_cpu_model_eval(int model_id, int what, int n, const double* x, const double* u, double h, double* out) {
+    switch (model_id) {
+        case MODEL_PENDULUM: return model_eval<PendulumModel>(what, n, x, u, h, out);
+        case MODEL_QUADROTOR: return model_eval<QuadrotorModel>(what, n, x, u, h, out);
+        case MODEL_ROCKET: return model_eval<RocketModel>(what, n, x, u, h, out);
+    }
+    return -1;
+}

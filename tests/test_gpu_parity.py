@@ -849,3 +849,26 @@ def test_soft_constrained_nmpc_vs_oracle_golden(name):
     sb = NLPSoftConstraints(cfg["N"], cfg["Q"], cfg["R"], m, cfg["Qf"], rho_soft=1e6, rho_soft_l1=1e6, batch=3)
     solb = sb.solve(np.stack([g["x0"]] * 3), x_guess=np.stack([g["X0"].T] * 3), u_guess=np.stack([g["U0"].T] * 3))
     assert solb["success"].all() and rel(solb["primal_x"][2], g["Xn"][0].T) < TOL_TRAJ
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_ddyn_and_residual_vs_the_reference_sources_executed_numerically(name):
+    """CUDA `ddyn_kernel` / `linearize_kernel` against tests/golden/refdyn_*.npz: the outputs of the reference's OWN dyn/*.py
+    and dyn/model.py statements (imported unmodified with a numeric CasADi stand-in, oracle/ref_models.py) at 32 seeded points,
+    half of them across the whole state box.  1e-12 relative (fp64 round-off of ~200 operations per RK4 stage)."""
+    g = load(f"refdyn_{name}.npz")
+    m, cfg, s = make_solver(name, 32)
+    N, nx, nu = cfg["N"], m.nx, m.nu
+    xs, us = g["x"], g["u"]
+    scale = lambda a: np.maximum(1.0, np.abs(a))
+    xp = np_(s.ddyn(xs, us))
+    assert (np.abs(xp - g["xp"]) / scale(g["xp"])).max() < 1e-12
+    xp = np_(s.ddyn(xs, us, h=0.02))
+    assert (np.abs(xp - g["xp_h002"]) / scale(g["xp_h002"])).max() < 1e-12
+    # c_k = f(x_k, u_k) - x_{k+1} of the linearisation (SCP_SLS_jit.py:300-310) with x_{k+1} = the reference's own f
+    n = len(xs)
+    X = np.zeros((n, N + 1, nx)); U = np.zeros((n, N, nu))
+    X[:, 0], U[:, 0], X[:, 1] = xs, us, g["xp"]
+    _, _, c = (np_(t) for t in s.linearize(X, U))
+    assert (np.abs(c[:, 0]) / scale(g["xp"])).max() < 1e-12
+    s.close()

@@ -301,3 +301,37 @@ def test_restated_osqp_polish_lands_on_the_exact_oracle_solution(name):
         else:
             raise AssertionError(f"{name} fixture {i}: the polish never identified the active set")
     assert n >= 2 and n_default >= 1
+
+
+@pytest.mark.parametrize("name", ["pendulum", "quadrotor", "rocket"])
+def test_models_match_the_reference_sources_executed_numerically(name):
+    """tests/golden/refdyn_*.npz hold the outputs of the reference's OWN dyn/*.py statements (imported unmodified with a numeric
+    CasADi stand-in, oracle/ref_models.py).  Against them: the oracle's transcription (oracle/models.py), the product's model header
+    compiled for the host (csrc/rnmpc_models.cuh through the C++ port), and the constant tables.  Where the reference tree is
+    present the fixture is also regenerated and must reproduce bit for bit."""
+    import ctypes as C
+    from oracle import cpu_port, ref_models as rm
+    g = load(f"refdyn_{name}.npz")
+    m = om.MODELS[name]()
+    xs, us = g["x"], g["u"]
+    scale = lambda a: np.maximum(1.0, np.abs(a))
+    ode = np.array([np.asarray(m.ode(x, u), float) for x, u in zip(xs, us)])
+    assert (np.abs(ode - g["ode"]) / scale(g["ode"])).max() < 1e-14
+    for key, h in (("xp", 0.05), ("xp_h002", 0.02)):
+        xp = np.array([m.ddyn(x, u, h) for x, u in zip(xs, us)])
+        assert (np.abs(xp - g[key]) / scale(g[key])).max() < 1e-14
+    assert (np.abs(xs + 0.05 * ode - g["xp_euler"]) / scale(g["xp_euler"])).max() < 1e-14      # dyn/model.py:23-26
+    for key in ("G", "g", "Gf", "gf", "E"):
+        assert np.array_equal(np.asarray(getattr(m, key), float).reshape(g[key].shape), g[key]), key
+    # the product's model header on the host
+    lib = cpu_port.load()
+    out = np.empty_like(xs)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    xs_c, us_c = np.ascontiguousarray(xs), np.ascontiguousarray(us)
+    for what, h, key in ((0, 0.0, "ode"), (1, 0.05, "xp"), (1, 0.02, "xp_h002")):
+        assert lib.rnmpc_cpu_model_eval(m.model_id, what, len(xs), vp(xs_c), vp(us_c), C.c_double(h), vp(out)) == 0
+        assert (np.abs(out - g[key]) / scale(g[key])).max() < 1e-13, (name, key)
+    if rm.available():
+        ref = rm.load()[name]()
+        again = np.array([rm.ddyn(ref, x, u, 0.05) for x, u in zip(xs, us)])
+        assert np.array_equal(again, g["xp"])
