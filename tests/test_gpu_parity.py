@@ -872,3 +872,18 @@ def test_ddyn_and_residual_vs_the_reference_sources_executed_numerically(name):
     _, _, c = (np_(t) for t in s.linearize(X, U))
     assert (np.abs(c[:, 0]) / scale(g["xp"])).max() < 1e-12
     s.close()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_sls_duals_vs_the_reference_methods_executed_here(name):
+    """CUDA fast-SLS pass from QP multipliers (`rnmpc_sls_duals`: eta fused, Riccati, propagation, back-offs) against two
+    consecutive passes of the reference's OWN fast_SLS.evaluate_dual_eta / backward_solve / update_tightening
+    (tests/golden/refglue_*.npz, generated by oracle/ref_glue.py from the unmodified reference class)."""
+    g = load(f"refglue_{name}.npz")
+    _, cfg, s = make_solver(name, 2)
+    for p in range(2):
+        out = s.sls_duals(g["A"][None], g["B"][None], np.ascontiguousarray(g[f"p{p}_mu"].T)[None], g[f"p{p}_mu_f"][None],
+                          g[f"p{p}_beta_in"][None], g[f"p{p}_beta_f_in"][None], want_phi=False)
+        for key in ("K", "beta", "beta_f", "backoff", "backoff_f"):
+            assert rel(np_(out[key])[0], g[f"p{p}_{key}"]) < TOL_FP, (name, p, key)
+    s.close()

@@ -335,3 +335,34 @@ def test_models_match_the_reference_sources_executed_numerically(name):
         ref = rm.load()[name]()
         again = np.array([rm.ddyn(ref, x, u, 0.05) for x, u in zip(xs, us)])
         assert np.array_equal(again, g["xp"])
+
+
+@pytest.mark.parametrize("name", ["pendulum", "quadrotor", "rocket"])
+def test_fast_sls_glue_matches_the_reference_methods_executed_here(name):
+    """tests/golden/refglue_*.npz hold two consecutive passes of the reference's OWN fast_SLS.evaluate_dual_eta / backward_solve /
+    update_tightening / check_convergence_socp (unbound methods of the reference class on an attribute bag, oracle/ref_glue.py).
+    The oracle's FastSLS must reproduce every output: eta, gains, beta, back-offs, backoff_x / backoff_u (Q7), the tightened
+    upper bounds handed to the QP (Q4: un-shifted gf) and the Q3 decisions."""
+    g = load(f"refglue_{name}.npz")
+    m, cfg = om.CONFIGS[name]()
+    N = cfg["N"]
+    s = oscp.SCPSLS(N, cfg["Q"], cfg["R"], m, cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], rti=1, fast_sls_rti_steps=2)
+    s.set_nominal(g["X"], g["U"])
+    s.update_jacobian()
+    f = s.fast
+    assert rel(np.array(f.A), g["A"]) < 1e-15 and rel(np.array(f.c_list), g["c"]) < 1e-15
+    for p in range(2):
+        c = f.cur
+        c["dual_mu"], c["dual_mu_f"] = g[f"p{p}_mu"].copy(), g[f"p{p}_mu_f"].copy()
+        c["beta"], c["beta_f"] = g[f"p{p}_beta_in"].copy(), g[f"p{p}_beta_f_in"].copy()
+        f.evaluate_dual_eta(); f.backward_solve(); f.update_tightening()
+        for key in ("eta", "eta_f", "K", "beta", "beta_f", "backoff", "backoff_f", "backoff_x", "backoff_u"):
+            assert rel(c[key], g[f"p{p}_{key}"]) < 1e-12, (name, p, key)
+        assert rel(f.ubg, g[f"p{p}_ubg"]) < 1e-12
+    f._prev_primal_vec = None
+    q3 = []
+    for pv in g["q3_inputs"]:
+        f.cur["primal_vec"] = pv
+        q3.append(f.check_convergence_socp())
+    assert q3 == list(g["p1_q3"])
+    assert list(g["p1_q3"][-2:]) == [True, False]        # 5e-4 inside, 2e-3 outside the hard-coded 1e-3
