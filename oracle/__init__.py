@@ -13,6 +13,8 @@ Parity pinning:
   * Riccati backward sweep, Phi propagation and tube back-offs are pinned against the reference's OWN Numba
     kernels (``solver/fast_SLS_jit.py:43-188``), imported in the build container under import stubs by
     ``oracle/gen_golden.py``; their outputs are committed as ``tests/golden/sls_*.npz``.
+  * The QP handed to OSQP (assembly, bounds, x0 rows, unpacking) is pinned against the reference's own ``QP``
+    class driven over a recording ``osqp`` stand-in (``oracle/ref_qp.py`` -> ``tests/golden/refqp_*.npz``).
   * The fast-SLS glue (dual weights eta, tightening with quirks Q4 / Q7, the Q3 test) is pinned against the
     reference's own ``fast_SLS`` methods called unbound on an attribute bag (``oracle/ref_glue.py`` ->
     ``tests/golden/refglue_*.npz``).

@@ -887,3 +887,25 @@ def test_sls_duals_vs_the_reference_methods_executed_here(name):
         for key in ("K", "beta", "beta_f", "backoff", "backoff_f"):
             assert rel(np_(out[key])[0], g[f"p{p}_{key}"]) < TOL_FP, (name, p, key)
     s.close()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_qp_vs_the_reference_qp_class_executed_here(name):
+    """CUDA interior-point QP against the dictionaries the reference's OWN QP class returned (tests/golden/refqp_*.npz: solver/qp_jit.py
+    imported unmodified -- assembly, bound bookkeeping, x0 rows, _pack_solution are the reference's statements -- with the restated OSQP,
+    polished, as the engine; oracle/ref_qp.py): the nominal QP and the tightened QP of one fast-SLS pass, measured state 2 % of the box
+    off the nominal trajectory."""
+    g = load(f"refqp_{name}.npz")
+    m, cfg, s = make_solver(name, 2)
+    X, U, x0 = g["X"].T[None], g["U"].T[None], g["x0"][None]
+    A, B, c = s.linearize(X, U)
+    for p in range(2):
+        out = s.qp(A, B, c, X, U, x0, g["backoff"][None] if p else None, g["backoff_f"][None] if p else None)
+        out = {k: np_(v)[0] for k, v in out.items()}
+        assert out["status"] == 0
+        assert relf(out["dX"], g[f"p{p}_primal_x"].T) < TOL_TRAJ and relf(out["dU"], g[f"p{p}_primal_u"].T) < TOL_TRAJ
+        scale = max(np.abs(g[f"p{p}_dual_mu"]).max(), 1.0)
+        assert np.abs(out["mu"] - g[f"p{p}_dual_mu"].T).max() < TOL_TRAJ * scale
+        assert np.abs(out["mu_f"] - g[f"p{p}_dual_mu_f"]).max() < TOL_TRAJ * scale
+        assert abs(out["cost"] - float(g[f"p{p}_cost"])) < 1e-4 * max(1.0, abs(float(g[f"p{p}_cost"])))
+    s.close()

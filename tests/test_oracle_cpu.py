@@ -13,7 +13,7 @@ from oracle import qp as oqp
 from oracle import scp as oscp
 from oracle import sls as osls
 from oracle.gen_golden import jac_points, sls_inputs
-from tests.helpers import load, rel
+from tests.helpers import load, rel, relf
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -366,3 +366,41 @@ def test_fast_sls_glue_matches_the_reference_methods_executed_here(name):
         q3.append(f.check_convergence_socp())
     assert q3 == list(g["p1_q3"])
     assert list(g["p1_q3"][-2:]) == [True, False]        # 5e-4 inside, 2e-3 outside the hard-coded 1e-3
+
+
+@pytest.mark.parametrize("name", ["pendulum", "quadrotor", "rocket"])
+def test_qp_assembly_matches_the_reference_qp_class_executed_here(name):
+    """tests/golden/refqp_*.npz hold what the reference's OWN QP class (solver/qp_jit.py, imported unmodified over a numeric CasADi
+    stand-in and a recording `osqp` stand-in, oracle/ref_qp.py) hands to OSQP for the nominal and the tightened QP of one fast-SLS
+    pass, and the dictionaries its solve() returns with the restated OSQP as the engine.  The oracle's dense assembly must be the same
+    QP entry for entry (P = 2H, A, q, l, u -- u up to the documented stage-0 policy), and its exact solution must be what the
+    reference's _pack_solution returned (polished): primal, dual_mu (ni, N), dual_mu_f, cost."""
+    g = load(f"refqp_{name}.npz")
+    m, cfg = om.CONFIGS[name]()
+    N, nx, nu = cfg["N"], m.nx, m.nu
+    nz = nx + nu
+    s = oscp.SCPSLS(N, cfg["Q"], cfg["R"], m, cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], rti=1, fast_sls_rti_steps=2)
+    s.set_nominal(g["X"], g["U"])
+    s.update_jacobian()
+    f = s.fast
+    dx0 = g["X"][:, 0] - g["x0"]
+    assert "'polishing': True" in str(g["setup_settings"]) and "eps" not in str(g["setup_settings"])     # quirk Q1: OSQP defaults
+    for p in range(2):
+        assert np.array_equal(g[f"p{p}_P"], 2 * f.qp.H)
+        assert np.array_equal(g[f"p{p}_A"], f.qp.Acon)
+        assert np.array_equal(g[f"p{p}_q"], np.asarray(f.q, float).ravel())
+        l, u = f.qp.bounds(f.lbg, f.ubg, dx0)
+        policy = np.zeros(len(u), bool)
+        policy[nx:2 * nx] = policy[nx + nz:nx + nz + nx] = True          # stage-0 state rows of G (dropped: they restate the pinned x(0))
+        assert np.array_equal(g[f"p{p}_l"], l)
+        assert np.array_equal(g[f"p{p}_u"][~policy], u[~policy])
+        assert (u[policy] >= oqp.BIG).all() and (g[f"p{p}_u"][policy] < oqp.BIG).all()
+        assert bool(g[f"p{p}_polished"])
+        assert f.forward_solve(dx0)
+        c = f.cur
+        for key, tol in (("primal_vec", 1e-6), ("primal_x", 1e-6), ("primal_u", 1e-6), ("dual_mu", 1e-6), ("dual_mu_f", 1e-6)):
+            assert c[key].shape == g[f"p{p}_{key}"].shape
+            assert relf(c[key], g[f"p{p}_{key}"]) < tol, (name, p, key, relf(c[key], g[f"p{p}_{key}"]))
+        # the restated OSQP's polish sits on one end of the +-1e-10 equality intervals, the oracle on their midpoint: x costates
+        assert abs(c["cost_nominal"] - float(g[f"p{p}_cost"])) < 1e-4 * max(1.0, abs(float(g[f"p{p}_cost"])))
+        f.evaluate_dual_eta(); f.backward_solve(); f.update_tightening()
