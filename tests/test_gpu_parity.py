@@ -909,3 +909,18 @@ def test_qp_vs_the_reference_qp_class_executed_here(name):
         assert np.abs(out["mu_f"] - g[f"p{p}_dual_mu_f"]).max() < TOL_TRAJ * scale
         assert abs(out["cost"] - float(g[f"p{p}_cost"])) < 1e-4 * max(1.0, abs(float(g[f"p{p}_cost"])))
     s.close()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_shift_kernel_vs_the_reference_reset_warm_start_executed_here(name):
+    """CUDA `shift_kernel` (rnmpc_reset_warm_start) against the outputs of the reference's OWN SCP_SLS.reset_warm_start
+    (tests/golden/refshift_*.npz, oracle/ref_scp.py): x_k <- x_{k+1}, u_k <- u_{k+1}, last input repeated, X_N = f(X_N, U_{N-1})."""
+    g = load(f"refshift_{name}.npz")
+    _, cfg, s = make_solver(name, 2)
+    s.set_nominal(g["X_in"].T[None], g["U_in"].T[None])
+    s.reset_warm_start(1)
+    X, U = s.buffer("X", 1)[0], s.buffer("U", 1)[0]
+    N = cfg["N"]
+    assert np.array_equal(X[:N], g["X"].T[:N]) and np.array_equal(U, g["U"].T)
+    assert np.abs(X[N] - g["X"][:, N]).max() < 1e-12 * max(1.0, np.abs(g["X"]).max())
+    s.close()

@@ -404,3 +404,33 @@ def test_qp_assembly_matches_the_reference_qp_class_executed_here(name):
         # the restated OSQP's polish sits on one end of the +-1e-10 equality intervals, the oracle on their midpoint: x costates
         assert abs(c["cost_nominal"] - float(g[f"p{p}_cost"])) < 1e-4 * max(1.0, abs(float(g[f"p{p}_cost"])))
         f.evaluate_dual_eta(); f.backward_solve(); f.update_tightening()
+
+
+@pytest.mark.parametrize("name", ["pendulum", "quadrotor", "rocket"])
+def test_warm_start_shift_and_layout_match_the_reference_methods_executed_here(name):
+    """tests/golden/refshift_*.npz: outputs of the reference's OWN SCP_SLS.reset_warm_start and OCP.pack / unpack_primal_nominal
+    (unbound methods of the unmodified classes, model = the reference's dyn/*.py; oracle/ref_scp.py).  Against them: the oracle's
+    shift (bit for bit up to the RK4 round-off of X_N), its packing, and the product's host mirror solver/ocp.py."""
+    import rnmpc_b200  # noqa: F401
+    from rnmpc_b200.solver.ocp import OCP
+    g = load(f"refshift_{name}.npz")
+    m, cfg = om.CONFIGS[name]()
+    N = cfg["N"]
+    s = oscp.SCPSLS(N, cfg["Q"], cfg["R"], m, cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], rti=1, fast_sls_rti_steps=1)
+    s.set_nominal(g["X_in"], g["U_in"])
+    s.reset_warm_start()
+    X, U = s.cur["primal_x"], s.cur["primal_u"]
+    assert np.array_equal(X[:, :N], g["X"][:, :N]) and np.array_equal(U, g["U"])
+    assert np.abs(X[:, N] - g["X"][:, N]).max() < 1e-14 * max(1.0, np.abs(g["X"]).max())
+    assert list(g["calls"]) == ["reset_solver_to_zeros"]
+    # layout (solver/ocp.py:43-74) executed by the reference: oracle packing and the product's mirror
+    assert np.array_equal(s.fast.qp.pack(g["X"], g["U"]), g["primal_vec"])
+    o = OCP(N, cfg["Q"], cfg["R"], m, cfg["Qf"])
+    assert np.array_equal(np.asarray(o.pack_primal_nominal(g["X"], g["U"]), float).ravel(), g["primal_vec"])
+    X2, U2 = o.unpack_primal_nominal(g["primal_vec"])
+    assert np.array_equal(np.asarray(X2, float), g["unpacked_X"]) and np.array_equal(np.asarray(U2, float), g["unpacked_U"])
+    # the shifted inequality bounds the reference stashes (applied only with warm_start_ubg_shift): columns 1.. then the last repeated
+    nx, ni = m.nx, m.ni
+    stage = g["ubg_in"][:N * (nx + ni)].reshape((nx + ni, N), order="F")[nx:]
+    want = np.concatenate([stage[:, 1:], stage[:, -1:]], axis=1).reshape(-1, order="F")
+    assert np.array_equal(want, g["pending"])
