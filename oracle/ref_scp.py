@@ -86,5 +86,98 @@ def main():
         print(name, "written", out["X"].shape, out["primal_vec"].shape, out["calls"])
 
 
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# SCP control flow (row a10): the reference's own SCP_SLS.solve / socp_step / check_convergence_scp / post_processing_solution /
+# reset_warm_start (solver/SCP_SLS_jit.py:65-152, 404-483, 500-551, 610-622) run unbound on an attribute bag.  What they call that
+# needs CasADi's symbolic differentiation or the generated OSQP module -- update_jacobian and the fast_SLS object -- is supplied by
+# the oracle (whose pieces are pinned separately: refdyn_*, refglue_*, refqp_*, sls_*); everything else -- the RTI loop, the nominal
+# update, cost, the signed-max primal_infeasibility, success / iterations bookkeeping, the result dictionary -- is the reference's.
+class _Col(np.ndarray):
+    """A CasADi DM column: combined with a flat NumPy vector it stays a column (CasADi coerces the (n,) operand to (n, 1)),
+    where NumPy would broadcast to (n, n).  SCP_SLS_jit.py:452-454 relies on this."""
+    __array_priority__ = 100.0
+
+    def __sub__(self, other):
+        other = np.asarray(other, float)
+        return (np.asarray(self) - (other.reshape(-1, 1) if other.ndim == 1 else other)).view(_Col)
+
+    def __add__(self, other):
+        other = np.asarray(other, float)
+        return (np.asarray(self) + (other.reshape(-1, 1) if other.ndim == 1 else other)).view(_Col)
+
+
+def reference_closed_loop_steps(name, x0s, X, U, rti=1, sls_steps=1):
+    """Runs solve(x0s[0]), reset_warm_start(), solve(x0s[1]), ... and returns the list of result dictionaries."""
+    import scipy.sparse as sp
+
+    from . import ref_qp
+    from . import scp as oscp
+    mod = load()
+    mod.ca.DM = ref_qp.DM
+    ref_model = ref_models.load()[name]()
+    m, cfg = om.CONFIGS[name]()
+    N = cfg["N"]
+    orc = oscp.SCPSLS(N, cfg["Q"], cfg["R"], m, cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], rti=rti, fast_sls_rti_steps=sls_steps)
+    model = SimpleNamespace(nx=m.nx, nu=m.nu, ni=m.ni, ni_f=m.ni_f,
+                            ddyn=lambda x, u: ref_models.ddyn(ref_model, x, u).reshape(-1, 1).view(_Col))
+    bag = SimpleNamespace(N=N, m=model, Q=np.array(cfg["Q"], float), R=np.array(cfg["R"], float), Qf=np.array(cfg["Qf"], float),
+                          verbose=False, rti=rti, MAX_ITER_SCP=100, epsilon_convergence=1e-6, save_it_data=False, it_data={},
+                          convergence_data_scp={}, current_iteration_scp={}, H_mat=sp.csc_matrix(orc.fast.qp.H))
+    cls = mod.SCP_SLS
+    bag.pack_primal_nominal = lambda Xn, Un: mod.OCP.pack_primal_nominal(bag, Xn, Un)
+    bag.unpack_primal_nominal = lambda y: mod.OCP.unpack_primal_nominal(bag, y)
+    bag.scipy_csc_to_casadi_dm = lambda A: A.toarray()
+    bag.eval_deviation_mismatch = lambda e, d: {}                      # diagnostic, result unused (SCP_SLS_jit.py:422)
+    bag.socp_step = lambda x0: cls.socp_step(bag, x0)
+    bag.check_convergence_scp = lambda: cls.check_convergence_scp(bag)
+    bag.post_processing_solution = lambda: cls.post_processing_solution(bag)
+
+    def update_jacobian():                                             # SCP_SLS_jit.py:251-366, by the oracle
+        c = bag.current_iteration_scp
+        orc.set_nominal(np.array(c["primal_x"], float), np.array(c["primal_u"], float))
+        orc.update_jacobian()
+    bag.update_jacobian = update_jacobian
+    bag.fast_SLS_solver = SimpleNamespace(solve=lambda dx0: orc.fast.solve(np.asarray(dx0, float).reshape(-1)),
+                                          reset_solver_to_zeros=orc.fast.reset_solver_to_zeros,
+                                          solver_forward=SimpleNamespace(ubg=np.zeros(N * (m.nx + m.ni) + m.ni_f)))
+    c = bag.current_iteration_scp
+    c["primal_x"], c["primal_u"] = np.array(X, float), np.array(U, float)
+    c["primal_vec"] = np.array(bag.pack_primal_nominal(c["primal_x"], c["primal_u"]), float)
+    results = []
+    for i, x0 in enumerate(x0s):
+        if i > 0:
+            bag.fast_SLS_solver.solver_forward.ubg = np.array(orc.fast.ubg, float)
+            cls.reset_warm_start(bag)
+        results.append(cls.solve(bag, np.asarray(x0, float)))
+    return results
+
+
+KEYS = ("primal_x", "primal_u", "primal_vec", "delta_vec", "dual_mu", "dual_mu_f", "cost", "cost_QP", "primal_infeasibility",
+        "backoff", "backoff_x", "backoff_u", "dual_eta_f", "SOCP_steps", "iterations", "success")
+
+
+def main_solve():
+    from .gen_golden_ref_glue import scenario
+    for name, rti, steps in (("pendulum", 3, 2), ("quadrotor", 3, 2), ("rocket", 1, 1)):         # the drivers' settings
+        m, cfg, _, x0, X, U = scenario(name)
+        rng = np.random.default_rng(9)
+        # measured states: the start state, then the shifted nominal's first state plus a disturbance E w, |w| <= 1
+        x1 = X[:, 1] + m.E @ rng.uniform(-1, 1, m.nx)
+        res = reference_closed_loop_steps(name, [x0, x1], X, U, rti=rti, sls_steps=steps)
+        out = dict(X_in=X, U_in=U, x0s=np.array([x0, x1]), rti=rti, sls_steps=steps)
+        for i, r in enumerate(res):
+            assert r["success"], (name, i)
+            out.update({f"s{i}_{k}": np.asarray(r[k], float) for k in KEYS})
+            out[f"s{i}_keys"] = np.array(sorted(r.keys()))
+        np.savez_compressed(os.path.join(OUT, f"refsolve_{name}.npz"),
+                            source="reference SCP_SLS.solve / socp_step / reset_warm_start control flow executed through oracle/ref_scp.py "
+                                   "(update_jacobian and the fast_SLS object supplied by the oracle)", **out)
+        print(name, "written; cost", [float(np.asarray(r["cost"]).ravel()[0]) for r in res], "infeas", [float(np.asarray(r["primal_infeasibility"]).ravel()[0]) for r in res],
+              "iterations", [r["iterations"] for r in res])
+
+
 if __name__ == "__main__":
     main()
+    main_solve()

@@ -924,3 +924,33 @@ def test_shift_kernel_vs_the_reference_reset_warm_start_executed_here(name):
     assert np.array_equal(X[:N], g["X"].T[:N]) and np.array_equal(U, g["U"].T)
     assert np.abs(X[N] - g["X"][:, N]).max() < 1e-12 * max(1.0, np.abs(g["X"]).max())
     s.close()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_scp_sls_class_vs_the_reference_solve_executed_here(name):
+    """This package's `solver.SCP_SLS_jit.SCP_SLS` (CUDA engine underneath) against two MPC steps run by the reference's OWN
+    SCP_SLS.solve / socp_step / reset_warm_start control flow (tests/golden/refsolve_*.npz, oracle/ref_scp.py) at each driver's
+    rti / fast_sls_rti_steps: nominal trajectory, back-offs, multipliers, cost, the signed-max primal_infeasibility, iterations."""
+    import importlib
+    from rnmpc_b200.solver.SCP_SLS_jit import SCP_SLS
+    g = load(f"refsolve_{name}.npz")
+    mo, cfg = om.CONFIGS[name]()
+    cls = getattr(importlib.import_module(f"rnmpc_b200.dyn.{name}"), name.capitalize())
+    m = cls()
+    m.E = mo.E
+    solver = SCP_SLS(cfg["N"], cfg["Q"], cfg["R"], m, cfg["Qf"], Q_reg=cfg["Q_reg"], R_reg=cfg["R_reg"], Q_reg_f=cfg["Q_reg_f"],
+                     rti=int(g["rti"]), fast_sls_rti_steps=int(g["sls_steps"]), verbose=False)
+    solver.set_nominal_trajectory(g["X_in"], g["U_in"])
+    for i, x0 in enumerate(g["x0s"]):
+        if i > 0:
+            solver.reset_warm_start()
+        sol = solver.solve(x0)
+        assert bool(sol["success"]) == bool(g[f"s{i}_success"]) and int(sol["iterations"]) == int(g[f"s{i}_iterations"])
+        for key in ("primal_x", "primal_u", "backoff_x", "backoff_u", "backoff"):
+            assert relf(np.asarray(sol[key]), g[f"s{i}_{key}"].reshape(np.shape(sol[key]))) < TOL_TRAJ, (name, i, key)
+        scale = max(1.0, np.abs(g[f"s{i}_dual_mu"]).max())
+        assert np.abs(np.asarray(sol["dual_mu"]) - g[f"s{i}_dual_mu"]).max() < 1e-5 * scale
+        want = float(g[f"s{i}_cost"].ravel()[0])
+        assert abs(float(sol["cost"]) - want) < 1e-6 * max(1.0, abs(want))
+        want = float(g[f"s{i}_primal_infeasibility"].ravel()[0])
+        assert abs(float(sol["primal_infeasibility"]) - want) < 1e-6 * max(1.0, abs(want))

@@ -434,3 +434,30 @@ def test_warm_start_shift_and_layout_match_the_reference_methods_executed_here(n
     stage = g["ubg_in"][:N * (nx + ni)].reshape((nx + ni, N), order="F")[nx:]
     want = np.concatenate([stage[:, 1:], stage[:, -1:]], axis=1).reshape(-1, order="F")
     assert np.array_equal(want, g["pending"])
+
+
+@pytest.mark.parametrize("name", ["pendulum", "quadrotor", "rocket"])
+def test_scp_control_flow_matches_the_reference_solve_executed_here(name):
+    """tests/golden/refsolve_*.npz: two MPC steps run by the reference's OWN SCP_SLS.solve / socp_step / check_convergence_scp /
+    post_processing_solution / reset_warm_start (unbound methods of the unmodified class at the driver's rti / fast_sls_rti_steps;
+    linearisation and the fast_SLS object supplied by the oracle, oracle/ref_scp.py).  The oracle's own SCPSLS.solve /
+    reset_warm_start must walk the same path: every numeric key, `iterations`, `success`."""
+    g = load(f"refsolve_{name}.npz")
+    m, cfg = om.CONFIGS[name]()
+    N = cfg["N"]
+    s = oscp.SCPSLS(N, cfg["Q"], cfg["R"], m, cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], rti=int(g["rti"]),
+                    fast_sls_rti_steps=int(g["sls_steps"]))
+    s.set_nominal(g["X_in"], g["U_in"])
+    for i, x0 in enumerate(g["x0s"]):
+        if i > 0:
+            s.reset_warm_start()
+        sol = s.solve(x0)
+        assert bool(sol["success"]) == bool(g[f"s{i}_success"]) and sol["iterations"] == int(g[f"s{i}_iterations"])
+        for key in ("primal_x", "primal_u", "primal_vec", "delta_vec", "dual_mu", "dual_mu_f", "backoff", "backoff_x", "backoff_u", "dual_eta_f"):
+            assert relf(sol[key], g[f"s{i}_{key}"].reshape(np.shape(sol[key]))) < 1e-9, (name, i, key)
+        for key in ("cost", "cost_QP", "primal_infeasibility"):
+            want = float(g[f"s{i}_{key}"].ravel()[0])
+            assert abs(float(sol[key]) - want) < 1e-9 * max(1.0, abs(want)), (name, i, key, float(sol[key]), want)
+        assert int(sol["SOCP_steps"]) == int(g[f"s{i}_SOCP_steps"])
+        # the reference's result dictionary has the keys the drivers read (SURVEY 8b)
+        assert {"primal_x", "primal_u", "backoff_x", "backoff_u", "t_qp_ms", "t_backward_ms", "success", "iterations", "it_data"} <= set(g[f"s{i}_keys"])
