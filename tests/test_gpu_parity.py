@@ -954,3 +954,36 @@ def test_scp_sls_class_vs_the_reference_solve_executed_here(name):
         assert abs(float(sol["cost"]) - want) < 1e-6 * max(1.0, abs(want))
         want = float(g[f"s{i}_primal_infeasibility"].ravel()[0])
         assert abs(float(sol["primal_infeasibility"]) - want) < 1e-6 * max(1.0, abs(want))
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_fast_sls_class_vs_the_reference_solve_executed_here(name):
+    """This package's `solver.fast_SLS_jit.fast_SLS` (CUDA QP + CUDA fast-SLS pass underneath) against two consecutive fast_SLS.solve
+    calls run end to end by the reference's OWN statements (tests/golden/reffast_*.npz, oracle/ref_fast_sls.py): pendulum in
+    iterate-until-Q3 mode, quadrotor 2 and rocket 1 RTI steps; same call sequence as SCP_SLS_jit.py:386-388, 356-366."""
+    import importlib
+    from rnmpc_b200.dyn.LTV import LTV
+    from rnmpc_b200.solver.fast_SLS_jit import fast_SLS
+    g = load(f"reffast_{name}.npz")
+    mo, cfg = om.CONFIGS[name]()
+    N = cfg["N"]
+    m = getattr(importlib.import_module(f"rnmpc_b200.dyn.{name}"), name.capitalize())()
+    m.E = mo.E
+    ref = oscp.SCPSLS(N, cfg["Q"], cfg["R"], mo, cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], rti=1, fast_sls_rti_steps=1)
+    ref.set_nominal(g["X"], g["U"])
+    ref.update_jacobian()                       # the linearisation handed to both (its CUDA counterpart: the jac_* / refdyn_* tests)
+    A, B, c, g_list = ref.cur["A_list"], ref.cur["B_list"], ref.cur["c_offset_list"], ref.cur["g_list"]
+    f = fast_SLS(N, cfg["Q"], cfg["R"], LTV(m, N), cfg["Qf"])
+    f.Q_reg, f.R_reg, f.Q_reg_f = cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"]
+    f.verbose = False
+    f.set_rti_steps(int(g["rti_steps"]) or None)
+    f.update_dynamics_list(A, B, [mo.E] * (N + 1), g_list, [ci.reshape(-1, 1) for ci in c])
+    f.update_linear_cost(2 * (ref.H @ ref.cur["primal_vec"]))
+    for i, dx0 in enumerate(g["dx0s"]):
+        f.current_iteration['iteration_number'] = 0         # the counter accumulates across calls (fast_SLS_jit.py:325); the fixture zeroes it too
+        sol = f.solve(dx0)
+        assert bool(sol["success"]) == bool(g[f"s{i}_success"]) and int(sol["iteration_number"]) == int(g[f"s{i}_iteration_number"])
+        for key in ("primal_x", "primal_u", "K", "beta", "backoff", "backoff_x", "backoff_u"):
+            assert relf(np.asarray(sol[key]), g[f"s{i}_{key}"].reshape(np.shape(sol[key]))) < 2 * TOL_TRAJ, (name, i, key)
+        scale = max(1.0, np.abs(g[f"s{i}_dual_mu"]).max())
+        assert np.abs(np.asarray(sol["dual_mu"]) - g[f"s{i}_dual_mu"]).max() < 1e-5 * scale

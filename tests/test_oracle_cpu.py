@@ -461,3 +461,28 @@ def test_scp_control_flow_matches_the_reference_solve_executed_here(name):
         assert int(sol["SOCP_steps"]) == int(g[f"s{i}_SOCP_steps"])
         # the reference's result dictionary has the keys the drivers read
         assert {"primal_x", "primal_u", "backoff_x", "backoff_u", "t_qp_ms", "t_backward_ms", "success", "iterations", "it_data"} <= set(g[f"s{i}_keys"])
+
+
+@pytest.mark.parametrize("name", ["pendulum", "quadrotor", "rocket"])
+def test_fast_sls_iteration_matches_the_reference_solve_executed_here(name):
+    """tests/golden/reffast_*.npz: two consecutive fast_SLS.solve calls run END TO END by the reference's own statements (control flow,
+    QP class, Numba kernels; only OSQP's ADMM is the restated one, polished; oracle/ref_fast_sls.py) -- pendulum in iterate-until-Q3
+    mode, quadrotor with 2 and rocket with 1 RTI step.  The oracle's FastSLS.solve must return the same dictionaries: iteration counts
+    and success exactly (incl. the Q3 early return of the second pendulum call), everything numeric to 1e-6."""
+    g = load(f"reffast_{name}.npz")
+    assert bool(g["all_polished"])
+    m, cfg = om.CONFIGS[name]()
+    N = cfg["N"]
+    s = oscp.SCPSLS(N, cfg["Q"], cfg["R"], m, cfg["Qf"], cfg["Q_reg"], cfg["R_reg"], cfg["Q_reg_f"], rti=1, fast_sls_rti_steps=int(g["rti_steps"]) or None)
+    s.set_nominal(g["X"], g["U"])
+    s.update_jacobian()
+    for i, dx0 in enumerate(g["dx0s"]):
+        s.fast.cur["iteration_number"] = 0
+        sol = s.fast.solve(dx0)
+        assert bool(sol["success"]) == bool(g[f"s{i}_success"]) and int(sol["iteration_number"]) == int(g[f"s{i}_iteration_number"])
+        for key in ("primal_x", "primal_u", "primal_vec", "dual_mu", "dual_mu_f", "eta_f", "K", "beta", "beta_f", "backoff", "backoff_f",
+                    "backoff_x", "backoff_u"):
+            assert relf(sol[key], g[f"s{i}_{key}"].reshape(np.shape(sol[key]))) < 1e-6, (name, i, key, relf(sol[key], g[f"s{i}_{key}"].reshape(np.shape(sol[key]))))
+        assert relf(sol["eta"], g[f"s{i}_eta"]) < 2e-6
+    if name == "pendulum":
+        assert int(g["s0_iteration_number"]) >= 1 and int(g["s1_iteration_number"]) == 0        # Q3: the history carries over
