@@ -35,9 +35,10 @@ def main():
         ode = np.array([rm.ode(ref, x, u) for x, u in zip(xs, us)])
         xp = np.array([rm.ddyn(ref, x, u, 0.05) for x, u in zip(xs, us)])
         xp02 = np.array([rm.ddyn(ref, x, u, 0.02) for x, u in zip(xs, us)])
+        AB = [rm.jacobians(ref, x, u, 0.05) for x, u in zip(xs, us)]
         ref.discretization_method = "euler"
         xe = np.array([rm.ddyn(ref, x, u, 0.05) for x, u in zip(xs, us)])
-        np.savez(os.path.join(OUT, f"refdyn_{name}.npz"), x=xs, u=us, ode=ode, xp=xp, xp_h002=xp02, xp_euler=xe,
+        np.savez(os.path.join(OUT, f"refdyn_{name}.npz"), x=xs, u=us, ode=ode, xp=xp, xp_h002=xp02, xp_euler=xe, A=np.array([a for a, _ in AB]), B=np.array([b for _, b in AB]),
                  G=np.asarray(ref.G, float), g=np.asarray(ref.g, float).ravel(), Gf=np.asarray(ref.Gf, float),
                  gf=np.asarray(ref.gf, float).ravel(), E=np.asarray(ref.E, float),
                  source=f"reference dyn/{name}.py + dyn/model.py executed through oracle/ref_models.py (numeric CasADi stand-in)")

@@ -30,7 +30,9 @@ def available():
 
 def _mat(a):
     """CasADi semantics: everything is a 2-D matrix; scalars are 1 x 1, flat sequences are columns."""
-    a = np.asarray(a, dtype=float)
+    a = np.asarray(a)
+    if not np.iscomplexobj(a):
+        a = a.astype(float)
     if a.ndim == 0:
         return a.reshape(1, 1)
     if a.ndim == 1:
@@ -117,3 +119,22 @@ def ode(model, x, u):
 def ddyn(model, x, u, h=0.05):
     """``Model.ddyn`` (dyn/model.py:15-34; RK4 unless the instance says 'euler')."""
     return np.asarray(model.ddyn(_mat(x), _mat(u), h), float).ravel()
+
+
+def jacobians(model, x, u, h=0.05, step=1e-30):
+    """A = d ddyn / dx, B = d ddyn / du of the reference's own discretised map by the complex-step derivative
+    (Im f(x + i step e_j) / step: no subtraction, exact to rounding for the analytic functions the models use) -- what the
+    reference obtains from ``ca.jacobian`` (solver/SCP_SLS_jit.py:199-218)."""
+    x, u = np.asarray(x, float), np.asarray(u, float)
+    f = lambda xx, uu: np.asarray(model.ddyn(_mat(xx), _mat(uu), h)).ravel()
+    A = np.empty((len(x), len(x)))
+    B = np.empty((len(x), len(u)))
+    for j in range(len(x)):
+        xc = x.astype(complex)
+        xc[j] += 1j * step
+        A[:, j] = f(xc, u.astype(complex)).imag / step
+    for j in range(len(u)):
+        uc = u.astype(complex)
+        uc[j] += 1j * step
+        B[:, j] = f(x.astype(complex), uc).imag / step
+    return A, B

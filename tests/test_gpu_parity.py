@@ -869,8 +869,11 @@ def test_ddyn_and_residual_vs_the_reference_sources_executed_numerically(name):
     n = len(xs)
     X = np.zeros((n, N + 1, nx)); U = np.zeros((n, N, nu))
     X[:, 0], U[:, 0], X[:, 1] = xs, us, g["xp"]
-    _, _, c = (np_(t) for t in s.linearize(X, U))
+    A, B, c = (np_(t) for t in s.linearize(X, U))
     assert (np.abs(c[:, 0]) / scale(g["xp"])).max() < 1e-12
+    # A_k, B_k against the complex-step derivative of the reference's own RK4 map (what ca.jacobian returns, SCP_SLS_jit.py:199-218)
+    assert np.abs(A[:, 0] - g["A"]).max() < 1e-10 * max(1.0, np.abs(g["A"]).max())
+    assert np.abs(B[:, 0] - g["B"]).max() < 1e-10 * max(1.0, np.abs(g["B"]).max())
     s.close()
 
 

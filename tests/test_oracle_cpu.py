@@ -323,6 +323,10 @@ def test_models_match_the_reference_sources_executed_numerically(name):
     assert (np.abs(xs + 0.05 * ode - g["xp_euler"]) / scale(g["xp_euler"])).max() < 1e-14      # dyn/model.py:23-26
     for key in ("G", "g", "Gf", "gf", "E"):
         assert np.array_equal(np.asarray(getattr(m, key), float).reshape(g[key].shape), g[key]), key
+    # A, B: complex-step derivative of the reference's own RK4 map (what ca.jacobian returns, SCP_SLS_jit.py:199-218)
+    for x, u, A, B in zip(xs, us, g["A"], g["B"]):
+        a, b = m.jacobians(x, u)
+        assert np.abs(a - A).max() < 1e-12 * max(1.0, np.abs(A).max()) and np.abs(b - B).max() < 1e-12 * max(1.0, np.abs(B).max())
     # the product's model header on the host
     lib = cpu_port.load()
     out = np.empty_like(xs)
