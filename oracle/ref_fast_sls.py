@@ -26,9 +26,39 @@ METHODS = ("_step", "forward_solve", "evaluate_dual_eta", "check_convergence_soc
            "initialize_backoff", "post_processing_solution", "_finish_success", "_finish_failure")
 
 
-def reference_fast_sls(name, A, B, E, g_list, c_list, q, dx0s, rti_steps, eps):
-    """One ``fast_SLS`` object of the reference; ``solve(dx0)`` for every dx0 in turn (the Q3 history carries over, as in the
-    reference).  Returns the result dictionaries."""
+class ReferenceFastSLS:
+    """A long-lived ``fast_SLS`` of the reference (attribute bag + unbound methods + the reference's own QP object), with the
+    interface ``SCP_SLS`` uses: update_dynamics_list, update_linear_cost, solve, reset_solver_to_zeros, solver_forward."""
+
+    def __init__(self, name, rti_steps, eps):
+        self.m, cfg = om.CONFIGS[name]()
+        self.bag, self.cls, self.solver_forward, self.rec = _make_bag(name, rti_steps, eps)
+
+    def update_dynamics_list(self, A, B, E, g_list, c_list):
+        self.cls.update_dynamics_list(self.bag, [np.array(a, float) for a in A], [np.array(b, float) for b in B],
+                                      [np.array(e, float) for e in E], [np.array(g, float).reshape(-1, 1) for g in g_list],
+                                      [np.array(c, float).reshape(-1, 1) for c in c_list])
+
+    def update_linear_cost(self, q):
+        self.cls.update_linear_cost(self.bag, np.array(q, float).reshape(-1, 1))
+
+    def solve(self, dx0):
+        return self.cls.solve(self.bag, np.asarray(dx0, float).reshape(-1, 1))
+
+    def reset_solver_to_zeros(self):
+        """fast_SLS_jit.py:424-442 without the list re-initialisation of the OCP base class: initialize_solver + initialize_backoff
+        (both the reference's own) and the QP's reset_ubg / reset_lbg / reset_q_cost_lin; ``_prev_primal_vec`` survives (Q3)."""
+        b = self.bag
+        b.A_list, b.B_list, b.E_list, b.c_offset_list, b.g_list = [], [], [], [], []
+        self.cls.initialize_solver(b)
+        b.current_iteration.update(success=False)
+        b.initialize_backoff()
+        self.solver_forward.reset_ubg()
+        self.solver_forward.reset_lbg()
+        self.solver_forward.reset_q_cost_lin()
+
+
+def _make_bag(name, rti_steps, eps):
     m, cfg = om.CONFIGS[name]()
     N = cfg["N"]
     rec = ref_qp._Recorder()
@@ -43,6 +73,15 @@ def reference_fast_sls(name, A, B, E, g_list, c_list, q, dx0s, rti_steps, eps):
                           reset_solver_to_zeros=lambda: None)
     for name_ in METHODS:
         setattr(bag, name_, (lambda fn: (lambda *a: fn(bag, *a)))(getattr(cls, name_)))
+    return bag, cls, qp, rec
+
+
+def reference_fast_sls(name, A, B, E, g_list, c_list, q, dx0s, rti_steps, eps):
+    """One ``fast_SLS`` object of the reference; ``solve(dx0)`` for every dx0 in turn (the Q3 history carries over, as in the
+    reference).  Returns the result dictionaries."""
+    m, cfg = om.CONFIGS[name]()
+    N = cfg["N"]
+    bag, cls, qp, rec = _make_bag(name, rti_steps, eps)
     # fast_SLS.update_dynamics_list (:250-273), fast_SLS.update_linear_cost (:575)
     bag.A_list, bag.B_list = [np.array(a, float) for a in A], [np.array(b, float) for b in B]
     bag.E_list = [np.array(e, float) for e in E]

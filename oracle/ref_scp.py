@@ -108,8 +108,11 @@ class _Col(np.ndarray):
         return (np.asarray(self) + (other.reshape(-1, 1) if other.ndim == 1 else other)).view(_Col)
 
 
-def reference_closed_loop_steps(name, x0s, X, U, rti=1, sls_steps=1):
-    """Runs solve(x0s[0]), reset_warm_start(), solve(x0s[1]), ... and returns the list of result dictionaries."""
+def reference_closed_loop_steps(name, x0s, X, U, rti=1, sls_steps=1, fast="oracle", eps=1e-6, plant=None):
+    """Runs solve(x0s[0]), reset_warm_start(), solve(x0s[1]), ... and returns the list of result dictionaries.
+    fast = "reference": the fast_SLS object is the reference's own too (oracle/ref_fast_sls.py: its solve iteration, QP class and
+    Numba kernels; ADMM restated), and only the VALUES of the linearisation come from the oracle.  plant: optional callable
+    (step index, x, u0) -> next measured state; then x0s[0] starts a closed loop of len(x0s) steps (the other entries are ignored)."""
     import scipy.sparse as sp
 
     from . import ref_qp
@@ -139,18 +142,37 @@ def reference_closed_loop_steps(name, x0s, X, U, rti=1, sls_steps=1):
         orc.set_nominal(np.array(c["primal_x"], float), np.array(c["primal_u"], float))
         orc.update_jacobian()
     bag.update_jacobian = update_jacobian
-    bag.fast_SLS_solver = SimpleNamespace(solve=lambda dx0: orc.fast.solve(np.asarray(dx0, float).reshape(-1)),
+    ref_fast = None
+    if fast == "reference":
+        from .ref_fast_sls import ReferenceFastSLS
+        ref_fast = ReferenceFastSLS(name, sls_steps, eps)
+
+        def update_jacobian():                                         # values by the oracle, pushed as SCP_SLS_jit.py:343-366 does
+            c = bag.current_iteration_scp
+            Xc, Uc = np.array(c["primal_x"], float), np.array(c["primal_u"], float)
+            A, B, cl, g_list = orc.linearize(Xc, Uc)
+            ref_fast.update_dynamics_list(A, B, [m.E] * (N + 1), g_list, cl)
+            ref_fast.update_linear_cost(2 * (orc.H @ np.array(c["primal_vec"], float).ravel()))
+        bag.update_jacobian = update_jacobian
+    bag.fast_SLS_solver = ref_fast if ref_fast is not None else SimpleNamespace(solve=lambda dx0: orc.fast.solve(np.asarray(dx0, float).reshape(-1)),
                                           reset_solver_to_zeros=orc.fast.reset_solver_to_zeros,
                                           solver_forward=SimpleNamespace(ubg=np.zeros(N * (m.nx + m.ni) + m.ni_f)))
     c = bag.current_iteration_scp
     c["primal_x"], c["primal_u"] = np.array(X, float), np.array(U, float)
     c["primal_vec"] = np.array(bag.pack_primal_nominal(c["primal_x"], c["primal_u"]), float)
     results = []
+    x = np.asarray(x0s[0], float)
     for i, x0 in enumerate(x0s):
         if i > 0:
-            bag.fast_SLS_solver.solver_forward.ubg = np.array(orc.fast.ubg, float)
+            if ref_fast is None:
+                bag.fast_SLS_solver.solver_forward.ubg = np.array(orc.fast.ubg, float)
             cls.reset_warm_start(bag)
-        results.append(cls.solve(bag, np.asarray(x0, float)))
+        x = x if plant is not None else np.asarray(x0, float)
+        sol = cls.solve(bag, x)
+        sol["x_measured"] = x.copy()
+        results.append(sol)
+        if plant is not None and sol.get("success"):
+            x = plant(i, x, np.asarray(sol["primal_u"], float)[:, 0])
     return results
 
 
@@ -181,3 +203,29 @@ def main_solve():
 if __name__ == "__main__":
     main()
     main_solve()
+    main_loop()
+
+
+def main_loop():
+    """tests/golden/refloop_*.npz: closed loops run by the reference's own MPC stack -- SCP_SLS.solve / reset_warm_start over its own
+    fast_SLS.solve, QP class and Numba kernels, plant = its own Model.ddyn + E w -- with only the VALUES of the linearisation (oracle,
+    pinned by refdyn_*) and OSQP's ADMM iteration (restated, polished) supplied."""
+    from .gen_golden_ref_glue import scenario
+    for name, rti, sls_steps, steps, eps in (("pendulum", 3, 2, 6, 1e-6), ("quadrotor", 3, 2, 3, 1e-6), ("rocket", 1, 1, 3, 1e-5)):
+        m, cfg, _, x0, X, U = scenario(name)
+        refm = ref_models.load()[name]()
+        W = np.random.default_rng(123).uniform(-1, 1, (steps, m.nx))
+        states = [np.array(x0, float)]
+
+        def plant(i, x, u):
+            states.append(ref_models.ddyn(refm, x, u) + m.E @ W[i])
+            return states[-1]
+        res = reference_closed_loop_steps(name, [x0] * steps, X, U, rti=rti, sls_steps=sls_steps, fast="reference", eps=eps, plant=plant)
+        assert all(bool(r["success"]) for r in res), name
+        out = dict(X_in=X, U_in=U, x0=x0, W=W, rti=rti, sls_steps=sls_steps, states=np.array(states))
+        for key in ("primal_x", "primal_u", "backoff_x", "backoff_u", "cost", "primal_infeasibility", "dual_mu"):
+            out[key] = np.array([np.asarray(r[key], float) for r in res])
+        np.savez_compressed(os.path.join(OUT, f"refloop_{name}.npz"),
+                            source="reference SCP_SLS.solve / reset_warm_start over the reference's fast_SLS.solve, QP class and Numba kernels "
+                                   f"(oracle/ref_scp.py, fast='reference'); linearisation values by the oracle, ADMM restated at eps {eps:g}", **out)
+        print(name, "written;", steps, "steps, cost", out["cost"].ravel())

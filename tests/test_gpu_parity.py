@@ -990,3 +990,30 @@ def test_fast_sls_class_vs_the_reference_solve_executed_here(name):
             assert relf(np.asarray(sol[key]), g[f"s{i}_{key}"].reshape(np.shape(sol[key]))) < 2 * TOL_TRAJ, (name, i, key)
         scale = max(1.0, np.abs(g[f"s{i}_dual_mu"]).max())
         assert np.abs(np.asarray(sol["dual_mu"]) - g[f"s{i}_dual_mu"]).max() < 1e-5 * scale
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_closed_loop_vs_the_reference_stack_executed_here(name):
+    """The driver loop (expe/main_rocket_compare_closed_loop.py:142-159) on this package's `SCP_SLS` and model classes against closed loops
+    run by the reference's OWN MPC stack (tests/golden/refloop_*.npz: SCP_SLS.solve / reset_warm_start over its own fast_SLS.solve, QP
+    class, Numba kernels and Model.ddyn; only the linearisation values and OSQP's ADMM iteration supplied, oracle/ref_scp.py):
+    closed-loop states 1e-5, nominal trajectory and back-offs 1e-6 -- the north star's contract, against executed reference code."""
+    import importlib
+    from rnmpc_b200.solver.SCP_SLS_jit import SCP_SLS
+    g = load(f"refloop_{name}.npz")
+    mo, cfg = om.CONFIGS[name]()
+    m = getattr(importlib.import_module(f"rnmpc_b200.dyn.{name}"), name.capitalize())()
+    m.E = mo.E
+    solver = SCP_SLS(cfg["N"], cfg["Q"], cfg["R"], m, cfg["Qf"], Q_reg=cfg["Q_reg"], R_reg=cfg["R_reg"], Q_reg_f=cfg["Q_reg_f"],
+                     rti=int(g["rti"]), fast_sls_rti_steps=int(g["sls_steps"]), verbose=False)
+    solver.set_nominal_trajectory(g["X_in"], g["U_in"])
+    x = g["x0"].copy()
+    for i in range(len(g["W"])):
+        if i > 0:
+            solver.reset_warm_start()
+        sol = solver.solve(x)
+        assert sol["success"]
+        assert relf(np.asarray(sol["primal_x"]), g["primal_x"][i]) < TOL_TRAJ and relf(np.asarray(sol["primal_u"]), g["primal_u"][i]) < TOL_TRAJ
+        assert relf(np.asarray(sol["backoff_x"]), g["backoff_x"][i]) < TOL_TRAJ and relf(np.asarray(sol["backoff_u"]), g["backoff_u"][i]) < TOL_TRAJ
+        x = np.array(m.ddyn(x, sol["primal_u"][:, 0]) + m.E @ g["W"][i]).reshape(-1)
+        assert np.abs(x - g["states"][i + 1]).max() < TOL_STATE * max(1.0, np.abs(g["states"]).max())

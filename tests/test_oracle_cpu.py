@@ -490,3 +490,21 @@ def test_fast_sls_iteration_matches_the_reference_solve_executed_here(name):
         assert relf(sol["eta"], g[f"s{i}_eta"]) < 2e-6
     if name == "pendulum":
         assert int(g["s0_iteration_number"]) >= 1 and int(g["s1_iteration_number"]) == 0        # Q3: the history carries over
+
+
+@pytest.mark.parametrize("name", ["pendulum", "quadrotor", "rocket"])
+def test_closed_loop_matches_the_reference_stack_executed_here(name):
+    """tests/golden/refloop_*.npz: closed loops (pendulum 6, quadrotor 3, rocket 3 MPC steps, disturbed) run by the reference's OWN MPC
+    stack -- SCP_SLS.solve / reset_warm_start over its own fast_SLS.solve, QP class, Numba kernels and Model.ddyn; only the values of the
+    linearisation and OSQP's ADMM iteration are supplied (oracle/ref_scp.py).  The oracle's closed loop must follow: closed-loop states
+    1e-5 (north star), nominal trajectories and back-offs 1e-6."""
+    g = load(f"refloop_{name}.npz")
+    m, cfg = om.CONFIGS[name]()
+    cfg = dict(cfg, rti=int(g["rti"]), fast_sls_rti_steps=int(g["sls_steps"]))
+    steps = len(g["W"])
+    out = oscp.closed_loop(m, cfg, g["x0"], g["W"], steps, X0=g["X_in"], U0=g["U_in"])
+    assert all(out["success"]) and len(out["X"]) == steps + 1
+    assert relf(np.array(out["X"]), g["states"]) < 1e-5
+    for i in range(steps):
+        assert relf(out["Xn"][i], g["primal_x"][i]) < 1e-6 and relf(out["Un"][i], g["primal_u"][i]) < 1e-6
+        assert relf(out["backoff_x"][i], g["backoff_x"][i]) < 1e-6 and relf(out["backoff_u"][i], g["backoff_u"][i]) < 1e-6
