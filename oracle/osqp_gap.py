@@ -1,7 +1,7 @@
 """Gap between "OSQP with default settings + polish" (restated: oracle/osqp_restated.py) and the exact solution of the
 nominal QP (oracle/qp.py, what the CUDA interior point computes) on the committed QP fixtures, with the bounds exactly
 as the reference hands them over (solver/qp_jit.py:370-386: +-1e20 for infinity, x0 rows +-1e-10, stage-0 state rows
-of G kept).  CPU only:  python tools/osqp_gap.py > profiles/r3f_osqp_restated_gap.txt"""
+of G kept).  CPU only:  python -m oracle.osqp_gap > profiles/r3f_osqp_restated_gap.txt"""
 import os
 import sys
 import time

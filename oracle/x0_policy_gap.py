@@ -1,7 +1,7 @@
 """What "OSQP with default settings" (restated: oracle/osqp_restated.py) does when the measured state x(0) lies outside the
 state box by d, i.e. when the stage-0 state row of G contradicts the pinned x(0) (solver/qp_jit.py:370-386 keeps both).
 The exact solvers of this repository (oracle/qp.py, the CUDA interior point) drop those rows for d <= 1e-3 and fail the
-instance beyond (X0_TOL).  CPU only:  python tools/x0_policy_gap.py > profiles/r3f_x0_policy_gap.txt"""
+instance beyond (X0_TOL).  CPU only:  python -m oracle.x0_policy_gap > profiles/r3f_x0_policy_gap.txt"""
 import os
 import sys
 
@@ -9,7 +9,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import osqp_restated as osr, qp as oqp  # noqa: E402
-from tools.osqp_gap import fixture_qps  # noqa: E402
+from oracle.osqp_gap import fixture_qps  # noqa: E402
 
 print("fixture     d       status             iters  polish  excess over the stage-0 row  x0-row residual  |x - x*(rows dropped)| rel")
 for name, idx in (("pendulum", 0), ("quadrotor", 0), ("rocket", 3)):

@@ -280,7 +280,7 @@ def test_restated_osqp_polish_lands_on_the_exact_oracle_solution(name):
     ADMM iterate to identify the active set -- the default 1e-3 on most fixtures, 1e-4 / 1e-5 on the others
     (profiles/r3f_osqp_restated_gap.txt) -- while the un-polished ADMM point stays within a few eps of it."""
     from oracle import osqp_restated as osr
-    from tools.osqp_gap import fixture_qps, gaps
+    from oracle.osqp_gap import fixture_qps, gaps
     n_default = n = 0
     for i, tight, qp, P, q, A, l, u, y, mu in fixture_qps(name):
         if name == "rocket" and i in (0, 2):
