@@ -990,6 +990,8 @@ def test_fast_sls_class_vs_the_reference_solve_executed_here(name):
             assert relf(np.asarray(sol[key]), g[f"s{i}_{key}"].reshape(np.shape(sol[key]))) < 2 * TOL_TRAJ, (name, i, key)
         scale = max(1.0, np.abs(g[f"s{i}_dual_mu"]).max())
         assert np.abs(np.asarray(sol["dual_mu"]) - g[f"s{i}_dual_mu"]).max() < 1e-5 * scale
+        if int(sol["iteration_number"]) > 0:        # block-matrix form of the gains (util/SLS.py:49-63 through post_processing_solution)
+            assert sol["K_mat"].shape == g[f"s{i}_K_mat"].shape and relf(sol["K_mat"], g[f"s{i}_K_mat"]) < 2 * TOL_TRAJ
 
 
 @pytest.mark.parametrize("name", MODELS)
