@@ -146,6 +146,9 @@ def reference_closed_loop_steps(name, x0s, X, U, rti=1, sls_steps=1, fast="oracl
     if fast == "reference":
         from .ref_fast_sls import ReferenceFastSLS
         ref_fast = ReferenceFastSLS(name, sls_steps, eps)
+        if isinstance(plant, dict):                                    # diagnostics: {'plant': callable, 'rec': list} collects the QP records
+            plant["rec"].append(ref_fast.rec)
+            plant = plant["plant"]
 
         def update_jacobian():                                         # values by the oracle, pushed as SCP_SLS_jit.py:343-366 does
             c = bag.current_iteration_scp
